@@ -1,0 +1,99 @@
+/* b200ani -- C ABI of the B200-native engine behind pyani's pairwise-comparison hot path.
+ *
+ * Drop-in boundary: pyani has no FFI; today the path sits behind "shell command string
+ * + output file + 4-tuple".  Each entry point below names the reference interface it replaces
+ * (file:line relative to widdowquinn/pyani @ v0.3.0-alpha).  INTEGRATION.md shows the ctypes stub a
+ * pyani maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; all buffers are caller-owned HOST memory; every call is
+ * blocking; one context drives ONE GPU from one host thread (one process per GPU; multi-GPU sharding
+ * lives above this ABI, see pyani_b200/dist.py); return 0 = OK, negative = error with text in
+ * b200ani_last_error().  There is no CPU fallback: without a CUDA device b200ani_create() fails.
+ */
+#ifndef B200ANI_H
+#define B200ANI_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200ani_ctx b200ani_ctx;
+
+#define B200ANI_OK 0
+#define B200ANI_ERR_CUDA (-1)
+#define B200ANI_ERR_ARG (-2)
+#define B200ANI_ERR_NOMEM (-3)
+#define B200ANI_ERR_CAPACITY (-4)
+
+/* per-pair soft status (anim.py:481-486 "Zero length alignment!" becomes a status, not an abort) */
+#define B200ANI_STATUS_OK 0
+#define B200ANI_STATUS_NO_ALIGNMENT 1
+
+/* Context = device, stream, HBM arenas.  Replaces the process pool of
+ * run_multiprocessing.multiprocessing_run (run_multiprocessing.py:113-152). */
+int b200ani_create(b200ani_ctx **out, int device_id);
+void b200ani_destroy(b200ani_ctx *ctx);
+/* Goes into Comparison.version like anim.get_version's string (anim.py:94-151). */
+const char *b200ani_version(void);
+const char *b200ani_last_error(const b200ani_ctx *ctx);
+
+/* Stage one genome in HBM: raw residues of all records concatenated (no newlines/headers) plus record
+ * offsets (n_contigs+1 entries, off[0]=0).  Replaces the FASTA paths handed to nucmer / SeqIO.parse
+ * (anim.py:280, tetra.py:98).  Packs to 2 bit/base + 1 bit/base ambiguity mask on the device.
+ * Genome length = off[n_contigs], ambiguity symbols included (pyani_files.py:137-141). */
+int b200ani_add_genome(b200ani_ctx *ctx, const uint8_t *ascii, const uint64_t *contig_off, uint32_t n_contigs,
+                       int32_t *out_genome_id);
+int b200ani_genome_count(const b200ani_ctx *ctx);
+int64_t b200ani_genome_length(const b200ani_ctx *ctx, int32_t genome_id);
+
+/* ---- TETRA (tetra.py) ---- */
+/* Both-strand di/tri/tetra-nucleotide counts exactly as tetra.calculate_tetra_zscore accumulates them
+ * (tetra.py:92-116, including the never-counted last tetramer of each strand of each record).
+ * c2[16], c3[64], c4[256], index = base-4 number of the k-mer with A=0,C=1,G=2,T=3. */
+int b200ani_tetra_counts(b200ani_ctx *ctx, int32_t genome_id, int64_t *c2, int64_t *c3, int64_t *c4);
+/* Z-scores of n genomes, z[n][256] in AAAA..TTTT order; observed[n][256]=0 where the reference dict
+ * would have no key (tetra.py:120).  Replaces tetra.calculate_tetra_zscore (tetra.py:78-139). */
+int b200ani_tetra_zscores(b200ani_ctx *ctx, const int32_t *genome_ids, int n, double *z, uint8_t *observed);
+/* Pearson correlation matrix corr[n][n] from z[n][256] over the tetramers with mask[t]!=0, serial
+ * left-to-right fp64 sums in sorted tetramer order.  Replaces tetra.calculate_correlations
+ * (tetra.py:158-194). */
+int b200ani_tetra_corr(b200ani_ctx *ctx, const double *z, const uint8_t *mask, int n, double *corr);
+
+/* ---- ANIm (anim.py) ---- */
+/* One directed comparison; ref = pyani "query" = nucmer reference (subcmd_anim.py:323-333).
+ * Fields are anim.parse_delta's return (anim.py:411) kept as exact integers:
+ * identity = sum_weighted / sum_aligned (anim.py:396). */
+typedef struct {
+    int64_t ref_aln_len;  /* parse_delta()[0] */
+    int64_t qry_aln_len;  /* parse_delta()[1] */
+    int64_t sum_aligned;  /* sum(aligned_bases), anim.py:386-387 */
+    int64_t sum_weighted; /* sum(weighted_identical_bases), anim.py:391-393 */
+    int64_t sim_errs;     /* parse_delta()[3] */
+    int32_t n_alignments; /* alignment headers that would be in the .filter (or .delta if nofilter) */
+    int32_t status;       /* B200ANI_STATUS_* */
+} b200ani_anim_result;    /* 48 bytes */
+
+/* All m directed pairs (pairs[2*i]=ref genome id, pairs[2*i+1]=qry genome id).  Replaces, per pair, the
+ * nucmer + delta-filter subprocesses (anim.py:240-289) and anim.parse_delta (anim.py:292-411).
+ * maxmatch: anim.py:276-279 (only --mum semantics, maxmatch=0, are implemented in this version).
+ * nofilter: subcmd_anim.py:341-344 (skip the 1-to-1 filter stage). */
+int b200ani_anim(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch, int nofilter,
+                 b200ani_anim_result *out);
+
+/* Alignment headers of ONE directed pair, as rows of 7 int64 (ref_contig, qry_contig, rs, re, qs, qe,
+ * errs) in .delta conventions (1-based, closed, reverse strand has qs > qe; anim.py:300-310).  Used to
+ * emit minimal .filter files for an unmodified subcmd_anim.update_comparison_results and by tests.
+ * Returns the number of alignments (<= cap rows written) or a negative error. */
+int64_t b200ani_anim_alignments(b200ani_ctx *ctx, int32_t ref_id, int32_t qry_id, int maxmatch, int nofilter,
+                                int64_t *rows, int64_t cap);
+
+/* Stage timers of the last b200ani_anim call in milliseconds (CUDA events on the engine stream) and
+ * the number of kernel launches it issued; used by bench.py for the roofline and gpu_launches. */
+#define B200ANI_N_STAGES 16
+int b200ani_last_profile(const b200ani_ctx *ctx, double *stage_ms /*B200ANI_N_STAGES*/, int64_t *counters /*B200ANI_N_STAGES*/);
+const char *b200ani_stage_name(int stage);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,136 @@
+"""CPU oracle for the pyani pairwise hot path -- TEST INFRASTRUCTURE, not product code.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this package.  ``pyani_b200`` (the product) never does: it fails loudly if its CUDA
+library is missing instead of falling back here.
+
+The arithmetic lives in the plain-C files next to this one (each function cites the reference
+file:line it restates); this module is the ctypes shim plus the two text parsers
+(`.delta` headers, anim.py:366-393) needed to feed the reference's checked-in aligner output to it.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+
+
+def build(force: bool = False) -> Path:
+    so = _HERE / "liboracle.so"
+    srcs = sorted(_HERE.glob("oracle_*.c")) + sorted(_HERE.glob("*.h"))
+    if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
+        subprocess.run(["make", "-s", "-C", str(_HERE), "liboracle.so"], check=True)
+    return so
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        so = _HERE / "liboracle.so"
+        if not so.exists() or os.environ.get("ORACLE_REBUILD"):
+            build()
+        else:
+            try:
+                build()
+            except Exception:  # GPU box without make/gcc still has the shipped .so
+                pass
+        _LIB = ctypes.CDLL(str(so))
+    return _LIB
+
+
+def _p(a, t):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+# ----------------------------------------------------------------------------- TETRA
+def tetra_counts(ascii_u8: np.ndarray, contig_off: np.ndarray):
+    ascii_u8 = np.ascontiguousarray(ascii_u8, dtype=np.uint8)
+    contig_off = np.ascontiguousarray(contig_off, dtype=np.uint64)
+    c2, c3, c4 = (np.zeros(k, dtype=np.int64) for k in (16, 64, 256))
+    lib().orc_tetra_counts(_p(ascii_u8, ctypes.c_uint8), _p(contig_off, ctypes.c_uint64),
+                           ctypes.c_uint32(len(contig_off) - 1),
+                           _p(c2, ctypes.c_int64), _p(c3, ctypes.c_int64), _p(c4, ctypes.c_int64))
+    return c2, c3, c4
+
+
+def tetra_zscores(c2, c3, c4):
+    z = np.zeros(256, dtype=np.float64)
+    obs = np.zeros(256, dtype=np.uint8)
+    lib().orc_tetra_zscores(_p(c2, ctypes.c_int64), _p(c3, ctypes.c_int64), _p(c4, ctypes.c_int64),
+                            _p(z, ctypes.c_double), _p(obs, ctypes.c_uint8))
+    return z, obs
+
+
+def tetra_corr(z: np.ndarray, mask: np.ndarray | None = None):
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    n = z.shape[0]
+    mask = np.ones(256, np.uint8) if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+    corr = np.zeros((n, n), dtype=np.float64)
+    lib().orc_tetra_corr(_p(z, ctypes.c_double), _p(mask, ctypes.c_uint8), ctypes.c_int(n), _p(corr, ctypes.c_double))
+    return corr
+
+
+TETRAMERS = ["".join("ACGT"[(t >> s) & 3] for s in (6, 4, 2, 0)) for t in range(256)]
+
+
+# ----------------------------------------------------------------------------- ANIm reduction
+def parse_delta_text(path) -> np.ndarray:
+    """Rows (ref_seq_id, qry_seq_id, rs, re, qs, qe, errs) from a .delta/.filter file.
+
+    Restates the line classification of anim.py:366-393: '>' lines switch the current sequence
+    pair, 7-field lines are alignment headers, everything else (indel offsets) is ignored.
+    Sequence names are mapped to integer ids per side (ids only need to be distinct per name).
+    """
+    rid, qid, rows = {}, {}, []
+    cr = cq = -1
+    with open(path) as fh:
+        for raw in fh:
+            f = raw.strip().split()
+            if not f or f[0] == "NUCMER":
+                continue
+            if f[0].startswith(">"):
+                cr = rid.setdefault(f[0][1:], len(rid))
+                cq = qid.setdefault(f[1], len(qid))
+            elif len(f) == 7:
+                rows.append((cr, cq, int(f[0]), int(f[1]), int(f[2]), int(f[3]), int(f[4])))
+    return np.asarray(rows, dtype=np.int64).reshape(-1, 7)
+
+
+def parse_delta_reduce(aln: np.ndarray):
+    """-> (ref_aln_len, qry_aln_len, identity, sim_errs) exactly as anim.parse_delta (anim.py:411)."""
+    aln = np.ascontiguousarray(aln, dtype=np.int64).reshape(-1, 7)
+    out = np.zeros(5, dtype=np.int64)
+    lib().orc_parse_delta_reduce(_p(aln, ctypes.c_int64), ctypes.c_int64(aln.shape[0]), _p(out, ctypes.c_int64))
+    if out[2] == 0:
+        raise ZeroDivisionError("no alignments (anim.py:396 divides by sum(aligned_bases))")
+    return int(out[0]), int(out[1]), int(out[3]) / int(out[2]), int(out[4])
+
+
+# ----------------------------------------------------------------------------- FASTA (host helper)
+def read_fasta(path):
+    """-> (ascii uint8 array of all residues, contig_off uint64[n+1], [record ids]). Ns are kept."""
+    ids, chunks, lens = [], [], []
+    cur = None
+    with open(path, "rb") as fh:
+        for line in fh:
+            if line.startswith(b">"):
+                if cur is not None:
+                    lens.append(sum(len(c) for c in cur)); chunks.extend(cur)
+                ids.append(line[1:].split()[0].decode() if line[1:].split() else "")
+                cur = []
+            elif cur is not None:
+                s = line.strip()
+                if s:
+                    cur.append(s)
+    if cur is not None:
+        lens.append(sum(len(c) for c in cur)); chunks.extend(cur)
+    data = np.frombuffer(b"".join(chunks), dtype=np.uint8).copy()
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(np.asarray(lens, dtype=np.uint64))
+    return data, off, ids

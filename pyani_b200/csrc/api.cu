@@ -1,0 +1,179 @@
+// C ABI of the engine (include/b200ani.h): context, genome staging, TETRA entry points.
+// The ANIm entry points live in anim_host.cu.
+#include <cstring>
+
+#include "common.cuh"
+
+static const char *kVersion = "b200ani 0.1.0 (sm_100a)";
+
+extern "C" {
+
+const char *b200ani_version(void) { return kVersion; }
+
+const char *b200ani_last_error(const b200ani_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int b200ani_create(b200ani_ctx **out, int device_id) {
+    if (!out) return B200ANI_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device_id < 0 || device_id >= n) {
+        fprintf(stderr, "b200ani_create: no usable CUDA device %d (%s); there is no CPU fallback\n", device_id,
+                e == cudaSuccess ? "device id out of range" : cudaGetErrorString(e));
+        return B200ANI_ERR_CUDA;
+    }
+    b200ani_ctx *ctx = new b200ani_ctx();
+    ctx->device = device_id;
+    if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return B200ANI_ERR_CUDA;
+    }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
+    // keep freed async allocations cached in the pool: the engine re-allocates the same sizes per batch
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return B200ANI_OK;
+}
+
+void b200ani_destroy(b200ani_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &g : ctx->genomes) {
+        cudaFree(g.d_seq);
+        cudaFree(g.d_mask);
+        cudaFree(g.d_goff);
+        free_index(g.index);
+    }
+    free_anim_workspace(ctx->anim_ws);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int b200ani_genome_count(const b200ani_ctx *ctx) { return ctx ? (int)ctx->genomes.size() : 0; }
+
+int64_t b200ani_genome_length(const b200ani_ctx *ctx, int32_t id) {
+    if (!ctx || id < 0 || id >= (int32_t)ctx->genomes.size()) return -1;
+    return ctx->genomes[id].n_bases;
+}
+
+int b200ani_add_genome(b200ani_ctx *ctx, const uint8_t *ascii, const uint64_t *contig_off, uint32_t n_contigs,
+                       int32_t *out_id) {
+    if (!ctx) return B200ANI_ERR_ARG;
+    if (!contig_off || n_contigs == 0 || contig_off[0] != 0) FAIL(B200ANI_ERR_ARG, "add_genome: need >=1 record and off[0]==0");
+    for (uint32_t c = 0; c < n_contigs; ++c)
+        if (contig_off[c + 1] < contig_off[c]) FAIL(B200ANI_ERR_ARG, "add_genome: record offsets must be non-decreasing");
+    const int64_t n_bases = (int64_t)contig_off[n_contigs];
+    if (n_bases > 0 && !ascii) FAIL(B200ANI_ERR_ARG, "add_genome: null residues");
+    if (n_bases + n_contigs >= (1ll << 31) - 1024) FAIL(B200ANI_ERR_CAPACITY, "add_genome: genome exceeds 2^31 positions");
+    CK(cudaSetDevice(ctx->device));
+    Genome g;
+    g.n_bases = n_bases;
+    g.n_contigs = n_contigs;
+    g.n_pos = n_bases + n_contigs;
+    g.n_pad = ((g.n_pos + 256 + 127) / 128) * 128;
+    g.h_goff.resize(n_contigs + 1);
+    for (uint32_t c = 0; c <= n_contigs; ++c) g.h_goff[c] = contig_off[c] + c;
+    uint8_t *d_ascii = nullptr;
+    CK(cudaMalloc(&g.d_seq, (size_t)g.n_pad / 4 + 64));
+    CK(cudaMalloc(&g.d_mask, (size_t)g.n_pad / 8 + 64));
+    CK(cudaMalloc(&g.d_goff, sizeof(uint64_t) * (n_contigs + 1)));
+    CK(cudaMemsetAsync(g.d_seq, 0, (size_t)g.n_pad / 4 + 64, ctx->stream));
+    CK(cudaMemsetAsync(g.d_mask, 0xff, (size_t)g.n_pad / 8 + 64, ctx->stream));
+    CK(cudaMallocAsync(&d_ascii, (size_t)n_bases + 64, ctx->stream));
+    // pageable or pinned: the caller owns the buffer; cudaMemcpyAsync degrades gracefully for pageable
+    if (n_bases) CK(cudaMemcpyAsync(d_ascii, ascii, (size_t)n_bases, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(g.d_goff, g.h_goff.data(), sizeof(uint64_t) * (n_contigs + 1), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_pack(ctx, d_ascii, g.d_goff, g);
+    if (rc) return rc;
+    CK(cudaFreeAsync(d_ascii, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // h_goff / caller buffer lifetimes end here
+    ctx->genomes.push_back(std::move(g));
+    if (out_id) *out_id = (int32_t)ctx->genomes.size() - 1;
+    return B200ANI_OK;
+}
+
+// ------------------------------------------------------------------------------------------ TETRA
+static int tetra_totals_for(b200ani_ctx *ctx, const int32_t *ids, int n, unsigned long long *d_tot) {
+    for (int i = 0; i < n; ++i) {
+        if (ids[i] < 0 || ids[i] >= (int32_t)ctx->genomes.size()) FAIL(B200ANI_ERR_ARG, "tetra: bad genome id");
+        int rc = tetra_counts_device(ctx, ctx->genomes[ids[i]], d_tot + (size_t)i * 336);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int b200ani_tetra_counts(b200ani_ctx *ctx, int32_t id, int64_t *c2, int64_t *c3, int64_t *c4) {
+    if (!ctx || !c2 || !c3 || !c4) return B200ANI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long *d_tot = nullptr, h[336];
+    CK(cudaMallocAsync(&d_tot, sizeof h, ctx->stream));
+    int rc = tetra_totals_for(ctx, &id, 1, d_tot);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h, d_tot, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaFreeAsync(d_tot, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 16; ++i) c2[i] = (int64_t)h[i];
+    for (int i = 0; i < 64; ++i) c3[i] = (int64_t)h[16 + i];
+    for (int i = 0; i < 256; ++i) c4[i] = (int64_t)h[80 + i];
+    return B200ANI_OK;
+}
+
+int b200ani_tetra_zscores(b200ani_ctx *ctx, const int32_t *ids, int n, double *z, uint8_t *observed) {
+    if (!ctx || !ids || n <= 0 || !z || !observed) return B200ANI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long *d_tot = nullptr;
+    double *d_z = nullptr;
+    uint8_t *d_obs = nullptr;
+    CK(cudaMallocAsync(&d_tot, sizeof(unsigned long long) * 336 * (size_t)n, ctx->stream));
+    CK(cudaMallocAsync(&d_z, sizeof(double) * 256 * (size_t)n, ctx->stream));
+    CK(cudaMallocAsync(&d_obs, 256 * (size_t)n, ctx->stream));
+    int rc = tetra_totals_for(ctx, ids, n, d_tot);
+    if (rc) return rc;
+    rc = tetra_zscores_device(ctx, d_tot, n, d_z, d_obs);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(z, d_z, sizeof(double) * 256 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(observed, d_obs, 256 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaFreeAsync(d_tot, ctx->stream));
+    CK(cudaFreeAsync(d_z, ctx->stream));
+    CK(cudaFreeAsync(d_obs, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200ANI_OK;
+}
+
+int b200ani_tetra_corr(b200ani_ctx *ctx, const double *z, const uint8_t *mask, int n, double *corr) {
+    if (!ctx || !z || n <= 0 || !corr) return B200ANI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int idx[256], m = 0;
+    for (int t = 0; t < 256; ++t)
+        if (!mask || mask[t]) idx[m++] = t;
+    if (m == 0) FAIL(B200ANI_ERR_ARG, "tetra_corr: empty tetramer mask");
+    double *d_z = nullptr, *d_corr = nullptr;
+    int *d_idx = nullptr;
+    CK(cudaMallocAsync(&d_z, sizeof(double) * 256 * (size_t)n, ctx->stream));
+    CK(cudaMallocAsync(&d_corr, sizeof(double) * (size_t)n * n, ctx->stream));
+    CK(cudaMallocAsync(&d_idx, sizeof idx, ctx->stream));
+    CK(cudaMemcpyAsync(d_z, z, sizeof(double) * 256 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_idx, idx, sizeof idx, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = tetra_corr_device(ctx, d_z, d_idx, m, n, d_corr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(corr, d_corr, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaFreeAsync(d_z, ctx->stream));
+    CK(cudaFreeAsync(d_corr, ctx->stream));
+    CK(cudaFreeAsync(d_idx, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200ANI_OK;
+}
+
+int b200ani_last_profile(const b200ani_ctx *ctx, double *stage_ms, int64_t *counters) {
+    if (!ctx) return B200ANI_ERR_ARG;
+    if (stage_ms) memcpy(stage_ms, ctx->stage_ms, sizeof ctx->stage_ms);
+    if (counters) memcpy(counters, ctx->counters, sizeof ctx->counters);
+    return B200ANI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+"""Host-side handle on one GPU's b200ani context (one Engine per process / per GPU)."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .fasta import read_fasta
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib_path() -> Path:
+    return _lib.LIB_PATH
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """Owns a ``b200ani_ctx``: genomes staged in HBM, TETRA and ANIm entry points.
+
+    >>> eng = Engine(device=0)
+    >>> gid = eng.add_fasta("genome.fna")
+    >>> z, observed = eng.tetra_zscores([gid])
+    """
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.b200ani_create(C.byref(h), int(device))
+        if rc != 0 or not h:
+            raise EngineError(f"b200ani_create(device={device}) failed with rc={rc}: a CUDA device is required (no CPU fallback)")
+        self._h = h
+        self.device = int(device)
+        self.names: List[str] = []
+        self.contig_ids: List[List[str]] = []
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200ani_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise EngineError(f"{what}: rc={rc}: {self._lib.b200ani_last_error(self._h).decode()}")
+
+    @property
+    def version(self) -> str:
+        return self._lib.b200ani_version().decode()
+
+    # -- genomes
+    def add_genome(self, residues: np.ndarray, contig_off: np.ndarray, name: str = "", contig_ids: Optional[List[str]] = None) -> int:
+        residues = np.ascontiguousarray(residues, dtype=np.uint8)
+        contig_off = np.ascontiguousarray(contig_off, dtype=np.uint64)
+        gid = C.c_int32(-1)
+        rc = self._lib.b200ani_add_genome(self._h, _ptr(residues), _ptr(contig_off), len(contig_off) - 1, C.byref(gid))
+        self._check(rc, "add_genome")
+        self.names.append(name or f"genome{gid.value}")
+        self.contig_ids.append(contig_ids or [str(i) for i in range(len(contig_off) - 1)])
+        return gid.value
+
+    def add_fasta(self, path) -> int:
+        arr, off, ids = read_fasta(path)
+        return self.add_genome(arr, off, Path(path).stem, ids)
+
+    def genome_length(self, gid: int) -> int:
+        return int(self._lib.b200ani_genome_length(self._h, gid))
+
+    def __len__(self):
+        return int(self._lib.b200ani_genome_count(self._h))
+
+    # -- TETRA
+    def tetra_counts(self, gid: int):
+        c2, c3, c4 = (np.zeros(k, dtype=np.int64) for k in (16, 64, 256))
+        self._check(self._lib.b200ani_tetra_counts(self._h, gid, _ptr(c2), _ptr(c3), _ptr(c4)), "tetra_counts")
+        return c2, c3, c4
+
+    def tetra_zscores(self, gids: Sequence[int]):
+        ids = np.ascontiguousarray(gids, dtype=np.int32)
+        z = np.zeros((len(ids), 256), dtype=np.float64)
+        obs = np.zeros((len(ids), 256), dtype=np.uint8)
+        self._check(self._lib.b200ani_tetra_zscores(self._h, _ptr(ids), len(ids), _ptr(z), _ptr(obs)), "tetra_zscores")
+        return z, obs
+
+    def tetra_corr(self, z: np.ndarray, mask: Optional[np.ndarray] = None) -> np.ndarray:
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        n = z.shape[0]
+        mask_arr = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        corr = np.zeros((n, n), dtype=np.float64)
+        self._check(self._lib.b200ani_tetra_corr(self._h, _ptr(z), None if mask_arr is None else _ptr(mask_arr), n, _ptr(corr)), "tetra_corr")
+        return corr
+
+    # -- ANIm
+    def anim(self, pairs: np.ndarray, maxmatch: bool = False, nofilter: bool = False) -> np.ndarray:
+        """pairs: (m,2) int32 of (ref genome id, qry genome id) -> structured array of AnimResult."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        out = np.zeros(len(pairs), dtype=ANIM_DTYPE)
+        if len(pairs):
+            self._check(self._lib.b200ani_anim(self._h, _ptr(pairs), len(pairs), int(maxmatch), int(nofilter), _ptr(out)), "anim")
+        return out
+
+    def anim_alignments(self, ref: int, qry: int, maxmatch: bool = False, nofilter: bool = False, cap: int = 1 << 16) -> np.ndarray:
+        rows = np.zeros((cap, 7), dtype=np.int64)
+        n = self._lib.b200ani_anim_alignments(self._h, ref, qry, int(maxmatch), int(nofilter), _ptr(rows), cap)
+        if n < 0:
+            self._check(int(n), "anim_alignments")
+        return rows[: min(n, cap)].copy()
+
+    def last_profile(self) -> Tuple[Dict[str, float], Dict[str, int]]:
+        ms = np.zeros(_lib.N_STAGES, dtype=np.float64)
+        cnt = np.zeros(_lib.N_STAGES, dtype=np.int64)
+        self._lib.b200ani_last_profile(self._h, _ptr(ms), _ptr(cnt))
+        names = [self._lib.b200ani_stage_name(i).decode() for i in range(_lib.N_STAGES)]
+        return ({n: float(v) for n, v in zip(names, ms) if n}, {n: int(v) for n, v in zip(names, cnt) if n})
+
+
+ANIM_DTYPE = np.dtype(
+    [("ref_aln_len", "<i8"), ("qry_aln_len", "<i8"), ("sum_aligned", "<i8"), ("sum_weighted", "<i8"),
+     ("sim_errs", "<i8"), ("n_alignments", "<i4"), ("status", "<i4")]
+)
+assert ANIM_DTYPE.itemsize == 48

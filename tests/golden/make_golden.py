@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Generate the committed golden vectors by running THE REFERENCE ITSELF in the build container.
+
+Run from the repo root:  python tests/golden/make_golden.py
+Needs /root/reference (read-only) and the stub modules under oracle/refstubs (Biopython /
+intervaltree / matplotlib are not installed here).  Outputs (small, committed):
+  tests/golden/tetra_reference.json      Z-scores + correlations from pyani.tetra on the 4 fixture
+                                         genomes and on small inline edge-case FASTAs
+  tests/golden/anim_parse_delta.json     anim.parse_delta tuples on every checked-in .delta/.filter
+  tests/golden/anim_alignments.npz       the 7-int alignment headers of those files (inputs)
+It also copies the fixture genomes the GPU tests read into oracle/_ref/fixtures/ (git-ignored, but
+shipped to the GPU box by gpurun, where /root/reference does not exist).
+"""
+import json
+import shutil
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+REF = Path("/root/reference")
+sys.path[:0] = [str(ROOT / "oracle" / "refstubs"), str(REF), str(ROOT)]
+
+from pyani import anim, tetra  # noqa: E402  (the reference)
+import oracle  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+FIX = ROOT / "oracle" / "_ref" / "fixtures"
+
+EDGE_FASTAS = {
+    # name -> FASTA text; exercise lower case, Ns/IUPAC, multi-record, short records (L<5) etc.
+    "edge_multi": ">r1 first\nACGTTGCAAGGCTTAACCGGTTAAGGCCTTAGCATCGATCGGATCGATTTAGC\nGATTACAGATTACAGGGCATCGA\n>r2\nTTGACCAGTAGGCATTTACGAGCAGT\n>r3\nACG\n>r4\nACGT\n>r5\nACGTA\n",
+    "edge_lower_n": ">x\nacgtnnacgtacgatcgatcgatcgRYacgatgcatgcatgcatcgatcgatgcatgcatgcNacgt\nACGATCGATCAGCTAGCTAGCATCGATCGATCGATCGACTAGCTAGCATCGATGCAT\n",
+}
+
+
+def rand_fasta(seed, n_rec, length, p_n=0.002):
+    rng = np.random.default_rng(seed)
+    out = []
+    for r in range(n_rec):
+        s = rng.choice(list("ACGT"), size=length, p=[0.2, 0.3, 0.3, 0.2])
+        s[rng.random(length) < p_n] = "N"
+        s = "".join(s)
+        out.append(">rec%d d\n" % r + "\n".join(s[i : i + 70] for i in range(0, len(s), 70)) + "\n")
+    return "".join(out)
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    FIX.mkdir(parents=True, exist_ok=True)
+    EDGE_FASTAS["edge_rand3x4k"] = rand_fasta(11, 3, 4000)
+    EDGE_FASTAS["edge_rand1x20k"] = rand_fasta(12, 1, 20000, p_n=0.0)
+
+    # ---- fixture genomes for the GPU box
+    for sub in ("fixtures/sequences", "test_targets/legacy_scripts/C_blochmannia"):
+        dst = FIX / Path(sub).name
+        dst.mkdir(exist_ok=True)
+        for f in sorted((REF / "tests" / sub).glob("*.fna")):
+            shutil.copyfile(f, dst / f.name)
+    dd = FIX / "anim_deltadir"
+    dd.mkdir(exist_ok=True)
+    for f in sorted((REF / "tests/fixtures/anim/deltadir").glob("*/*_vs_*")):
+        if f.suffix in (".delta", ".filter"):
+            shutil.copyfile(f, dd / f.name)
+
+    # ---- TETRA
+    gold = {"tetramers": oracle.TETRAMERS, "genomes": {}, "edge": {}}
+    zs = {}
+    for f in sorted((REF / "tests/fixtures/sequences").glob("*.fna")):
+        z = tetra.calculate_tetra_zscore(f)
+        zs[f.stem] = z
+        gold["genomes"][f.stem] = {k: z[k] for k in sorted(z)}
+        print("tetra", f.stem, len(z))
+    corr = tetra.calculate_correlations(zs)
+    gold["corr_py312_sum"] = {"orgs": list(corr.index), "matrix": corr.values.tolist()}
+    # the reference's own checked-in tables
+    gold["zscore_json_NC_002696"] = json.load(open(REF / "tests/fixtures/targets/tetra/zscore.json"))
+    tab = [l.rstrip("\n").split("\t") for l in open(REF / "tests/target_TETRA_output/TETRA_correlations.tab")]
+    gold["corr_checked_in"] = {"orgs": tab[0][1:], "matrix": [[float(x) for x in r[1:]] for r in tab[1:]]}
+    with tempfile.TemporaryDirectory() as td:
+        for name, txt in EDGE_FASTAS.items():
+            p = Path(td) / (name + ".fna")
+            p.write_text(txt)
+            z = tetra.calculate_tetra_zscore(p)
+            gold["edge"][name] = {"fasta": txt, "z": {k: z[k] for k in sorted(z)}}
+    json.dump(gold, open(OUT / "tetra_reference.json", "w"))
+
+    # ---- ANIm reduction
+    files = sorted((REF / "tests/fixtures/anim/deltadir").glob("*/*.filter"))
+    files += sorted((REF / "tests/fixtures/anim/deltadir").glob("*/*.delta"))
+    files += [REF / "tests/fixtures/anim/test.delta"]
+    tuples, arrays = {}, {}
+    for f in files:
+        tuples[f.name] = list(anim.parse_delta(f))
+        arrays[f.name] = oracle.parse_delta_text(f).astype(np.int32)
+    json.dump(tuples, open(OUT / "anim_parse_delta.json", "w"), indent=0)
+    np.savez_compressed(OUT / "anim_alignments.npz", **arrays)
+    print("anim", len(tuples))
+
+
+if __name__ == "__main__":
+    main()
