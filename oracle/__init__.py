@@ -33,6 +33,9 @@ def lib() -> ctypes.CDLL:
     global _LIB
     if _LIB is None:
         so = _HERE / "liboracle.so"
+        if os.environ.get("ORACLE_SO"):  # parameter-sweep builds (tests/tools only)
+            _LIB = ctypes.CDLL(os.environ["ORACLE_SO"])
+            return _LIB
         if not so.exists() or os.environ.get("ORACLE_REBUILD"):
             build()
         else:
@@ -134,3 +137,67 @@ def read_fasta(path):
     off = np.zeros(len(lens) + 1, dtype=np.uint64)
     off[1:] = np.cumsum(np.asarray(lens, dtype=np.uint64))
     return data, off, ids
+
+
+# ----------------------------------------------------------------------------- ANIm aligner (oracle_anim.c)
+ANIM_NSTATS = 8
+ANIM_STAT_NAMES = ["anchors", "links", "cut_links", "segments", "gap_cells", "ext_cells", "ext_tiles", "seed_hits"]
+
+
+class OGenome:
+    """Oracle-side genome handle (byte-per-base g-space + unique-minimizer index)."""
+
+    def __init__(self, ascii_u8: np.ndarray, contig_off: np.ndarray):
+        L = lib()
+        L.orc_genome_create.restype = ctypes.c_void_p
+        L.orc_genome_free.argtypes = [ctypes.c_void_p]
+        L.orc_genome_n_mini.restype = ctypes.c_int64
+        L.orc_genome_n_mini.argtypes = [ctypes.c_void_p]
+        a = np.ascontiguousarray(ascii_u8, dtype=np.uint8)
+        o = np.ascontiguousarray(contig_off, dtype=np.uint64)
+        self.n_bases = int(o[-1])
+        self.contig_off = o
+        self._h = ctypes.c_void_p(L.orc_genome_create(_p(a, ctypes.c_uint8), _p(o, ctypes.c_uint64), ctypes.c_uint32(len(o) - 1)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().orc_genome_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def n_mini(self):
+        return int(lib().orc_genome_n_mini(self._h))
+
+    def minimizers(self):
+        n = self.n_mini
+        k = np.zeros(n, np.uint32); pf = np.zeros(n, np.uint32)
+        lib().orc_genome_minimizers.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib().orc_genome_minimizers(self._h, k.ctypes.data, pf.ctypes.data)
+        return k, pf
+
+
+def anim_align(R: OGenome, Q: OGenome, cap: int = 1 << 16):
+    """Unfiltered alignments of R (nucmer reference) vs Q: rows (rc, qc, rs, re, qs, qe, errs, score) + stats dict."""
+    L = lib()
+    L.orc_anim_align.restype = ctypes.c_int64
+    L.orc_anim_align.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    rows = np.zeros((cap, 8), dtype=np.int64)
+    stats = np.zeros(ANIM_NSTATS, dtype=np.int64)
+    n = L.orc_anim_align(R._h, Q._h, rows.ctypes.data, cap, stats.ctypes.data)
+    assert n <= cap, "alignment capacity exceeded"
+    return rows[:n].copy(), dict(zip(ANIM_STAT_NAMES, stats.tolist()))
+
+
+def filter_1to1(rows: np.ndarray) -> np.ndarray:
+    """delta-filter -1 restatement: boolean keep mask for alignment rows (n x 8, score column unused)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    if rows.shape[1] == 7:
+        rows = np.concatenate([rows, np.zeros((len(rows), 1), np.int64)], axis=1)
+    keep = np.zeros(len(rows), dtype=np.uint8)
+    L = lib()
+    L.orc_filter_1to1.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    L.orc_filter_1to1(rows.ctypes.data, len(rows), keep.ctypes.data)
+    return keep.astype(bool)

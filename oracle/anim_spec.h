@@ -1,0 +1,37 @@
+/* Algorithm constants of the ANIm-equivalent aligner ("b200-nucmer"), shared BY VALUE between the CPU
+ * oracle (oracle/oracle_anim.c) and the CUDA engine (pyani_b200/csrc/anim_params.cuh keeps its own copy;
+ * tests/test_abi.py checks the two files agree).  DESIGN.md "ANIm algorithm" explains every constant
+ * and which MUMmer 3.23 default it stands in for ([EXT] recollection).
+ *
+ * The nucmer/delta-filter binaries and sources are absent, so this aligner is a
+ * from-scratch restatement of their published pipeline: maximal unique matches >= 20 bp -> colinear
+ * clustering -> banded affine DP between / beyond anchors -> 1-to-1 filter.  PARITY WITH NUCMER ON NEW
+ * GENOMES IS UNPINNED; on the reference's fixture genomes it is checked against the checked-in nucmer
+ * output within tests/test_concordance.py's own tolerance (tests/test_anim_oracle_fixtures.py).
+ */
+#ifndef ANIM_SPEC_H
+#define ANIM_SPEC_H
+
+#define AN_K 16          /* seed k-mer length (2-bit packed -> one u32) */
+#define AN_W 5           /* minimizer window: K+W-1 = 20 = nucmer -l 20 => every match >= 20 is seeded */
+#define AN_MINLEN 20     /* minimum maximal-exact-match length (nucmer -l 20) */
+#define AN_LOOKBACK 32   /* chaining: predecessor searched among the previous 32 anchors */
+#define AN_GAPMAX 1000   /* chaining: max gap between linked anchors on either genome */
+#define AN_DMAX 16       /* chaining: max |gap_q - gap_r| (diagonal drift) of a link */
+#define AN_MINCLUSTER 65 /* min matched bases of an alignment's anchors (mgaps -l 65) */
+#define AN_BAND 16       /* DP band reaches AN_BAND diagonals below the centre ... */
+#define AN_BANDW 32      /* ... and is 32 diagonals wide: k in [c-16, c+15] */
+#define AN_TILE 128      /* extension tile rows */
+#define AN_MAXTILES 64   /* extension rounds cap */
+#define AN_MATCH 3       /* sw_align scores [EXT]: match 3, mismatch -7 */
+#define AN_MISMATCH 7
+#define AN_GAPOPEN 10    /* cost of the first column of a gap */
+#define AN_GAPEXT 4      /* cost of each further gap column */
+#define AN_BREAK 94      /* rows without a new best before an extension/link gives up (nucmer -b 200 anti-diagonals) */
+#define AN_CLUSTGAP 90   /* anchors closer than this on both genomes form a cluster (mgaps -s 90) */
+#define AN_FILT_OLAP 75  /* delta-filter -o 75: max overlap % of either alignment in a kept chain */
+#define AN_FILT_POW 2    /* alignment weight = length * identity^POW */
+#define AN_PACK 4096     /* DP value = score*PACK - errs */
+#define AN_NEG (-(1 << 29))
+
+#endif

@@ -1,0 +1,516 @@
+/* ORACLE (test infrastructure, NOT product code): CPU restatement of the ANIm-equivalent aligner.
+ *
+ * What it stands in for: the external `nucmer --mum` + `delta-filter -1` binaries pyani shells out to
+ * (anim.py:280, anim.py:285-288; MUMmer 3.23 pinned in requirements-thirdparty-linux.txt:3), whose
+ * sources are NOT under /root/reference.  The published pipeline is restated from scratch
+ * (SURVEY.md 8a-M2/M3 [EXT]): maximal unique matches >= 20 bp -> colinear clustering -> banded affine DP
+ * between and beyond anchors -> 1-to-1 filter, then pyani's own reduction (oracle_delta.c).
+ *
+ * PARITY STATUS: "unpinned" against nucmer on arbitrary genomes (no binary, no source).  Pinned only
+ *  (a) stage by stage against the reference's checked-in nucmer 3.1 output for the four Caulobacter
+ *      fixture genomes (tests/test_anim_oracle_fixtures.py: identity within the reference's own
+ *      +-0.1 %-point JSpecies tolerance, tests/test_concordance.py:157-159,203), and
+ *  (b) bit-exactly against the CUDA engine, which implements the identical specification
+ *      (constants in anim_spec.h).
+ *
+ * Deliberately simple: byte-per-base sequences, O(n log n) sorts, scalar DP.  Single-threaded per call;
+ * callers parallelise over pairs with Python threads (ctypes releases the GIL).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "anim_spec.h"
+
+/* ------------------------------------------------------------------ genome in "g-space"
+ * records back to back, one separator position (code 4) after each record; code 0..3 = ACGT,
+ * 4 = anything else.  rc[] is the reverse complement of the whole g-space array. */
+typedef struct {
+    int64_t n_pos, n_bases;
+    uint32_t n_contigs;
+    uint64_t *goff; /* n_contigs+1 */
+    uint8_t *fw, *rc;
+    /* index: unique canonical minimizers */
+    int64_t n_mini;
+    uint32_t *mini_kmer;    /* sorted by position */
+    uint32_t *mini_posflag; /* pos | orient<<31 */
+    uint64_t *table;        /* open addressing: kmer<<32 | posflag ; empty = ~0 */
+    uint32_t table_bits;
+} orc_genome;
+
+static inline int base_code(uint8_t c) {
+    switch (c & 0xDF) {
+    case 'A': return 0;
+    case 'C': return 1;
+    case 'G': return 2;
+    case 'T': return 3;
+    default: return 4;
+    }
+}
+
+static inline uint32_t fmix32(uint32_t h) { /* murmur3 finalizer */
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+
+/* table addressing must be independent of the selection hash: minimizers are by construction the
+ * k-mers with SMALL fmix32 values, so slot = top bits of fmix32 would pile them into the first slots */
+static inline uint32_t table_hash(uint32_t kmer) { return fmix32(kmer ^ 0x5bd1e995u); }
+
+static int cmp_u64(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : x > y;
+}
+
+void orc_genome_free(orc_genome *g) {
+    if (!g) return;
+    free(g->goff); free(g->fw); free(g->rc); free(g->mini_kmer); free(g->mini_posflag); free(g->table);
+    free(g);
+}
+
+orc_genome *orc_genome_create(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs) {
+    orc_genome *g = (orc_genome *)calloc(1, sizeof *g);
+    g->n_contigs = n_contigs;
+    g->n_bases = (int64_t)off[n_contigs];
+    g->n_pos = g->n_bases + n_contigs;
+    g->goff = (uint64_t *)malloc(sizeof(uint64_t) * (n_contigs + 1));
+    for (uint32_t c = 0; c <= n_contigs; ++c) g->goff[c] = off[c] + c;
+    g->fw = (uint8_t *)malloc((size_t)g->n_pos + 1);
+    g->rc = (uint8_t *)malloc((size_t)g->n_pos + 1);
+    for (uint32_t c = 0; c < n_contigs; ++c) {
+        int64_t L = (int64_t)(off[c + 1] - off[c]);
+        for (int64_t i = 0; i < L; ++i) g->fw[g->goff[c] + i] = (uint8_t)base_code(ascii[off[c] + i]);
+        g->fw[g->goff[c] + L] = 4;
+    }
+    for (int64_t i = 0; i < g->n_pos; ++i) {
+        uint8_t b = g->fw[g->n_pos - 1 - i];
+        g->rc[i] = (uint8_t)(b < 4 ? 3 - b : 4);
+    }
+    /* ---- minimizer selection: position p is selected iff its canonical-k-mer hash is <= every hash in
+     * at least one window of AN_W consecutive k-mer start positions containing p (ties select all). */
+    int64_t n = g->n_pos;
+    uint64_t *hv = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(n + 1));
+    uint32_t *canon = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n + 1));
+    uint8_t *orient = (uint8_t *)malloc((size_t)n + 1);
+    const uint64_t INF = 1ull << 32;
+    for (int64_t p = 0; p < n; ++p) {
+        hv[p] = INF;
+        if (p + AN_K > n) continue;
+        uint32_t f = 0, r = 0;
+        int ok = 1;
+        for (int i = 0; i < AN_K; ++i) {
+            uint8_t b = g->fw[p + i];
+            if (b > 3) { ok = 0; break; }
+            f = (f << 2) | b;                                  /* first base most significant */
+            r |= (uint32_t)(3 - b) << (2 * i);                 /* reverse complement */
+        }
+        if (!ok || f == r) continue;                           /* palindromes carry no orientation */
+        canon[p] = f < r ? f : r;
+        orient[p] = (uint8_t)(r < f);
+        hv[p] = fmix32(canon[p]);
+    }
+    uint64_t *sel = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(n + 1)); /* kmer<<32 | posflag */
+    int64_t ns = 0;
+    for (int64_t p = 0; p < n; ++p) {
+        if (hv[p] == INF) continue;
+        int chosen = 0;
+        for (int o = 0; o < AN_W && !chosen; ++o) { /* window [p-o, p-o+W-1] */
+            int64_t lo = p - o, hi = lo + AN_W - 1;
+            int is_min = 1;
+            for (int64_t x = lo; x <= hi; ++x) {
+                uint64_t h = (x < 0 || x >= n) ? INF : hv[x];
+                if (h < hv[p]) { is_min = 0; break; }
+            }
+            chosen = is_min;
+        }
+        if (chosen) sel[ns++] = ((uint64_t)canon[p] << 32) | (uint32_t)p | ((uint32_t)orient[p] << 31);
+    }
+    /* ---- keep k-mers that occur once among the selected (--mum uniqueness, approximated on seeds) */
+    qsort(sel, (size_t)ns, sizeof(uint64_t), cmp_u64);
+    int64_t nu = 0;
+    for (int64_t i = 0; i < ns;) {
+        int64_t j = i + 1;
+        while (j < ns && (sel[j] >> 32) == (sel[i] >> 32)) ++j;
+        if (j - i == 1) sel[nu++] = sel[i];
+        i = j;
+    }
+    g->n_mini = nu;
+    uint32_t bits = 4;
+    while ((1ll << bits) < 2 * nu) ++bits;
+    g->table_bits = bits;
+    g->table = (uint64_t *)malloc(sizeof(uint64_t) << bits);
+    memset(g->table, 0xff, sizeof(uint64_t) << bits);
+    for (int64_t i = 0; i < nu; ++i) {
+        uint32_t k = (uint32_t)(sel[i] >> 32);
+        uint64_t s = table_hash(k) >> (32 - bits);
+        while (g->table[s] != ~0ull) s = (s + 1) & ((1ull << bits) - 1);
+        g->table[s] = sel[i];
+    }
+    /* position-sorted list (what a query streams through the reference's table) */
+    uint64_t *bypos = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(nu + 1));
+    for (int64_t i = 0; i < nu; ++i) bypos[i] = ((uint64_t)((uint32_t)sel[i] & 0x7fffffffu) << 33) | ((sel[i] >> 31 & 1) << 32) | (sel[i] >> 32);
+    qsort(bypos, (size_t)nu, sizeof(uint64_t), cmp_u64);
+    g->mini_kmer = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(nu + 1));
+    g->mini_posflag = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(nu + 1));
+    for (int64_t i = 0; i < nu; ++i) {
+        g->mini_kmer[i] = (uint32_t)bypos[i];
+        g->mini_posflag[i] = (uint32_t)(bypos[i] >> 33) | ((uint32_t)(bypos[i] >> 32 & 1) << 31);
+    }
+    free(bypos); free(sel); free(hv); free(canon); free(orient);
+    return g;
+}
+
+int64_t orc_genome_n_mini(const orc_genome *g) { return g->n_mini; }
+void orc_genome_minimizers(const orc_genome *g, uint32_t *kmer, uint32_t *posflag) {
+    memcpy(kmer, g->mini_kmer, sizeof(uint32_t) * (size_t)g->n_mini);
+    memcpy(posflag, g->mini_posflag, sizeof(uint32_t) * (size_t)g->n_mini);
+}
+
+static inline int lookup(const orc_genome *g, uint32_t kmer, uint32_t *posflag) {
+    uint64_t mask = (1ull << g->table_bits) - 1, s = table_hash(kmer) >> (32 - g->table_bits);
+    while (g->table[s] != ~0ull) {
+        if ((uint32_t)(g->table[s] >> 32) == kmer) { *posflag = (uint32_t)g->table[s]; return 1; }
+        s = (s + 1) & mask;
+    }
+    return 0;
+}
+
+/* record index of a g-space position (separator belongs to the record it ends) */
+static uint32_t contig_of(const uint64_t *goff, uint32_t n, int64_t pos) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if ((int64_t)goff[mid] <= pos) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+/* ------------------------------------------------------------------ banded affine DP
+ * value = score*AN_PACK - errs ; cell (i,j): i bases of R, j bases of Q consumed; diagonal k = j - i in
+ * [klo, klo+AN_BANDW-1] (AN_BANDW = 32 diagonals = one 64-bit window of 2-bit query bases).  R/Q are read as R[rs*i'] with stride rs = +1 / -1 (left extensions read
+ * backwards).  Both modes track the best cell so far (row-major first maximum, starting with (0,0)=0)
+ * and give up ("stopped") as soon as a row ends more than AN_BREAK rows after the best cell's row --
+ * nucmer's break length: an extension must reach a new high score within -b 200 anti-diagonals
+ * (~100 rows) or it is abandoned [EXT].
+ * mode 0: link alignment to the target corner, returns H[lr][lq] (meaningless if stopped).
+ * mode 1: extension tile over at most lr rows and lq columns; returns the best cell in bi,bj. */
+typedef struct { int32_t val, bi, bj, stopped; int64_t cells; } dp_out;
+
+static dp_out dp_band(const uint8_t *R, int rstride, const uint8_t *Q, int qstride, int lr, int lq, int klo, int mode) {
+    enum { BW = AN_BANDW };
+    const int32_t go = AN_GAPOPEN * AN_PACK + 1, ge = AN_GAPEXT * AN_PACK + 1;
+    const int32_t sm = AN_MATCH * AN_PACK, sx = -(AN_MISMATCH * AN_PACK + 1);
+    int32_t Hp[BW + 2], Fp[BW + 2], Hc[BW + 2], Ec[BW + 2], Fc[BW + 2];
+    dp_out o = {0, 0, 0, 0, 0};
+    for (int kk = 0; kk < BW; ++kk) { /* row 0 */
+        int j = klo + kk;
+        Fp[kk] = AN_NEG;
+        if (j < 0 || j > lq) Hp[kk] = AN_NEG;
+        else if (j == 0) Hp[kk] = 0;
+        else Hp[kk] = -(go + (j - 1) * ge);
+    }
+    Hp[BW] = Fp[BW] = AN_NEG;
+    int32_t best = 0;
+    for (int i = 1; i <= lr; ++i) {
+        uint8_t rb = R[(int64_t)rstride * (i - 1)];
+        int32_t rowmax = AN_NEG, hleft = AN_NEG, eleft = AN_NEG;
+        for (int kk = 0; kk < BW; ++kk) {
+            int j = i + klo + kk;
+            int32_t h, e, f;
+            if (j < 0 || j > lq) { h = e = f = AN_NEG; }
+            else {
+                o.cells++;
+                int32_t e1 = eleft - ge, e2 = hleft - go;
+                e = e1 > e2 ? e1 : e2;
+                int32_t f1 = Fp[kk + 1] - ge, f2 = Hp[kk + 1] - go;
+                f = f1 > f2 ? f1 : f2;
+                int32_t d = AN_NEG;
+                if (j >= 1) {
+                    uint8_t qb = Q[(int64_t)qstride * (j - 1)];
+                    d = Hp[kk] + ((rb == qb && rb < 4) ? sm : sx);
+                }
+                h = d > e ? d : e;
+                h = h > f ? h : f;
+                if (h < AN_NEG) h = AN_NEG;
+                if (e < AN_NEG) e = AN_NEG;
+                if (f < AN_NEG) f = AN_NEG;
+                if (h > rowmax) rowmax = h;
+                if (h > best) { best = h; o.bi = i; o.bj = j; }
+            }
+            Hc[kk] = h; Ec[kk] = e; Fc[kk] = f;
+            hleft = h; eleft = e;
+        }
+        memcpy(Hp, Hc, sizeof(int32_t) * BW);
+        memcpy(Fp, Fc, sizeof(int32_t) * BW);
+        (void)Ec;
+        (void)rowmax;
+        if (i - o.bi > AN_BREAK) { o.stopped = 1; break; }
+    }
+    if (mode == 0) {
+        int kk = (lq - lr) - klo;
+        o.val = Hp[kk];
+    } else
+        o.val = best;
+    return o;
+}
+
+/* value = score*PACK - errs with 0 <= errs < PACK  ->  score = ceil(value / PACK) */
+static inline int32_t pack_score(int32_t v) { return (v + AN_PACK - 1) >> 12; } /* arithmetic shift = floor */
+static inline int32_t pack_errs(int32_t v) { return pack_score(v) * AN_PACK - v; }
+
+/* ------------------------------------------------------------------ one directed pair */
+typedef struct { int32_t strand, r, q, len; } anchor;
+
+static int cmp_anchor(const void *a, const void *b) {
+    const anchor *x = (const anchor *)a, *y = (const anchor *)b;
+    if (x->strand != y->strand) return x->strand - y->strand;
+    if (x->r != y->r) return x->r < y->r ? -1 : 1;
+    if (x->q != y->q) return x->q < y->q ? -1 : 1;
+    return x->len - y->len;
+}
+
+/* stats[]: 0 anchors, 1 links, 2 cut links, 3 segments kept, 4 gap cells, 5 ext cells, 6 ext tiles,
+ *          7 seed hits */
+#define ORC_NSTATS 8
+
+/* Alignments of R (reference = pyani query, anim.py:280) vs Q before the 1-to-1 filter.
+ * rows: up to cap rows of 8 int64: ref_contig, qry_contig, rs, re, qs, qe, errs, score  (.delta
+ * conventions: 1-based closed, reverse strand qs > qe).  Returns the number of alignments. */
+int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int64_t *rows, int64_t cap, int64_t *stats) {
+    memset(stats, 0, sizeof(int64_t) * ORC_NSTATS);
+    /* ---- seeds -> maximal exact matches */
+    int64_t acap = 1 << 16, na = 0;
+    anchor *A = (anchor *)malloc(sizeof(anchor) * (size_t)acap);
+    int64_t last_d[2] = {0, 0}, last_r0[2] = {-1, -1}, last_r1[2] = {-1, -1}; /* last match per strand */
+    for (int64_t t = 0; t < Q->n_mini; ++t) {
+        uint32_t rpf;
+        if (!lookup(R, Q->mini_kmer[t], &rpf)) continue;
+        stats[7]++;
+        uint32_t qpf = Q->mini_posflag[t];
+        int strand = (int)((rpf ^ qpf) >> 31);
+        int64_t r0 = rpf & 0x7fffffffu, qpos = qpf & 0x7fffffffu;
+        int64_t q0 = strand ? Q->n_pos - AN_K - qpos : qpos;
+        const uint8_t *Qs = strand ? Q->rc : Q->fw;
+        /* a seed inside the match found by the previous seed of this strand yields the same match
+         * (pure speed-up: the anchor list is a set, see the sort + unique below) */
+        if (r0 - q0 == last_d[strand] && r0 >= last_r0[strand] && r0 + AN_K <= last_r1[strand]) continue;
+        int64_t l = 0, rr = 0;
+        while (r0 - l - 1 >= 0 && q0 - l - 1 >= 0 && R->fw[r0 - l - 1] < 4 && R->fw[r0 - l - 1] == Qs[q0 - l - 1]) ++l;
+        while (r0 + AN_K + rr < R->n_pos && q0 + AN_K + rr < Q->n_pos && R->fw[r0 + AN_K + rr] < 4 &&
+               R->fw[r0 + AN_K + rr] == Qs[q0 + AN_K + rr]) ++rr;
+        int64_t len = AN_K + l + rr;
+        last_d[strand] = r0 - q0; last_r0[strand] = r0 - l; last_r1[strand] = r0 - l + len;
+        if (len < AN_MINLEN) continue;
+        if (na == acap) { acap *= 2; A = (anchor *)realloc(A, sizeof(anchor) * (size_t)acap); }
+        A[na].strand = strand; A[na].r = (int32_t)(r0 - l); A[na].q = (int32_t)(q0 - l); A[na].len = (int32_t)len;
+        ++na;
+    }
+    qsort(A, (size_t)na, sizeof(anchor), cmp_anchor);
+    int64_t nu = 0;
+    for (int64_t i = 0; i < na; ++i)
+        if (i == 0 || cmp_anchor(&A[i], &A[i - 1]) != 0) A[nu++] = A[i];
+    na = nu;
+    stats[0] = na;
+
+    int32_t *pred = (int32_t *)malloc(sizeof(int32_t) * (size_t)(na + 1));
+    int32_t *succ = (int32_t *)malloc(sizeof(int32_t) * (size_t)(na + 1));
+    int32_t *trim = (int32_t *)calloc((size_t)(na + 1), sizeof(int32_t));
+    int32_t *gval = (int32_t *)calloc((size_t)(na + 1), sizeof(int32_t)); /* packed gap value of link pred->i */
+    int32_t *head = (int32_t *)malloc(sizeof(int32_t) * (size_t)(na + 1));
+    uint32_t *rc_of = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(na + 1));
+    uint32_t *qc_of = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(na + 1));
+    for (int64_t i = 0; i < na; ++i) {
+        rc_of[i] = contig_of(R->goff, R->n_contigs, A[i].r);
+        int64_t qf = A[i].strand ? Q->n_pos - 1 - A[i].q : A[i].q; /* any base of the anchor identifies the record */
+        qc_of[i] = contig_of(Q->goff, Q->n_contigs, qf);
+    }
+    /* ---- linking: nearest compatible predecessor within the lookback, then each predecessor keeps
+     * only its nearest successor */
+    for (int64_t i = 0; i < na; ++i) { pred[i] = -1; succ[i] = 0x7fffffff; }
+    for (int64_t i = 0; i < na; ++i) {
+        for (int64_t j = i - 1; j >= 0 && j >= i - AN_LOOKBACK; --j) {
+            if (A[j].strand != A[i].strand) break;
+            if (rc_of[j] != rc_of[i] || qc_of[j] != qc_of[i]) continue;
+            int64_t rej = (int64_t)A[j].r + A[j].len, qej = (int64_t)A[j].q + A[j].len;
+            int64_t ov = 0;
+            if (rej - A[i].r > ov) ov = rej - A[i].r;
+            if (qej - A[i].q > ov) ov = qej - A[i].q;
+            if (ov >= A[i].len) continue;
+            int64_t gr = A[i].r + ov - rej, gq = A[i].q + ov - qej;
+            if (gr > AN_GAPMAX || gq > AN_GAPMAX) continue;
+            int64_t dd = gq - gr;
+            if (dd > AN_DMAX || dd < -AN_DMAX) continue;
+            pred[i] = (int32_t)j; trim[i] = (int32_t)ov;
+            break;
+        }
+    }
+    for (int64_t i = 0; i < na; ++i)
+        if (pred[i] >= 0 && succ[pred[i]] > (int32_t)i) succ[pred[i]] = (int32_t)i;
+    for (int64_t i = 0; i < na; ++i)
+        if (pred[i] >= 0 && succ[pred[i]] != (int32_t)i) { pred[i] = -1; trim[i] = 0; }
+    /* ---- gap alignments of the links; cut bad links */
+    for (int64_t i = 0; i < na; ++i) {
+        if (pred[i] < 0) continue;
+        stats[1]++;
+        const anchor *a = &A[pred[i]], *b = &A[i];
+        int64_t rej = (int64_t)a->r + a->len, qej = (int64_t)a->q + a->len;
+        int lr = (int)(b->r + trim[i] - rej), lq = (int)(b->q + trim[i] - qej);
+        int32_t v;
+        if (lr == 0 && lq == 0) v = 0;
+        else if (lr == 0 || lq == 0) {
+            int L = lr + lq;
+            v = -((AN_GAPOPEN + (L - 1) * AN_GAPEXT) * AN_PACK + L);
+        } else {
+            int d = lq - lr, c = d >= 0 ? d / 2 : -((-d) / 2);
+            const uint8_t *Qs = b->strand ? Q->rc : Q->fw;
+            dp_out o = dp_band(R->fw + rej, 1, Qs + qej, 1, lr, lq, c - AN_BAND, 0);
+            v = o.val;
+            stats[4] += o.cells;
+            if (o.stopped) { pred[i] = -1; trim[i] = 0; v = 0; stats[2]++; }
+        }
+        gval[i] = v;
+    }
+    /* ---- segments (chains of intact links): head, matched bases, summed gap values, tail */
+    int64_t *wsum = (int64_t *)calloc((size_t)(na + 1), sizeof(int64_t));
+    int64_t *ssum = (int64_t *)calloc((size_t)(na + 1), sizeof(int64_t)); /* gap scores */
+    int64_t *esum = (int64_t *)calloc((size_t)(na + 1), sizeof(int64_t)); /* gap errors */
+    int32_t *tail = (int32_t *)malloc(sizeof(int32_t) * (size_t)(na + 1));
+    /* clusters = runs of intact links whose gaps are <= AN_CLUSTGAP on both genomes (mgaps -s 90); a
+     * segment is reported only if one of its clusters holds >= AN_MINCLUSTER matched bases (mgaps -l 65) */
+    int32_t *chead = (int32_t *)malloc(sizeof(int32_t) * (size_t)(na + 1));
+    int64_t *cw = (int64_t *)calloc((size_t)(na + 1), sizeof(int64_t));
+    uint8_t *strong = (uint8_t *)calloc((size_t)(na + 1), 1);
+    for (int64_t i = 0; i < na; ++i) {
+        chead[i] = (int32_t)i;
+        if (pred[i] >= 0) {
+            const anchor *a = &A[pred[i]], *b = &A[i];
+            int64_t gr = b->r + trim[i] - ((int64_t)a->r + a->len), gq = b->q + trim[i] - ((int64_t)a->q + a->len);
+            if (gr <= AN_CLUSTGAP && gq <= AN_CLUSTGAP) chead[i] = chead[pred[i]];
+        }
+        cw[chead[i]] += A[i].len - trim[i];
+    }
+    for (int64_t i = 0; i < na; ++i) {
+        head[i] = pred[i] < 0 ? (int32_t)i : head[pred[i]];
+        int32_t h = head[i];
+        if (cw[chead[i]] >= AN_MINCLUSTER) strong[h] = 1;
+        wsum[h] += A[i].len - trim[i];
+        ssum[h] += pack_score(gval[i]);
+        esum[h] += pack_errs(gval[i]);
+        tail[h] = (int32_t)i;
+    }
+    /* ---- extend both ends of every kept segment, emit alignments */
+    int64_t nout = 0;
+    for (int64_t h = 0; h < na; ++h) {
+        if (head[h] != (int32_t)h || !strong[h]) continue;
+        stats[3]++;
+        const anchor *f = &A[h], *l = &A[tail[h]];
+        const uint8_t *Qs = f->strand ? Q->rc : Q->fw;
+        uint32_t rc = rc_of[h], qc = qc_of[h];
+        /* record bounds in the (possibly reversed) coordinate spaces */
+        int64_t r_lo = (int64_t)R->goff[rc], r_hi = (int64_t)R->goff[rc + 1] - 1; /* [lo,hi) bases */
+        int64_t q_lo = (int64_t)Q->goff[qc], q_hi = (int64_t)Q->goff[qc + 1] - 1;
+        if (f->strand) { int64_t a = Q->n_pos - q_hi, b = Q->n_pos - q_lo; q_lo = a; q_hi = b; }
+        int64_t rs = f->r, qs = f->q, re = (int64_t)l->r + l->len, qe = (int64_t)l->q + l->len; /* [s,e) */
+        int64_t score = ssum[h] + wsum[h] * AN_MATCH, errs = esum[h];
+        for (int side = 0; side < 2; ++side) {
+            for (int t = 0; t < AN_MAXTILES; ++t) {
+                int64_t ar = side ? r_hi - re : rs - r_lo, aq = side ? q_hi - qe : qs - q_lo;
+                int lr = (int)(ar < AN_TILE ? ar : AN_TILE), lq = (int)(aq < AN_TILE + AN_BAND ? aq : AN_TILE + AN_BAND);
+                if (lr <= 0 || lq <= 0) break;
+                dp_out o = side ? dp_band(R->fw + re, 1, Qs + qe, 1, lr, lq, -AN_BAND, 1)
+                                : dp_band(R->fw + rs - 1, -1, Qs + qs - 1, -1, lr, lq, -AN_BAND, 1);
+                stats[5] += o.cells; stats[6]++;
+                if (o.bi == 0 && o.bj == 0) break;
+                score += pack_score(o.val);
+                errs += pack_errs(o.val);
+                if (side) { re += o.bi; qe += o.bj; } else { rs -= o.bi; qs -= o.bj; }
+                if (o.stopped) break;
+            }
+        }
+        if (nout < cap) {
+            int64_t *o = rows + 8 * nout;
+            o[0] = rc; o[1] = qc;
+            o[2] = rs - (int64_t)R->goff[rc] + 1; o[3] = re - 1 - (int64_t)R->goff[rc] + 1;
+            if (!f->strand) { o[4] = qs - (int64_t)Q->goff[qc] + 1; o[5] = qe - 1 - (int64_t)Q->goff[qc] + 1; }
+            else { o[4] = (Q->n_pos - 1 - qs) - (int64_t)Q->goff[qc] + 1; o[5] = (Q->n_pos - qe) - (int64_t)Q->goff[qc] + 1; }
+            o[6] = errs; o[7] = score;
+        }
+        ++nout;
+    }
+    free(A); free(pred); free(succ); free(trim); free(gval); free(head); free(rc_of); free(qc_of);
+    free(chead); free(cw); free(strong); free(wsum); free(ssum); free(esum); free(tail);
+    return nout;
+}
+
+/* ------------------------------------------------------------------ 1-to-1 filter (delta-filter -1)
+ * Restated from MUMmer's documentation [EXT]: "-r/-q: length*identity weighted LIS ... leave only the
+ * alignments which form the longest consistent set for the reference/query", "-o 75: maximum alignment
+ * overlap as a percent of the alignment length", "-1: intersection of -r and -q".
+ * Per sequence of one genome: alignments sorted by (lo, hi, input order); chain DP
+ *   best[i] = w_i + max(0, max_{j<i compatible} best[j] - overlap(j,i) * idy_i^P)
+ * where overlap = hi_j - lo_i + 1 (if positive) must not exceed AN_FILT_OLAP % of alignment j's length, and
+ * w_i = len_i * idy_i^P, idy_i = 1 - 2*errs/(rl+ql).  All weights are integers (fixed point, see
+ * filt_weight) so CPU and GPU agree bit for bit.  The chain ending at the best score is kept.
+ * keep[i] = 1 iff alignment i is in the kept chain of BOTH its reference and its query sequence. */
+typedef struct { int64_t seq, lo, hi, idx; } filt_iv;
+static int filt_cmp(const void *a, const void *b) {
+    const filt_iv *x = (const filt_iv *)a, *y = (const filt_iv *)b;
+    if (x->seq != y->seq) return x->seq < y->seq ? -1 : 1;
+    if (x->lo != y->lo) return x->lo < y->lo ? -1 : 1;
+    if (x->hi != y->hi) return x->hi < y->hi ? -1 : 1;
+    return x->idx < y->idx ? -1 : x->idx > y->idx;
+}
+/* per-base weight in 1/65536 units: idy^AN_FILT_POW with idy = 1 - 2*errs/(rl+ql), integer arithmetic */
+static int64_t filt_unit(int64_t rl, int64_t ql, int64_t errs) {
+    int64_t tot = rl + ql, good = tot - 2 * errs;
+    if (good < 0) good = 0;
+    int64_t u = (good << 16) / tot; /* idy in Q16 */
+    int64_t w = 1 << 16;
+    for (int p = 0; p < AN_FILT_POW; ++p) w = (w * u) >> 16;
+    return w;
+}
+static void filt_axis(const int64_t *rows, int64_t n, int axis, uint8_t *flag) {
+    filt_iv *iv = (filt_iv *)malloc(sizeof(filt_iv) * (size_t)(n + 1));
+    int64_t *best = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    int64_t *from = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    int64_t *unit = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t *a = rows + 8 * i;
+        int64_t s = a[2 + 2 * axis], e = a[3 + 2 * axis];
+        iv[i].seq = a[axis]; iv[i].lo = s < e ? s : e; iv[i].hi = s < e ? e : s; iv[i].idx = i;
+    }
+    qsort(iv, (size_t)n, sizeof(filt_iv), filt_cmp);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t *a = rows + 8 * iv[i].idx;
+        int64_t rl = (a[3] > a[2] ? a[3] - a[2] : a[2] - a[3]) + 1, ql = (a[5] > a[4] ? a[5] - a[4] : a[4] - a[5]) + 1;
+        unit[i] = filt_unit(rl, ql, a[6]);
+    }
+    for (int64_t s = 0; s < n;) { /* one sequence at a time */
+        int64_t e = s;
+        while (e < n && iv[e].seq == iv[s].seq) ++e;
+        int64_t arg = -1, top = -1;
+        for (int64_t i = s; i < e; ++i) {
+            int64_t leni = iv[i].hi - iv[i].lo + 1;
+            best[i] = leni * unit[i];
+            from[i] = -1;
+            for (int64_t j = s; j < i; ++j) {
+                int64_t ol = iv[j].hi - iv[i].lo + 1, lenj = iv[j].hi - iv[j].lo + 1;
+                if (ol < 0) ol = 0;
+                if (ol * 100 > AN_FILT_OLAP * lenj) continue; /* calibrated on the reference's .delta -> .filter fixtures */
+                int64_t sc = best[j] + (leni - ol) * unit[i];
+                if (sc > best[i]) { best[i] = sc; from[i] = j; }
+            }
+            if (best[i] > top) { top = best[i]; arg = i; }
+        }
+        for (int64_t i = arg; i >= 0; i = from[i]) flag[iv[i].idx] |= (uint8_t)(1 << axis);
+        s = e;
+    }
+    free(iv); free(best); free(from); free(unit);
+}
+void orc_filter_1to1(const int64_t *rows /* n x 8 */, int64_t n, uint8_t *keep) {
+    uint8_t *flag = (uint8_t *)calloc((size_t)(n + 1), 1);
+    filt_axis(rows, n, 0, flag);
+    filt_axis(rows, n, 1, flag);
+    for (int64_t i = 0; i < n; ++i) keep[i] = flag[i] == 3;
+    free(flag);
+}

