@@ -91,7 +91,8 @@ int64_t b200ani_anim_alignments(b200ani_ctx *ctx, int32_t ref_id, int32_t qry_id
  * the number of kernel launches it issued; used by bench.py for the roofline and gpu_launches. */
 #define B200ANI_N_STAGES 16
 int b200ani_last_profile(const b200ani_ctx *ctx, double *stage_ms /*B200ANI_N_STAGES*/, int64_t *counters /*B200ANI_N_STAGES*/);
-const char *b200ani_stage_name(int stage);
+/* i in [0,16): stage name; i in [16,32): name of counter i-16 ("" = unused slot) */
+const char *b200ani_stage_name(int i);
 
 #ifdef __cplusplus
 }

@@ -201,3 +201,18 @@ def filter_1to1(rows: np.ndarray) -> np.ndarray:
     L.orc_filter_1to1.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     L.orc_filter_1to1(rows.ctypes.data, len(rows), keep.ctypes.data)
     return keep.astype(bool)
+
+
+def anim_pair(R: OGenome, Q: OGenome, nofilter: bool = False):
+    """One directed comparison through the whole oracle pipeline.
+
+    -> (result dict with the fields of b200ani_anim_result, kept rows (n,7), stats)."""
+    rows, stats = anim_align(R, Q)
+    keep = np.ones(len(rows), bool) if nofilter else filter_1to1(rows)
+    kept = rows[keep][:, :7]
+    out = np.zeros(5, dtype=np.int64)
+    a = np.ascontiguousarray(kept, dtype=np.int64)
+    lib().orc_parse_delta_reduce(_p(a, ctypes.c_int64), ctypes.c_int64(len(a)), _p(out, ctypes.c_int64))
+    res = dict(ref_aln_len=int(out[0]), qry_aln_len=int(out[1]), sum_aligned=int(out[2]), sum_weighted=int(out[3]),
+               sim_errs=int(out[4]), n_alignments=int(len(a)), status=0 if len(a) else 1)
+    return res, kept, stats

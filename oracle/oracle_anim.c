@@ -446,7 +446,7 @@ int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int64_t *rows, 
  * Restated from MUMmer's documentation [EXT]: "-r/-q: length*identity weighted LIS ... leave only the
  * alignments which form the longest consistent set for the reference/query", "-o 75: maximum alignment
  * overlap as a percent of the alignment length", "-1: intersection of -r and -q".
- * Per sequence of one genome: alignments sorted by (lo, hi, input order); chain DP
+ * Per sequence of one genome: alignments sorted by (lo, input order); chain DP
  *   best[i] = w_i + max(0, max_{j<i compatible} best[j] - overlap(j,i) * idy_i^P)
  * where overlap = hi_j - lo_i + 1 (if positive) must not exceed AN_FILT_OLAP % of alignment j's length, and
  * w_i = len_i * idy_i^P, idy_i = 1 - 2*errs/(rl+ql).  All weights are integers (fixed point, see
@@ -457,7 +457,6 @@ static int filt_cmp(const void *a, const void *b) {
     const filt_iv *x = (const filt_iv *)a, *y = (const filt_iv *)b;
     if (x->seq != y->seq) return x->seq < y->seq ? -1 : 1;
     if (x->lo != y->lo) return x->lo < y->lo ? -1 : 1;
-    if (x->hi != y->hi) return x->hi < y->hi ? -1 : 1;
     return x->idx < y->idx ? -1 : x->idx > y->idx;
 }
 /* per-base weight in 1/65536 units: idy^AN_FILT_POW with idy = 1 - 2*errs/(rl+ql), integer arithmetic */

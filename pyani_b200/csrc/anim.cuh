@@ -1,0 +1,161 @@
+// ANIm-equivalent aligner on the device: shared structures and device helpers.
+// Stands in for `nucmer --mum` + `delta-filter -1` (anim.py:280,285-288) and anim.parse_delta
+// (anim.py:292-411).  The algorithm specification is DESIGN.md "ANIm algorithm"; the CPU oracle
+// (oracle/oracle_anim.c) implements the same specification independently and the parity tests compare
+// the two bit for bit.
+#pragma once
+#include "anim_params.cuh"
+#include "common.cuh"
+
+struct MinimizerIndex {
+    int64_t n_mini = 0;
+    uint32_t *d_kmer = nullptr;     // unique canonical minimizers, sorted by position
+    uint32_t *d_posflag = nullptr;  // position | orientation << 31
+    uint64_t *d_table = nullptr;    // open addressing, slot = kmer << 32 | posflag, empty = ~0
+    uint32_t table_bits = 0;
+};
+
+// One directed comparison of a batch, as the kernels see it.
+struct PairDesc {
+    const uint64_t *r_seq, *q_seq;    // 2-bit packed, 32 bases per u64
+    const uint32_t *r_mask, *q_mask;  // 1 bit per base
+    const uint64_t *r_goff, *q_goff;  // record starts in g-space
+    const uint64_t *r_table;
+    const uint32_t *q_kmer, *q_posflag;
+    int64_t q_nmini;
+    int64_t probe_base;  // offset of this pair's probes in the flattened probe index
+    int32_t r_npos, q_npos;
+    uint32_t r_ncontigs, q_ncontigs, r_table_bits;
+    int32_t pad;
+};
+
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+// table addressing must be independent of the selection hash (minimizers are the k-mers with small fmix32)
+__device__ __forceinline__ uint32_t table_hash(uint32_t kmer) { return fmix32(kmer ^ 0x5bd1e995u); }
+
+__device__ __forceinline__ bool table_lookup(const uint64_t *__restrict__ table, uint32_t bits, uint32_t kmer, uint32_t &posflag) {
+    const uint32_t msk = (1u << bits) - 1u;
+    uint32_t s = table_hash(kmer) >> (32 - bits);
+    while (true) {
+        uint64_t e = __ldg(table + s);
+        if (e == ~0ull) return false;
+        if ((uint32_t)(e >> 32) == kmer) { posflag = (uint32_t)e; return true; }
+        s = (s + 1) & msk;
+    }
+}
+
+// Oriented view of a genome: rev=0 is g-space, rev=1 is the reverse complement of the whole g-space
+// array (x' = n-1-x, base complemented).  code 0..3, 4 = masked / out of range.
+struct SeqView {
+    const uint64_t *s;
+    const uint32_t *m;
+    int32_t n;
+    int32_t rev;
+};
+__device__ __forceinline__ int view_code(const SeqView &v, int64_t x) {
+    if (x < 0 || x >= v.n) return 4;
+    int64_t p = v.rev ? (int64_t)v.n - 1 - x : x;
+    if ((v.m[p >> 5] >> (p & 31)) & 1u) return 4;
+    int c = (int)((v.s[p >> 5] >> ((p & 31) << 1)) & 3ull);
+    return v.rev ? 3 - c : c;
+}
+__device__ __forceinline__ uint64_t rc64(uint64_t x) {  // reverse complement of 32 packed bases
+    uint64_t y = __brevll(~x);
+    return ((y & 0x5555555555555555ull) << 1) | ((y >> 1) & 0x5555555555555555ull);
+}
+// 32 bases x..x+31 of the view as packed codes + their mask bits. Caller guarantees 0 <= x and, for the
+// reversed view, x + 32 <= n (the forward view may run into the masked padding).
+__device__ __forceinline__ uint64_t view_chunk(const SeqView &v, int64_t x, uint32_t &mk) {
+    int64_t p = v.rev ? (int64_t)v.n - 32 - x : x;
+    int64_t w = p >> 5;
+    int sh = (int)(p & 31);
+    uint64_t a = v.s[w], ma = v.m[w];
+    if (sh) {
+        uint64_t b = v.s[w + 1], mb = v.m[w + 1];
+        a = (a >> (2 * sh)) | (b << (64 - 2 * sh));
+        ma = (ma >> sh) | (mb << (32 - sh));
+    }
+    uint32_t m32 = (uint32_t)ma;
+    if (v.rev) { a = rc64(a); m32 = __brev(m32); }
+    mk = m32;
+    return a;
+}
+
+__device__ __forceinline__ uint32_t contig_of(const uint64_t *__restrict__ goff, uint32_t n, int64_t pos) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if ((int64_t)goff[mid] <= pos) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int pack_score(int v) { return (v + AN_PACK - 1) >> 12; }
+__device__ __forceinline__ int pack_errs(int v) { return pack_score(v) * AN_PACK - v; }
+
+// anchor key/value encoding (sorted by key, ties by value)
+//   key = pair_local << 32 | strand << 31 | r      val = q << 32 | len
+__device__ __forceinline__ uint32_t key_pair(uint64_t k) { return (uint32_t)(k >> 32); }
+__device__ __forceinline__ int key_strand(uint64_t k) { return (int)((k >> 31) & 1); }
+__device__ __forceinline__ int key_r(uint64_t k) { return (int)(k & 0x7fffffffu); }
+__device__ __forceinline__ int val_q(uint64_t v) { return (int)(v >> 32); }
+__device__ __forceinline__ int val_len(uint64_t v) { return (int)(v & 0xffffffffu); }
+
+struct ChainArrays {
+    const uint64_t *keys, *vals;  // sorted unique anchors
+    int64_t n;
+    uint32_t *rc_of, *qc_of;
+    int *pred, *trim, *succ, *gval;
+    int *head, *chead;
+    int *cw;                      // cluster matched bases (at cluster head)
+    int *wsum, *tail;             // at segment head
+    long long *ssum, *esum;       // at segment head
+    uint8_t *strong;              // at segment head
+};
+
+
+// link geometry shared with the DP stage
+__device__ __forceinline__ void link_box(const ChainArrays &A, int64_t i, int64_t &rej, int64_t &qej, int &lr, int &lq) {
+    int p = A.pred[i];
+    uint64_t kj = A.keys[p], vj = A.vals[p];
+    rej = (int64_t)key_r(kj) + val_len(vj);
+    qej = (int64_t)val_q(vj) + val_len(vj);
+    lr = (int)(key_r(A.keys[i]) + A.trim[i] - rej);
+    lq = (int)(val_q(A.vals[i]) + A.trim[i] - qej);
+}
+
+
+// One alignment under construction (a kept segment = chain of intact links), extended tile by tile.
+struct SegArrays {
+    int64_t n;
+    int *pair, *strand, *head;
+    uint32_t *rc, *qc;                 // record indices
+    int *rs, *qs, *re, *qe;            // [s,e) in view coordinates (reference g-space / query view)
+    int *r_lo, *r_hi, *q_lo, *q_hi;    // record bounds in the same coordinates
+    long long *score, *errs;
+    uint8_t *active;                   // [2*n]: side 0 = left extension, side 1 = right extension
+};
+
+// rows: n x 8 int32 (pair, ref record, qry record, rs, re, qs, qe, errs), grouped by pair.
+struct FiltArrays {
+    const int *rows;
+    int64_t n;
+    // per axis (0 = reference, 1 = query), in (pair, record, lo, input order) order:
+    int *sidx[2];
+    int *slo[2], *shi[2], *sseq[2];
+    long long *best;   // scratch, sorted order
+    int *from;         // scratch
+    long long *unit;   // per alignment (input order), identity^2 in Q16
+    uint8_t *flag;     // per alignment: bit a set = kept on axis a
+};
+
+
+// stage / counter slots of b200ani_last_profile
+enum {
+    ST_INDEX = 0, ST_SEED, ST_SORT, ST_LINK, ST_GAPDP, ST_LABEL, ST_EXTDP, ST_FILTER, ST_REDUCE, ST_TOTAL,
+    CT_PROBES = 0, CT_SEEDHITS, CT_ANCHORS, CT_LINKS, CT_CUTS, CT_SEGMENTS, CT_GAPCELLS, CT_EXTCELLS, CT_EXTTILES, CT_ALIGNMENTS, CT_LAUNCHES,
+    CT_GAPTASKS, CT_PAIRS
+};

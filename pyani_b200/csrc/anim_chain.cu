@@ -1,0 +1,126 @@
+// Chaining stage: anchors -> links -> clusters / segments.  Stands in for MUMmer's mgaps clustering and
+// postnuc's cluster merging (SURVEY.md 8a-M2 [EXT]); every step is a flat kernel over all anchors of
+// the batch (thread per anchor) so 10^5..10^7 anchors of hundreds of pairs are processed together.
+#include "anim.cuh"
+
+__global__ void contig_kernel(ChainArrays A, const PairDesc *__restrict__ pairs) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    uint64_t k = A.keys[i], v = A.vals[i];
+    const PairDesc &P = pairs[key_pair(k)];
+    A.rc_of[i] = contig_of(P.r_goff, P.r_ncontigs, key_r(k));
+    int64_t q = val_q(v);
+    int64_t qf = key_strand(k) ? (int64_t)P.q_npos - 1 - q : q;
+    A.qc_of[i] = contig_of(P.q_goff, P.q_ncontigs, qf);
+    A.pred[i] = -1;
+    A.trim[i] = 0;
+    A.succ[i] = 0x7fffffff;
+    A.gval[i] = 0;
+}
+
+// nearest compatible predecessor among the previous AN_LOOKBACK anchors of the same pair and strand
+__global__ void link_kernel(ChainArrays A) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    const uint64_t ki = A.keys[i], vi = A.vals[i];
+    const uint64_t group = ki >> 31;  // pair + strand
+    const int ri = key_r(ki), qi = val_q(vi), leni = val_len(vi);
+    const uint32_t rci = A.rc_of[i], qci = A.qc_of[i];
+    for (int64_t j = i - 1; j >= 0 && j >= i - AN_LOOKBACK; --j) {
+        const uint64_t kj = A.keys[j];
+        if ((kj >> 31) != group) break;
+        if (A.rc_of[j] != rci || A.qc_of[j] != qci) continue;
+        const uint64_t vj = A.vals[j];
+        int64_t rej = (int64_t)key_r(kj) + val_len(vj), qej = (int64_t)val_q(vj) + val_len(vj);
+        int64_t ov = max((int64_t)0, max(rej - ri, qej - qi));
+        if (ov >= leni) continue;
+        int64_t gr = ri + ov - rej, gq = qi + ov - qej;
+        if (gr > AN_GAPMAX || gq > AN_GAPMAX) continue;
+        int64_t dd = gq - gr;
+        if (dd > AN_DMAX || dd < -AN_DMAX) continue;
+        A.pred[i] = (int)j;
+        A.trim[i] = (int)ov;
+        atomicMin(&A.succ[j], (int)i);
+        break;
+    }
+}
+
+// a predecessor keeps only its nearest successor; links that lose become chain heads
+__global__ void link_validate_kernel(ChainArrays A, unsigned long long *__restrict__ n_links) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    int p = A.pred[i];
+    if (p < 0) return;
+    if (A.succ[p] != (int)i) { A.pred[i] = -1; A.trim[i] = 0; }
+    else atomicAdd(n_links, 1ull);
+}
+
+// trivial links are scored here; the others become DP tasks (sort key = rows, descending)
+__global__ void gap_task_kernel(ChainArrays A, uint32_t *__restrict__ task_key, uint32_t *__restrict__ task_idx, unsigned long long *__restrict__ n_tasks) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n || A.pred[i] < 0) return;
+    int64_t rej, qej;
+    int lr, lq;
+    link_box(A, i, rej, qej, lr, lq);
+    if (lr == 0 && lq == 0) { A.gval[i] = 0; return; }
+    if (lr == 0 || lq == 0) {
+        int L = lr + lq;
+        A.gval[i] = -((AN_GAPOPEN + (L - 1) * AN_GAPEXT) * AN_PACK + L);
+        return;
+    }
+    unsigned long long s = atomicAdd(n_tasks, 1ull);
+    task_key[s] = (uint32_t)(AN_GAPMAX + 1 - lr);
+    task_idx[s] = (uint32_t)i;
+}
+
+// ---- labels by pointer jumping ------------------------------------------------------------------
+__global__ void label_init_kernel(ChainArrays A) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    int p = A.pred[i];
+    A.head[i] = p >= 0 ? p : (int)i;
+    int c = (int)i;
+    if (p >= 0) {
+        int64_t rej, qej;
+        int lr, lq;
+        link_box(A, i, rej, qej, lr, lq);
+        if (lr <= AN_CLUSTGAP && lq <= AN_CLUSTGAP) c = p;
+    }
+    A.chead[i] = c;
+    A.cw[i] = 0; A.wsum[i] = 0; A.tail[i] = -1; A.ssum[i] = 0; A.esum[i] = 0; A.strong[i] = 0;
+}
+
+__global__ void label_jump_kernel(ChainArrays A, int *__restrict__ changed) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    int h = A.head[i], hh = A.head[h];
+    int c = A.chead[i], cc = A.chead[c];
+    if (hh != h) { A.head[i] = hh; *changed = 1; }
+    if (cc != c) { A.chead[i] = cc; *changed = 1; }
+}
+
+__global__ void cluster_weight_kernel(ChainArrays A) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    atomicAdd(&A.cw[A.chead[i]], val_len(A.vals[i]) - A.trim[i]);
+}
+
+__global__ void segment_accum_kernel(ChainArrays A) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    int h = A.head[i];
+    if (A.cw[A.chead[i]] >= AN_MINCLUSTER) A.strong[h] = 1;
+    atomicAdd(&A.wsum[h], val_len(A.vals[i]) - A.trim[i]);
+    int g = A.gval[i];
+    if (g != 0) {
+        atomicAdd((unsigned long long *)&A.ssum[h], (unsigned long long)(long long)pack_score(g));
+        atomicAdd((unsigned long long *)&A.esum[h], (unsigned long long)(long long)pack_errs(g));
+    }
+    atomicMax(&A.tail[h], (int)i);
+}
+
+__global__ void segment_flag_kernel(ChainArrays A, uint8_t *__restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    flag[i] = (A.head[i] == (int)i) && A.strong[i];
+}

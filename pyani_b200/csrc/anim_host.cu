@@ -1,0 +1,415 @@
+// Host orchestration of the ANIm pipeline and its C ABI (b200ani_anim, b200ani_anim_alignments).
+// One batch = up to MAX_BATCH_PAIRS directed comparisons flowing through flat kernels together:
+//   seed -> sort/unique -> link -> link DP -> labels -> extension DP rounds -> rows -> filter -> reduce
+// replacing, per pair, one nucmer and one delta-filter subprocess plus anim.parse_delta
+// (anim.py:240-289,292-411; run_multiprocessing.py:113-152).
+#include <algorithm>
+#include <cub/cub.cuh>
+#include <cstring>
+
+#include "anim.cuh"
+
+int build_index(b200ani_ctx *ctx, Genome &g);
+
+// kernels defined in the other translation units
+__global__ void seed_kernel(const PairDesc *, int, int64_t, uint64_t *, uint64_t *, unsigned long long *, unsigned long long);
+__global__ void tie_fix_kernel(uint64_t *, uint64_t *, int64_t);
+__global__ void flag_unique_kernel(const uint64_t *, const uint64_t *, int64_t, uint8_t *);
+__global__ void contig_kernel(ChainArrays, const PairDesc *);
+__global__ void link_kernel(ChainArrays);
+__global__ void link_validate_kernel(ChainArrays, unsigned long long *);
+__global__ void gap_task_kernel(ChainArrays, uint32_t *, uint32_t *, unsigned long long *);
+__global__ void label_init_kernel(ChainArrays);
+__global__ void label_jump_kernel(ChainArrays, int *);
+__global__ void cluster_weight_kernel(ChainArrays);
+__global__ void segment_accum_kernel(ChainArrays);
+__global__ void segment_flag_kernel(ChainArrays, uint8_t *);
+__global__ void gap_dp_kernel(ChainArrays, const PairDesc *, const uint32_t *, int64_t, unsigned long long *);
+__global__ void segment_init_kernel(ChainArrays, const PairDesc *, const int *, SegArrays);
+__global__ void ext_dp_kernel(SegArrays, const PairDesc *, unsigned long long *);
+__global__ void emit_rows_kernel(SegArrays, const PairDesc *, int *);
+__global__ void filt_key_kernel(FiltArrays, int, uint64_t *, int *);
+__global__ void filt_gather_kernel(FiltArrays, int, const int *);
+__global__ void pair_range_kernel(const int *, int64_t, int, int *);
+__global__ void filt_dp_kernel(FiltArrays, int, const int *, int);
+__global__ void reduce_kernel(FiltArrays, const int *, int, int, b200ani_anim_result *);
+
+static const char *kStageNames[B200ANI_N_STAGES] = {"index", "seed", "sort", "link", "gap_dp", "label", "ext_dp", "filter", "reduce", "total",
+                                                    "", "", "", "", "", ""};
+static const char *kCounterNames[B200ANI_N_STAGES] = {"probes", "seed_hits", "anchors", "links", "cut_links", "segments", "gap_cells", "ext_cells",
+                                                      "ext_tiles", "alignments", "launches", "gap_tasks", "pairs", "", "", ""};
+
+constexpr int MAX_BATCH_PAIRS = 128;
+constexpr int64_t ANCHOR_CAP = 24ll << 20;
+
+struct AnimWorkspace {
+    uint64_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr;
+    uint8_t *flag = nullptr;
+    unsigned long long *counters = nullptr;  // 16 device counters
+    int *changed = nullptr;
+    PairDesc *d_pairs = nullptr;
+    b200ani_anim_result *d_results = nullptr;
+    void *cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    cudaEvent_t ev[2 * B200ANI_N_STAGES];
+    bool ok = false;
+};
+
+void free_anim_workspace(void *p) {
+    AnimWorkspace *w = (AnimWorkspace *)p;
+    if (!w) return;
+    cudaFree(w->keys_a); cudaFree(w->vals_a); cudaFree(w->keys_b); cudaFree(w->vals_b); cudaFree(w->flag);
+    cudaFree(w->counters); cudaFree(w->changed); cudaFree(w->d_pairs); cudaFree(w->d_results); cudaFree(w->cub_tmp);
+    if (w->ok) for (auto &e : w->ev) cudaEventDestroy(e);
+    delete w;
+}
+
+static int get_workspace(b200ani_ctx *ctx, AnimWorkspace **out) {
+    if (ctx->anim_ws) { *out = (AnimWorkspace *)ctx->anim_ws; return 0; }
+    AnimWorkspace *w = new AnimWorkspace();
+    ctx->anim_ws = w;
+    CK(cudaMalloc(&w->keys_a, sizeof(uint64_t) * ANCHOR_CAP));
+    CK(cudaMalloc(&w->vals_a, sizeof(uint64_t) * ANCHOR_CAP));
+    CK(cudaMalloc(&w->keys_b, sizeof(uint64_t) * ANCHOR_CAP));
+    CK(cudaMalloc(&w->vals_b, sizeof(uint64_t) * ANCHOR_CAP));
+    CK(cudaMalloc(&w->flag, ANCHOR_CAP));
+    CK(cudaMalloc(&w->counters, 16 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&w->changed, sizeof(int)));
+    CK(cudaMalloc(&w->d_pairs, sizeof(PairDesc) * MAX_BATCH_PAIRS));
+    CK(cudaMalloc(&w->d_results, sizeof(b200ani_anim_result) * MAX_BATCH_PAIRS));
+    size_t a = 0, b = 0, c = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, w->keys_a, w->keys_b, w->vals_a, w->vals_b, ANCHOR_CAP, 0, 64, ctx->stream);
+    cub::DeviceSelect::Flagged(nullptr, b, w->keys_a, w->flag, w->keys_b, (int *)w->changed, ANCHOR_CAP, ctx->stream);
+    cub::DeviceSelect::Flagged(nullptr, c, cub::CountingInputIterator<int>(0), w->flag, (int *)w->keys_b, (int *)w->changed, ANCHOR_CAP, ctx->stream);
+    w->cub_bytes = std::max(a, std::max(b, c)) + 256;
+    CK(cudaMalloc(&w->cub_tmp, w->cub_bytes));
+    for (auto &e : w->ev) CK(cudaEventCreate(&e));
+    w->ok = true;
+    *out = w;
+    return 0;
+}
+
+template <typename T>
+static int dalloc(b200ani_ctx *ctx, T **p, int64_t n) {
+    CK(cudaMallocAsync((void **)p, sizeof(T) * (size_t)std::max<int64_t>(n, 1), ctx->stream));
+    return 0;
+}
+#define DA(p, n) do { int rc__ = dalloc(ctx, &(p), (n)); if (rc__) return rc__; } while (0)
+#define DF(p) CK(cudaFreeAsync((p), ctx->stream))
+#define LAUNCHED(k) do { CK(cudaGetLastError()); ctx->counters[CT_LAUNCHES] += (k); } while (0)
+#define GRID(n) (unsigned)std::max<int64_t>(1, ceil_div((n), 256)), 256, 0, st
+#define T0(s) CK(cudaEventRecord(W->ev[2 * (s)], st))
+#define T1(s) do { CK(cudaEventRecord(W->ev[2 * (s) + 1], st)); used[(s)] = true; } while (0)
+
+// rows_out (optional): host buffer receiving the batch's alignment rows (n x 8 int32) + keep flags
+struct RowDump {
+    std::vector<int> rows;
+    std::vector<uint8_t> flag;
+};
+
+static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, b200ani_anim_result *out, RowDump *dump) {
+    cudaStream_t st = ctx->stream;
+    bool used[B200ANI_N_STAGES] = {false};
+    // ---- pair descriptors
+    std::vector<PairDesc> hp(nb);
+    int64_t n_probes = 0;
+    for (int p = 0; p < nb; ++p) {
+        const Genome &R = ctx->genomes[pairs[2 * p]], &Q = ctx->genomes[pairs[2 * p + 1]];
+        PairDesc &d = hp[p];
+        d.r_seq = (const uint64_t *)R.d_seq; d.q_seq = (const uint64_t *)Q.d_seq;
+        d.r_mask = R.d_mask; d.q_mask = Q.d_mask;
+        d.r_goff = R.d_goff; d.q_goff = Q.d_goff;
+        d.r_table = R.index->d_table; d.r_table_bits = R.index->table_bits;
+        d.q_kmer = Q.index->d_kmer; d.q_posflag = Q.index->d_posflag; d.q_nmini = Q.index->n_mini;
+        d.probe_base = n_probes;
+        d.r_npos = (int32_t)R.n_pos; d.q_npos = (int32_t)Q.n_pos;
+        d.r_ncontigs = R.n_contigs; d.q_ncontigs = Q.n_contigs;
+        d.pad = 0;
+        n_probes += Q.index->n_mini;
+    }
+    CK(cudaMemcpyAsync(W->d_pairs, hp.data(), sizeof(PairDesc) * nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(W->counters, 0, 16 * sizeof(unsigned long long), st));
+    unsigned long long hc[16];
+    ctx->counters[CT_PROBES] += n_probes;
+    ctx->counters[CT_PAIRS] += nb;
+
+    // ---- seeds -> anchors
+    T0(ST_SEED);
+    if (n_probes) {
+        int blocks = (int)std::min<int64_t>(ceil_div(n_probes, 256), (int64_t)ctx->sm_count * 16);
+        seed_kernel<<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->keys_a, W->vals_a, W->counters, (unsigned long long)ANCHOR_CAP);
+        LAUNCHED(1);
+    }
+    T1(ST_SEED);
+    CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int64_t n_raw = (int64_t)hc[0];
+    ctx->counters[CT_SEEDHITS] += (int64_t)hc[1];
+    if (n_raw > ANCHOR_CAP) return 1;  // caller splits the batch
+
+    // ---- sort by (pair, strand, r), ties by (q, len); drop duplicates
+    T0(ST_SORT);
+    int64_t n = 0;
+    if (n_raw) {
+        int pair_bits = 1;
+        while ((1 << pair_bits) < nb) ++pair_bits;
+        size_t tb = W->cub_bytes;
+        cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb, W->keys_a, W->keys_b, W->vals_a, W->vals_b, n_raw, 0, 32 + pair_bits, st);
+        tie_fix_kernel<<<GRID(n_raw)>>>(W->keys_b, W->vals_b, n_raw);
+        flag_unique_kernel<<<GRID(n_raw)>>>(W->keys_b, W->vals_b, n_raw, W->flag);
+        LAUNCHED(2);
+        tb = W->cub_bytes;
+        cub::DeviceSelect::Flagged(W->cub_tmp, tb, W->keys_b, W->flag, W->keys_a, W->changed, n_raw, st);
+        tb = W->cub_bytes;
+        cub::DeviceSelect::Flagged(W->cub_tmp, tb, W->vals_b, W->flag, W->vals_a, W->changed, n_raw, st);
+        int hn = 0;
+        CK(cudaMemcpyAsync(&hn, W->changed, sizeof hn, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        n = hn;
+    }
+    T1(ST_SORT);
+    ctx->counters[CT_ANCHORS] += n;
+
+    // ---- chain arrays
+    ChainArrays A{};
+    A.keys = W->keys_a; A.vals = W->vals_a; A.n = n;
+    uint32_t *task_key = nullptr, *task_idx = nullptr, *task_key2 = nullptr, *task_idx2 = nullptr;
+    int *seg_head = nullptr;
+    DA(A.rc_of, n); DA(A.qc_of, n); DA(A.pred, n); DA(A.trim, n); DA(A.succ, n); DA(A.gval, n);
+    DA(A.head, n); DA(A.chead, n); DA(A.cw, n); DA(A.wsum, n); DA(A.tail, n); DA(A.ssum, n); DA(A.esum, n); DA(A.strong, n);
+    DA(task_key, n); DA(task_idx, n); DA(task_key2, n); DA(task_idx2, n); DA(seg_head, n);
+    int64_t n_seg = 0;
+    if (n) {
+        T0(ST_LINK);
+        contig_kernel<<<GRID(n)>>>(A, W->d_pairs);
+        link_kernel<<<GRID(n)>>>(A);
+        link_validate_kernel<<<GRID(n)>>>(A, W->counters + 2);
+        gap_task_kernel<<<GRID(n)>>>(A, task_key, task_idx, W->counters + 3);
+        LAUNCHED(4);
+        T1(ST_LINK);
+        CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->counters[CT_LINKS] += (int64_t)hc[2];
+        const int64_t n_tasks = (int64_t)hc[3];
+        ctx->counters[CT_GAPTASKS] += n_tasks;
+        // ---- link alignments
+        T0(ST_GAPDP);
+        if (n_tasks) {
+            size_t tb = W->cub_bytes;
+            cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb, task_key, task_key2, task_idx, task_idx2, n_tasks, 0, 11, st);
+            gap_dp_kernel<<<(unsigned)ceil_div(n_tasks, 128), 128, 0, st>>>(A, W->d_pairs, task_idx2, n_tasks, W->counters + 4);
+            LAUNCHED(1);
+        }
+        T1(ST_GAPDP);
+        // ---- clusters and segments
+        T0(ST_LABEL);
+        label_init_kernel<<<GRID(n)>>>(A);
+        LAUNCHED(1);
+        for (int round = 0; round < 8; ++round) {
+            CK(cudaMemsetAsync(W->changed, 0, sizeof(int), st));
+            for (int k = 0; k < 4; ++k) label_jump_kernel<<<GRID(n)>>>(A, W->changed);
+            LAUNCHED(4);
+            int ch = 0;
+            CK(cudaMemcpyAsync(&ch, W->changed, sizeof ch, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (!ch) break;
+        }
+        cluster_weight_kernel<<<GRID(n)>>>(A);
+        segment_accum_kernel<<<GRID(n)>>>(A);
+        segment_flag_kernel<<<GRID(n)>>>(A, W->flag);
+        LAUNCHED(3);
+        size_t tb = W->cub_bytes;
+        cub::DeviceSelect::Flagged(W->cub_tmp, tb, cub::CountingInputIterator<int>(0), W->flag, seg_head, W->changed, n, st);
+        int hs = 0;
+        CK(cudaMemcpyAsync(&hs, W->changed, sizeof hs, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        T1(ST_LABEL);
+        n_seg = hs;
+        ctx->counters[CT_GAPCELLS] += (int64_t)hc[4];
+        ctx->counters[CT_CUTS] += (int64_t)hc[5];
+    }
+    ctx->counters[CT_SEGMENTS] += n_seg;
+
+    // ---- extension rounds
+    SegArrays S{};
+    S.n = n_seg;
+    int *rows = nullptr;
+    DA(S.pair, n_seg); DA(S.strand, n_seg); DA(S.head, n_seg); DA(S.rc, n_seg); DA(S.qc, n_seg);
+    DA(S.rs, n_seg); DA(S.qs, n_seg); DA(S.re, n_seg); DA(S.qe, n_seg);
+    DA(S.r_lo, n_seg); DA(S.r_hi, n_seg); DA(S.q_lo, n_seg); DA(S.q_hi, n_seg);
+    DA(S.score, n_seg); DA(S.errs, n_seg); DA(S.active, 2 * n_seg); DA(rows, 8 * n_seg);
+    if (n_seg) {
+        T0(ST_EXTDP);
+        segment_init_kernel<<<GRID(n_seg)>>>(A, W->d_pairs, seg_head, S);
+        LAUNCHED(1);
+        for (int round = 0; round < AN_MAXTILES; ++round) {
+            CK(cudaMemsetAsync(W->counters + 8, 0, sizeof(unsigned long long), st));
+            ext_dp_kernel<<<(unsigned)ceil_div(2 * n_seg, 128), 128, 0, st>>>(S, W->d_pairs, W->counters + 6);
+            LAUNCHED(1);
+            CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (hc[8] == 0) break;
+        }
+        emit_rows_kernel<<<GRID(n_seg)>>>(S, W->d_pairs, rows);
+        LAUNCHED(1);
+        T1(ST_EXTDP);
+        ctx->counters[CT_EXTCELLS] += (int64_t)hc[6];
+        ctx->counters[CT_EXTTILES] += (int64_t)hc[7];
+    }
+
+    // ---- 1-to-1 filter + parse_delta reduction
+    FiltArrays F{};
+    F.rows = rows; F.n = n_seg;
+    uint64_t *fkey = nullptr, *fkey2 = nullptr;
+    int *fidx = nullptr, *fidx2 = nullptr, *pair_start = nullptr;
+    for (int a = 0; a < 2; ++a) { DA(F.sidx[a], n_seg); DA(F.slo[a], n_seg); DA(F.shi[a], n_seg); DA(F.sseq[a], n_seg); }
+    DA(F.best, n_seg); DA(F.from, n_seg); DA(F.unit, n_seg); DA(F.flag, n_seg);
+    DA(fkey, n_seg); DA(fkey2, n_seg); DA(fidx, n_seg); DA(fidx2, n_seg); DA(pair_start, nb + 2);
+    T0(ST_FILTER);
+    pair_range_kernel<<<(unsigned)ceil_div(nb + 1, 128), 128, 0, st>>>(rows, n_seg, nb, pair_start);
+    LAUNCHED(1);
+    for (int axis = 0; axis < 2 && n_seg; ++axis) {
+        filt_key_kernel<<<GRID(n_seg)>>>(F, axis, fkey, fidx);
+        size_t tb = W->cub_bytes;
+        cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb, fkey, fkey2, fidx, fidx2, n_seg, 0, 64, st);
+        filt_gather_kernel<<<GRID(n_seg)>>>(F, axis, fidx2);
+        LAUNCHED(2);
+        if (!nofilter) {
+            filt_dp_kernel<<<(unsigned)ceil_div((int64_t)nb * 32, 128), 128, 0, st>>>(F, axis, pair_start, nb);
+            LAUNCHED(1);
+        }
+    }
+    T1(ST_FILTER);
+    T0(ST_REDUCE);
+    reduce_kernel<<<(unsigned)ceil_div((int64_t)nb * 32, 128), 128, 0, st>>>(F, pair_start, nb, nofilter, W->d_results);
+    LAUNCHED(1);
+    CK(cudaMemcpyAsync(out, W->d_results, sizeof(b200ani_anim_result) * nb, cudaMemcpyDeviceToHost, st));
+    T1(ST_REDUCE);
+    if (dump) {
+        dump->rows.resize((size_t)8 * n_seg);
+        dump->flag.resize((size_t)n_seg);
+        if (n_seg) {
+            CK(cudaMemcpyAsync(dump->rows.data(), rows, sizeof(int) * 8 * n_seg, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(dump->flag.data(), F.flag, (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    // ---- release
+    DF(A.rc_of); DF(A.qc_of); DF(A.pred); DF(A.trim); DF(A.succ); DF(A.gval); DF(A.head); DF(A.chead); DF(A.cw); DF(A.wsum);
+    DF(A.tail); DF(A.ssum); DF(A.esum); DF(A.strong); DF(task_key); DF(task_idx); DF(task_key2); DF(task_idx2); DF(seg_head);
+    DF(S.pair); DF(S.strand); DF(S.head); DF(S.rc); DF(S.qc); DF(S.rs); DF(S.qs); DF(S.re); DF(S.qe);
+    DF(S.r_lo); DF(S.r_hi); DF(S.q_lo); DF(S.q_hi); DF(S.score); DF(S.errs); DF(S.active); DF(rows);
+    for (int a = 0; a < 2; ++a) { DF(F.sidx[a]); DF(F.slo[a]); DF(F.shi[a]); DF(F.sseq[a]); }
+    DF(F.best); DF(F.from); DF(F.unit); DF(F.flag); DF(fkey); DF(fkey2); DF(fidx); DF(fidx2); DF(pair_start);
+    CK(cudaStreamSynchronize(st));
+    for (int s = 0; s < B200ANI_N_STAGES; ++s)
+        if (used[s]) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, W->ev[2 * s], W->ev[2 * s + 1]));
+            ctx->stage_ms[s] += ms;
+        }
+    int64_t kept = 0;
+    for (int p = 0; p < nb; ++p) kept += out[p].n_alignments;
+    ctx->counters[CT_ALIGNMENTS] += kept;
+    return 0;
+}
+
+static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int64_t m, int nofilter, b200ani_anim_result *out, RowDump *dump) {
+    for (int64_t b0 = 0; b0 < m;) {
+        int nb = (int)std::min<int64_t>(MAX_BATCH_PAIRS, m - b0);
+        while (true) {
+            int rc = run_batch(ctx, W, pairs + 2 * b0, nb, nofilter, out + b0, dump);
+            if (rc == 0) break;
+            if (rc < 0) return rc;
+            if (nb == 1) FAIL(B200ANI_ERR_CAPACITY, "anim: a single pair exceeds the anchor capacity");
+            nb = (nb + 1) / 2;  // anchor buffer overflow: retry with half the pairs
+        }
+        b0 += nb;
+    }
+    return 0;
+}
+
+static int prepare(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch, AnimWorkspace **W) {
+    if (maxmatch) FAIL(B200ANI_ERR_ARG, "anim: --maxmatch anchoring is not implemented in this version (only --mum semantics)");
+    CK(cudaSetDevice(ctx->device));
+    const int32_t ng = (int32_t)ctx->genomes.size();
+    for (int64_t i = 0; i < 2 * m; ++i)
+        if (pairs[i] < 0 || pairs[i] >= ng) FAIL(B200ANI_ERR_ARG, "anim: genome id out of range");
+    int rc = get_workspace(ctx, W);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    cudaEvent_t e0 = (*W)->ev[2 * ST_INDEX], e1 = (*W)->ev[2 * ST_INDEX + 1];
+    bool any = false;
+    CK(cudaEventRecord(e0, st));
+    for (int64_t i = 0; i < 2 * m; ++i) {
+        Genome &g = ctx->genomes[pairs[i]];
+        if (g.n_contigs >= 65535) FAIL(B200ANI_ERR_CAPACITY, "anim: genomes with >= 65535 records are not supported");
+        if (!g.index) {
+            rc = build_index(ctx, g);
+            if (rc) return rc;
+            any = true;
+        }
+    }
+    CK(cudaEventRecord(e1, st));
+    CK(cudaStreamSynchronize(st));
+    if (any) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        ctx->stage_ms[ST_INDEX] += ms;
+    }
+    return 0;
+}
+
+extern "C" {
+
+const char *b200ani_stage_name(int i) {
+    if (i < 0 || i >= 2 * B200ANI_N_STAGES) return "";
+    return i < B200ANI_N_STAGES ? kStageNames[i] : kCounterNames[i - B200ANI_N_STAGES];
+}
+
+int b200ani_anim(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch, int nofilter, b200ani_anim_result *out) {
+    if (!ctx || !pairs || !out || m < 0) return B200ANI_ERR_ARG;
+    memset(ctx->stage_ms, 0, sizeof ctx->stage_ms);
+    memset(ctx->counters, 0, sizeof ctx->counters);
+    AnimWorkspace *W = nullptr;
+    cudaEvent_t t0, t1;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventCreate(&t0));
+    CK(cudaEventCreate(&t1));
+    CK(cudaEventRecord(t0, ctx->stream));
+    int rc = prepare(ctx, pairs, m, maxmatch, &W);
+    if (rc == 0) rc = run_range(ctx, W, pairs, m, nofilter, out, nullptr);
+    CK(cudaEventRecord(t1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, t0, t1));
+    ctx->stage_ms[ST_TOTAL] = ms;
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    return rc;
+}
+
+int64_t b200ani_anim_alignments(b200ani_ctx *ctx, int32_t ref_id, int32_t qry_id, int maxmatch, int nofilter, int64_t *rows, int64_t cap) {
+    if (!ctx || (!rows && cap > 0)) return B200ANI_ERR_ARG;
+    int32_t pr[2] = {ref_id, qry_id};
+    AnimWorkspace *W = nullptr;
+    int rc = prepare(ctx, pr, 1, maxmatch, &W);
+    if (rc) return rc;
+    RowDump dump;
+    b200ani_anim_result res;
+    rc = run_range(ctx, W, pr, 1, nofilter, &res, &dump);
+    if (rc) return rc;
+    int64_t k = 0;
+    for (size_t i = 0; i < dump.flag.size(); ++i) {
+        if (!nofilter && dump.flag[i] != 3) continue;
+        if (k < cap) {
+            const int *a = dump.rows.data() + 8 * i;
+            int64_t *o = rows + 7 * k;
+            o[0] = a[1]; o[1] = a[2]; o[2] = a[3]; o[3] = a[4]; o[4] = a[5]; o[5] = a[6]; o[6] = a[7];
+        }
+        ++k;
+    }
+    return k;
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+// Per-genome seed index: canonical (w=5,k=16) minimizers that are unique within the genome.
+// Built once per genome and reused by every comparison the genome takes part in -- nucmer instead
+// rebuilds its suffix tree for each of the N-1 runs a genome is the reference of.
+#include <cub/cub.cuh>
+
+#include "anim.cuh"
+
+// k-mer at position p in little-endian packed form (first base in the low bits) + "all 16 bases clean".
+__device__ __forceinline__ bool kmer_at(const uint64_t *__restrict__ s, const uint32_t *__restrict__ m, int64_t p, int64_t n_pos, uint32_t &g) {
+    if (p < 0 || p + AN_K > n_pos) return false;
+    int64_t w = p >> 5;
+    int sh = (int)(p & 31);
+    uint64_t a = s[w] >> (2 * sh);
+    uint64_t ma = (uint64_t)m[w] >> sh;
+    if (sh > 16) {
+        a |= s[w + 1] << (64 - 2 * sh);
+        ma |= (uint64_t)m[w + 1] << (32 - sh);
+    }
+    g = (uint32_t)a;
+    return (ma & 0xffffu) == 0;
+}
+
+// hash of the canonical k-mer, or 2^32 if the position carries no usable k-mer (masked or palindrome)
+__device__ __forceinline__ uint64_t kmer_hash(const uint64_t *s, const uint32_t *m, int64_t p, int64_t n_pos, uint32_t &canon, uint32_t &orient) {
+    uint32_t g;
+    if (!kmer_at(s, m, p, n_pos, g)) return 1ull << 32;
+    uint32_t y = __brev(g);
+    uint32_t f = ((y & 0x55555555u) << 1) | ((y >> 1) & 0x55555555u);  // first base most significant
+    uint32_t r = ~g;                                                    // reverse complement, same convention
+    if (f == r) return 1ull << 32;
+    canon = f < r ? f : r;
+    orient = r < f;
+    return fmix32(canon);
+}
+
+// A position is selected iff its hash is <= every hash of at least one window of AN_W consecutive
+// k-mer starts containing it (ties select all, which keeps the selection strand-symmetric).
+__global__ void __launch_bounds__(256) minimizer_select_kernel(const uint64_t *__restrict__ s, const uint32_t *__restrict__ m, int64_t n_pos,
+                                                               uint64_t *__restrict__ out, unsigned long long *__restrict__ n_out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pos; p += stride) {
+        uint32_t canon = 0, orient = 0, c2, o2;
+        uint64_t h = kmer_hash(s, m, p, n_pos, canon, orient);
+        bool chosen = false;
+        if (h != (1ull << 32)) {
+            uint64_t hv[2 * AN_W - 1];
+#pragma unroll
+            for (int d = 0; d < 2 * AN_W - 1; ++d) hv[d] = (d == AN_W - 1) ? h : kmer_hash(s, m, p + d - (AN_W - 1), n_pos, c2, o2);
+#pragma unroll
+            for (int o = 0; o < AN_W; ++o) {  // window [p-o, p-o+W-1] = hv[W-1-o .. 2W-2-o]
+                bool is_min = true;
+#pragma unroll
+                for (int x = 0; x < AN_W; ++x) is_min = is_min && !(hv[AN_W - 1 - o + x] < h);
+                chosen = chosen || is_min;
+            }
+        }
+        if (chosen) {
+            unsigned long long slot = atomicAdd(n_out, 1ull);
+            out[slot] = ((uint64_t)canon << 32) | (uint32_t)p | (orient << 31);
+        }
+    }
+}
+
+__global__ void mark_unique_kernel(const uint64_t *__restrict__ sorted, int64_t n, uint8_t *__restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = (uint32_t)(sorted[i] >> 32);
+    bool u = (i == 0 || (uint32_t)(sorted[i - 1] >> 32) != k) && (i + 1 == n || (uint32_t)(sorted[i + 1] >> 32) != k);
+    flag[i] = u;
+}
+
+__global__ void table_insert_kernel(const uint64_t *__restrict__ uniq, int64_t n, uint64_t *table, uint32_t bits, uint64_t *__restrict__ bypos) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t e = uniq[i];
+    uint32_t k = (uint32_t)(e >> 32), msk = (1u << bits) - 1u;
+    uint32_t s = table_hash(k) >> (32 - bits);
+    while (atomicCAS((unsigned long long *)&table[s], ~0ull, (unsigned long long)e) != ~0ull) s = (s + 1) & msk;
+    // key for the by-position order: pos << 33 | orient << 32 | kmer
+    uint32_t pf = (uint32_t)e;
+    bypos[i] = ((uint64_t)(pf & 0x7fffffffu) << 33) | ((uint64_t)(pf >> 31) << 32) | k;
+}
+
+__global__ void split_bypos_kernel(const uint64_t *__restrict__ bypos, int64_t n, uint32_t *__restrict__ kmer, uint32_t *__restrict__ posflag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t b = bypos[i];
+    kmer[i] = (uint32_t)b;
+    posflag[i] = (uint32_t)(b >> 33) | ((uint32_t)((b >> 32) & 1) << 31);
+}
+
+void free_index(MinimizerIndex *ix) {
+    if (!ix) return;
+    cudaFree(ix->d_kmer);
+    cudaFree(ix->d_posflag);
+    cudaFree(ix->d_table);
+    delete ix;
+}
+
+int build_index(b200ani_ctx *ctx, Genome &g) {
+    if (g.index) return 0;
+    cudaStream_t st = ctx->stream;
+    const int64_t n = g.n_pos;
+    uint64_t *d_sel = nullptr, *d_sorted = nullptr, *d_uniq = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    uint8_t *d_flag = nullptr;
+    void *d_tmp = nullptr;
+    CK(cudaMallocAsync(&d_sel, sizeof(uint64_t) * (size_t)(n + 1), st));
+    CK(cudaMallocAsync(&d_sorted, sizeof(uint64_t) * (size_t)(n + 1), st));
+    CK(cudaMallocAsync(&d_uniq, sizeof(uint64_t) * (size_t)(n + 1), st));
+    CK(cudaMallocAsync(&d_cnt, 2 * sizeof(unsigned long long), st));
+    CK(cudaMallocAsync(&d_flag, (size_t)n + 1, st));
+    CK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
+    int blocks = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->sm_count * 16);
+    minimizer_select_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint64_t *>(g.d_seq), g.d_mask, n, d_sel, d_cnt);
+    CK(cudaGetLastError());
+    unsigned long long h_cnt = 0;
+    CK(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int64_t ns = (int64_t)h_cnt;
+    size_t tmp_bytes = 0, tb2 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_sel, d_sorted, ns, 0, 64, st);
+    cub::DeviceSelect::Flagged(nullptr, tb2, d_sorted, d_flag, d_uniq, (int *)d_cnt, ns, st);
+    tmp_bytes = std::max(tmp_bytes, tb2);
+    CK(cudaMallocAsync(&d_tmp, tmp_bytes + 16, st));
+    cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_sel, d_sorted, ns, 0, 64, st);
+    if (ns) mark_unique_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(d_sorted, ns, d_flag);
+    CK(cudaGetLastError());
+    int *d_nu = (int *)(d_cnt + 1);
+    cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_sorted, d_flag, d_uniq, d_nu, ns, st);
+    int h_nu = 0;
+    CK(cudaMemcpyAsync(&h_nu, d_nu, sizeof h_nu, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    MinimizerIndex *ix = new MinimizerIndex();
+    ix->n_mini = h_nu;
+    uint32_t bits = 4;
+    while ((1ll << bits) < 2ll * h_nu) ++bits;
+    ix->table_bits = bits;
+    CK(cudaMalloc(&ix->d_table, sizeof(uint64_t) << bits));
+    CK(cudaMalloc(&ix->d_kmer, sizeof(uint32_t) * (size_t)(h_nu + 1)));
+    CK(cudaMalloc(&ix->d_posflag, sizeof(uint32_t) * (size_t)(h_nu + 1)));
+    CK(cudaMemsetAsync(ix->d_table, 0xff, sizeof(uint64_t) << bits, st));
+    if (h_nu) {
+        table_insert_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, st>>>(d_uniq, h_nu, ix->d_table, bits, d_sel);
+        CK(cudaGetLastError());
+        cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_sel, d_sorted, h_nu, 33, 64, st);
+        split_bypos_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, st>>>(d_sorted, h_nu, ix->d_kmer, ix->d_posflag);
+        CK(cudaGetLastError());
+    }
+    ctx->counters[CT_LAUNCHES] += 7;
+    CK(cudaFreeAsync(d_sel, st));
+    CK(cudaFreeAsync(d_sorted, st));
+    CK(cudaFreeAsync(d_uniq, st));
+    CK(cudaFreeAsync(d_cnt, st));
+    CK(cudaFreeAsync(d_flag, st));
+    CK(cudaFreeAsync(d_tmp, st));
+    g.index = ix;
+    return 0;
+}

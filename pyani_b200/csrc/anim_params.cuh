@@ -1,0 +1,26 @@
+// Algorithm constants of the ANIm-equivalent aligner.  The specification (what every constant means,
+// which MUMmer default it stands in for) is DESIGN.md "ANIm algorithm"; the CPU oracle keeps an
+// independent copy in oracle/anim_spec.h and tests/test_abi.py asserts that the two agree.
+#pragma once
+
+#define AN_K 16
+#define AN_W 5
+#define AN_MINLEN 20
+#define AN_LOOKBACK 32
+#define AN_GAPMAX 1000
+#define AN_DMAX 16
+#define AN_MINCLUSTER 65
+#define AN_BAND 16
+#define AN_BANDW 32
+#define AN_TILE 128
+#define AN_MAXTILES 64
+#define AN_MATCH 3
+#define AN_MISMATCH 7
+#define AN_GAPOPEN 10
+#define AN_GAPEXT 4
+#define AN_BREAK 94
+#define AN_CLUSTGAP 90
+#define AN_FILT_OLAP 75
+#define AN_FILT_POW 2
+#define AN_PACK 4096
+#define AN_NEG (-(1 << 29))

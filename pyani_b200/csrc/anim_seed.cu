@@ -1,0 +1,114 @@
+// Seed stage: stream every query minimizer through the reference's table, turn hits into maximal
+// exact matches (anchors).  Stands in for nucmer's suffix-tree MUM search (`mummer -mum -b -l 20`,
+// SURVEY.md 8a-M2 [EXT]).  Bound: L2/HBM random access -- one 8-byte table probe per query minimizer,
+// sequence bytes only for hits.
+#include "anim.cuh"
+
+// bases matching to the right of (r,q) in the two views, stopping at the first mismatch / masked base
+__device__ int64_t match_right(const SeqView &R, const SeqView &Q, int64_t r, int64_t q) {
+    int64_t o = 0;
+    while (true) {
+        int64_t rr = r + o, qq = q + o;
+        if (rr >= R.n || qq >= Q.n) return o;
+        if (qq + 32 <= Q.n && rr + 32 <= R.n) {  // 32-base chunk compare
+            uint32_t mr, mq;
+            uint64_t a = view_chunk(R, rr, mr), b = view_chunk(Q, qq, mq);
+            uint64_t d = a ^ b;
+            d = (d | (d >> 1)) & 0x5555555555555555ull;
+            int first = d ? (__ffsll((long long)d) - 1) >> 1 : 32;
+            uint32_t mk = mr | mq;
+            int fm = mk ? __ffs((int)mk) - 1 : 32;
+            first = min(first, fm);
+            if (first < 32) return o + first;
+            o += 32;
+        } else {
+            int a = view_code(R, rr), b = view_code(Q, qq);
+            if (a > 3 || a != b) return o;
+            ++o;
+        }
+    }
+}
+
+__device__ int64_t match_left(const SeqView &R, const SeqView &Q, int64_t r, int64_t q) {
+    int64_t l = 0;
+    while (true) {
+        int64_t rr = r - l - 1, qq = q - l - 1;
+        if (rr < 0 || qq < 0) return l;
+        int a = view_code(R, rr), b = view_code(Q, qq);
+        if (a > 3 || a != b) return l;
+        ++l;
+    }
+}
+
+// One thread per (pair, query minimizer).  key/val encoding: anim.cuh.
+__global__ void __launch_bounds__(256) seed_kernel(const PairDesc *__restrict__ pairs, int n_pairs, int64_t n_probes, uint64_t *__restrict__ keys,
+                                                   uint64_t *__restrict__ vals, unsigned long long *__restrict__ counters /*0: anchors, 1: hits*/,
+                                                   unsigned long long cap) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < n_probes; gi += stride) {
+        int lo = 0, hi = n_pairs;  // pair p with probe_base[p] <= gi < probe_base[p+1]
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (pairs[mid].probe_base <= gi) lo = mid; else hi = mid;
+        }
+        const PairDesc &P = pairs[lo];
+        const int64_t t = gi - P.probe_base;
+        uint32_t rpf;
+        if (!table_lookup(P.r_table, P.r_table_bits, P.q_kmer[t], rpf)) continue;
+        atomicAdd(&counters[1], 1ull);
+        const uint32_t qpf = P.q_posflag[t];
+        const int strand = (int)((rpf ^ qpf) >> 31);
+        const int64_t r0 = rpf & 0x7fffffffu, qpos = qpf & 0x7fffffffu;
+        const int64_t q0 = strand ? (int64_t)P.q_npos - AN_K - qpos : qpos;
+        SeqView R{P.r_seq, P.r_mask, P.r_npos, 0}, Q{P.q_seq, P.q_mask, P.q_npos, strand};
+        // redundancy: the minimizer just before this one in view order seeds the same match if it hits the
+        // same diagonal and everything in between matches -> let that one report it
+        {
+            int64_t tn = strand ? t + 1 : t - 1;
+            if (tn >= 0 && tn < P.q_nmini) {
+                uint32_t qpfn = P.q_posflag[tn], rpfn;
+                int64_t qn = strand ? (int64_t)P.q_npos - AN_K - (qpfn & 0x7fffffffu) : (qpfn & 0x7fffffffu);
+                if (qn < q0 && q0 - qn <= 64 && table_lookup(P.r_table, P.r_table_bits, P.q_kmer[tn], rpfn) &&
+                    (int)((rpfn ^ qpfn) >> 31) == strand && (int64_t)(rpfn & 0x7fffffffu) - qn == r0 - q0) {
+                    bool same = true;
+                    for (int64_t x = qn + AN_K; x < q0 && same; ++x) {
+                        int a = view_code(R, x + (r0 - q0)), b = view_code(Q, x);
+                        same = a < 4 && a == b;
+                    }
+                    if (same) continue;
+                }
+            }
+        }
+        int64_t l = match_left(R, Q, r0, q0);
+        int64_t rr = match_right(R, Q, r0 + AN_K, q0 + AN_K);
+        int64_t len = AN_K + l + rr;
+        if (len < AN_MINLEN) continue;
+        unsigned long long slot = atomicAdd(&counters[0], 1ull);
+        if (slot < cap) {
+            keys[slot] = ((uint64_t)lo << 32) | ((uint64_t)strand << 31) | (uint64_t)(r0 - l);
+            vals[slot] = ((uint64_t)(q0 - l) << 32) | (uint64_t)len;
+        }
+    }
+}
+
+// After the radix sort by key: order runs of equal keys by value (rare: two matches starting at the same
+// reference position), then flag the first of each group of identical (key, value).
+__global__ void tie_fix_kernel(uint64_t *__restrict__ keys, uint64_t *__restrict__ vals, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i > 0 && keys[i - 1] == keys[i]) return;  // not a run head
+    int64_t e = i + 1;
+    while (e < n && keys[e] == keys[i]) ++e;
+    for (int64_t a = i + 1; a < e; ++a) {  // insertion sort of the run's values
+        uint64_t v = vals[a];
+        int64_t b = a - 1;
+        while (b >= i && vals[b] > v) { vals[b + 1] = vals[b]; --b; }
+        vals[b + 1] = v;
+    }
+}
+
+__global__ void flag_unique_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals, int64_t n, uint8_t *__restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flag[i] = !(i > 0 && keys[i - 1] == keys[i] && vals[i - 1] == vals[i]);
+}

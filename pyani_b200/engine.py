@@ -131,7 +131,8 @@ class Engine:
         cnt = np.zeros(_lib.N_STAGES, dtype=np.int64)
         self._lib.b200ani_last_profile(self._h, _ptr(ms), _ptr(cnt))
         names = [self._lib.b200ani_stage_name(i).decode() for i in range(_lib.N_STAGES)]
-        return ({n: float(v) for n, v in zip(names, ms) if n}, {n: int(v) for n, v in zip(names, cnt) if n})
+        cnames = [self._lib.b200ani_stage_name(_lib.N_STAGES + i).decode() for i in range(_lib.N_STAGES)]
+        return ({n: float(v) for n, v in zip(names, ms) if n}, {n: int(v) for n, v in zip(cnames, cnt) if n})
 
 
 ANIM_DTYPE = np.dtype(

@@ -51,3 +51,18 @@ def test_product_never_imports_oracle():
         if p.suffix in (".py", ".cu", ".cuh", ".h", ".cpp"):
             txt = p.read_text()
             assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, p
+
+
+def test_algorithm_constants_agree_between_oracle_and_engine():
+    """oracle/anim_spec.h and pyani_b200/csrc/anim_params.cuh are independent copies of one specification."""
+    def defs(path):
+        out = {}
+        for line in path.read_text().splitlines():
+            m = re.match(r"#define\s+(AN_[A-Z_]+)\s+(.+?)\s*(/\*.*)?$", line)
+            if m:
+                out[m.group(1)] = m.group(2).strip()
+        return out
+
+    a = defs(ROOT / "oracle" / "anim_spec.h")
+    b = defs(ROOT / "pyani_b200" / "csrc" / "anim_params.cuh")
+    assert a == b and len(a) >= 20

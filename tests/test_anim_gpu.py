@@ -1,0 +1,119 @@
+"""CUDA ANIm path (through the C ABI) vs the CPU oracle: bit-exact on every integer the engine returns."""
+import json
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, fixture_genomes
+
+pytestmark = pytest.mark.gpu
+FIELDS = ["ref_aln_len", "qry_aln_len", "sum_aligned", "sum_weighted", "sim_errs", "n_alignments", "status"]
+
+
+@pytest.fixture(scope="module")
+def small_set(engine):
+    from pyani_b200 import synth
+
+    gs = synth.make_set(3, 2, 300_000, seed=20260924, n_rate=3e-4)
+    gids = [engine.add_genome(g.residues, g.contig_off, g.name) for g in gs]
+    og = [oracle.OGenome(g.residues, g.contig_off) for g in gs]
+    return gs, gids, og
+
+
+def _check(engine, gids, og, pairs, nofilter):
+    gp = np.array([[gids[r], gids[q]] for r, q in pairs], dtype=np.int32)
+    res = engine.anim(gp, nofilter=nofilter)
+    tot = {}
+    for (r, q), got in zip(pairs, res):
+        want, _, st = oracle.anim_pair(og[r], og[q], nofilter=nofilter)
+        for k, v in st.items():
+            tot[k] = tot.get(k, 0) + v
+        for f in FIELDS:
+            assert int(got[f]) == want[f], (r, q, f, int(got[f]), want[f])
+    return res, tot
+
+
+def test_all_pairs_bit_exact(engine, small_set):
+    from pyani_b200 import synth
+
+    gs, gids, og = small_set
+    pairs = [tuple(p) for p in synth.all_directed_pairs(len(gs))]
+    res, tot = _check(engine, gids, og, pairs, nofilter=False)
+    ms, cnt = engine.last_profile()
+    # deterministic work counters agree with the oracle's (cells are counted identically)
+    for a, b in [("anchors", "anchors"), ("links", "links"), ("cut_links", "cut_links"), ("segments", "segments"),
+                 ("gap_cells", "gap_cells"), ("ext_cells", "ext_cells"), ("ext_tiles", "ext_tiles")]:
+        assert cnt[a] == tot[b], (a, cnt[a], tot[b])
+    assert cnt["launches"] > 0 and cnt["pairs"] == len(pairs)
+    assert (res["status"] == 0).sum() >= 6  # within-clade pairs always align
+    _check(engine, gids, og, pairs[:8], nofilter=True)
+
+
+def test_alignment_rows_match(engine, small_set):
+    gs, gids, og = small_set
+    for r, q in [(0, 1), (1, 0), (0, 2), (4, 1)]:
+        for nofilter in (False, True):
+            want = oracle.anim_pair(og[r], og[q], nofilter=nofilter)[1]
+            got = engine.anim_alignments(gids[r], gids[q], nofilter=nofilter)
+            assert got.shape == want.shape and (got == want).all(), (r, q, nofilter)
+
+
+def test_self_and_unrelated(engine, small_set):
+    gs, gids, og = small_set
+    rng = np.random.default_rng(3)
+    arr = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=150_000)
+    off = np.array([0, 150_000], dtype=np.uint64)
+    gid = engine.add_genome(arr, off, "unrelated")
+    res = engine.anim(np.array([[gids[0], gids[0]], [gids[0], gid], [gid, gids[0]]], dtype=np.int32))
+    n0 = int(gs[0].contig_off[-1])
+    # a genome against itself: every base aligned once, no errors except around Ns
+    assert res[0]["status"] == 0 and res[0]["sim_errs"] == oracle.anim_pair(og[0], og[0])[0]["sim_errs"]
+    assert res[0]["ref_aln_len"] == res[0]["qry_aln_len"] <= n0
+    assert res[0]["ref_aln_len"] > 0.99 * n0
+    # unrelated sequence: soft status instead of the reference's sys.exit (anim.py:481-486)
+    assert res[1]["status"] == 1 and res[1]["n_alignments"] == 0 and res[2]["status"] == 1
+
+
+def test_size_independent_properties(engine):
+    """A larger case the oracle is not run on: inserting random records into a genome must not change
+    its comparison against the original records (alignments never cross record separators), and
+    A->B vs B->A swap the aligned lengths' roles for a pure-substitution pair."""
+    from pyani_b200 import synth
+
+    rng = np.random.default_rng(11)
+    base = synth.random_codes(rng, 1_500_000, 0.5)
+    mut = synth.substitute(rng, base, 0.03)
+    a = np.frombuffer(b"ACGT", np.uint8)[base]
+    b = np.frombuffer(b"ACGT", np.uint8)[mut]
+    junk = np.frombuffer(b"ACGT", np.uint8)[synth.random_codes(rng, 200_000, 0.5)]
+    ga = engine.add_genome(a, np.array([0, len(a)], np.uint64))
+    gb = engine.add_genome(b, np.array([0, len(b)], np.uint64))
+    gb2 = engine.add_genome(np.concatenate([junk, b]), np.array([0, len(junk), len(junk) + len(b)], np.uint64))
+    r = engine.anim(np.array([[ga, gb], [gb, ga], [ga, gb2]], np.int32))
+    assert r[0]["ref_aln_len"] == r[1]["qry_aln_len"] and r[0]["qry_aln_len"] == r[1]["ref_aln_len"]
+    assert r[0]["sim_errs"] == r[1]["sim_errs"]
+    for f in FIELDS:
+        assert r[0][f] == r[2][f], f
+    ident = r[0]["sum_weighted"] / r[0]["sum_aligned"]
+    assert abs(ident - 0.97) < 0.002 and r[0]["ref_aln_len"] > 0.995 * len(a)
+
+
+@pytest.mark.skipif(not fixture_genomes(), reason="fixture genomes not shipped")
+def test_reference_fixture_genomes(engine):
+    """The four Caulobacter genomes of the reference's ANIm tests: GPU == oracle bit-exact, and both within
+    the reference's concordance tolerance of the checked-in nucmer results (see test_anim_oracle_fixtures)."""
+    gold = json.load(open(GOLDEN / "anim_parse_delta.json"))
+    files = fixture_genomes()
+    gids, og = [], []
+    for f in files:
+        arr, off, _ = oracle.read_fasta(f)
+        gids.append(engine.add_genome(arr, off, f.stem))
+        og.append(oracle.OGenome(arr, off))
+    pairs = [(i, j) for i in range(4) for j in range(4) if i != j]
+    res, _ = _check(engine, gids, og, pairs, nofilter=False)
+    for (i, j), r in zip(pairs, res):
+        g = gold[f"{files[i].stem}_vs_{files[j].stem}.filter"]
+        ident = r["sum_weighted"] / r["sum_aligned"]
+        assert abs(100 * (ident - g[2])) < 0.15
+        assert abs(r["ref_aln_len"] / g[0] - 1) < 0.01
