@@ -43,6 +43,11 @@ const char *b200ani_last_error(const b200ani_ctx *ctx);
  * Genome length = off[n_contigs], ambiguity symbols included (pyani_files.py:137-141). */
 int b200ani_add_genome(b200ani_ctx *ctx, const uint8_t *ascii, const uint64_t *contig_off, uint32_t n_contigs,
                        int32_t *out_genome_id);
+/* Drop every staged genome (and its index); genome ids restart at 0.  Lets a long-lived context serve
+ * successive runs, like a fresh process pool per pyani invocation. */
+int b200ani_clear(b200ani_ctx *ctx);
+/* Drop only the per-genome seed indexes (rebuilt lazily by the next b200ani_anim). */
+int b200ani_reset_indexes(b200ani_ctx *ctx);
 int b200ani_genome_count(const b200ani_ctx *ctx);
 int64_t b200ani_genome_length(const b200ani_ctx *ctx, int32_t genome_id);
 
@@ -93,6 +98,11 @@ int64_t b200ani_anim_alignments(b200ani_ctx *ctx, int32_t ref_id, int32_t qry_id
 int b200ani_last_profile(const b200ani_ctx *ctx, double *stage_ms /*B200ANI_N_STAGES*/, int64_t *counters /*B200ANI_N_STAGES*/);
 /* i in [0,16): stage name; i in [16,32): name of counter i-16 ("" = unused slot) */
 const char *b200ani_stage_name(int i);
+
+/* Measured issue rate of the DPX-class max-plus instruction the extend kernel is bound by
+ * (__viaddmax_s32), in 10^9 thread-level operations per second on this device; the integer-DP roofline
+ * denominator of SURVEY.md 8(d).  ~20 ms micro-benchmark. */
+int b200ani_dpx_peak(b200ani_ctx *ctx, double *gops);
 
 #ifdef __cplusplus
 }

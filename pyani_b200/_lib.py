@@ -30,6 +30,9 @@ SIGNATURES = {
     "b200ani_version": (C.c_char_p, []),
     "b200ani_last_error": (C.c_char_p, [C.c_void_p]),
     "b200ani_add_genome": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_int32)]),
+    "b200ani_clear": (C.c_int, [C.c_void_p]),
+    "b200ani_reset_indexes": (C.c_int, [C.c_void_p]),
+    "b200ani_dpx_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "b200ani_genome_count": (C.c_int, [C.c_void_p]),
     "b200ani_genome_length": (C.c_int64, [C.c_void_p, C.c_int32]),
     "b200ani_tetra_counts": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -10,6 +10,8 @@
 //
 // Both modes keep the best cell so far (row-major first maximum, starting from H[0][0]=0) and stop when
 // a row ends more than AN_BREAK rows below it (nucmer's break length).
+#include <algorithm>
+
 #include "anim.cuh"
 
 struct DpResult {
@@ -190,4 +192,48 @@ __global__ void emit_rows_kernel(SegArrays S, const PairDesc *__restrict__ pairs
     if (!S.strand[s]) { o[5] = (int)(S.qs[s] - qg + 1); o[6] = (int)(S.qe[s] - 1 - qg + 1); }
     else { o[5] = (int)(((int64_t)P.q_npos - 1 - S.qs[s]) - qg + 1); o[6] = (int)(((int64_t)P.q_npos - S.qe[s]) - qg + 1); }
     o[7] = (int)S.errs[s];
+}
+
+// ---- integer-DP roofline denominator: issue rate of __viaddmax_s32 (8 independent chains per thread)
+__global__ void __launch_bounds__(256) dpx_peak_kernel(int iters, int seed, int *__restrict__ sink) {
+    int a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = seed + threadIdx.x * (k + 1);
+    const int b = seed | 1, c = -seed;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = __viaddmax_s32(a[k], b, c + k + it);
+    }
+    int r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r ^= a[k];
+    if (r == 0x7fffffff) sink[0] = r;
+}
+
+extern "C" int b200ani_dpx_peak(b200ani_ctx *ctx, double *gops) {
+    if (!ctx || !gops) return B200ANI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int *sink = nullptr;
+    CK(cudaMallocAsync(&sink, sizeof(int), ctx->stream));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int iters = 1 << 14, blocks = ctx->sm_count * 8;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        dpx_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(iters, 3 + rep, sink);
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        double ops = (double)blocks * 256 * 8 * iters;
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3) / 1e9);
+    }
+    CK(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CK(cudaFreeAsync(sink, ctx->stream));
+    *gops = best;
+    return B200ANI_OK;
 }

@@ -6,6 +6,8 @@
 
 static const char *kVersion = "b200ani 0.1.0 (sm_100a)";
 
+static void release_genome(Genome &g);
+
 extern "C" {
 
 const char *b200ani_version(void) { return kVersion; }
@@ -43,15 +45,40 @@ void b200ani_destroy(b200ani_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto &g : ctx->genomes) {
-        cudaFree(g.d_seq);
-        cudaFree(g.d_mask);
-        cudaFree(g.d_goff);
-        free_index(g.index);
-    }
+    for (auto &g : ctx->genomes) release_genome(g);
     free_anim_workspace(ctx->anim_ws);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+}  // extern "C"
+static void release_genome(Genome &g) {
+    cudaFree(g.d_seq);
+    cudaFree(g.d_mask);
+    cudaFree(g.d_goff);
+    free_index(g.index);
+    g.index = nullptr;
+}
+extern "C" {
+
+int b200ani_clear(b200ani_ctx *ctx) {
+    if (!ctx) return B200ANI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto &g : ctx->genomes) release_genome(g);
+    ctx->genomes.clear();
+    return B200ANI_OK;
+}
+
+int b200ani_reset_indexes(b200ani_ctx *ctx) {
+    if (!ctx) return B200ANI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto &g : ctx->genomes) {
+        free_index(g.index);
+        g.index = nullptr;
+    }
+    return B200ANI_OK;
 }
 
 int b200ani_genome_count(const b200ani_ctx *ctx) { return ctx ? (int)ctx->genomes.size() : 0; }

@@ -83,6 +83,19 @@ class Engine:
         arr, off, ids = read_fasta(path)
         return self.add_genome(arr, off, Path(path).stem, ids)
 
+    def clear(self):
+        """Drop all staged genomes (ids restart at 0)."""
+        self._check(self._lib.b200ani_clear(self._h), "clear")
+        self.names, self.contig_ids = [], []
+
+    def reset_indexes(self):
+        self._check(self._lib.b200ani_reset_indexes(self._h), "reset_indexes")
+
+    def dpx_peak_gops(self) -> float:
+        v = C.c_double(0)
+        self._check(self._lib.b200ani_dpx_peak(self._h, C.byref(v)), "dpx_peak")
+        return v.value
+
     def genome_length(self, gid: int) -> int:
         return int(self._lib.b200ani_genome_length(self._h, gid))
 
