@@ -1,0 +1,187 @@
+"""ANIm on the B200 engine behind the reference's interfaces for the path (pyani/anim.py, pyani_tools.py).
+
+Three levels of drop-in, all thin host code over ``Engine.anim``:
+
+* :func:`parse_result` -- the 4-tuple ``anim.parse_delta`` returns (anim.py:411) from one result struct;
+* :func:`calculate_anim` -- in-memory equivalent of ``generate_nucmer_jobs`` + scheduler +
+  ``process_deltadir`` (anim.py:155-237,415-497) filling an :class:`ANIResults` exactly like the legacy
+  driver does (including its last-file-wins symmetric cells);
+* :func:`run_dependency_graph` -- same call shape as ``run_multiprocessing.run_dependency_graph``
+  (run_multiprocessing.py:56-84): takes the ``Job`` graph pyani built, recognises the nucmer command
+  lines (anim.py:280), runs the comparisons on the GPU and writes minimal ``.delta``/``.filter`` files
+  where nucmer / delta-filter would have, so ``subcmd_anim.update_comparison_results``
+  (subcmd_anim.py:418-459) and ``process_deltadir`` run unmodified.  Returns 0 like a clean pool run.
+"""
+from __future__ import annotations
+
+import re
+from pathlib import Path
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .engine import Engine
+from .fasta import read_fasta
+
+
+class PyaniB200Exception(Exception):
+    """Raised where the reference raises PyaniException / PyaniANImException."""
+
+
+# ------------------------------------------------------------------------------------------------
+def parse_result(res) -> Tuple[int, int, float, int]:
+    """``(ref_aln_len, qry_aln_len, identity, sim_errs)`` exactly as ``anim.parse_delta`` (anim.py:411).
+
+    An alignment-free comparison raises ``ZeroDivisionError`` like the reference does on an empty
+    ``.filter`` (``sum(weighted)/sum(aligned)``, anim.py:396)."""
+    if int(res["sum_aligned"]) == 0:
+        raise ZeroDivisionError("no alignments between the two genomes (anim.py:396)")
+    return (int(res["ref_aln_len"]), int(res["qry_aln_len"]), int(res["sum_weighted"]) / int(res["sum_aligned"]), int(res["sim_errs"]))
+
+
+class ANIResults:
+    """Same five tables and fill semantics as ``pyani_tools.ANIResults`` (pyani_tools.py:85-196)."""
+
+    def __init__(self, labels: List[str], mode: str = "ANIm") -> None:
+        import pandas as pd
+
+        self.alignment_lengths = pd.DataFrame(index=labels, columns=labels, dtype=float)
+        self.similarity_errors = pd.DataFrame(index=labels, columns=labels, dtype=float).fillna(0)
+        self.percentage_identity = pd.DataFrame(index=labels, columns=labels, dtype=float).fillna(1.0)
+        self.alignment_coverage = pd.DataFrame(index=labels, columns=labels, dtype=float).fillna(1.0)
+        self.zero_error = False
+        self.mode = mode
+
+    def add_tot_length(self, qname, sname, query_alignment_length, subject_alignment_length=None):
+        self.alignment_lengths.loc[qname, sname] = query_alignment_length
+        if subject_alignment_length:
+            self.alignment_lengths.loc[sname, qname] = subject_alignment_length
+
+    def add_sim_errors(self, qname, sname, value, sym=True):
+        self.similarity_errors.loc[qname, sname] = value
+        if sym:
+            self.similarity_errors.loc[sname, qname] = value
+
+    def add_pid(self, qname, sname, perc_id):
+        self.percentage_identity.loc[qname, sname] = perc_id
+
+    def add_coverage(self, qname, sname, qcover, scover=None):
+        self.alignment_coverage.loc[qname, sname] = qcover
+        if scover:
+            self.alignment_coverage.loc[sname, qname] = scover
+
+    @property
+    def hadamard(self):
+        return self.percentage_identity * self.alignment_coverage
+
+
+def fill_aniresults(org_lengths: Dict[str, int], tuples: Dict[Tuple[str, str], Tuple[int, int, float, int]]) -> ANIResults:
+    """``process_deltadir`` (anim.py:415-497) given the per-file 4-tuples instead of files.
+
+    ``tuples[(qname, sname)]`` is the result of the run ``<qname>_vs_<sname>`` (qname = nucmer reference).
+    Files are visited in the order of ``sorted(delta_dir.glob("*/*.filter"))`` (anim.py:438), i.e. sorted by
+    ``<qname>/<qname>_vs_<sname>.filter``, and both directions write the symmetric cells, so the later
+    file wins."""
+    results = ANIResults(list(org_lengths.keys()), "ANIm")
+    for org, length in org_lengths.items():
+        results.alignment_lengths.loc[org, org] = length
+    for qname, sname in sorted(tuples, key=lambda k: f"{k[0]}/{k[0]}_vs_{k[1]}.filter"):
+        if qname not in org_lengths or sname not in org_lengths:
+            continue
+        q_len, s_len, ident, errs = tuples[(qname, sname)]
+        if s_len == 0:
+            raise SystemExit("Zero length alignment!")  # anim.py:481-486
+        results.add_tot_length(qname, sname, q_len, s_len)
+        results.add_sim_errors(qname, sname, errs)
+        results.add_pid(qname, sname, ident)
+        results.add_coverage(qname, sname, float(q_len) / org_lengths[qname], float(s_len) / org_lengths[sname])
+    return results
+
+
+def calculate_anim(infiles: Sequence[Path], org_lengths: Optional[Dict[str, int]] = None, engine: Optional[Engine] = None,
+                   maxmatch: bool = False, nofilter: bool = False) -> ANIResults:
+    """All directed comparisons between ``infiles`` on the GPU -> ANIResults (legacy driver semantics,
+    average_nucleotide_identity.py:489-575)."""
+    eng = engine or Engine(0)
+    files = sorted(Path(f) for f in infiles)  # anim.py:217: sorted file list, both directions
+    gids = {f.stem: eng.add_fasta(f) for f in files}
+    stems = [f.stem for f in files]
+    if org_lengths is None:
+        org_lengths = {s: eng.genome_length(gids[s]) for s in stems}
+    pairs = [(a, b) for a in stems for b in stems if a != b]
+    res = eng.anim(np.array([[gids[a], gids[b]] for a, b in pairs], dtype=np.int32), maxmatch=maxmatch, nofilter=nofilter)
+    tuples = {}
+    for (a, b), r in zip(pairs, res):
+        tuples[(a, b)] = parse_result(r)
+    return fill_aniresults(org_lengths, tuples)
+
+
+# ------------------------------------------------------------------------------------------------
+_NUCMER_RE = re.compile(r"(?:^|\s)(--mum|--maxmatch)\s+-p\s+(\S+)\s+(\S+)\s+(\S+)\s*$")
+
+
+def _iter_jobs(jobgraph) -> Iterable:
+    seen = set()
+    stack = list(jobgraph)
+    while stack:
+        j = stack.pop()
+        if id(j) in seen:
+            continue
+        seen.add(id(j))
+        yield j
+        stack.extend(getattr(j, "dependencies", []))
+
+
+def write_minimal_delta(path: Path, ref_path: str, qry_path: str, rows: np.ndarray, ref_ids: List[str], qry_ids: List[str],
+                        ref_lens: Sequence[int], qry_lens: Sequence[int]) -> None:
+    """A .delta/.filter file holding what ``parse_delta`` and ``nucmer.DeltaIterator`` read: header, one
+    '>' line per record pair, 7-field alignment headers, each followed by the terminating ``0`` of an empty
+    indel list (format: anim.py:300-325, nucmer.py:317-351).  rows: (ref_rec, qry_rec, rs, re, qs, qe, errs)."""
+    path.parent.mkdir(parents=True, exist_ok=True)
+    with open(path, "w") as fh:
+        fh.write(f"{ref_path} {qry_path}\nNUCMER\n")
+        order = np.lexsort((rows[:, 2], rows[:, 1], rows[:, 0])) if len(rows) else []
+        cur = None
+        for i in order:
+            rc, qc, rs, re_, qs, qe, errs = (int(x) for x in rows[i])
+            if (rc, qc) != cur:
+                fh.write(f">{ref_ids[rc]} {qry_ids[qc]} {ref_lens[rc]} {qry_lens[qc]}\n")
+                cur = (rc, qc)
+            fh.write(f"{rs} {re_} {qs} {qe} {errs} {errs} 0\n0\n")
+
+
+def run_dependency_graph(jobgraph, workers: Optional[int] = None, logger=None, engine: Optional[Engine] = None) -> int:
+    """GPU stand-in for ``run_multiprocessing.run_dependency_graph(jobgraph, workers, logger) -> int``.
+
+    ``workers`` is accepted and ignored (one GPU does the work of the pool).  Returns 0 on success, 1 if any
+    comparison could not be run -- the caller's ``if cumval > 0: raise PyaniException`` logic
+    (subcmd_anim.py:396-401) keeps working."""
+    eng = engine or Engine(0)
+    todo = []
+    for job in _iter_jobs(jobgraph):
+        cmd = getattr(job, "command", None) or getattr(job, "script", "")
+        m = _NUCMER_RE.search(cmd)
+        if m and "delta-filter" not in cmd:
+            todo.append((m.group(1) == "--maxmatch", m.group(2), m.group(3), m.group(4)))
+    if not todo:
+        return 0
+    cache: Dict[str, Tuple[int, list, np.ndarray]] = {}
+
+    def stage(path: str):
+        if path not in cache:
+            arr, off, ids = read_fasta(path)
+            cache[path] = (eng.add_genome(arr, off, Path(path).stem, ids), ids, np.diff(off.astype(np.int64)))
+        return cache[path]
+
+    rc = 0
+    for maxmatch, prefix, f1, f2 in todo:
+        try:
+            (g1, ids1, len1), (g2, ids2, len2) = stage(f1), stage(f2)
+            for nofilter, suffix in ((True, ".delta"), (False, ".filter")):
+                rows = eng.anim_alignments(g1, g2, maxmatch=maxmatch, nofilter=nofilter)
+                write_minimal_delta(Path(prefix + suffix), f1, f2, rows, ids1, ids2, len1, len2)
+        except Exception as exc:  # mirrors a non-zero subprocess return code
+            if logger:
+                logger.error("b200ani comparison %s vs %s failed: %s", f1, f2, exc)
+            rc += 1
+    return rc

@@ -96,6 +96,18 @@ def main():
         tuples[f.name] = list(anim.parse_delta(f))
         arrays[f.name] = oracle.parse_delta_text(f).astype(np.int32)
     json.dump(tuples, open(OUT / "anim_parse_delta.json", "w"), indent=0)
+    # legacy matrices: the reference's process_deltadir on its own fixture directory (anim.py:415-497)
+    from pyani import pyani_files
+
+    seqdir = REF / "tests/fixtures/anim/sequences"
+    org_lengths = pyani_files.get_sequence_lengths(pyani_files.get_fasta_files(seqdir))
+    res = anim.process_deltadir(REF / "tests/fixtures/anim/deltadir", org_lengths)
+    legacy = {"org_lengths": org_lengths}
+    for name in ("alignment_lengths", "similarity_errors", "percentage_identity", "alignment_coverage"):
+        df = getattr(res, name)
+        legacy[name] = {"index": list(df.index), "columns": list(df.columns), "values": df.values.tolist()}
+    legacy["deltadir_result_csv"] = (REF / "tests/fixtures/anim/dataframes/deltadir_result.csv").read_text()
+    json.dump(legacy, open(OUT / "anim_process_deltadir.json", "w"))
     np.savez_compressed(OUT / "anim_alignments.npz", **arrays)
     print("anim", len(tuples))
 

@@ -1,0 +1,96 @@
+"""Host-side mirror of the reference's ANIm interfaces (pyani_b200/anim.py) -- no GPU needed."""
+import io
+import json
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import GOLDEN
+from pyani_b200 import anim as banim
+from pyani_b200.engine import ANIM_DTYPE
+
+
+def _gold():
+    tuples = json.load(open(GOLDEN / "anim_parse_delta.json"))
+    legacy = json.load(open(GOLDEN / "anim_process_deltadir.json"))
+    return tuples, legacy
+
+
+def test_fill_aniresults_matches_reference_process_deltadir():
+    """anim.process_deltadir (run by the reference itself on its fixture directory) vs fill_aniresults fed the
+    per-file tuples: every cell of all four tables, including the last-file-wins symmetric cells (A.2)."""
+    tuples, legacy = _gold()
+    per_file = {}
+    for name, t in tuples.items():
+        if name.endswith(".filter"):
+            q, s = name[: -len(".filter")].split("_vs_")
+            per_file[(q, s)] = tuple(t)
+    res = banim.fill_aniresults(legacy["org_lengths"], per_file)
+    for tab in ("alignment_lengths", "similarity_errors", "percentage_identity", "alignment_coverage"):
+        g = legacy[tab]
+        want = pd.DataFrame(g["values"], index=g["index"], columns=g["columns"])
+        got = getattr(res, tab).loc[g["index"], g["columns"]]
+        assert (got.values == want.values).all(), tab
+    # the reference's own asserted table (tests/test_anim.py:243-255)
+    csv = pd.read_csv(io.StringIO(legacy["deltadir_result_csv"]), index_col=0)
+    got = res.percentage_identity.loc[csv.index, csv.columns]
+    assert np.allclose(got.values, csv.values, atol=5e-7)
+    # Appendix A.2
+    assert res.alignment_lengths.loc["NC_002696", "NC_010338"] == 1385260
+    assert res.similarity_errors.loc["NC_002696", "NC_010338"] == 206821
+
+
+def test_parse_result_tuple_and_empty():
+    r = np.zeros(1, dtype=ANIM_DTYPE)[0]
+    r["ref_aln_len"], r["qry_aln_len"], r["sum_aligned"], r["sum_weighted"], r["sim_errs"] = 10, 11, 33, 23, 5
+    assert banim.parse_result(r) == (10, 11, 23 / 33, 5)  # the docstring example of anim.py:329-344
+    with pytest.raises(ZeroDivisionError):
+        banim.parse_result(np.zeros(1, dtype=ANIM_DTYPE)[0])
+
+
+class _FakeEngine:
+    """Stands in for Engine so the job-graph backend can be tested without a GPU."""
+
+    def __init__(self):
+        self.n = 0
+        self.calls = []
+
+    def add_genome(self, arr, off, name, ids):
+        self.n += 1
+        return self.n - 1
+
+    def anim_alignments(self, g1, g2, maxmatch=False, nofilter=False):
+        self.calls.append((g1, g2, maxmatch, nofilter))
+        rows = [[0, 0, 1, 10, 1, 11, 5], [0, 0, 15, 20, 30, 25, 0]]
+        return np.array(rows if nofilter else rows[:1], dtype=np.int64)
+
+
+class _Job:  # shape of pyani_jobs.Job (pyani_jobs.py:76-120)
+    def __init__(self, name, command):
+        self.name, self.command, self.dependencies = name, command, []
+
+    def add_dependency(self, job):
+        self.dependencies.append(job)
+
+
+def test_run_dependency_graph_writes_files_parse_delta_can_read(tmp_path):
+    import oracle
+
+    fa, fb = tmp_path / "A.fna", tmp_path / "B.fna"
+    fa.write_text(">a1 d\nACGTACGTAC\nGTACGTAC\n")
+    fb.write_text(">b1 d\nACGTACGTACGTAC\n>b2\nACGT\n")
+    out = tmp_path / "out" / "nucmer_output" / "A" / "A_vs_B"
+    # command strings exactly as anim.construct_nucmer_cmdline builds them (anim.py:280-288)
+    njob = _Job("t_000000-n", f"nucmer --mum -p {out} {fa} {fb}")
+    fjob = _Job("t_000000-f", f"delta_filter_wrapper.py delta-filter -1 {out}.delta {out}.filter")
+    fjob.add_dependency(njob)
+    eng = _FakeEngine()
+    assert banim.run_dependency_graph([fjob], workers=4, engine=eng) == 0
+    assert [c[3] for c in eng.calls] == [True, False]
+    d = oracle.parse_delta_text(str(out) + ".delta")
+    f = oracle.parse_delta_text(str(out) + ".filter")
+    assert d[:, 2:].tolist() == [[1, 10, 1, 11, 5], [15, 20, 30, 25, 0]] and f[:, 2:].tolist() == [[1, 10, 1, 11, 5]]
+    text = open(str(out) + ".filter").read().splitlines()
+    assert text[1] == "NUCMER" and text[2] == ">a1 b1 18 14" and text[3].split() == "1 10 1 11 5 5 0".split()
+    assert oracle.parse_delta_reduce(d)[2] == pytest.approx(0.696969696969697)  # anim.py:343 worked example
