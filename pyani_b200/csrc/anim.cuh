@@ -136,7 +136,6 @@ struct SegArrays {
     int *rs, *qs, *re, *qe;            // [s,e) in view coordinates (reference g-space / query view)
     int *r_lo, *r_hi, *q_lo, *q_hi;    // record bounds in the same coordinates
     long long *score, *errs;
-    uint8_t *active;                   // [2*n]: side 0 = left extension, side 1 = right extension
 };
 
 // rows: n x 8 int32 (pair, ref record, qry record, rs, re, qs, qe, errs), grouped by pair.

@@ -19,66 +19,144 @@ struct DpResult {
     long long cells;
 };
 
-// MODE 0: link alignment to the corner (lr,lq) -> val = H[lr][lq].  MODE 1: extension tile -> best cell.
+__device__ __forceinline__ uint64_t rev2_64(uint64_t x) {  // reverse the order of 32 packed bases (no complement)
+    uint64_t y = __brevll(x);
+    return ((y & 0x5555555555555555ull) << 1) | ((y >> 1) & 0x5555555555555555ull);
+}
+
+__device__ __noinline__ uint64_t stream_chunk_slow(const SeqView &v, int64_t p, int step, uint32_t &mk) {
+    uint64_t c = 0;
+    uint32_t m = 0;
+#pragma unroll 1
+    for (int k = 0; k < 32; ++k) {
+        int code = view_code(v, p + (int64_t)step * k);
+        if (code > 3) m |= 1u << k; else c |= (uint64_t)code << (2 * k);
+    }
+    mk = m;
+    return c;
+}
+
+// 32 bases of a view in READ order: view positions p, p+step, ..., p+31*step (step = +1 / -1); bases
+// outside [0, n) come back masked.  Fast path = one aligned-window fetch, slow path near the ends.
+__device__ __forceinline__ uint64_t stream_chunk(const SeqView &v, int64_t p, int step, uint32_t &mk) {
+    const int64_t lo = step > 0 ? p : p - 31;
+    if (lo >= 0 && lo + 32 <= v.n) {
+        uint64_t c = view_chunk(v, lo, mk);
+        if (step < 0) { c = rev2_64(c); mk = __brev(mk); }
+        return c;
+    }
+    return stream_chunk_slow(v, p, step, mk);
+}
+
+// Sequential reader over a view: next() yields (code & 3, masked flag) of consecutive bases in read order.
+struct BaseStream {
+    uint64_t buf;
+    uint32_t mbuf;
+    int left;
+    int64_t next_p;  // view position of the first base of the next refill
+    __device__ __forceinline__ void refill(const SeqView &v, int step) {
+        buf = stream_chunk(v, next_p, step, mbuf);
+        next_p += 32 * step;
+        left = 32;
+    }
+};
+
+// MODE 0: link alignment to the corner (lr,lq) -> val = H[lr][lq], best ROW tracked for the break rule.
+// MODE 1: extension tile -> best cell (value, bi, bj).
 // Base b (0-based) of the reference is at view position r0 + rstep*b; likewise for the query.
+// Registers hold Hg[kk] = H - go (so E and F updates are single viaddmax ops on it) and F[kk]; the
+// match/mismatch constants carry the +go back (d = Hg_diag + s + go).
 template <int MODE>
 __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rstep, const SeqView &Q, int64_t q0, int qstep, int lr, int lq, int klo) {
     constexpr int go = AN_GAPOPEN * AN_PACK + 1, ge = AN_GAPEXT * AN_PACK + 1;
-    constexpr int sm = AN_MATCH * AN_PACK, sx = -(AN_MISMATCH * AN_PACK + 1);
-    int H[AN_BANDW], F[AN_BANDW];
+    constexpr int smg = AN_MATCH * AN_PACK + go, sxg = -(AN_MISMATCH * AN_PACK + 1) + go;
+    // extension tiles are short: values stay within +-2^24, which leaves 5 low bits for the column tag
+    constexpr int NEGV = MODE ? -(1 << 25) : AN_NEG;
+    int Hg[AN_BANDW], F[AN_BANDW];
     DpResult o{0, 0, 0, 0, 0};
 #pragma unroll
     for (int kk = 0; kk < AN_BANDW; ++kk) {  // row 0
         int j = klo + kk;
-        F[kk] = AN_NEG;
-        H[kk] = (j < 0 || j > lq) ? AN_NEG : (j == 0 ? 0 : -(go + (j - 1) * ge));
+        F[kk] = NEGV;
+        Hg[kk] = ((j < 0 || j > lq) ? NEGV : (j == 0 ? 0 : -(go + (j - 1) * ge))) - go;
     }
-    // query window for row 1: column kk holds query base index klo + kk (base of column j = i + klo + kk)
-    uint64_t qwin = 0, nwin = 0;
-#pragma unroll 4
-    for (int kk = 0; kk < AN_BANDW; ++kk) {
-        int b = klo + kk;
-        int c = b < 0 ? 4 : view_code(Q, q0 + (int64_t)qstep * b);
-        if (c > 3) nwin |= 1ull << (2 * kk); else qwin |= (uint64_t)c << (2 * kk);
+    // query window of row 1: column kk holds query base index klo + kk; klo is always in [-24, -8], so the
+    // window is the first chunk shifted up, the rest of that chunk feeds the stream
+    BaseStream qs, rs;
+    qs.next_p = q0; rs.next_p = r0;
+    qs.refill(Q, qstep);
+    rs.refill(R, rstep);
+    const int sh = -klo;  // 8..24 columns before the first query base
+    uint64_t qwin = qs.buf << (2 * sh);
+    uint64_t nwin = (0x5555555555555555ull >> (64 - 2 * sh));                 // columns without a base: never match
+    {
+        uint64_t m = qs.mbuf;                                                    // spread mask bits to even positions
+        m = (m | (m << 16)) & 0x0000FFFF0000FFFFull; m = (m | (m << 8)) & 0x00FF00FF00FF00FFull;
+        m = (m | (m << 4)) & 0x0F0F0F0F0F0F0F0Full;  m = (m | (m << 2)) & 0x3333333333333333ull;
+        m = (m | (m << 1)) & 0x5555555555555555ull;
+        nwin |= m << (2 * sh);
     }
+    qs.buf >>= 2 * (32 - sh); qs.mbuf >>= (32 - sh); qs.left = sh;
     int best = 0;
     for (int i = 1; i <= lr; ++i) {
-        const int rb = view_code(R, r0 + (int64_t)rstep * (i - 1));
-        uint64_t x = qwin ^ ((uint64_t)(rb & 3) * 0x5555555555555555ull);
+        if (rs.left == 0) rs.refill(R, rstep);
+        const uint32_t rb = (uint32_t)rs.buf & 3u, rn = rs.mbuf & 1u;
+        rs.buf >>= 2; rs.mbuf >>= 1; --rs.left;
+        uint64_t x = qwin ^ ((uint64_t)rb * 0x5555555555555555ull);
         uint64_t mm = ((x | (x >> 1)) & 0x5555555555555555ull) | nwin;
-        if (rb > 3) mm = 0x5555555555555555ull;
+        if (rn) mm = 0x5555555555555555ull;
+        const uint32_t mlo = (uint32_t)mm, mhi = (uint32_t)(mm >> 32);
         const int kkhi = lq - i - klo;  // columns with j <= lq
-        int hleft = AN_NEG, eleft = AN_NEG;
+        int hgleft = NEGV, eleft = NEGV;
+        int rowkey = MODE ? (int)0x80000000 : NEGV;
+        if (kkhi >= AN_BANDW - 1) {
 #pragma unroll
-        for (int kk = 0; kk < AN_BANDW; ++kk) {
-            int e = max(eleft - ge, hleft - go);
-            int uph = kk + 1 < AN_BANDW ? H[kk + 1] : AN_NEG, upf = kk + 1 < AN_BANDW ? F[kk + 1] : AN_NEG;
-            int f = max(upf - ge, uph - go);
-            int s = ((mm >> (2 * kk)) & 1ull) ? sx : sm;
-            int h = max(max(H[kk] + s, e), f);
-            H[kk] = h;
-            F[kk] = f;
-            hleft = h;
-            eleft = e;
-            if (kk <= kkhi && h > best) { best = h; o.bi = i; o.bj = i + klo + kk; }
+            for (int kk = 0; kk < AN_BANDW; ++kk) {
+                const uint32_t bit = (kk < 16 ? mlo : mhi) & (1u << ((2 * kk) & 31));
+                int e = __viaddmax_s32(eleft, -ge, hgleft);
+                int f = kk + 1 < AN_BANDW ? __viaddmax_s32(F[kk + 1], -ge, Hg[kk + 1]) : NEGV;
+                int h = __vimax3_s32(Hg[kk] + (bit ? sxg : smg), e, f);
+                Hg[kk] = h - go;
+                F[kk] = f;
+                hgleft = h - go;
+                eleft = e;
+                rowkey = MODE ? max(rowkey, (h << 5) | (31 - kk)) : max(rowkey, h);
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < AN_BANDW; ++kk) {
+                const uint32_t bit = (kk < 16 ? mlo : mhi) & (1u << ((2 * kk) & 31));
+                int e = __viaddmax_s32(eleft, -ge, hgleft);
+                int f = kk + 1 < AN_BANDW ? __viaddmax_s32(F[kk + 1], -ge, Hg[kk + 1]) : NEGV;
+                int h = __vimax3_s32(Hg[kk] + (bit ? sxg : smg), e, f);
+                Hg[kk] = h - go;
+                F[kk] = f;
+                hgleft = h - go;
+                eleft = e;
+                if (kk <= kkhi) rowkey = MODE ? max(rowkey, (h << 5) | (31 - kk)) : max(rowkey, h);
+            }
+        }
+        if (MODE) {
+            if ((rowkey >> 5) > best) { best = rowkey >> 5; o.bi = i; o.bj = i + klo + 31 - (rowkey & 31); }
+        } else {
+            if (rowkey > best) { best = rowkey; o.bi = i; }
         }
         {   // cells with 0 <= j <= lq in this row
             int lo = max(0, -(i + klo)), hi = min(AN_BANDW - 1, kkhi);
             if (hi >= lo) o.cells += hi - lo + 1;
         }
         if (i - o.bi > AN_BREAK) { o.stopped = 1; break; }
-        // slide the query window: drop column 0, append the base of column j = (i+1) + klo + 31
-        qwin >>= 2;
-        nwin >>= 2;
-        int b = i + klo + AN_BANDW - 1;
-        int c = b < 0 ? 4 : view_code(Q, q0 + (int64_t)qstep * b);
-        if (c > 3) nwin |= 1ull << 62; else qwin |= (uint64_t)c << 62;
+        // slide the query window: drop column 0, append the next base of the stream
+        if (qs.left == 0) qs.refill(Q, qstep);
+        qwin = (qwin >> 2) | ((qs.buf & 3ull) << 62);
+        nwin = (nwin >> 2) | ((uint64_t)(qs.mbuf & 1u) << 62);
+        qs.buf >>= 2; qs.mbuf >>= 1; --qs.left;
     }
     if (MODE == 0) {
         const int kend = (lq - lr) - klo;
         int v = AN_NEG;
 #pragma unroll
-        for (int kk = 0; kk < AN_BANDW; ++kk) v = (kk == kend) ? H[kk] : v;
+        for (int kk = 0; kk < AN_BANDW; ++kk) v = (kk == kend) ? Hg[kk] + go : v;
         o.val = v;
     } else {
         o.val = best;
@@ -135,17 +213,21 @@ __global__ void segment_init_kernel(ChainArrays A, const PairDesc *__restrict__ 
     S.r_lo[s] = (int)r_lo; S.r_hi[s] = (int)r_hi; S.q_lo[s] = (int)q_lo; S.q_hi[s] = (int)q_hi;
     S.score[s] = A.ssum[h] + (long long)A.wsum[h] * AN_MATCH;
     S.errs[s] = A.esum[h];
-    S.active[2 * s] = 1; S.active[2 * s + 1] = 1;
 }
 
-// One extension tile for every still-active (segment, side).
-__global__ void __launch_bounds__(128) ext_dp_kernel(SegArrays S, const PairDesc *__restrict__ pairs, unsigned long long *__restrict__ counters /*0: cells, 1: tiles, 2: active after*/) {
+// One extension tile for every task of the round's (dense) task list; tasks that must continue are
+// appended to the next round's list, so every launch runs full warps of equally sized tiles.
+// task id = 2 * segment + side (side 0 = left extension, side 1 = right extension).
+__global__ void __launch_bounds__(128) ext_dp_kernel(SegArrays S, const PairDesc *__restrict__ pairs, const uint32_t *__restrict__ list_in,
+                                                     const unsigned long long *__restrict__ n_in, uint32_t *__restrict__ list_out,
+                                                     unsigned long long *__restrict__ counters /*0: cells, 1: tiles, 2: n_out*/) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     long long cells = 0;
-    int tiles = 0, still = 0;
-    if (t < 2 * S.n && S.active[t]) {
-        const int64_t s = t >> 1;
-        const int side = (int)(t & 1);
+    int tiles = 0;
+    if (t < (int64_t)*n_in) {
+        const uint32_t task = list_in ? list_in[t] : (uint32_t)t;
+        const int64_t s = task >> 1;
+        const int side = (int)(task & 1);
         const PairDesc &P = pairs[S.pair[s]];
         SeqView R{P.r_seq, P.r_mask, P.r_npos, 0}, Q{P.q_seq, P.q_mask, P.q_npos, S.strand[s]};
         int64_t ar = side ? S.r_hi[s] - S.re[s] : S.rs[s] - S.r_lo[s];
@@ -164,18 +246,15 @@ __global__ void __launch_bounds__(128) ext_dp_kernel(SegArrays S, const PairDesc
                 on = !o.stopped;
             }
         }
-        S.active[t] = on;
-        still = on;
+        if (on) list_out[atomicAdd(&counters[2], 1ull)] = task;
     }
     for (int off = 16; off; off >>= 1) {
         cells += __shfl_down_sync(0xffffffffu, cells, off);
         tiles += __shfl_down_sync(0xffffffffu, tiles, off);
-        still += __shfl_down_sync(0xffffffffu, still, off);
     }
     if ((threadIdx.x & 31) == 0) {
         if (cells) atomicAdd(&counters[0], (unsigned long long)cells);
         if (tiles) atomicAdd(&counters[1], (unsigned long long)tiles);
-        if (still) atomicAdd(&counters[2], (unsigned long long)still);
     }
 }
 

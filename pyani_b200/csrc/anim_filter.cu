@@ -44,32 +44,36 @@ __global__ void pair_range_kernel(const int *__restrict__ rows, int64_t n, int n
     pair_start[p] = (int)lo;
 }
 
-// Weighted chain DP of one axis: warp per pair, i sequential, j across lanes.
+// Weighted chain DP of one axis: one block per pair, i sequential, j across the block's threads.
 //   best[i] = w_i + max(0, max_{j<i same record, overlap <= 75 % of len_j} best[j] - overlap * unit_i)
 // The chain ending at the (first) best score of each record is kept.
-__global__ void __launch_bounds__(128) filt_dp_kernel(FiltArrays A, int axis, const int *__restrict__ pair_start, int n_pairs) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= n_pairs) return;
-    const int s0 = pair_start[warp], e0 = pair_start[warp + 1];
+constexpr int FD_THREADS = 256;
+__global__ void __launch_bounds__(FD_THREADS) filt_dp_kernel(FiltArrays A, int axis, const int *__restrict__ pair_start, int n_pairs) {
+    __shared__ long long w_sc[FD_THREADS / 32];
+    __shared__ int w_j[FD_THREADS / 32];
+    __shared__ long long r_sc;
+    __shared__ int r_j;
+    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (pair >= n_pairs) return;
+    const int s0 = pair_start[pair], e0 = pair_start[pair + 1];
     const int *slo = A.slo[axis], *shi = A.shi[axis], *sseq = A.sseq[axis], *sidx = A.sidx[axis];
     int gs = s0;  // start of the current record group
     long long top = -1;
     int arg = -1;
     for (int i = s0; i <= e0; ++i) {
         if (i == e0 || (i > gs && sseq[i] != sseq[gs])) {  // close the group [gs, i)
-            if (lane == 0)
+            if (tid == 0)
                 for (int x = arg; x >= 0; x = A.from[x]) A.flag[sidx[x]] |= (uint8_t)(1 << axis);
-            __syncwarp();
             gs = i; top = -1; arg = -1;
             if (i == e0) break;
         }
         const long long leni = shi[i] - slo[i] + 1, ui = A.unit[sidx[i]];
-        long long bsc = leni * ui;  // starting a new chain
-        int bj = -1;
+        const int loi = slo[i];
         long long lsc = -1;
         int lj = 0x7fffffff;
-        for (int j = gs + lane; j < i; j += 32) {
-            long long ol = (long long)shi[j] - slo[i] + 1, lenj = shi[j] - slo[j] + 1;
+        for (int j = gs + tid; j < i; j += FD_THREADS) {
+            long long hj = shi[j];
+            long long ol = hj - loi + 1, lenj = hj - slo[j] + 1;
             if (ol < 0) ol = 0;
             if (ol * 100 > (long long)AN_FILT_OLAP * lenj) continue;
             long long sc = __ldcg(&A.best[j]) + (leni - ol) * ui;
@@ -80,10 +84,24 @@ __global__ void __launch_bounds__(128) filt_dp_kernel(FiltArrays A, int axis, co
             int oj = __shfl_xor_sync(0xffffffffu, lj, off);
             if (osc > lsc || (osc == lsc && oj < lj)) { lsc = osc; lj = oj; }
         }
-        if (lsc > bsc) { bsc = lsc; bj = lj; }
-        if (lane == 0) { A.best[i] = bsc; A.from[i] = bj; }
-        __syncwarp();
-        if (bsc > top) { top = bsc; arg = i; }
+        if (lane == 0) { w_sc[wid] = lsc; w_j[wid] = lj; }
+        __syncthreads();
+        if (tid == 0) {
+            long long bsc = leni * ui;  // starting a new chain
+            int bj = -1;
+            long long msc = -1;
+            int mj = 0x7fffffff;
+            for (int w = 0; w < FD_THREADS / 32; ++w)
+                if (w_sc[w] > msc || (w_sc[w] == msc && w_j[w] < mj)) { msc = w_sc[w]; mj = w_j[w]; }
+            if (msc > bsc) { bsc = msc; bj = mj; }
+            A.best[i] = bsc;
+            A.from[i] = bj;
+            r_sc = bsc;
+            r_j = bj;
+            __threadfence_block();
+        }
+        __syncthreads();
+        if (r_sc > top) { top = r_sc; arg = i; }
     }
 }
 

@@ -26,7 +26,7 @@ __global__ void segment_accum_kernel(ChainArrays);
 __global__ void segment_flag_kernel(ChainArrays, uint8_t *);
 __global__ void gap_dp_kernel(ChainArrays, const PairDesc *, const uint32_t *, int64_t, unsigned long long *);
 __global__ void segment_init_kernel(ChainArrays, const PairDesc *, const int *, SegArrays);
-__global__ void ext_dp_kernel(SegArrays, const PairDesc *, unsigned long long *);
+__global__ void ext_dp_kernel(SegArrays, const PairDesc *, const uint32_t *, const unsigned long long *, uint32_t *, unsigned long long *);
 __global__ void emit_rows_kernel(SegArrays, const PairDesc *, int *);
 __global__ void filt_key_kernel(FiltArrays, int, uint64_t *, int *);
 __global__ void filt_gather_kernel(FiltArrays, int, const int *);
@@ -243,12 +243,18 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     DA(S.pair, n_seg); DA(S.strand, n_seg); DA(S.head, n_seg); DA(S.rc, n_seg); DA(S.qc, n_seg);
     DA(S.rs, n_seg); DA(S.qs, n_seg); DA(S.re, n_seg); DA(S.qe, n_seg);
     DA(S.r_lo, n_seg); DA(S.r_hi, n_seg); DA(S.q_lo, n_seg); DA(S.q_hi, n_seg);
-    DA(S.score, n_seg); DA(S.errs, n_seg); DA(S.active, 2 * n_seg); DA(rows, 8 * n_seg);
+    DA(S.score, n_seg); DA(S.errs, n_seg); DA(rows, 8 * n_seg);
+    uint32_t *ext_list[2] = {nullptr, nullptr};
+    DA(ext_list[0], 2 * n_seg); DA(ext_list[1], 2 * n_seg);
     if (n_seg) {
         T0(ST_EXTDP);
         segment_init_kernel<<<GRID(n_seg)>>>(A, W->d_pairs, seg_head, S);
         LAUNCHED(1);
-        for (int round = 0; round < AN_MAXTILES; ++round) {
+        // round r runs the dense list of tasks still extending; counters[9] = size of the current list,
+        // counters[8] = size of the list being built
+        unsigned long long n_cur = 2ull * n_seg;
+        CK(cudaMemcpyAsync(W->counters + 9, &n_cur, sizeof n_cur, cudaMemcpyHostToDevice, st));
+        for (int round = 0; round < AN_MAXTILES && n_cur; ++round) {
             CK(cudaMemsetAsync(W->counters + 8, 0, sizeof(unsigned long long), st));
             if ((size_t)(2 * n_ext_launch + 2) > W->kev.size()) {
                 cudaEvent_t a, b;
@@ -258,13 +264,15 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
                 W->kev.push_back(b);
             }
             CK(cudaEventRecord(W->kev[2 * n_ext_launch], st));
-            ext_dp_kernel<<<(unsigned)ceil_div(2 * n_seg, 128), 128, 0, st>>>(S, W->d_pairs, W->counters + 6);
+            ext_dp_kernel<<<(unsigned)ceil_div((int64_t)n_cur, 128), 128, 0, st>>>(S, W->d_pairs, round ? ext_list[round & 1] : nullptr, W->counters + 9,
+                                                                                ext_list[(round + 1) & 1], W->counters + 6);
             CK(cudaEventRecord(W->kev[2 * n_ext_launch + 1], st));
             ++n_ext_launch;
             LAUNCHED(1);
+            CK(cudaMemcpyAsync(W->counters + 9, W->counters + 8, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
             CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            if (hc[8] == 0) break;
+            n_cur = hc[8];
         }
         emit_rows_kernel<<<GRID(n_seg)>>>(S, W->d_pairs, rows);
         LAUNCHED(1);
@@ -291,7 +299,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         filt_gather_kernel<<<GRID(n_seg)>>>(F, axis, fidx2);
         LAUNCHED(2);
         if (!nofilter) {
-            filt_dp_kernel<<<(unsigned)ceil_div((int64_t)nb * 32, 128), 128, 0, st>>>(F, axis, pair_start, nb);
+            filt_dp_kernel<<<nb, 256, 0, st>>>(F, axis, pair_start, nb);
             LAUNCHED(1);
         }
     }
@@ -313,7 +321,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     DF(A.rc_of); DF(A.qc_of); DF(A.pred); DF(A.trim); DF(A.succ); DF(A.gval); DF(A.head); DF(A.chead); DF(A.cw); DF(A.wsum);
     DF(A.tail); DF(A.ssum); DF(A.esum); DF(A.strong); DF(task_key); DF(task_idx); DF(task_key2); DF(task_idx2); DF(seg_head);
     DF(S.pair); DF(S.strand); DF(S.head); DF(S.rc); DF(S.qc); DF(S.rs); DF(S.qs); DF(S.re); DF(S.qe);
-    DF(S.r_lo); DF(S.r_hi); DF(S.q_lo); DF(S.q_hi); DF(S.score); DF(S.errs); DF(S.active); DF(rows);
+    DF(S.r_lo); DF(S.r_hi); DF(S.q_lo); DF(S.q_hi); DF(S.score); DF(S.errs); DF(rows); DF(ext_list[0]); DF(ext_list[1]);
     for (int a = 0; a < 2; ++a) { DF(F.sidx[a]); DF(F.slo[a]); DF(F.shi[a]); DF(F.sseq[a]); }
     DF(F.best); DF(F.from); DF(F.unit); DF(F.flag); DF(fkey); DF(fkey2); DF(fidx); DF(fidx2); DF(pair_start);
     CK(cudaStreamSynchronize(st));
