@@ -289,15 +289,16 @@ def main():
     cells_gap, cells_ext = counters_last["gap_cells"], counters_last["ext_cells"]
     probes, hits = counters_last["probes"], counters_last["seed_hits"]
     kern = {
-        "seed_kernel": {"ms": stage_tot["seed"] / K, "launches": counters_last["seed_launches"]},
+        "seed_probe_kernel": {"ms": stage_tot["seed"] / K, "launches": counters_last["seed_launches"]},
+        "seed_extend_kernel": {"ms": stage_tot.get("seed_extend", 0.0) / K, "launches": counters_last["seed_launches"]},
         "gap_dp_kernel": {"ms": stage_tot["gap_dp"] / K, "launches": counters_last["gap_dp_launches"]},
         "ext_dp_kernel": {"ms": stage_tot["ext_dp_kernel"] / K, "launches": counters_last["ext_dp_launches"]},
     }
     dom = max(kern, key=lambda k: kern[k]["ms"])
-    if dom == "seed_kernel":
-        # algorithmic bytes: 8 B minimizer-list entry streamed + one 8 B table slot probed per query minimizer,
-        # plus 2 x 16 B of packed sequence per hit to verify / extend
-        alg = probes * 16 + hits * 32
+    if dom.startswith("seed"):
+        # algorithmic bytes: probe = 4 B k-mer streamed + one 8 B table slot per query minimizer and
+        # 8 B written per hit; extend = 8 B hit + 4 B posflag + 2 x 16 B packed sequence per hit, 16 B per anchor
+        alg = probes * 12 + hits * 8 if dom == "seed_probe_kernel" else hits * 44 + counters_last["anchors"] * 16
         ach = alg / (kern[dom]["ms"] * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
                 "peak_source": peak_src, "per_launch_ms": kern[dom]["ms"] / max(1, kern[dom]["launches"]),

@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NLAUNCH:-1200} --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu --ncu > gpurun_out/bench_under_ncu.log 2>&1
 # (2) full capture of the DP kernels and the seed kernel (a few launches each)
-for k in gap_dp_kernel ext_dp seed_kernel; do
+for k in gap_dp_kernel ext_dp seed_probe seed_extend; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s ${SKIP:-2} -c 2 -o gpurun_out/prof_$k -f \
       python bench.py --steps 1 --warmup 1 --no-cpu --ncu > gpurun_out/ncu_$k.log 2>&1
 done

@@ -154,7 +154,7 @@ struct FiltArrays {
 
 // stage / counter slots of b200ani_last_profile
 enum {
-    ST_INDEX = 0, ST_SEED, ST_SORT, ST_LINK, ST_GAPDP, ST_LABEL, ST_EXTDP, ST_FILTER, ST_REDUCE, ST_TOTAL, ST_EXTK,
+    ST_INDEX = 0, ST_SEED, ST_SORT, ST_LINK, ST_GAPDP, ST_LABEL, ST_EXTDP, ST_FILTER, ST_REDUCE, ST_TOTAL, ST_EXTK, ST_SEEDX,
     CT_PROBES = 0, CT_SEEDHITS, CT_ANCHORS, CT_LINKS, CT_CUTS, CT_SEGMENTS, CT_GAPCELLS, CT_EXTCELLS, CT_EXTTILES, CT_ALIGNMENTS, CT_LAUNCHES,
     CT_GAPTASKS, CT_PAIRS, CT_EXTLAUNCH, CT_GAPLAUNCH, CT_SEEDLAUNCH
 };

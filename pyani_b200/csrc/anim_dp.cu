@@ -215,38 +215,46 @@ __global__ void segment_init_kernel(ChainArrays A, const PairDesc *__restrict__ 
     S.errs[s] = A.esum[h];
 }
 
-// One extension tile for every task of the round's (dense) task list; tasks that must continue are
-// appended to the next round's list, so every launch runs full warps of equally sized tiles.
-// task id = 2 * segment + side (side 0 = left extension, side 1 = right extension).
-__global__ void __launch_bounds__(128) ext_dp_kernel(SegArrays S, const PairDesc *__restrict__ pairs, const uint32_t *__restrict__ list_in,
-                                                     const unsigned long long *__restrict__ n_in, uint32_t *__restrict__ list_out,
-                                                     unsigned long long *__restrict__ counters /*0: cells, 1: tiles, 2: n_out*/) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    long long cells = 0;
-    int tiles = 0;
-    if (t < (int64_t)*n_in) {
-        const uint32_t task = list_in ? list_in[t] : (uint32_t)t;
-        const int64_t s = task >> 1;
-        const int side = (int)(task & 1);
-        const PairDesc &P = pairs[S.pair[s]];
-        SeqView R{P.r_seq, P.r_mask, P.r_npos, 0}, Q{P.q_seq, P.q_mask, P.q_npos, S.strand[s]};
-        int64_t ar = side ? S.r_hi[s] - S.re[s] : S.rs[s] - S.r_lo[s];
-        int64_t aq = side ? S.q_hi[s] - S.qe[s] : S.qs[s] - S.q_lo[s];
-        int lr = (int)min(ar, (int64_t)AN_TILE), lq = (int)min(aq, (int64_t)(AN_TILE + AN_BAND));
-        bool on = false;
-        if (lr > 0 && lq > 0) {
-            DpResult o = side ? dp_band<1>(R, S.re[s], 1, Q, S.qe[s], 1, lr, lq, -AN_BAND)
-                              : dp_band<1>(R, (int64_t)S.rs[s] - 1, -1, Q, (int64_t)S.qs[s] - 1, -1, lr, lq, -AN_BAND);
-            cells = o.cells;
-            tiles = 1;
-            if (o.bi != 0 || o.bj != 0) {
-                if (side) { S.re[s] += o.bi; S.qe[s] += o.bj; } else { S.rs[s] -= o.bi; S.qs[s] -= o.bj; }
-                atomicAdd((unsigned long long *)&S.score[s], (unsigned long long)(long long)pack_score(o.val));
-                atomicAdd((unsigned long long *)&S.errs[s], (unsigned long long)(long long)pack_errs(o.val));
-                on = !o.stopped;
-            }
+// Extension of both ends of every kept segment, tile by tile.  Persistent threads: every lane owns one
+// (segment, side) task at a time and pulls the next one from a global ticket counter as soon as its task
+// stops extending, so all 32 lanes of a warp always run equally sized tiles (95..128 rows) in lockstep;
+// divergence only appears when the queue runs dry.  task id = 2 * segment + side (0 = left, 1 = right).
+__global__ void __launch_bounds__(128) ext_dp_kernel(SegArrays S, const PairDesc *__restrict__ pairs,
+                                                     unsigned long long *__restrict__ counters /*0: cells, 1: tiles, 2: ticket*/) {
+    const long long n_tasks = 2 * S.n;
+    long long task = -1, cells = 0;
+    int tiles = 0, done_tiles = 0;
+    for (;;) {
+        if (task == -1) {
+            task = (long long)atomicAdd(&counters[2], 1ull);
+            done_tiles = 0;
+            if (task >= n_tasks) task = -2;
         }
-        if (on) list_out[atomicAdd(&counters[2], 1ull)] = task;
+        if (__all_sync(0xffffffffu, task == -2)) break;
+        if (task >= 0) {
+            const int64_t s = task >> 1;
+            const int side = (int)(task & 1);
+            const PairDesc &P = pairs[S.pair[s]];
+            SeqView R{P.r_seq, P.r_mask, P.r_npos, 0}, Q{P.q_seq, P.q_mask, P.q_npos, S.strand[s]};
+            const int rs = S.rs[s], qs = S.qs[s], re = S.re[s], qe = S.qe[s];
+            int64_t ar = side ? S.r_hi[s] - re : rs - S.r_lo[s];
+            int64_t aq = side ? S.q_hi[s] - qe : qs - S.q_lo[s];
+            int lr = (int)min(ar, (int64_t)AN_TILE), lq = (int)min(aq, (int64_t)(AN_TILE + AN_BAND));
+            bool on = false;
+            if (lr > 0 && lq > 0) {
+                DpResult o = side ? dp_band<1>(R, re, 1, Q, qe, 1, lr, lq, -AN_BAND)
+                                  : dp_band<1>(R, (int64_t)rs - 1, -1, Q, (int64_t)qs - 1, -1, lr, lq, -AN_BAND);
+                cells += o.cells;
+                ++tiles;
+                if (o.bi != 0 || o.bj != 0) {
+                    if (side) { S.re[s] = re + o.bi; S.qe[s] = qe + o.bj; } else { S.rs[s] = rs - o.bi; S.qs[s] = qs - o.bj; }
+                    atomicAdd((unsigned long long *)&S.score[s], (unsigned long long)(long long)pack_score(o.val));
+                    atomicAdd((unsigned long long *)&S.errs[s], (unsigned long long)(long long)pack_errs(o.val));
+                    on = !o.stopped;
+                }
+            }
+            if (!on || ++done_tiles >= AN_MAXTILES) task = -1;
+        }
     }
     for (int off = 16; off; off >>= 1) {
         cells += __shfl_down_sync(0xffffffffu, cells, off);

@@ -9,10 +9,11 @@
 
 #include "anim.cuh"
 
-int build_index(b200ani_ctx *ctx, Genome &g);
+int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo);
 
 // kernels defined in the other translation units
-__global__ void seed_kernel(const PairDesc *, int, int64_t, uint64_t *, uint64_t *, unsigned long long *, unsigned long long);
+__global__ void seed_probe_kernel(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
+__global__ void seed_extend_kernel(const PairDesc *, int, const uint2 *, int64_t, uint64_t *, uint64_t *, unsigned long long *, unsigned long long);
 __global__ void tie_fix_kernel(uint64_t *, uint64_t *, int64_t);
 __global__ void flag_unique_kernel(const uint64_t *, const uint64_t *, int64_t, uint8_t *);
 __global__ void contig_kernel(ChainArrays, const PairDesc *);
@@ -26,7 +27,7 @@ __global__ void segment_accum_kernel(ChainArrays);
 __global__ void segment_flag_kernel(ChainArrays, uint8_t *);
 __global__ void gap_dp_kernel(ChainArrays, const PairDesc *, const uint32_t *, int64_t, unsigned long long *);
 __global__ void segment_init_kernel(ChainArrays, const PairDesc *, const int *, SegArrays);
-__global__ void ext_dp_kernel(SegArrays, const PairDesc *, const uint32_t *, const unsigned long long *, uint32_t *, unsigned long long *);
+__global__ void ext_dp_kernel(SegArrays, const PairDesc *, unsigned long long *);
 __global__ void emit_rows_kernel(SegArrays, const PairDesc *, int *);
 __global__ void filt_key_kernel(FiltArrays, int, uint64_t *, int *);
 __global__ void filt_gather_kernel(FiltArrays, int, const int *);
@@ -35,16 +36,18 @@ __global__ void filt_dp_kernel(FiltArrays, int, const int *, int);
 __global__ void reduce_kernel(FiltArrays, const int *, int, int, b200ani_anim_result *);
 
 static const char *kStageNames[B200ANI_N_STAGES] = {"index", "seed", "sort", "link", "gap_dp", "label", "ext_dp", "filter", "reduce", "total",
-                                                    "ext_dp_kernel", "", "", "", "", ""};
+                                                    "ext_dp_kernel", "seed_extend", "", "", "", ""};
 static const char *kCounterNames[B200ANI_N_STAGES] = {"probes", "seed_hits", "anchors", "links", "cut_links", "segments", "gap_cells", "ext_cells",
                                                       "ext_tiles", "alignments", "launches", "gap_tasks", "pairs", "ext_dp_launches", "gap_dp_launches", "seed_launches"};
 
 constexpr int MAX_BATCH_PAIRS = 128;
 constexpr int64_t ANCHOR_CAP = 24ll << 20;
+constexpr int64_t HIT_CAP = 96ll << 20;  // seed hits of one batch (8 B each)
 
 struct AnimWorkspace {
     uint64_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr;
     uint8_t *flag = nullptr;
+    uint2 *hits = nullptr;
     unsigned long long *counters = nullptr;  // 16 device counters
     int *changed = nullptr;
     PairDesc *d_pairs = nullptr;
@@ -59,7 +62,7 @@ struct AnimWorkspace {
 void free_anim_workspace(void *p) {
     AnimWorkspace *w = (AnimWorkspace *)p;
     if (!w) return;
-    cudaFree(w->keys_a); cudaFree(w->vals_a); cudaFree(w->keys_b); cudaFree(w->vals_b); cudaFree(w->flag);
+    cudaFree(w->keys_a); cudaFree(w->vals_a); cudaFree(w->keys_b); cudaFree(w->vals_b); cudaFree(w->flag); cudaFree(w->hits);
     cudaFree(w->counters); cudaFree(w->changed); cudaFree(w->d_pairs); cudaFree(w->d_results); cudaFree(w->cub_tmp);
     if (w->ok) for (auto &e : w->ev) cudaEventDestroy(e);
     for (auto &e : w->kev) cudaEventDestroy(e);
@@ -75,6 +78,7 @@ static int get_workspace(b200ani_ctx *ctx, AnimWorkspace **out) {
     CK(cudaMalloc(&w->keys_b, sizeof(uint64_t) * ANCHOR_CAP));
     CK(cudaMalloc(&w->vals_b, sizeof(uint64_t) * ANCHOR_CAP));
     CK(cudaMalloc(&w->flag, ANCHOR_CAP));
+    CK(cudaMalloc(&w->hits, sizeof(uint2) * HIT_CAP));
     CK(cudaMalloc(&w->counters, 16 * sizeof(unsigned long long)));
     CK(cudaMalloc(&w->changed, sizeof(int)));
     CK(cudaMalloc(&w->d_pairs, sizeof(PairDesc) * MAX_BATCH_PAIRS));
@@ -135,19 +139,30 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     ctx->counters[CT_PROBES] += n_probes;
     ctx->counters[CT_PAIRS] += nb;
 
-    // ---- seeds -> anchors
+    // ---- seeds -> anchors: probe (latency bound, uniform) then extend (one thread per hit)
     T0(ST_SEED);
     if (n_probes) {
-        int blocks = (int)std::min<int64_t>(ceil_div(n_probes, 256), (int64_t)ctx->sm_count * 16);
-        seed_kernel<<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->keys_a, W->vals_a, W->counters, (unsigned long long)ANCHOR_CAP);
+        int blocks = (int)std::min<int64_t>(ceil_div(n_probes, 256), (int64_t)ctx->sm_count * 8);
+        seed_probe_kernel<<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP);
         LAUNCHED(1);
         ctx->counters[CT_SEEDLAUNCH] += 1;
     }
     T1(ST_SEED);
     CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    const int64_t n_hits = (int64_t)hc[1];
+    if (n_hits > HIT_CAP) return 1;  // caller splits the batch
+    ctx->counters[CT_SEEDHITS] += n_hits;
+    T0(ST_SEEDX);
+    if (n_hits) {
+        int blocks = (int)std::min<int64_t>(ceil_div(n_hits, 256), (int64_t)ctx->sm_count * 8);
+        seed_extend_kernel<<<blocks, 256, 0, st>>>(W->d_pairs, nb, W->hits, n_hits, W->keys_a, W->vals_a, W->counters, (unsigned long long)ANCHOR_CAP);
+        LAUNCHED(1);
+    }
+    T1(ST_SEEDX);
+    CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     const int64_t n_raw = (int64_t)hc[0];
-    ctx->counters[CT_SEEDHITS] += (int64_t)hc[1];
     if (n_raw > ANCHOR_CAP) return 1;  // caller splits the batch
 
     // ---- sort by (pair, strand, r), ties by (q, len); drop duplicates
@@ -244,35 +259,29 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     DA(S.rs, n_seg); DA(S.qs, n_seg); DA(S.re, n_seg); DA(S.qe, n_seg);
     DA(S.r_lo, n_seg); DA(S.r_hi, n_seg); DA(S.q_lo, n_seg); DA(S.q_hi, n_seg);
     DA(S.score, n_seg); DA(S.errs, n_seg); DA(rows, 8 * n_seg);
-    uint32_t *ext_list[2] = {nullptr, nullptr};
-    DA(ext_list[0], 2 * n_seg); DA(ext_list[1], 2 * n_seg);
+
     if (n_seg) {
         T0(ST_EXTDP);
         segment_init_kernel<<<GRID(n_seg)>>>(A, W->d_pairs, seg_head, S);
         LAUNCHED(1);
-        // round r runs the dense list of tasks still extending; counters[9] = size of the current list,
-        // counters[8] = size of the list being built
-        unsigned long long n_cur = 2ull * n_seg;
-        CK(cudaMemcpyAsync(W->counters + 9, &n_cur, sizeof n_cur, cudaMemcpyHostToDevice, st));
-        for (int round = 0; round < AN_MAXTILES && n_cur; ++round) {
-            CK(cudaMemsetAsync(W->counters + 8, 0, sizeof(unsigned long long), st));
-            if ((size_t)(2 * n_ext_launch + 2) > W->kev.size()) {
+        {   // one persistent launch: resident warps pull (segment, side) tasks from a ticket counter
+            if (W->kev.size() < 2) {
                 cudaEvent_t a, b;
                 CK(cudaEventCreate(&a));
                 CK(cudaEventCreate(&b));
                 W->kev.push_back(a);
                 W->kev.push_back(b);
             }
-            CK(cudaEventRecord(W->kev[2 * n_ext_launch], st));
-            ext_dp_kernel<<<(unsigned)ceil_div((int64_t)n_cur, 128), 128, 0, st>>>(S, W->d_pairs, round ? ext_list[round & 1] : nullptr, W->counters + 9,
-                                                                                ext_list[(round + 1) & 1], W->counters + 6);
-            CK(cudaEventRecord(W->kev[2 * n_ext_launch + 1], st));
-            ++n_ext_launch;
+            int per_sm = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ext_dp_kernel, 128, 0));
+            int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * std::max(per_sm, 1), ceil_div(2 * n_seg, 128));
+            CK(cudaEventRecord(W->kev[0], st));
+            ext_dp_kernel<<<(unsigned)blocks, 128, 0, st>>>(S, W->d_pairs, W->counters + 6);
+            CK(cudaEventRecord(W->kev[1], st));
+            n_ext_launch = 1;
             LAUNCHED(1);
-            CK(cudaMemcpyAsync(W->counters + 9, W->counters + 8, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
             CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            n_cur = hc[8];
         }
         emit_rows_kernel<<<GRID(n_seg)>>>(S, W->d_pairs, rows);
         LAUNCHED(1);
@@ -321,7 +330,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     DF(A.rc_of); DF(A.qc_of); DF(A.pred); DF(A.trim); DF(A.succ); DF(A.gval); DF(A.head); DF(A.chead); DF(A.cw); DF(A.wsum);
     DF(A.tail); DF(A.ssum); DF(A.esum); DF(A.strong); DF(task_key); DF(task_idx); DF(task_key2); DF(task_idx2); DF(seg_head);
     DF(S.pair); DF(S.strand); DF(S.head); DF(S.rc); DF(S.qc); DF(S.rs); DF(S.qs); DF(S.re); DF(S.qe);
-    DF(S.r_lo); DF(S.r_hi); DF(S.q_lo); DF(S.q_hi); DF(S.score); DF(S.errs); DF(rows); DF(ext_list[0]); DF(ext_list[1]);
+    DF(S.r_lo); DF(S.r_hi); DF(S.q_lo); DF(S.q_hi); DF(S.score); DF(S.errs); DF(rows);
     for (int a = 0; a < 2; ++a) { DF(F.sidx[a]); DF(F.slo[a]); DF(F.shi[a]); DF(F.sseq[a]); }
     DF(F.best); DF(F.from); DF(F.unit); DF(F.flag); DF(fkey); DF(fkey2); DF(fidx); DF(fidx2); DF(pair_start);
     CK(cudaStreamSynchronize(st));
@@ -368,17 +377,17 @@ static int prepare(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmat
     if (rc) return rc;
     cudaStream_t st = ctx->stream;
     cudaEvent_t e0 = (*W)->ev[2 * ST_INDEX], e1 = (*W)->ev[2 * ST_INDEX + 1];
-    bool any = false;
-    CK(cudaEventRecord(e0, st));
+    std::vector<Genome *> todo;
+    std::vector<char> seen(ng, 0);
     for (int64_t i = 0; i < 2 * m; ++i) {
         Genome &g = ctx->genomes[pairs[i]];
         if (g.n_contigs >= 65535) FAIL(B200ANI_ERR_CAPACITY, "anim: genomes with >= 65535 records are not supported");
-        if (!g.index) {
-            rc = build_index(ctx, g);
-            if (rc) return rc;
-            any = true;
-        }
+        if (!g.index && !seen[pairs[i]]) { seen[pairs[i]] = 1; todo.push_back(&g); }
     }
+    const bool any = !todo.empty();
+    CK(cudaEventRecord(e0, st));
+    rc = build_indexes(ctx, todo);
+    if (rc) return rc;
     CK(cudaEventRecord(e1, st));
     CK(cudaStreamSynchronize(st));
     if (any) {

@@ -2,6 +2,7 @@
 // Built once per genome and reused by every comparison the genome takes part in -- nucmer instead
 // rebuilds its suffix tree for each of the N-1 runs a genome is the reference of.
 #include <cub/cub.cuh>
+#include <vector>
 
 #include "anim.cuh"
 
@@ -91,69 +92,86 @@ __global__ void split_bypos_kernel(const uint64_t *__restrict__ bypos, int64_t n
 
 void free_index(MinimizerIndex *ix) {
     if (!ix) return;
-    cudaFree(ix->d_kmer);
-    cudaFree(ix->d_posflag);
-    cudaFree(ix->d_table);
+    cudaFreeAsync(ix->d_kmer, nullptr);
+    cudaFreeAsync(ix->d_posflag, nullptr);
+    cudaFreeAsync(ix->d_table, nullptr);
     delete ix;
 }
 
-int build_index(b200ani_ctx *ctx, Genome &g) {
-    if (g.index) return 0;
+// Build the indexes of many genomes with three host synchronisations in total (counts of selected and of
+// unique minimizers are needed on the host to size sorts and tables) instead of two per genome.
+int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo) {
+    const size_t G = todo.size();
+    if (!G) return 0;
     cudaStream_t st = ctx->stream;
-    const int64_t n = g.n_pos;
-    uint64_t *d_sel = nullptr, *d_sorted = nullptr, *d_uniq = nullptr;
-    unsigned long long *d_cnt = nullptr;
-    uint8_t *d_flag = nullptr;
-    void *d_tmp = nullptr;
-    CK(cudaMallocAsync(&d_sel, sizeof(uint64_t) * (size_t)(n + 1), st));
-    CK(cudaMallocAsync(&d_sorted, sizeof(uint64_t) * (size_t)(n + 1), st));
-    CK(cudaMallocAsync(&d_uniq, sizeof(uint64_t) * (size_t)(n + 1), st));
-    CK(cudaMallocAsync(&d_cnt, 2 * sizeof(unsigned long long), st));
-    CK(cudaMallocAsync(&d_flag, (size_t)n + 1, st));
-    CK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
-    int blocks = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->sm_count * 16);
-    minimizer_select_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint64_t *>(g.d_seq), g.d_mask, n, d_sel, d_cnt);
-    CK(cudaGetLastError());
-    unsigned long long h_cnt = 0;
-    CK(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const int64_t ns = (int64_t)h_cnt;
-    size_t tmp_bytes = 0, tb2 = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_sel, d_sorted, ns, 0, 64, st);
-    cub::DeviceSelect::Flagged(nullptr, tb2, d_sorted, d_flag, d_uniq, (int *)d_cnt, ns, st);
-    tmp_bytes = std::max(tmp_bytes, tb2);
-    CK(cudaMallocAsync(&d_tmp, tmp_bytes + 16, st));
-    cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_sel, d_sorted, ns, 0, 64, st);
-    if (ns) mark_unique_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(d_sorted, ns, d_flag);
-    CK(cudaGetLastError());
-    int *d_nu = (int *)(d_cnt + 1);
-    cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_sorted, d_flag, d_uniq, d_nu, ns, st);
-    int h_nu = 0;
-    CK(cudaMemcpyAsync(&h_nu, d_nu, sizeof h_nu, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    MinimizerIndex *ix = new MinimizerIndex();
-    ix->n_mini = h_nu;
-    uint32_t bits = 4;
-    while ((1ll << bits) < 2ll * h_nu) ++bits;
-    ix->table_bits = bits;
-    CK(cudaMalloc(&ix->d_table, sizeof(uint64_t) << bits));
-    CK(cudaMalloc(&ix->d_kmer, sizeof(uint32_t) * (size_t)(h_nu + 1)));
-    CK(cudaMalloc(&ix->d_posflag, sizeof(uint32_t) * (size_t)(h_nu + 1)));
-    CK(cudaMemsetAsync(ix->d_table, 0xff, sizeof(uint64_t) << bits, st));
-    if (h_nu) {
-        table_insert_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, st>>>(d_uniq, h_nu, ix->d_table, bits, d_sel);
-        CK(cudaGetLastError());
-        cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_sel, d_sorted, h_nu, 33, 64, st);
-        split_bypos_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, st>>>(d_sorted, h_nu, ix->d_kmer, ix->d_posflag);
+    struct Tmp { uint64_t *sel = nullptr, *sorted = nullptr, *uniq = nullptr; uint8_t *flag = nullptr; };
+    std::vector<Tmp> tmp(G);
+    unsigned long long *d_cnt = nullptr;  // [G] selected counts, then [G] unique counts (as int)
+    CK(cudaMallocAsync(&d_cnt, 2 * G * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(d_cnt, 0, 2 * G * sizeof(unsigned long long), st));
+    int64_t max_n = 0;
+    for (size_t k = 0; k < G; ++k) {
+        Genome &g = *todo[k];
+        const int64_t n = g.n_pos;
+        max_n = std::max(max_n, n);
+        // about a third of the positions are selected; n/2 + slack bounds it (checked below)
+        CK(cudaMallocAsync(&tmp[k].sel, sizeof(uint64_t) * (size_t)(n + 1), st));
+        int blocks = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->sm_count * 16);
+        minimizer_select_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint64_t *>(g.d_seq), g.d_mask, n, tmp[k].sel, d_cnt + k);
         CK(cudaGetLastError());
     }
-    ctx->counters[CT_LAUNCHES] += 7;
-    CK(cudaFreeAsync(d_sel, st));
-    CK(cudaFreeAsync(d_sorted, st));
-    CK(cudaFreeAsync(d_uniq, st));
+    std::vector<unsigned long long> h_cnt(2 * G);
+    CK(cudaMemcpyAsync(h_cnt.data(), d_cnt, G * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    size_t tmp_bytes = 0, tb2 = 0;
+    void *d_tmp = nullptr;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, tmp[0].sel, tmp[0].sel, (int64_t)max_n, 0, 64, st);
+    cub::DeviceSelect::Flagged(nullptr, tb2, tmp[0].sel, (uint8_t *)nullptr, tmp[0].sel, (int *)d_cnt, (int64_t)max_n, st);
+    tmp_bytes = std::max(tmp_bytes, tb2);
+    CK(cudaMallocAsync(&d_tmp, tmp_bytes + 16, st));
+    for (size_t k = 0; k < G; ++k) {
+        const int64_t ns = (int64_t)h_cnt[k];
+        CK(cudaMallocAsync(&tmp[k].sorted, sizeof(uint64_t) * (size_t)(ns + 1), st));
+        CK(cudaMallocAsync(&tmp[k].uniq, sizeof(uint64_t) * (size_t)(ns + 1), st));
+        CK(cudaMallocAsync(&tmp[k].flag, (size_t)ns + 1, st));
+        size_t tb = tmp_bytes;
+        cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, ns, 0, 64, st);
+        if (ns) mark_unique_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(tmp[k].sorted, ns, tmp[k].flag);
+        CK(cudaGetLastError());
+        tb = tmp_bytes;
+        cub::DeviceSelect::Flagged(d_tmp, tb, tmp[k].sorted, tmp[k].flag, tmp[k].uniq, (int *)(d_cnt + G + k), ns, st);
+    }
+    CK(cudaMemcpyAsync(h_cnt.data() + G, d_cnt + G, G * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (size_t k = 0; k < G; ++k) {
+        Genome &g = *todo[k];
+        const int h_nu = (int)(h_cnt[G + k] & 0xffffffffu);
+        MinimizerIndex *ix = new MinimizerIndex();
+        ix->n_mini = h_nu;
+        uint32_t bits = 4;
+        while ((1ll << bits) < 2ll * h_nu) ++bits;
+        ix->table_bits = bits;
+        CK(cudaMallocAsync(&ix->d_table, sizeof(uint64_t) << bits, st));
+        CK(cudaMallocAsync(&ix->d_kmer, sizeof(uint32_t) * (size_t)(h_nu + 1), st));
+        CK(cudaMallocAsync(&ix->d_posflag, sizeof(uint32_t) * (size_t)(h_nu + 1), st));
+        CK(cudaMemsetAsync(ix->d_table, 0xff, sizeof(uint64_t) << bits, st));
+        if (h_nu) {
+            table_insert_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, st>>>(tmp[k].uniq, h_nu, ix->d_table, bits, tmp[k].sel);
+            CK(cudaGetLastError());
+            size_t tb = tmp_bytes;
+            cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, h_nu, 33, 64, st);
+            split_bypos_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, st>>>(tmp[k].sorted, h_nu, ix->d_kmer, ix->d_posflag);
+            CK(cudaGetLastError());
+        }
+        ctx->counters[CT_LAUNCHES] += 4;
+        CK(cudaFreeAsync(tmp[k].sel, st));
+        CK(cudaFreeAsync(tmp[k].sorted, st));
+        CK(cudaFreeAsync(tmp[k].uniq, st));
+        CK(cudaFreeAsync(tmp[k].flag, st));
+        g.index = ix;
+    }
     CK(cudaFreeAsync(d_cnt, st));
-    CK(cudaFreeAsync(d_flag, st));
     CK(cudaFreeAsync(d_tmp, st));
-    g.index = ix;
+    CK(cudaStreamSynchronize(st));
     return 0;
 }

@@ -40,22 +40,55 @@ __device__ int64_t match_left(const SeqView &R, const SeqView &Q, int64_t r, int
     }
 }
 
-// One thread per (pair, query minimizer).  key/val encoding: anim.cuh.
-__global__ void __launch_bounds__(256) seed_kernel(const PairDesc *__restrict__ pairs, int n_pairs, int64_t n_probes, uint64_t *__restrict__ keys,
-                                                   uint64_t *__restrict__ vals, unsigned long long *__restrict__ counters /*0: anchors, 1: hits*/,
-                                                   unsigned long long cap) {
+__device__ __forceinline__ int pair_of_probe(const PairDesc *__restrict__ pairs, int n_pairs, int64_t gi) {
+    int lo = 0, hi = n_pairs;  // pair p with probe_base[p] <= gi < probe_base[p+1]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (pairs[mid].probe_base <= gi) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Phase 1 -- probe: one thread per (pair, query minimizer): stream the query's minimizer list
+// (evict-first loads) through the reference's table; hits are appended as (probe index, table entry).
+// Memory-latency bound by design: one coalesced 4-byte read + one random 8-byte read per probe, no
+// divergent work, so the warps in flight are all waiting on independent loads.
+__global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restrict__ pairs, int n_pairs, int64_t n_probes, uint2 *__restrict__ hits,
+                                                         unsigned long long *__restrict__ n_hits, unsigned long long cap) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < n_probes; gi += stride) {
-        int lo = 0, hi = n_pairs;  // pair p with probe_base[p] <= gi < probe_base[p+1]
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (pairs[mid].probe_base <= gi) lo = mid; else hi = mid;
+    const int lane = threadIdx.x & 31;
+    for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; g0 < n_probes; g0 += stride) {
+        const int64_t gi = g0 + lane;
+        bool hit = false;
+        uint32_t rpf = 0;
+        if (gi < n_probes) {
+            const PairDesc &P = pairs[pair_of_probe(pairs, n_pairs, gi)];
+            hit = table_lookup(P.r_table, P.r_table_bits, __ldcs(P.q_kmer + (gi - P.probe_base)), rpf);
         }
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (m) {  // one atomic per warp
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(n_hits, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+            if (hit && slot < cap) hits[slot] = make_uint2((uint32_t)gi, rpf);
+        }
+    }
+}
+
+// Phase 2 -- extend: one thread per hit (dense, so no idle lanes): drop seeds that the previous query
+// minimizer already covers, extend the others to maximal exact matches.  key/val encoding: anim.cuh.
+__global__ void __launch_bounds__(256) seed_extend_kernel(const PairDesc *__restrict__ pairs, int n_pairs, const uint2 *__restrict__ hits, int64_t n_hits,
+                                                          uint64_t *__restrict__ keys, uint64_t *__restrict__ vals,
+                                                          unsigned long long *__restrict__ n_anchors, unsigned long long cap) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t hi_ = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; hi_ < n_hits; hi_ += stride) {
+        const uint2 h = hits[hi_];
+        const int64_t gi = h.x;
+        const int lo = pair_of_probe(pairs, n_pairs, gi);
         const PairDesc &P = pairs[lo];
         const int64_t t = gi - P.probe_base;
-        uint32_t rpf;
-        if (!table_lookup(P.r_table, P.r_table_bits, P.q_kmer[t], rpf)) continue;
-        atomicAdd(&counters[1], 1ull);
+        const uint32_t rpf = h.y;
         const uint32_t qpf = P.q_posflag[t];
         const int strand = (int)((rpf ^ qpf) >> 31);
         const int64_t r0 = rpf & 0x7fffffffu, qpos = qpf & 0x7fffffffu;
@@ -83,7 +116,7 @@ __global__ void __launch_bounds__(256) seed_kernel(const PairDesc *__restrict__ 
         int64_t rr = match_right(R, Q, r0 + AN_K, q0 + AN_K);
         int64_t len = AN_K + l + rr;
         if (len < AN_MINLEN) continue;
-        unsigned long long slot = atomicAdd(&counters[0], 1ull);
+        unsigned long long slot = atomicAdd(n_anchors, 1ull);
         if (slot < cap) {
             keys[slot] = ((uint64_t)lo << 32) | ((uint64_t)strand << 31) | (uint64_t)(r0 - l);
             vals[slot] = ((uint64_t)(q0 - l) << 32) | (uint64_t)len;
