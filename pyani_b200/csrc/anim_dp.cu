@@ -216,22 +216,26 @@ __global__ void segment_init_kernel(ChainArrays A, const PairDesc *__restrict__ 
 }
 
 // Extension of both ends of every kept segment, tile by tile.  Persistent threads: every lane owns one
-// (segment, side) task at a time and pulls the next one from a global ticket counter as soon as its task
-// stops extending, so all 32 lanes of a warp always run equally sized tiles (95..128 rows) in lockstep;
-// divergence only appears when the queue runs dry.  task id = 2 * segment + side (0 = left, 1 = right).
-__global__ void __launch_bounds__(128) ext_dp_kernel(SegArrays S, const PairDesc *__restrict__ pairs,
-                                                     unsigned long long *__restrict__ counters /*0: cells, 1: tiles, 2: ticket*/) {
-    const long long n_tasks = 2 * S.n;
-    long long task = -1, cells = 0;
+// (segment, side) task at a time and pulls the next one from a ticket counter as soon as its task stops
+// extending, so the lanes of a warp keep running equally sized tiles (95..128 rows).  A task gets at most
+// `tiles_per_launch` tiles per launch; tasks that still extend are appended to `list_out` and continue in
+// the next launch, which bounds the tail a few long crawls (up to AN_MAXTILES tiles) would otherwise add.
+// task id = 2 * segment + side (0 = left, 1 = right).
+__global__ void __launch_bounds__(128) ext_dp_kernel(SegArrays S, const PairDesc *__restrict__ pairs, const uint32_t *__restrict__ list_in, long long n_tasks,
+                                                     uint32_t *__restrict__ list_out, int tiles_per_launch,
+                                                     unsigned long long *__restrict__ counters /*0: cells, 1: tiles, 2: n_out, 3: ticket*/) {
+    long long ticket = -1, cells = 0;
+    uint32_t task = 0;
     int tiles = 0, done_tiles = 0;
     for (;;) {
-        if (task == -1) {
-            task = (long long)atomicAdd(&counters[2], 1ull);
+        if (ticket == -1) {
+            ticket = (long long)atomicAdd(&counters[3], 1ull);
             done_tiles = 0;
-            if (task >= n_tasks) task = -2;
+            if (ticket >= n_tasks) ticket = -2;
+            else task = list_in ? list_in[ticket] : (uint32_t)ticket;
         }
-        if (__all_sync(0xffffffffu, task == -2)) break;
-        if (task >= 0) {
+        if (__all_sync(0xffffffffu, ticket == -2)) break;
+        if (ticket >= 0) {
             const int64_t s = task >> 1;
             const int side = (int)(task & 1);
             const PairDesc &P = pairs[S.pair[s]];
@@ -242,8 +246,9 @@ __global__ void __launch_bounds__(128) ext_dp_kernel(SegArrays S, const PairDesc
             int lr = (int)min(ar, (int64_t)AN_TILE), lq = (int)min(aq, (int64_t)(AN_TILE + AN_BAND));
             bool on = false;
             if (lr > 0 && lq > 0) {
-                DpResult o = side ? dp_band<1>(R, re, 1, Q, qe, 1, lr, lq, -AN_BAND)
-                                  : dp_band<1>(R, (int64_t)rs - 1, -1, Q, (int64_t)qs - 1, -1, lr, lq, -AN_BAND);
+                // one call site for both directions: the two sides differ only in start position and step
+                const int step = side ? 1 : -1;
+                DpResult o = dp_band<1>(R, side ? (int64_t)re : (int64_t)rs - 1, step, Q, side ? (int64_t)qe : (int64_t)qs - 1, step, lr, lq, -AN_BAND);
                 cells += o.cells;
                 ++tiles;
                 if (o.bi != 0 || o.bj != 0) {
@@ -253,7 +258,11 @@ __global__ void __launch_bounds__(128) ext_dp_kernel(SegArrays S, const PairDesc
                     on = !o.stopped;
                 }
             }
-            if (!on || ++done_tiles >= AN_MAXTILES) task = -1;
+            if (!on) ticket = -1;
+            else if (++done_tiles >= tiles_per_launch) {
+                list_out[atomicAdd(&counters[2], 1ull)] = task;
+                ticket = -1;
+            }
         }
     }
     for (int off = 16; off; off >>= 1) {

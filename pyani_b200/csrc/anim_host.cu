@@ -27,7 +27,7 @@ __global__ void segment_accum_kernel(ChainArrays);
 __global__ void segment_flag_kernel(ChainArrays, uint8_t *);
 __global__ void gap_dp_kernel(ChainArrays, const PairDesc *, const uint32_t *, int64_t, unsigned long long *);
 __global__ void segment_init_kernel(ChainArrays, const PairDesc *, const int *, SegArrays);
-__global__ void ext_dp_kernel(SegArrays, const PairDesc *, unsigned long long *);
+__global__ void ext_dp_kernel(SegArrays, const PairDesc *, const uint32_t *, long long, uint32_t *, int, unsigned long long *);
 __global__ void emit_rows_kernel(SegArrays, const PairDesc *, int *);
 __global__ void filt_key_kernel(FiltArrays, int, uint64_t *, int *);
 __global__ void filt_gather_kernel(FiltArrays, int, const int *);
@@ -40,9 +40,10 @@ static const char *kStageNames[B200ANI_N_STAGES] = {"index", "seed", "sort", "li
 static const char *kCounterNames[B200ANI_N_STAGES] = {"probes", "seed_hits", "anchors", "links", "cut_links", "segments", "gap_cells", "ext_cells",
                                                       "ext_tiles", "alignments", "launches", "gap_tasks", "pairs", "ext_dp_launches", "gap_dp_launches", "seed_launches"};
 
-constexpr int MAX_BATCH_PAIRS = 128;
-constexpr int64_t ANCHOR_CAP = 24ll << 20;
-constexpr int64_t HIT_CAP = 96ll << 20;  // seed hits of one batch (8 B each)
+constexpr int MAX_BATCH_PAIRS = 512;
+constexpr int64_t ANCHOR_CAP = 48ll << 20;
+constexpr int64_t HIT_CAP = 192ll << 20;
+constexpr int EXT_TILES_PER_LAUNCH = 8;  // seed hits of one batch (8 B each)
 
 struct AnimWorkspace {
     uint64_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr;
@@ -259,29 +260,38 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     DA(S.rs, n_seg); DA(S.qs, n_seg); DA(S.re, n_seg); DA(S.qe, n_seg);
     DA(S.r_lo, n_seg); DA(S.r_hi, n_seg); DA(S.q_lo, n_seg); DA(S.q_hi, n_seg);
     DA(S.score, n_seg); DA(S.errs, n_seg); DA(rows, 8 * n_seg);
+    uint32_t *ext_list[2] = {nullptr, nullptr};
+    DA(ext_list[0], 2 * n_seg); DA(ext_list[1], 2 * n_seg);
 
     if (n_seg) {
         T0(ST_EXTDP);
         segment_init_kernel<<<GRID(n_seg)>>>(A, W->d_pairs, seg_head, S);
         LAUNCHED(1);
-        {   // one persistent launch: resident warps pull (segment, side) tasks from a ticket counter
-            if (W->kev.size() < 2) {
-                cudaEvent_t a, b;
-                CK(cudaEventCreate(&a));
-                CK(cudaEventCreate(&b));
-                W->kev.push_back(a);
-                W->kev.push_back(b);
-            }
+        {   // persistent launches: resident warps pull (segment, side) tasks from a ticket counter; a task
+            // gets EXT_TILES_PER_LAUNCH tiles per launch, the still-extending ones go to the next launch
             int per_sm = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ext_dp_kernel, 128, 0));
-            int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * std::max(per_sm, 1), ceil_div(2 * n_seg, 128));
-            CK(cudaEventRecord(W->kev[0], st));
-            ext_dp_kernel<<<(unsigned)blocks, 128, 0, st>>>(S, W->d_pairs, W->counters + 6);
-            CK(cudaEventRecord(W->kev[1], st));
-            n_ext_launch = 1;
-            LAUNCHED(1);
-            CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+            long long n_cur = 2 * n_seg;
+            for (int round = 0; round * EXT_TILES_PER_LAUNCH < AN_MAXTILES && n_cur; ++round) {
+                CK(cudaMemsetAsync(W->counters + 8, 0, 2 * sizeof(unsigned long long), st));  // n_out, ticket
+                if ((size_t)(2 * n_ext_launch + 2) > W->kev.size()) {
+                    cudaEvent_t a, b;
+                    CK(cudaEventCreate(&a));
+                    CK(cudaEventCreate(&b));
+                    W->kev.push_back(a);
+                    W->kev.push_back(b);
+                }
+                int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * std::max(per_sm, 1), ceil_div(n_cur, 128));
+                CK(cudaEventRecord(W->kev[2 * n_ext_launch], st));
+                ext_dp_kernel<<<(unsigned)blocks, 128, 0, st>>>(S, W->d_pairs, round ? ext_list[round & 1] : nullptr, n_cur, ext_list[(round + 1) & 1],
+                                                               EXT_TILES_PER_LAUNCH, W->counters + 6);
+                CK(cudaEventRecord(W->kev[2 * n_ext_launch + 1], st));
+                ++n_ext_launch;
+                LAUNCHED(1);
+                CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                n_cur = (long long)hc[8];
+            }
         }
         emit_rows_kernel<<<GRID(n_seg)>>>(S, W->d_pairs, rows);
         LAUNCHED(1);
@@ -330,7 +340,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     DF(A.rc_of); DF(A.qc_of); DF(A.pred); DF(A.trim); DF(A.succ); DF(A.gval); DF(A.head); DF(A.chead); DF(A.cw); DF(A.wsum);
     DF(A.tail); DF(A.ssum); DF(A.esum); DF(A.strong); DF(task_key); DF(task_idx); DF(task_key2); DF(task_idx2); DF(seg_head);
     DF(S.pair); DF(S.strand); DF(S.head); DF(S.rc); DF(S.qc); DF(S.rs); DF(S.qs); DF(S.re); DF(S.qe);
-    DF(S.r_lo); DF(S.r_hi); DF(S.q_lo); DF(S.q_hi); DF(S.score); DF(S.errs); DF(rows);
+    DF(S.r_lo); DF(S.r_hi); DF(S.q_lo); DF(S.q_hi); DF(S.score); DF(S.errs); DF(rows); DF(ext_list[0]); DF(ext_list[1]);
     for (int a = 0; a < 2; ++a) { DF(F.sidx[a]); DF(F.slo[a]); DF(F.shi[a]); DF(F.sseq[a]); }
     DF(F.best); DF(F.from); DF(F.unit); DF(F.flag); DF(fkey); DF(fkey2); DF(fidx); DF(fidx2); DF(pair_start);
     CK(cudaStreamSynchronize(st));
