@@ -60,10 +60,29 @@ __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restr
     for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; g0 < n_probes; g0 += stride) {
         const int64_t gi = g0 + lane;
         bool hit = false;
-        uint32_t rpf = 0;
+        uint32_t rpf = 0, qpf = 0;
+        int pair = -1;
         if (gi < n_probes) {
-            const PairDesc &P = pairs[pair_of_probe(pairs, n_pairs, gi)];
-            hit = table_lookup(P.r_table, P.r_table_bits, __ldcs(P.q_kmer + (gi - P.probe_base)), rpf);
+            pair = pair_of_probe(pairs, n_pairs, gi);
+            const PairDesc &P = pairs[pair];
+            const int64_t t = gi - P.probe_base;
+            hit = table_lookup(P.r_table, P.r_table_bits, __ldcs(P.q_kmer + t), rpf);
+            if (hit) qpf = __ldcs(P.q_posflag + t);
+        }
+        // A hit whose neighbouring query minimizer (previous one on the forward strand, next one on the reverse
+        // strand) hits the same diagonal with overlapping / abutting k-mers lies in the same exact match: only
+        // the first seed of such a run is passed on (the match set is unchanged, see seed_extend_kernel).
+        {
+            const int strand = (int)((rpf ^ qpf) >> 31);
+            const int r0 = (int)(rpf & 0x7fffffffu), qp = (int)(qpf & 0x7fffffffu);
+            const int key = strand ? r0 + qp : r0 - qp;  // constant along a diagonal of that strand
+            const int nb = strand ? lane + 1 : lane - 1;
+            const bool nhit = __shfl_sync(0xffffffffu, (int)hit, nb & 31) != 0;
+            const int npair = __shfl_sync(0xffffffffu, pair, nb & 31);
+            const int nstrand = __shfl_sync(0xffffffffu, strand, nb & 31);
+            const int nkey = __shfl_sync(0xffffffffu, key, nb & 31);
+            const int nqp = __shfl_sync(0xffffffffu, qp, nb & 31);
+            if (hit && nb >= 0 && nb < 32 && nhit && npair == pair && nstrand == strand && nkey == key && abs(nqp - qp) <= AN_K) hit = false;
         }
         const uint32_t m = __ballot_sync(0xffffffffu, hit);
         if (m) {  // one atomic per warp

@@ -53,9 +53,9 @@ void b200ani_destroy(b200ani_ctx *ctx) {
 
 }  // extern "C"
 static void release_genome(Genome &g) {
-    cudaFree(g.d_seq);
-    cudaFree(g.d_mask);
-    cudaFree(g.d_goff);
+    cudaFreeAsync(g.d_seq, nullptr);
+    cudaFreeAsync(g.d_mask, nullptr);
+    cudaFreeAsync(g.d_goff, nullptr);
     free_index(g.index);
     g.index = nullptr;
 }
@@ -106,9 +106,9 @@ int b200ani_add_genome(b200ani_ctx *ctx, const uint8_t *ascii, const uint64_t *c
     g.h_goff.resize(n_contigs + 1);
     for (uint32_t c = 0; c <= n_contigs; ++c) g.h_goff[c] = contig_off[c] + c;
     uint8_t *d_ascii = nullptr;
-    CK(cudaMalloc(&g.d_seq, (size_t)g.n_pad / 4 + 64));
-    CK(cudaMalloc(&g.d_mask, (size_t)g.n_pad / 8 + 64));
-    CK(cudaMalloc(&g.d_goff, sizeof(uint64_t) * (n_contigs + 1)));
+    CK(cudaMallocAsync(&g.d_seq, (size_t)g.n_pad / 4 + 64, ctx->stream));  // stream-ordered pool: no device-wide sync
+    CK(cudaMallocAsync(&g.d_mask, (size_t)g.n_pad / 8 + 64, ctx->stream));
+    CK(cudaMallocAsync(&g.d_goff, sizeof(uint64_t) * (n_contigs + 1), ctx->stream));
     CK(cudaMemsetAsync(g.d_seq, 0, (size_t)g.n_pad / 4 + 64, ctx->stream));
     CK(cudaMemsetAsync(g.d_mask, 0xff, (size_t)g.n_pad / 8 + 64, ctx->stream));
     CK(cudaMallocAsync(&d_ascii, (size_t)n_bases + 64, ctx->stream));
