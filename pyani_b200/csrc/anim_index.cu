@@ -90,11 +90,11 @@ __global__ void split_bypos_kernel(const uint64_t *__restrict__ bypos, int64_t n
     posflag[i] = (uint32_t)(b >> 33) | ((uint32_t)((b >> 32) & 1) << 31);
 }
 
-void free_index(MinimizerIndex *ix) {
+void free_index(MinimizerIndex *ix, cudaStream_t st) {
     if (!ix) return;
-    cudaFreeAsync(ix->d_kmer, nullptr);
-    cudaFreeAsync(ix->d_posflag, nullptr);
-    cudaFreeAsync(ix->d_table, nullptr);
+    cudaFreeAsync(ix->d_kmer, st);
+    cudaFreeAsync(ix->d_posflag, st);
+    cudaFreeAsync(ix->d_table, st);
     delete ix;
 }
 

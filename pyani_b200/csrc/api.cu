@@ -6,7 +6,7 @@
 
 static const char *kVersion = "b200ani 0.1.0 (sm_100a)";
 
-static void release_genome(Genome &g);
+static void release_genome(Genome &g, cudaStream_t st);
 
 extern "C" {
 
@@ -45,18 +45,18 @@ void b200ani_destroy(b200ani_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto &g : ctx->genomes) release_genome(g);
+    for (auto &g : ctx->genomes) release_genome(g, ctx->stream);
     free_anim_workspace(ctx->anim_ws);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 }  // extern "C"
-static void release_genome(Genome &g) {
-    cudaFreeAsync(g.d_seq, nullptr);
-    cudaFreeAsync(g.d_mask, nullptr);
-    cudaFreeAsync(g.d_goff, nullptr);
-    free_index(g.index);
+static void release_genome(Genome &g, cudaStream_t st) {
+    cudaFreeAsync(g.d_seq, st);
+    cudaFreeAsync(g.d_mask, st);
+    cudaFreeAsync(g.d_goff, st);
+    free_index(g.index, st);
     g.index = nullptr;
 }
 extern "C" {
@@ -65,7 +65,7 @@ int b200ani_clear(b200ani_ctx *ctx) {
     if (!ctx) return B200ANI_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (auto &g : ctx->genomes) release_genome(g);
+    for (auto &g : ctx->genomes) release_genome(g, ctx->stream);
     ctx->genomes.clear();
     return B200ANI_OK;
 }
@@ -75,7 +75,7 @@ int b200ani_reset_indexes(b200ani_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     for (auto &g : ctx->genomes) {
-        free_index(g.index);
+        free_index(g.index, ctx->stream);
         g.index = nullptr;
     }
     return B200ANI_OK;

@@ -77,5 +77,5 @@ int launch_pack(b200ani_ctx *ctx, const uint8_t *d_ascii, const uint64_t *d_off,
 int tetra_counts_device(b200ani_ctx *ctx, const Genome &g, unsigned long long *d_tot /*336: c2|c3|c4*/);
 int tetra_zscores_device(b200ani_ctx *ctx, const unsigned long long *d_tot, int n, double *d_z, uint8_t *d_obs);
 int tetra_corr_device(b200ani_ctx *ctx, const double *d_z, const int *d_idx, int m, int n, double *d_corr);
-void free_index(MinimizerIndex *ix);
+void free_index(MinimizerIndex *ix, cudaStream_t st);
 void free_anim_workspace(void *ws);
