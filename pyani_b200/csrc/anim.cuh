@@ -8,6 +8,9 @@
 #include "common.cuh"
 
 struct MinimizerIndex {
+    bool valid = false;             // false after b200ani_reset_indexes: buffers are kept, content is rebuilt
+    int64_t cap_mini = 0;           // capacity of d_kmer / d_posflag
+    uint32_t cap_bits = 0;          // capacity of d_table = 2^cap_bits slots
     int64_t n_mini = 0;
     uint32_t *d_kmer = nullptr;     // unique canonical minimizers, sorted by position
     uint32_t *d_posflag = nullptr;  // position | orientation << 31

@@ -392,7 +392,7 @@ static int prepare(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmat
     for (int64_t i = 0; i < 2 * m; ++i) {
         Genome &g = ctx->genomes[pairs[i]];
         if (g.n_contigs >= 65535) FAIL(B200ANI_ERR_CAPACITY, "anim: genomes with >= 65535 records are not supported");
-        if (!g.index && !seen[pairs[i]]) { seen[pairs[i]] = 1; todo.push_back(&g); }
+        if (!index_valid(g.index) && !seen[pairs[i]]) { seen[pairs[i]] = 1; todo.push_back(&g); }
     }
     const bool any = !todo.empty();
     CK(cudaEventRecord(e0, st));

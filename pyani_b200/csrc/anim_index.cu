@@ -92,86 +92,133 @@ __global__ void split_bypos_kernel(const uint64_t *__restrict__ bypos, int64_t n
 
 void free_index(MinimizerIndex *ix, cudaStream_t st) {
     if (!ix) return;
-    cudaFreeAsync(ix->d_kmer, st);
-    cudaFreeAsync(ix->d_posflag, st);
-    cudaFreeAsync(ix->d_table, st);
+    (void)st;
+    cudaFree(ix->d_kmer);
+    cudaFree(ix->d_posflag);
+    cudaFree(ix->d_table);
     delete ix;
 }
+void invalidate_index(MinimizerIndex *ix) { if (ix) ix->valid = false; }
+bool index_valid(const MinimizerIndex *ix) { return ix && ix->valid; }
 
-// Build the indexes of many genomes with three host synchronisations in total (counts of selected and of
-// unique minimizers are needed on the host to size sorts and tables) instead of two per genome.
+// Build (or rebuild) the indexes of many genomes.  Scratch comes from one reusable workspace and the
+// index arrays of a genome are kept across rebuilds, so steady-state builds allocate nothing; genomes are
+// processed in chunks that fit the workspace with three host synchronisations per chunk (the counts of
+// selected and of unique minimizers are needed on the host to size the sorts and the table).
 int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo) {
-    const size_t G = todo.size();
-    if (!G) return 0;
+    if (todo.empty()) return 0;
     cudaStream_t st = ctx->stream;
-    struct Tmp { uint64_t *sel = nullptr, *sorted = nullptr, *uniq = nullptr; uint8_t *flag = nullptr; };
-    std::vector<Tmp> tmp(G);
-    unsigned long long *d_cnt = nullptr;  // [G] selected counts, then [G] unique counts (as int)
-    CK(cudaMallocAsync(&d_cnt, 2 * G * sizeof(unsigned long long), st));
-    CK(cudaMemsetAsync(d_cnt, 0, 2 * G * sizeof(unsigned long long), st));
-    int64_t max_n = 0;
-    for (size_t k = 0; k < G; ++k) {
-        Genome &g = *todo[k];
-        const int64_t n = g.n_pos;
-        max_n = std::max(max_n, n);
-        // about a third of the positions are selected; n/2 + slack bounds it (checked below)
-        CK(cudaMallocAsync(&tmp[k].sel, sizeof(uint64_t) * (size_t)(n + 1), st));
-        int blocks = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->sm_count * 16);
-        minimizer_select_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint64_t *>(g.d_seq), g.d_mask, n, tmp[k].sel, d_cnt + k);
-        CK(cudaGetLastError());
+    auto need = [](const Genome &g) { return (size_t)(g.n_pos + 64) * 25 + 4096; };  // sel + sorted + uniq (u64) + flag (u8)
+    size_t biggest = 0;
+    for (Genome *g : todo) biggest = std::max(biggest, need(*g));
+    size_t cub_bytes = 0, tb2 = 0;
+    {
+        int64_t max_n = 0;
+        for (Genome *g : todo) max_n = std::max(max_n, g->n_pos);
+        cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (uint64_t *)nullptr, (uint64_t *)nullptr, max_n, 0, 64, st);
+        cub::DeviceSelect::Flagged(nullptr, tb2, (uint64_t *)nullptr, (uint8_t *)nullptr, (uint64_t *)nullptr, (int *)nullptr, max_n, st);
+        cub_bytes = std::max(cub_bytes, tb2) + 256;
     }
-    std::vector<unsigned long long> h_cnt(2 * G);
-    CK(cudaMemcpyAsync(h_cnt.data(), d_cnt, G * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    size_t tmp_bytes = 0, tb2 = 0;
-    void *d_tmp = nullptr;
-    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, tmp[0].sel, tmp[0].sel, (int64_t)max_n, 0, 64, st);
-    cub::DeviceSelect::Flagged(nullptr, tb2, tmp[0].sel, (uint8_t *)nullptr, tmp[0].sel, (int *)d_cnt, (int64_t)max_n, st);
-    tmp_bytes = std::max(tmp_bytes, tb2);
-    CK(cudaMallocAsync(&d_tmp, tmp_bytes + 16, st));
-    for (size_t k = 0; k < G; ++k) {
-        const int64_t ns = (int64_t)h_cnt[k];
-        CK(cudaMallocAsync(&tmp[k].sorted, sizeof(uint64_t) * (size_t)(ns + 1), st));
-        CK(cudaMallocAsync(&tmp[k].uniq, sizeof(uint64_t) * (size_t)(ns + 1), st));
-        CK(cudaMallocAsync(&tmp[k].flag, (size_t)ns + 1, st));
-        size_t tb = tmp_bytes;
-        cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, ns, 0, 64, st);
-        if (ns) mark_unique_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(tmp[k].sorted, ns, tmp[k].flag);
-        CK(cudaGetLastError());
-        tb = tmp_bytes;
-        cub::DeviceSelect::Flagged(d_tmp, tb, tmp[k].sorted, tmp[k].flag, tmp[k].uniq, (int *)(d_cnt + G + k), ns, st);
+    const size_t want = std::max<size_t>(biggest + cub_bytes + 65536, (size_t)1536 << 20);
+    if (ctx->index_ws_bytes < biggest + cub_bytes + 65536) {
+        CK(cudaStreamSynchronize(st));
+        if (ctx->index_ws) CK(cudaFree(ctx->index_ws));
+        ctx->index_ws = nullptr;
+        CK(cudaMalloc(&ctx->index_ws, want));
+        ctx->index_ws_bytes = want;
     }
-    CK(cudaMemcpyAsync(h_cnt.data() + G, d_cnt + G, G * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    for (size_t k = 0; k < G; ++k) {
-        Genome &g = *todo[k];
-        const int h_nu = (int)(h_cnt[G + k] & 0xffffffffu);
-        MinimizerIndex *ix = new MinimizerIndex();
-        ix->n_mini = h_nu;
-        uint32_t bits = 4;
-        while ((1ll << bits) < 2ll * h_nu) ++bits;
-        ix->table_bits = bits;
-        CK(cudaMallocAsync(&ix->d_table, sizeof(uint64_t) << bits, st));
-        CK(cudaMallocAsync(&ix->d_kmer, sizeof(uint32_t) * (size_t)(h_nu + 1), st));
-        CK(cudaMallocAsync(&ix->d_posflag, sizeof(uint32_t) * (size_t)(h_nu + 1), st));
-        CK(cudaMemsetAsync(ix->d_table, 0xff, sizeof(uint64_t) << bits, st));
-        if (h_nu) {
-            table_insert_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, st>>>(tmp[k].uniq, h_nu, ix->d_table, bits, tmp[k].sel);
-            CK(cudaGetLastError());
-            size_t tb = tmp_bytes;
-            cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, h_nu, 33, 64, st);
-            split_bypos_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, st>>>(tmp[k].sorted, h_nu, ix->d_kmer, ix->d_posflag);
+    char *base = (char *)ctx->index_ws;
+    const size_t G_all = todo.size();
+    size_t done = 0;
+    while (done < G_all) {
+        // ---- chunk [done, end): carve the workspace
+        struct Tmp { uint64_t *sel, *sorted, *uniq; uint8_t *flag; };
+        std::vector<Tmp> tmp;
+        size_t off = 0, end = done;
+        unsigned long long *d_cnt = (unsigned long long *)base;  // [2 * 256] counters
+        off = 4096;
+        void *d_tmp = base + off;
+        off += (cub_bytes + 255) & ~(size_t)255;
+        while (end < G_all && tmp.size() < 256) {
+            const size_t n = (size_t)todo[end]->n_pos + 64;
+            const size_t bytes = ((n * 25 + 4096) + 255) & ~(size_t)255;
+            if (off + bytes > ctx->index_ws_bytes) break;
+            Tmp t;
+            t.sel = (uint64_t *)(base + off);
+            t.sorted = t.sel + n;
+            t.uniq = t.sorted + n;
+            t.flag = (uint8_t *)(t.uniq + n);
+            tmp.push_back(t);
+            off += bytes;
+            ++end;
+        }
+        const size_t G = end - done;
+        if (G == 0) FAIL(B200ANI_ERR_NOMEM, "index workspace too small");
+        CK(cudaMemsetAsync(d_cnt, 0, 2 * 256 * sizeof(unsigned long long), st));
+        for (size_t k = 0; k < G; ++k) {
+            Genome &g = *todo[done + k];
+            const int64_t n = g.n_pos;
+            int blocks = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->sm_count * 16);
+            minimizer_select_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint64_t *>(g.d_seq), g.d_mask, n, tmp[k].sel, d_cnt + k);
             CK(cudaGetLastError());
         }
-        ctx->counters[CT_LAUNCHES] += 4;
-        CK(cudaFreeAsync(tmp[k].sel, st));
-        CK(cudaFreeAsync(tmp[k].sorted, st));
-        CK(cudaFreeAsync(tmp[k].uniq, st));
-        CK(cudaFreeAsync(tmp[k].flag, st));
-        g.index = ix;
+        unsigned long long h_cnt[512];
+        CK(cudaMemcpyAsync(h_cnt, d_cnt, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (size_t k = 0; k < G; ++k) {
+            const int64_t ns = (int64_t)h_cnt[k];
+            size_t tb = cub_bytes;
+            cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, ns, 0, 64, st);
+            if (ns) mark_unique_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(tmp[k].sorted, ns, tmp[k].flag);
+            CK(cudaGetLastError());
+            tb = cub_bytes;
+            cub::DeviceSelect::Flagged(d_tmp, tb, tmp[k].sorted, tmp[k].flag, tmp[k].uniq, (int *)(d_cnt + 256 + k), ns, st);
+        }
+        CK(cudaMemcpyAsync(h_cnt + 256, d_cnt + 256, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (size_t k = 0; k < G; ++k) {
+            Genome &g = *todo[done + k];
+            const int h_nu = (int)(h_cnt[256 + k] & 0xffffffffu);
+            uint32_t bits = 4;
+            while ((1ll << bits) < 2ll * h_nu) ++bits;
+            if (!g.index) {  // prefer the buffers of a released genome that are large enough
+                for (size_t x = 0; x < ctx->spare_indexes.size(); ++x) {
+                    MinimizerIndex *sp = ctx->spare_indexes[x];
+                    if (sp->cap_bits >= bits && sp->cap_mini >= h_nu + 1) {
+                        g.index = sp;
+                        ctx->spare_indexes.erase(ctx->spare_indexes.begin() + x);
+                        break;
+                    }
+                }
+            }
+            MinimizerIndex *ix = g.index ? g.index : new MinimizerIndex();
+            g.index = ix;
+            ix->n_mini = h_nu;
+            ix->table_bits = bits;
+            if (ix->cap_bits < bits || ix->cap_mini < h_nu + 1) {  // first build (or a bigger genome): allocate once
+                CK(cudaStreamSynchronize(st));
+                cudaFree(ix->d_table); cudaFree(ix->d_kmer); cudaFree(ix->d_posflag);
+                ix->d_table = nullptr; ix->d_kmer = nullptr; ix->d_posflag = nullptr;
+                CK(cudaMalloc(&ix->d_table, sizeof(uint64_t) << bits));
+                CK(cudaMalloc(&ix->d_kmer, sizeof(uint32_t) * (size_t)(h_nu + 1)));
+                CK(cudaMalloc(&ix->d_posflag, sizeof(uint32_t) * (size_t)(h_nu + 1)));
+                ix->cap_bits = bits;
+                ix->cap_mini = h_nu + 1;
+            }
+            CK(cudaMemsetAsync(ix->d_table, 0xff, sizeof(uint64_t) << bits, st));
+            if (h_nu) {
+                table_insert_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, st>>>(tmp[k].uniq, h_nu, ix->d_table, bits, tmp[k].sel);
+                CK(cudaGetLastError());
+                size_t tb = cub_bytes;
+                cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, h_nu, 33, 64, st);
+                split_bypos_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, st>>>(tmp[k].sorted, h_nu, ix->d_kmer, ix->d_posflag);
+                CK(cudaGetLastError());
+            }
+            ctx->counters[CT_LAUNCHES] += 4;
+            ix->valid = true;
+        }
+        CK(cudaStreamSynchronize(st));  // the workspace is reused by the next chunk
+        done = end;
     }
-    CK(cudaFreeAsync(d_cnt, st));
-    CK(cudaFreeAsync(d_tmp, st));
-    CK(cudaStreamSynchronize(st));
     return 0;
 }

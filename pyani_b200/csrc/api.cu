@@ -6,7 +6,7 @@
 
 static const char *kVersion = "b200ani 0.1.0 (sm_100a)";
 
-static void release_genome(Genome &g, cudaStream_t st);
+static void release_genome(b200ani_ctx *ctx, Genome &g, cudaStream_t st);
 
 extern "C" {
 
@@ -45,18 +45,23 @@ void b200ani_destroy(b200ani_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto &g : ctx->genomes) release_genome(g, ctx->stream);
+    for (auto &g : ctx->genomes) release_genome(ctx, g, ctx->stream);
+    for (auto *ix : ctx->spare_indexes) free_index(ix, ctx->stream);
     free_anim_workspace(ctx->anim_ws);
+    cudaFree(ctx->index_ws);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 }  // extern "C"
-static void release_genome(Genome &g, cudaStream_t st) {
+static void release_genome(b200ani_ctx *ctx, Genome &g, cudaStream_t st) {
     cudaFreeAsync(g.d_seq, st);
     cudaFreeAsync(g.d_mask, st);
     cudaFreeAsync(g.d_goff, st);
-    free_index(g.index, st);
+    if (g.index) {  // keep the buffers for the next genome of similar size
+        invalidate_index(g.index);
+        ctx->spare_indexes.push_back(g.index);
+    }
     g.index = nullptr;
 }
 extern "C" {
@@ -65,7 +70,7 @@ int b200ani_clear(b200ani_ctx *ctx) {
     if (!ctx) return B200ANI_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (auto &g : ctx->genomes) release_genome(g, ctx->stream);
+    for (auto &g : ctx->genomes) release_genome(ctx, g, ctx->stream);
     ctx->genomes.clear();
     return B200ANI_OK;
 }
@@ -74,10 +79,7 @@ int b200ani_reset_indexes(b200ani_ctx *ctx) {
     if (!ctx) return B200ANI_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (auto &g : ctx->genomes) {
-        free_index(g.index, ctx->stream);
-        g.index = nullptr;
-    }
+    for (auto &g : ctx->genomes) invalidate_index(g.index);  // buffers stay, content is rebuilt on demand
     return B200ANI_OK;
 }
 

@@ -43,6 +43,9 @@ struct b200ani_ctx {
     double stage_ms[B200ANI_N_STAGES] = {0};
     int64_t counters[B200ANI_N_STAGES] = {0};
     void *anim_ws = nullptr;  // AnimWorkspace (anim_host.cu), reused between calls
+    std::vector<MinimizerIndex *> spare_indexes;  // index buffers of released genomes, reused by later builds
+    void *index_ws = nullptr;      // scratch of build_indexes (anim_index.cu), grown on demand, reused
+    size_t index_ws_bytes = 0;
 };
 
 #define CK(call)                                                                                     \
@@ -78,4 +81,6 @@ int tetra_counts_device(b200ani_ctx *ctx, const Genome &g, unsigned long long *d
 int tetra_zscores_device(b200ani_ctx *ctx, const unsigned long long *d_tot, int n, double *d_z, uint8_t *d_obs);
 int tetra_corr_device(b200ani_ctx *ctx, const double *d_z, const int *d_idx, int m, int n, double *d_corr);
 void free_index(MinimizerIndex *ix, cudaStream_t st);
+void invalidate_index(MinimizerIndex *ix);
+bool index_valid(const MinimizerIndex *ix);
 void free_anim_workspace(void *ws);
