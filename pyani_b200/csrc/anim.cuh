@@ -15,6 +15,7 @@ struct MinimizerIndex {
     uint32_t *d_kmer = nullptr;     // unique canonical minimizers, sorted by position
     uint32_t *d_posflag = nullptr;  // position | orientation << 31
     uint64_t *d_table = nullptr;    // open addressing, slot = kmer << 32 | posflag, empty = ~0
+    uint32_t *d_bitmap = nullptr;   // presence filter, 2^(table_bits+3) bits: answers most misses from L2
     uint32_t table_bits = 0;
 };
 
@@ -24,12 +25,13 @@ struct PairDesc {
     const uint32_t *r_mask, *q_mask;  // 1 bit per base
     const uint64_t *r_goff, *q_goff;  // record starts in g-space
     const uint64_t *r_table;
+    const uint32_t *r_bitmap;         // presence filter of the reference's table (8 bits per slot)
     const uint32_t *q_kmer, *q_posflag;
     int64_t q_nmini;
     int64_t probe_base;  // offset of this pair's probes in the flattened probe index
     int32_t r_npos, q_npos;
     uint32_t r_ncontigs, q_ncontigs, r_table_bits;
-    int32_t pad;
+    int32_t mirror;  // index (in the batch) of the opposite-direction pair fed from this pair's seeds, or -1
 };
 
 __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
@@ -38,6 +40,13 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
 }
 // table addressing must be independent of the selection hash (minimizers are the k-mers with small fmix32)
 __device__ __forceinline__ uint32_t table_hash(uint32_t kmer) { return fmix32(kmer ^ 0x5bd1e995u); }
+
+// presence filter: one bit per key at a hash independent of both the selection and the table hash
+__device__ __forceinline__ uint32_t bitmap_hash(uint32_t kmer, uint32_t table_bits) { return fmix32(kmer ^ 0x9e3779b9u) >> (32 - (table_bits + 3)); }
+__device__ __forceinline__ bool bitmap_test(const uint32_t *__restrict__ bm, uint32_t table_bits, uint32_t kmer) {
+    const uint32_t h = bitmap_hash(kmer, table_bits);
+    return (__ldg(bm + (h >> 5)) >> (h & 31)) & 1u;
+}
 
 __device__ __forceinline__ bool table_lookup(const uint64_t *__restrict__ table, uint32_t bits, uint32_t kmer, uint32_t &posflag) {
     const uint32_t msk = (1u << bits) - 1u;

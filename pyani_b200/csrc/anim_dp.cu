@@ -66,8 +66,16 @@ struct BaseStream {
 // Base b (0-based) of the reference is at view position r0 + rstep*b; likewise for the query.
 // Registers hold Hg[kk] = H - go (so E and F updates are single viaddmax ops on it) and F[kk]; the
 // match/mismatch constants carry the +go back (d = Hg_diag + s + go).
+// a + c issued on the FMA pipe (IMAD a*one+c with a run-time `one` = 1 the compiler cannot fold): the
+// recurrences' plain additions move off the ALU pipe, which the max-plus (DPX) instructions saturate.
+__device__ __forceinline__ int add_fma(int a, int c, int one) {
+    int d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(c));
+    return d;
+}
+
 template <int MODE>
-__device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rstep, const SeqView &Q, int64_t q0, int qstep, int lr, int lq, int klo) {
+__device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rstep, const SeqView &Q, int64_t q0, int qstep, int lr, int lq, int klo, int one) {
     constexpr int go = AN_GAPOPEN * AN_PACK + 1, ge = AN_GAPEXT * AN_PACK + 1;
     constexpr int smg = AN_MATCH * AN_PACK + go, sxg = -(AN_MISMATCH * AN_PACK + 1) + go;
     // extension tiles are short: values stay within +-2^24, which leaves 5 low bits for the column tag
@@ -115,12 +123,12 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
                 const uint32_t bit = (kk < 16 ? mlo : mhi) & (1u << ((2 * kk) & 31));
                 int e = __viaddmax_s32(eleft, -ge, hgleft);
                 int f = kk + 1 < AN_BANDW ? __viaddmax_s32(F[kk + 1], -ge, Hg[kk + 1]) : NEGV;
-                int h = __vimax3_s32(Hg[kk] + (bit ? sxg : smg), e, f);
-                Hg[kk] = h - go;
+                int h = __vimax3_s32(bit ? add_fma(Hg[kk], sxg, one) : add_fma(Hg[kk], smg, one), e, f);
+                hgleft = add_fma(h, -go, one);
+                Hg[kk] = hgleft;
                 F[kk] = f;
-                hgleft = h - go;
                 eleft = e;
-                rowkey = MODE ? max(rowkey, (h << 5) | (31 - kk)) : max(rowkey, h);
+                rowkey = MODE ? max(rowkey, add_fma(h, 31 - kk, one << 5)) : max(rowkey, h);
             }
         } else {
 #pragma unroll
@@ -128,12 +136,12 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
                 const uint32_t bit = (kk < 16 ? mlo : mhi) & (1u << ((2 * kk) & 31));
                 int e = __viaddmax_s32(eleft, -ge, hgleft);
                 int f = kk + 1 < AN_BANDW ? __viaddmax_s32(F[kk + 1], -ge, Hg[kk + 1]) : NEGV;
-                int h = __vimax3_s32(Hg[kk] + (bit ? sxg : smg), e, f);
-                Hg[kk] = h - go;
+                int h = __vimax3_s32(bit ? add_fma(Hg[kk], sxg, one) : add_fma(Hg[kk], smg, one), e, f);
+                hgleft = add_fma(h, -go, one);
+                Hg[kk] = hgleft;
                 F[kk] = f;
-                hgleft = h - go;
                 eleft = e;
-                if (kk <= kkhi) rowkey = MODE ? max(rowkey, (h << 5) | (31 - kk)) : max(rowkey, h);
+                if (kk <= kkhi) rowkey = MODE ? max(rowkey, add_fma(h, 31 - kk, one << 5)) : max(rowkey, h);
             }
         }
         if (MODE) {
@@ -167,7 +175,7 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
 // Link alignments.  Tasks arrive sorted by row count (descending) so the 32 lanes of a warp run
 // similar-length loops.  A link whose alignment gives up (break rule) is cut.
 __global__ void __launch_bounds__(128) gap_dp_kernel(ChainArrays A, const PairDesc *__restrict__ pairs, const uint32_t *__restrict__ task_idx, int64_t n_tasks,
-                                                     unsigned long long *__restrict__ counters /*0: cells, 1: cuts*/) {
+                                                     unsigned long long *__restrict__ counters /*0: cells, 1: cuts*/, int one) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     long long cells = 0;
     int cut = 0;
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(128) gap_dp_kernel(ChainArrays A, const PairDe
         const PairDesc &P = pairs[key_pair(k)];
         SeqView R{P.r_seq, P.r_mask, P.r_npos, 0}, Q{P.q_seq, P.q_mask, P.q_npos, key_strand(k)};
         int d = lq - lr, c = d >= 0 ? d / 2 : -((-d) / 2);
-        DpResult o = dp_band<0>(R, rej, 1, Q, qej, 1, lr, lq, c - AN_BAND);
+        DpResult o = dp_band<0>(R, rej, 1, Q, qej, 1, lr, lq, c - AN_BAND, one);
         cells = o.cells;
         if (o.stopped) { A.pred[i] = -1; A.trim[i] = 0; A.gval[i] = 0; cut = 1; }
         else A.gval[i] = o.val;
@@ -223,7 +231,7 @@ __global__ void segment_init_kernel(ChainArrays A, const PairDesc *__restrict__ 
 // task id = 2 * segment + side (0 = left, 1 = right).
 __global__ void __launch_bounds__(128) ext_dp_kernel(SegArrays S, const PairDesc *__restrict__ pairs, const uint32_t *__restrict__ list_in, long long n_tasks,
                                                      uint32_t *__restrict__ list_out, int tiles_per_launch,
-                                                     unsigned long long *__restrict__ counters /*0: cells, 1: tiles, 2: n_out, 3: ticket*/) {
+                                                     unsigned long long *__restrict__ counters /*0: cells, 1: tiles, 2: n_out, 3: ticket*/, int one) {
     long long ticket = -1, cells = 0;
     uint32_t task = 0;
     int tiles = 0, done_tiles = 0;
@@ -248,7 +256,7 @@ __global__ void __launch_bounds__(128) ext_dp_kernel(SegArrays S, const PairDesc
             if (lr > 0 && lq > 0) {
                 // one call site for both directions: the two sides differ only in start position and step
                 const int step = side ? 1 : -1;
-                DpResult o = dp_band<1>(R, side ? (int64_t)re : (int64_t)rs - 1, step, Q, side ? (int64_t)qe : (int64_t)qs - 1, step, lr, lq, -AN_BAND);
+                DpResult o = dp_band<1>(R, side ? (int64_t)re : (int64_t)rs - 1, step, Q, side ? (int64_t)qe : (int64_t)qs - 1, step, lr, lq, -AN_BAND, one);
                 cells += o.cells;
                 ++tiles;
                 if (o.bi != 0 || o.bj != 0) {

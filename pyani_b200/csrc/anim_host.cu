@@ -25,9 +25,9 @@ __global__ void label_jump_kernel(ChainArrays, int *);
 __global__ void cluster_weight_kernel(ChainArrays);
 __global__ void segment_accum_kernel(ChainArrays);
 __global__ void segment_flag_kernel(ChainArrays, uint8_t *);
-__global__ void gap_dp_kernel(ChainArrays, const PairDesc *, const uint32_t *, int64_t, unsigned long long *);
+__global__ void gap_dp_kernel(ChainArrays, const PairDesc *, const uint32_t *, int64_t, unsigned long long *, int);
 __global__ void segment_init_kernel(ChainArrays, const PairDesc *, const int *, SegArrays);
-__global__ void ext_dp_kernel(SegArrays, const PairDesc *, const uint32_t *, long long, uint32_t *, int, unsigned long long *);
+__global__ void ext_dp_kernel(SegArrays, const PairDesc *, const uint32_t *, long long, uint32_t *, int, unsigned long long *, int);
 __global__ void emit_rows_kernel(SegArrays, const PairDesc *, int *);
 __global__ void filt_key_kernel(FiltArrays, int, uint64_t *, int *);
 __global__ void filt_gather_kernel(FiltArrays, int, const int *);
@@ -126,13 +126,18 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         d.r_seq = (const uint64_t *)R.d_seq; d.q_seq = (const uint64_t *)Q.d_seq;
         d.r_mask = R.d_mask; d.q_mask = Q.d_mask;
         d.r_goff = R.d_goff; d.q_goff = Q.d_goff;
-        d.r_table = R.index->d_table; d.r_table_bits = R.index->table_bits;
+        d.r_table = R.index->d_table; d.r_table_bits = R.index->table_bits; d.r_bitmap = R.index->d_bitmap;
         d.q_kmer = Q.index->d_kmer; d.q_posflag = Q.index->d_posflag; d.q_nmini = Q.index->n_mini;
         d.probe_base = n_probes;
         d.r_npos = (int32_t)R.n_pos; d.q_npos = (int32_t)Q.n_pos;
         d.r_ncontigs = R.n_contigs; d.q_ncontigs = Q.n_contigs;
-        d.pad = 0;
-        n_probes += Q.index->n_mini;
+        // run_range puts the two directions of a genome pair next to each other: the first one probes and
+        // feeds both, the second one contributes no probes
+        const bool second = p > 0 && pairs[2 * p] == pairs[2 * p - 1] && pairs[2 * p + 1] == pairs[2 * p - 2] && hp[p - 1].mirror == p;
+        const bool first = !second && p + 1 < nb && pairs[2 * p + 2] == pairs[2 * p + 1] && pairs[2 * p + 3] == pairs[2 * p] &&
+                           pairs[2 * p] != pairs[2 * p + 1];
+        d.mirror = first ? p + 1 : -1;
+        if (!second) n_probes += Q.index->n_mini;
     }
     CK(cudaMemcpyAsync(W->d_pairs, hp.data(), sizeof(PairDesc) * nb, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(W->counters, 0, 16 * sizeof(unsigned long long), st));
@@ -216,7 +221,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
             size_t tb = W->cub_bytes;
             cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb, task_key, task_key2, task_idx, task_idx2, n_tasks, 0, 11, st);
             T0(ST_GAPDP);  // exactly the kernel: this is the roofline's launch duration
-            gap_dp_kernel<<<(unsigned)ceil_div(n_tasks, 128), 128, 0, st>>>(A, W->d_pairs, task_idx2, n_tasks, W->counters + 4);
+            gap_dp_kernel<<<(unsigned)ceil_div(n_tasks, 128), 128, 0, st>>>(A, W->d_pairs, task_idx2, n_tasks, W->counters + 4, 1);
             LAUNCHED(1);
             T1(ST_GAPDP);
             ctx->counters[CT_GAPLAUNCH] += 1;
@@ -284,7 +289,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
                 int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * std::max(per_sm, 1), ceil_div(n_cur, 128));
                 CK(cudaEventRecord(W->kev[2 * n_ext_launch], st));
                 ext_dp_kernel<<<(unsigned)blocks, 128, 0, st>>>(S, W->d_pairs, round ? ext_list[round & 1] : nullptr, n_cur, ext_list[(round + 1) & 1],
-                                                               EXT_TILES_PER_LAUNCH, W->counters + 6);
+                                                               EXT_TILES_PER_LAUNCH, W->counters + 6, 1);
                 CK(cudaEventRecord(W->kev[2 * n_ext_launch + 1], st));
                 ++n_ext_launch;
                 LAUNCHED(1);
@@ -362,18 +367,40 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     return 0;
 }
 
-static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int64_t m, int nofilter, b200ani_anim_result *out, RowDump *dump) {
+static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs_in, int64_t m, int nofilter, b200ani_anim_result *out_user, RowDump *dump) {
+    // Internal order: the two directions of a genome pair adjacent (one probe pass seeds both), genome pairs
+    // sorted by (min id, max id) so the probed reference table stays hot in L2.  Results go back in caller order.
+    std::vector<int64_t> order(m);
+    for (int64_t i = 0; i < m; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int64_t x, int64_t y) {
+        const int32_t ax = pairs_in[2 * x], bx = pairs_in[2 * x + 1], ay = pairs_in[2 * y], by = pairs_in[2 * y + 1];
+        const int32_t lx = std::min(ax, bx), hx = std::max(ax, bx), ly = std::min(ay, by), hy = std::max(ay, by);
+        if (lx != ly) return lx < ly;
+        if (hx != hy) return hx < hy;
+        if (ax != ay) return ax < ay;  // (lo,hi) before (hi,lo)
+        return x < y;
+    });
+    std::vector<int32_t> pairs(2 * m);
+    for (int64_t i = 0; i < m; ++i) { pairs[2 * i] = pairs_in[2 * order[i]]; pairs[2 * i + 1] = pairs_in[2 * order[i] + 1]; }
+    std::vector<b200ani_anim_result> out(m);
+    auto splits_mirror = [&](int64_t b0, int nb) {  // would a batch [b0, b0+nb) cut a (a,b),(b,a) couple in two?
+        const int64_t e = b0 + nb;
+        return e < m && e - 1 >= b0 && pairs[2 * e] == pairs[2 * e - 1] && pairs[2 * e + 1] == pairs[2 * e - 2] &&
+               !(e - 2 >= b0 && pairs[2 * (e - 1)] == pairs[2 * (e - 2) + 1] && pairs[2 * (e - 1) + 1] == pairs[2 * (e - 2)]);
+    };
     for (int64_t b0 = 0; b0 < m;) {
         int nb = (int)std::min<int64_t>(MAX_BATCH_PAIRS, m - b0);
         while (true) {
-            int rc = run_batch(ctx, W, pairs + 2 * b0, nb, nofilter, out + b0, dump);
+            if (nb > 1 && splits_mirror(b0, nb)) --nb;
+            int rc = run_batch(ctx, W, pairs.data() + 2 * b0, nb, nofilter, out.data() + b0, dump);
             if (rc == 0) break;
             if (rc < 0) return rc;
             if (nb == 1) FAIL(B200ANI_ERR_CAPACITY, "anim: a single pair exceeds the anchor capacity");
-            nb = (nb + 1) / 2;  // anchor buffer overflow: retry with half the pairs
+            nb = (nb + 1) / 2;  // buffer overflow: retry with half the pairs
         }
         b0 += nb;
     }
+    for (int64_t i = 0; i < m; ++i) out_user[order[i]] = out[i];
     return 0;
 }
 

@@ -70,13 +70,15 @@ __global__ void mark_unique_kernel(const uint64_t *__restrict__ sorted, int64_t 
     flag[i] = u;
 }
 
-__global__ void table_insert_kernel(const uint64_t *__restrict__ uniq, int64_t n, uint64_t *table, uint32_t bits, uint64_t *__restrict__ bypos) {
+__global__ void table_insert_kernel(const uint64_t *__restrict__ uniq, int64_t n, uint64_t *table, uint32_t *bitmap, uint32_t bits, uint64_t *__restrict__ bypos) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t e = uniq[i];
     uint32_t k = (uint32_t)(e >> 32), msk = (1u << bits) - 1u;
     uint32_t s = table_hash(k) >> (32 - bits);
     while (atomicCAS((unsigned long long *)&table[s], ~0ull, (unsigned long long)e) != ~0ull) s = (s + 1) & msk;
+    const uint32_t bh = bitmap_hash(k, bits);
+    atomicOr(&bitmap[bh >> 5], 1u << (bh & 31));
     // key for the by-position order: pos << 33 | orient << 32 | kmer
     uint32_t pf = (uint32_t)e;
     bypos[i] = ((uint64_t)(pf & 0x7fffffffu) << 33) | ((uint64_t)(pf >> 31) << 32) | k;
@@ -96,6 +98,7 @@ void free_index(MinimizerIndex *ix, cudaStream_t st) {
     cudaFree(ix->d_kmer);
     cudaFree(ix->d_posflag);
     cudaFree(ix->d_table);
+    cudaFree(ix->d_bitmap);
     delete ix;
 }
 void invalidate_index(MinimizerIndex *ix) { if (ix) ix->valid = false; }
@@ -197,17 +200,19 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo) {
             ix->table_bits = bits;
             if (ix->cap_bits < bits || ix->cap_mini < h_nu + 1) {  // first build (or a bigger genome): allocate once
                 CK(cudaStreamSynchronize(st));
-                cudaFree(ix->d_table); cudaFree(ix->d_kmer); cudaFree(ix->d_posflag);
-                ix->d_table = nullptr; ix->d_kmer = nullptr; ix->d_posflag = nullptr;
+                cudaFree(ix->d_table); cudaFree(ix->d_kmer); cudaFree(ix->d_posflag); cudaFree(ix->d_bitmap);
+                ix->d_table = nullptr; ix->d_kmer = nullptr; ix->d_posflag = nullptr; ix->d_bitmap = nullptr;
                 CK(cudaMalloc(&ix->d_table, sizeof(uint64_t) << bits));
+                CK(cudaMalloc(&ix->d_bitmap, sizeof(uint32_t) << (bits + 3 - 5)));
                 CK(cudaMalloc(&ix->d_kmer, sizeof(uint32_t) * (size_t)(h_nu + 1)));
                 CK(cudaMalloc(&ix->d_posflag, sizeof(uint32_t) * (size_t)(h_nu + 1)));
                 ix->cap_bits = bits;
                 ix->cap_mini = h_nu + 1;
             }
             CK(cudaMemsetAsync(ix->d_table, 0xff, sizeof(uint64_t) << bits, st));
+            CK(cudaMemsetAsync(ix->d_bitmap, 0, sizeof(uint32_t) << (bits + 3 - 5), st));
             if (h_nu) {
-                table_insert_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, st>>>(tmp[k].uniq, h_nu, ix->d_table, bits, tmp[k].sel);
+                table_insert_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, st>>>(tmp[k].uniq, h_nu, ix->d_table, ix->d_bitmap, bits, tmp[k].sel);
                 CK(cudaGetLastError());
                 size_t tb = cub_bytes;
                 cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, h_nu, 33, 64, st);
