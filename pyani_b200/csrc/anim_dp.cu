@@ -174,7 +174,7 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
 
 // Link alignments.  Tasks arrive sorted by row count (descending) so the 32 lanes of a warp run
 // similar-length loops.  A link whose alignment gives up (break rule) is cut.
-__global__ void __launch_bounds__(128) gap_dp_kernel(ChainArrays A, const PairDesc *__restrict__ pairs, const uint32_t *__restrict__ task_idx, int64_t n_tasks,
+__global__ void __launch_bounds__(128, 4) gap_dp_kernel(ChainArrays A, const PairDesc *__restrict__ pairs, const uint32_t *__restrict__ task_idx, int64_t n_tasks,
                                                      unsigned long long *__restrict__ counters /*0: cells, 1: cuts*/, int one) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     long long cells = 0;
@@ -229,7 +229,7 @@ __global__ void segment_init_kernel(ChainArrays A, const PairDesc *__restrict__ 
 // `tiles_per_launch` tiles per launch; tasks that still extend are appended to `list_out` and continue in
 // the next launch, which bounds the tail a few long crawls (up to AN_MAXTILES tiles) would otherwise add.
 // task id = 2 * segment + side (0 = left, 1 = right).
-__global__ void __launch_bounds__(128) ext_dp_kernel(SegArrays S, const PairDesc *__restrict__ pairs, const uint32_t *__restrict__ list_in, long long n_tasks,
+__global__ void __launch_bounds__(128, 4) ext_dp_kernel(SegArrays S, const PairDesc *__restrict__ pairs, const uint32_t *__restrict__ list_in, long long n_tasks,
                                                      uint32_t *__restrict__ list_out, int tiles_per_launch,
                                                      unsigned long long *__restrict__ counters /*0: cells, 1: tiles, 2: n_out, 3: ticket*/, int one) {
     long long ticket = -1, cells = 0;
