@@ -92,6 +92,32 @@ int b200ani_anim(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch
 int64_t b200ani_anim_alignments(b200ani_ctx *ctx, int32_t ref_id, int32_t qry_id, int maxmatch, int nofilter,
                                 int64_t *rows, int64_t cap);
 
+/* ---- ANIb (anib.py) ---- */
+/* One directed comparison: the 1020-nt fragments of the query genome against the subject genome.
+ * Fields are what anib.parse_blast_tab returns (anib.py:661-667), kept as exact integers:
+ *   mean_pid (percent) = pid_milli_sum / n_pass / 1000, pid of a fragment = round(100*nident/length, 3) like
+ *   BLAST's 3-decimal pident column; identity = 0.01 * mean_pid; coverage = aln_length / query genome length
+ *   (anib.process_blast, anib.py:556-563). */
+typedef struct {
+    int64_t aln_length;     /* sum of ani_alnlen = length - gaps of the kept HSPs (anib.py:664) */
+    int64_t sim_errs;       /* sum of mismatch + gaps (anib.py:665) */
+    int64_t pid_milli_sum;  /* sum over kept fragments of round(1e5 * nident / length) */
+    int32_t n_frags;        /* fragments of the query genome (anib.fragment_fasta_files, anib.py:164-203) */
+    int32_t n_pass;         /* fragments with an HSP passing coverage > 0.7 and identity > 0.3 (anib.py:646) */
+    int32_t n_hsps;         /* candidate HSPs examined */
+    int32_t status;         /* B200ANI_STATUS_* */
+} b200ani_anib_result;      /* 40 bytes */
+
+/* All m directed pairs (pairs[2*i] = QUERY genome id whose fragments are aligned, pairs[2*i+1] = SUBJECT id).
+ * Replaces, per pair, makeblastdb + blastn (anib.py:378-391,451-471) and anib.parse_blast_tab (anib.py:569-667).
+ * fragsize: pyani_config.FRAGSIZE = 1020. */
+int b200ani_anib(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fragsize, b200ani_anib_result *out);
+
+/* Kept HSP of every passing fragment of ONE pair, rows of 8 int64: fragment index (0-based, file order of
+ * anib.fragment_fasta_files), length, mismatch, gaps, nident, qlen, score, round(1e5*nident/length).  Returns the
+ * number of rows (<= cap written) or a negative error. */
+int64_t b200ani_anib_fragments(b200ani_ctx *ctx, int32_t qry_id, int32_t sbj_id, int fragsize, int64_t *rows, int64_t cap);
+
 /* Stage timers of the last b200ani_anim call in milliseconds (CUDA events on the engine stream) and
  * the number of kernel launches it issued; used by bench.py for the roofline and gpu_launches. */
 #define B200ANI_N_STAGES 16

@@ -216,3 +216,45 @@ def anim_pair(R: OGenome, Q: OGenome, nofilter: bool = False):
     res = dict(ref_aln_len=int(out[0]), qry_aln_len=int(out[1]), sum_aligned=int(out[2]), sum_weighted=int(out[3]),
                sim_errs=int(out[4]), n_alignments=int(len(a)), status=0 if len(a) else 1)
     return res, kept, stats
+
+
+# ----------------------------------------------------------------------------- ANIb reduction (anib.py:569-667)
+def parse_blast_tab_reduce(rows: np.ndarray):
+    """(aln_length, sim_errors, mean_pid) exactly as anib.parse_blast_tab(mode="ANIb").
+
+    rows: one row per BLAST HSP in file order: (fragment number, blast_alnlen, blast_mismatch, blast_pid, qlen,
+    blast_gaps) -- columns 1,3,4,5,7,15 of the reference's outfmt (anib.py:468-469).
+    Restates anib.py:641-665: ani_alnlen = alnlen - gaps; ani_alnids = ani_alnlen - mismatch;
+    keep rows with ani_alnlen/qlen > 0.7 and ani_alnids/qlen > 0.3 (strict); first kept row per fragment in
+    file order; mean of their blast_pid (0 if none, anib.py:661-663), sums of ani_alnlen and of mismatch+gaps."""
+    rows = np.asarray(rows, dtype=np.float64).reshape(-1, 6)
+    frag, alnlen, mism, pid, qlen, gaps = (rows[:, i] for i in range(6))
+    ani_alnlen = alnlen - gaps
+    ani_alnids = ani_alnlen - mism
+    keep = (ani_alnlen / qlen > 0.7) & (ani_alnids / qlen > 0.3)
+    idx = np.flatnonzero(keep)
+    _, first = np.unique(frag[idx], return_index=True)  # groupby(index).first(): groups sorted by fragment id
+    sel = idx[first]
+    if len(sel) == 0:
+        return 0, 0, 0.0
+    mean_pid = float(np.mean(pid[sel]))  # pandas' mean == numpy pairwise summation over the selected rows
+    return int(ani_alnlen[sel].sum()), int((mism[sel] + gaps[sel]).sum()), mean_pid
+
+
+# ----------------------------------------------------------------------------- ANIb aligner (oracle_anim.c)
+def anib_pair(Q: OGenome, S: OGenome, fragsize: int = 1020, cap: int = 1 << 15):
+    """Fragments of Q against S: -> (result dict, per-fragment rows (n,8), stats).
+
+    result: aln_length, sim_errs, pid_milli_sum, n_frags, n_pass, n_hsps; mean_pid (percent) = pid_milli_sum / n_pass / 1000
+    rows: frag, length, mismatch, gaps, nident, qlen, score, pid_milli  (one row per fragment that passes anib.py:646)"""
+    L = lib()
+    L.orc_anib_pair.restype = ctypes.c_int64
+    L.orc_anib_pair.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    out = np.zeros(6, dtype=np.int64)
+    rows = np.zeros((cap, 8), dtype=np.int64)
+    stats = np.zeros(ANIM_NSTATS, dtype=np.int64)
+    n = L.orc_anib_pair(Q._h, S._h, int(fragsize), out.ctypes.data, rows.ctypes.data, cap, stats.ctypes.data)
+    assert n <= cap
+    res = dict(aln_length=int(out[0]), sim_errs=int(out[1]), pid_milli_sum=int(out[2]), n_frags=int(out[3]), n_pass=int(out[4]),
+               n_hsps=int(out[5]), status=0 if out[4] else 1)
+    return res, rows[:n].copy(), dict(zip(ANIM_STAT_NAMES, stats.tolist()))

@@ -31,6 +31,11 @@
 #define AN_CLUSTGAP 90   /* anchors closer than this on both genomes form a cluster (mgaps -s 90) */
 #define AN_FILT_OLAP 75  /* delta-filter -o 75: max overlap % of either alignment in a kept chain */
 #define AN_FILT_POW 2    /* alignment weight = length * identity^POW */
+#define AB_MATCH 2       /* ANIb-equivalent scoring: blastn reward 2 ... */
+#define AB_MISMATCH 3    /* ... penalty -3 ... */
+#define AB_GAP 5         /* ... and 5 per gap column (linear; blastn: 5 + 2 per column) */
+#define AB_MINPIECE 11   /* shortest anchor piece kept after clipping to a fragment (blastn word size) */
+#define AB_FRAGSIZE 1020 /* pyani_config.FRAGSIZE (pyani_config.py:95) */
 #define AN_PACK 4096     /* DP value = score*PACK - errs */
 #define AN_NEG (-(1 << 29))
 

@@ -196,10 +196,14 @@ static uint32_t contig_of(const uint64_t *goff, uint32_t n, int64_t pos) {
  * mode 1: extension tile over at most lr rows and lq columns; returns the best cell in bi,bj. */
 typedef struct { int32_t val, bi, bj, stopped; int64_t cells; } dp_out;
 
-static dp_out dp_band(const uint8_t *R, int rstride, const uint8_t *Q, int qstride, int lr, int lq, int klo, int mode) {
+/* scoring model: {match, mismatch, first gap column, further gap columns} */
+static const int SC_ANIM[4] = {AN_MATCH, AN_MISMATCH, AN_GAPOPEN, AN_GAPEXT};
+static const int SC_ANIB[4] = {AB_MATCH, AB_MISMATCH, AB_GAP, AB_GAP};
+
+static dp_out dp_band_sc(const uint8_t *R, int rstride, const uint8_t *Q, int qstride, int lr, int lq, int klo, int mode, const int *sc) {
     enum { BW = AN_BANDW };
-    const int32_t go = AN_GAPOPEN * AN_PACK + 1, ge = AN_GAPEXT * AN_PACK + 1;
-    const int32_t sm = AN_MATCH * AN_PACK, sx = -(AN_MISMATCH * AN_PACK + 1);
+    const int32_t go = sc[2] * AN_PACK + 1, ge = sc[3] * AN_PACK + 1;
+    const int32_t sm = sc[0] * AN_PACK, sx = -(sc[1] * AN_PACK + 1);
     int32_t Hp[BW + 2], Fp[BW + 2], Hc[BW + 2], Ec[BW + 2], Fc[BW + 2];
     dp_out o = {0, 0, 0, 0, 0};
     for (int kk = 0; kk < BW; ++kk) { /* row 0 */
@@ -252,6 +256,10 @@ static dp_out dp_band(const uint8_t *R, int rstride, const uint8_t *Q, int qstri
     } else
         o.val = best;
     return o;
+}
+
+static dp_out dp_band(const uint8_t *R, int rstride, const uint8_t *Q, int qstride, int lr, int lq, int klo, int mode) {
+    return dp_band_sc(R, rstride, Q, qstride, lr, lq, klo, mode, SC_ANIM);
 }
 
 /* value = score*PACK - errs with 0 <= errs < PACK  ->  score = ceil(value / PACK) */
@@ -512,4 +520,210 @@ void orc_filter_1to1(const int64_t *rows /* n x 8 */, int64_t n, uint8_t *keep) 
     filt_axis(rows, n, 1, flag);
     for (int64_t i = 0; i < n; ++i) keep[i] = flag[i] == 3;
     free(flag);
+}
+
+
+/* ================================================================== ANIb-equivalent aligner ("b200-blastn")
+ * Stands in for `blastn -task blastn` of every 1020-nt fragment of the query genome against the subject
+ * genome (anib.py:164-203,451-471; BLAST+ is an external binary, unpinned, absent here -- SURVEY.md 8c) and
+ * for anib.parse_blast_tab's per-fragment filter (anib.py:641-665).  PARITY vs BLAST+: unpinned; checked
+ * on the reference's fixture genomes against its checked-in BLAST+ results within the reference's own ANIb
+ * tolerance (tests/test_concordance.py:118-153).
+ *
+ * Same machinery as the ANIm aligner with the subject as "reference" (table side):
+ *   anchors are clipped to the query's fragments (pieces >= AB_MINPIECE kept), linking / link alignment /
+ *   extension never leave the fragment, every chain is a candidate HSP; scoring +2 / -3 / 5 per gap column
+ *   (linear, so the gap columns follow from score, errors and consumed bases: G = L - 5E - score);
+ *   per fragment the best-scoring HSP with ani_alnlen/qlen > 0.7 and ani_alnids/qlen > 0.3 is kept.
+ * out[6]: aln_length (sum ani_alnlen), sim_errs (sum mismatch+gaps), pid_milli_sum (sum of round(1e5*nident/length)),
+ *         n_frags, n_pass, n_hsps.   frag_rows (optional, cap_rows x 8): frag, length, mismatch, gaps, nident, qlen, score, pid_milli */
+typedef struct { int32_t frag, strand, r, q, len; } fanchor;
+static int cmp_fanchor(const void *a, const void *b) {
+    const fanchor *x = (const fanchor *)a, *y = (const fanchor *)b;
+    if (x->frag != y->frag) return x->frag < y->frag ? -1 : 1;
+    if (x->strand != y->strand) return x->strand - y->strand;
+    if (x->r != y->r) return x->r < y->r ? -1 : 1;
+    if (x->q != y->q) return x->q < y->q ? -1 : 1;
+    return x->len - y->len;
+}
+
+int64_t orc_anib_pair(const orc_genome *Q, const orc_genome *S, int fragsize, int64_t *out, int64_t *frag_rows, int64_t cap_rows, int64_t *stats) {
+    memset(stats, 0, sizeof(int64_t) * ORC_NSTATS);
+    memset(out, 0, sizeof(int64_t) * 6);
+    const orc_genome *R = S; /* the subject plays nucmer's reference role: its table is probed */
+    /* fragment table of the query: record c holds ceil(len/fragsize) fragments, ids are global */
+    uint32_t *fbase = (uint32_t *)malloc(sizeof(uint32_t) * (Q->n_contigs + 1));
+    fbase[0] = 0;
+    for (uint32_t c = 0; c < Q->n_contigs; ++c) {
+        int64_t L = (int64_t)(Q->goff[c + 1] - Q->goff[c]) - 1;
+        fbase[c + 1] = fbase[c] + (uint32_t)((L + fragsize - 1) / fragsize);
+    }
+    const int64_t n_frags = fbase[Q->n_contigs];
+    out[3] = n_frags;
+    /* ---- seeds -> exact matches -> pieces clipped to fragments */
+    int64_t acap = 1 << 16, na = 0;
+    fanchor *A = (fanchor *)malloc(sizeof(fanchor) * (size_t)acap);
+    int64_t last_d[2] = {0, 0}, last_r0[2] = {-1, -1}, last_r1[2] = {-1, -1};
+    for (int64_t t = 0; t < Q->n_mini; ++t) {
+        uint32_t rpf;
+        if (!lookup(R, Q->mini_kmer[t], &rpf)) continue;
+        stats[7]++;
+        uint32_t qpf = Q->mini_posflag[t];
+        int strand = (int)((rpf ^ qpf) >> 31);
+        int64_t r0 = rpf & 0x7fffffffu, qpos = qpf & 0x7fffffffu;
+        int64_t q0 = strand ? Q->n_pos - AN_K - qpos : qpos;
+        const uint8_t *Qs = strand ? Q->rc : Q->fw;
+        if (r0 - q0 == last_d[strand] && r0 >= last_r0[strand] && r0 + AN_K <= last_r1[strand]) continue;
+        int64_t l = 0, rr = 0;
+        while (r0 - l - 1 >= 0 && q0 - l - 1 >= 0 && R->fw[r0 - l - 1] < 4 && R->fw[r0 - l - 1] == Qs[q0 - l - 1]) ++l;
+        while (r0 + AN_K + rr < R->n_pos && q0 + AN_K + rr < Q->n_pos && R->fw[r0 + AN_K + rr] < 4 &&
+               R->fw[r0 + AN_K + rr] == Qs[q0 + AN_K + rr]) ++rr;
+        int64_t len = AN_K + l + rr, rs = r0 - l, qs = q0 - l;
+        last_d[strand] = r0 - q0; last_r0[strand] = rs; last_r1[strand] = rs + len;
+        if (len < AN_MINLEN) continue;
+        /* forward query interval of the match and the record it lies in */
+        int64_t fa = strand ? Q->n_pos - qs - len : qs, fb = fa + len;
+        uint32_t c = contig_of(Q->goff, Q->n_contigs, fa);
+        int64_t rec0 = (int64_t)Q->goff[c];
+        for (int64_t k = (fa - rec0) / fragsize; rec0 + k * fragsize < fb; ++k) {
+            int64_t a = rec0 + k * fragsize, b = a + fragsize; /* fragment [a,b) (the last one of a record is shorter) */
+            if (a < fa) a = fa;
+            if (b > fb) b = fb;
+            if (b - a < AB_MINPIECE) continue;
+            int64_t t0 = strand ? (Q->n_pos - b) - qs : a - qs; /* offset of the piece inside the match */
+            if (na == acap) { acap *= 2; A = (fanchor *)realloc(A, sizeof(fanchor) * (size_t)acap); }
+            A[na].frag = (int32_t)(fbase[c] + k); A[na].strand = strand;
+            A[na].r = (int32_t)(rs + t0); A[na].q = (int32_t)(qs + t0); A[na].len = (int32_t)(b - a);
+            ++na;
+        }
+    }
+    qsort(A, (size_t)na, sizeof(fanchor), cmp_fanchor);
+    int64_t nu = 0;
+    for (int64_t i = 0; i < na; ++i)
+        if (i == 0 || cmp_fanchor(&A[i], &A[i - 1]) != 0) A[nu++] = A[i];
+    na = nu;
+    stats[0] = na;
+    int32_t *pred = (int32_t *)malloc(sizeof(int32_t) * (size_t)(na + 1));
+    int32_t *succ = (int32_t *)malloc(sizeof(int32_t) * (size_t)(na + 1));
+    int32_t *trim = (int32_t *)calloc((size_t)(na + 1), sizeof(int32_t));
+    int32_t *gval = (int32_t *)calloc((size_t)(na + 1), sizeof(int32_t));
+    int32_t *head = (int32_t *)malloc(sizeof(int32_t) * (size_t)(na + 1));
+    int32_t *tail = (int32_t *)malloc(sizeof(int32_t) * (size_t)(na + 1));
+    uint32_t *rc_of = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(na + 1));
+    int64_t *wsum = (int64_t *)calloc((size_t)(na + 1), sizeof(int64_t));
+    int64_t *ssum = (int64_t *)calloc((size_t)(na + 1), sizeof(int64_t));
+    int64_t *esum = (int64_t *)calloc((size_t)(na + 1), sizeof(int64_t));
+    for (int64_t i = 0; i < na; ++i) { rc_of[i] = contig_of(R->goff, R->n_contigs, A[i].r); pred[i] = -1; succ[i] = 0x7fffffff; }
+    for (int64_t i = 0; i < na; ++i) {
+        for (int64_t j = i - 1; j >= 0 && j >= i - AN_LOOKBACK; --j) {
+            if (A[j].frag != A[i].frag || A[j].strand != A[i].strand) break;
+            if (rc_of[j] != rc_of[i]) continue;
+            int64_t rej = (int64_t)A[j].r + A[j].len, qej = (int64_t)A[j].q + A[j].len, ov = 0;
+            if (rej - A[i].r > ov) ov = rej - A[i].r;
+            if (qej - A[i].q > ov) ov = qej - A[i].q;
+            if (ov >= A[i].len) continue;
+            int64_t gr = A[i].r + ov - rej, gq = A[i].q + ov - qej;
+            if (gr > AN_GAPMAX || gq > AN_GAPMAX) continue;
+            int64_t dd = gq - gr;
+            if (dd > AN_DMAX || dd < -AN_DMAX) continue;
+            pred[i] = (int32_t)j; trim[i] = (int32_t)ov;
+            break;
+        }
+    }
+    for (int64_t i = 0; i < na; ++i)
+        if (pred[i] >= 0 && succ[pred[i]] > (int32_t)i) succ[pred[i]] = (int32_t)i;
+    for (int64_t i = 0; i < na; ++i)
+        if (pred[i] >= 0 && succ[pred[i]] != (int32_t)i) { pred[i] = -1; trim[i] = 0; }
+    for (int64_t i = 0; i < na; ++i) {
+        if (pred[i] < 0) continue;
+        stats[1]++;
+        const fanchor *a = &A[pred[i]], *b = &A[i];
+        int64_t rej = (int64_t)a->r + a->len, qej = (int64_t)a->q + a->len;
+        int lr = (int)(b->r + trim[i] - rej), lq = (int)(b->q + trim[i] - qej);
+        int32_t v;
+        if (lr == 0 && lq == 0) v = 0;
+        else if (lr == 0 || lq == 0) {
+            int L = lr + lq;
+            v = -((AB_GAP + (L - 1) * AB_GAP) * AN_PACK + L);
+        } else {
+            int d = lq - lr, c = d >= 0 ? d / 2 : -((-d) / 2);
+            const uint8_t *Qs = b->strand ? Q->rc : Q->fw;
+            dp_out o = dp_band_sc(R->fw + rej, 1, Qs + qej, 1, lr, lq, c - AN_BAND, 0, SC_ANIB);
+            v = o.val;
+            stats[4] += o.cells;
+            if (o.stopped) { pred[i] = -1; trim[i] = 0; v = 0; stats[2]++; }
+        }
+        gval[i] = v;
+    }
+    for (int64_t i = 0; i < na; ++i) {
+        head[i] = pred[i] < 0 ? (int32_t)i : head[pred[i]];
+        int32_t h = head[i];
+        wsum[h] += A[i].len - trim[i];
+        ssum[h] += pack_score(gval[i]);
+        esum[h] += pack_errs(gval[i]);
+        tail[h] = (int32_t)i;
+    }
+    /* ---- every chain is a candidate HSP: extend inside the fragment, score, filter, best per fragment */
+    int64_t best_frag = -1, best_score = 0, best_row[8] = {0}, n_rows = 0;
+    for (int64_t h = 0; h <= na; ++h) {
+        int is_seg = h < na && head[h] == (int32_t)h;
+        if (h == na || (is_seg && A[h].frag != best_frag)) { /* close the previous fragment */
+            if (best_frag >= 0 && best_score > 0) {
+                out[0] += best_row[4] + best_row[2]; /* ani_alnlen = nident + mismatch */
+                out[1] += best_row[2] + best_row[3];
+                out[2] += best_row[7];
+                out[4] += 1;
+                if (frag_rows && n_rows < cap_rows) memcpy(frag_rows + 8 * n_rows, best_row, sizeof best_row);
+                ++n_rows;
+            }
+            best_score = 0;
+            best_frag = h < na ? A[h].frag : -1;
+        }
+        if (!is_seg) continue;
+        stats[3]++;
+        out[5] += 1;
+        const fanchor *f = &A[h], *l = &A[tail[h]];
+        const uint8_t *Qs = f->strand ? Q->rc : Q->fw;
+        uint32_t rc = rc_of[h];
+        int64_t r_lo = (int64_t)R->goff[rc], r_hi = (int64_t)R->goff[rc + 1] - 1;
+        /* fragment bounds: forward [fa,fb) -> view */
+        uint32_t qc = 0;
+        while (fbase[qc + 1] <= (uint32_t)f->frag) ++qc;
+        int64_t rec0 = (int64_t)Q->goff[qc], recL = (int64_t)(Q->goff[qc + 1] - Q->goff[qc]) - 1;
+        int64_t fa = rec0 + (int64_t)(f->frag - fbase[qc]) * fragsize, fb = fa + fragsize;
+        if (fb > rec0 + recL) fb = rec0 + recL;
+        int64_t qlen = fb - fa;
+        int64_t q_lo = f->strand ? Q->n_pos - fb : fa, q_hi = f->strand ? Q->n_pos - fa : fb;
+        int64_t rs = f->r, qs = f->q, re = (int64_t)l->r + l->len, qe = (int64_t)l->q + l->len;
+        int64_t score = ssum[h] + wsum[h] * AB_MATCH, errs = esum[h];
+        for (int side = 0; side < 2; ++side) {
+            for (int t = 0; t < AN_MAXTILES; ++t) {
+                int64_t ar = side ? r_hi - re : rs - r_lo, aq = side ? q_hi - qe : qs - q_lo;
+                int lr = (int)(ar < AN_TILE ? ar : AN_TILE), lq = (int)(aq < AN_TILE + AN_BAND ? aq : AN_TILE + AN_BAND);
+                if (lr <= 0 || lq <= 0) break;
+                dp_out o = side ? dp_band_sc(R->fw + re, 1, Qs + qe, 1, lr, lq, -AN_BAND, 1, SC_ANIB)
+                                : dp_band_sc(R->fw + rs - 1, -1, Qs + qs - 1, -1, lr, lq, -AN_BAND, 1, SC_ANIB);
+                stats[5] += o.cells; stats[6]++;
+                if (o.bi == 0 && o.bj == 0) break;
+                score += pack_score(o.val);
+                errs += pack_errs(o.val);
+                if (side) { re += o.bi; qe += o.bj; } else { rs -= o.bi; qs -= o.bj; }
+                if (o.stopped) break;
+            }
+        }
+        /* columns: L = consumed bases, G = L - 5E - score, X = E - G, M = (L - G)/2 - X */
+        int64_t L = (re - rs) + (qe - qs);
+        int64_t G = L - 5 * errs - score; /* score = L - 5E - G for (+2, -3, 5 per gap column) */
+        int64_t X = errs - G, M = (L - G) / 2 - X, length = M + X + G;
+        if (G < 0 || X < 0 || M < 0 || length <= 0) continue; /* cannot happen with the fixed scoring; guards the division */
+        if (!(10 * (M + X) > 7 * qlen && 10 * M > 3 * qlen)) continue; /* anib.py:646, strict */
+        if (score > best_score) {
+            best_score = score;
+            best_row[0] = f->frag; best_row[1] = length; best_row[2] = X; best_row[3] = G; best_row[4] = M;
+            best_row[5] = qlen; best_row[6] = score; best_row[7] = (100000 * M + length / 2) / length;
+        }
+    }
+    free(A); free(pred); free(succ); free(trim); free(gval); free(head); free(tail); free(rc_of);
+    free(wsum); free(ssum); free(esum); free(fbase);
+    return n_rows;
 }

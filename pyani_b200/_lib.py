@@ -23,6 +23,20 @@ class AnimResult(C.Structure):
     ]
 
 
+class AnibResult(C.Structure):
+    """struct b200ani_anib_result (40 bytes), fields = anib.parse_blast_tab's return kept exact."""
+
+    _fields_ = [
+        ("aln_length", C.c_int64),
+        ("sim_errs", C.c_int64),
+        ("pid_milli_sum", C.c_int64),
+        ("n_frags", C.c_int32),
+        ("n_pass", C.c_int32),
+        ("n_hsps", C.c_int32),
+        ("status", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); tests check every symbol of include/b200ani.h is listed and exported
 SIGNATURES = {
     "b200ani_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
@@ -40,6 +54,8 @@ SIGNATURES = {
     "b200ani_tetra_corr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200ani_anim": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "b200ani_anim_alignments": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int, C.c_int, C.c_void_p, C.c_int64]),
+    "b200ani_anib": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "b200ani_anib_fragments": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int, C.c_void_p, C.c_int64]),
     "b200ani_last_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200ani_stage_name": (C.c_char_p, [C.c_int]),
 }

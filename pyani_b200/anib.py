@@ -1,0 +1,86 @@
+"""ANIb on the B200 engine behind the reference's interfaces for the path (pyani/anib.py).
+
+* :func:`get_fraglength_dict` / :func:`fragment_lengths` -- what ``anib.fragment_fasta_files`` /
+  ``get_fraglength_dict`` (anib.py:164-232) produce, without writing fragment FASTA files: the engine fragments
+  by index arithmetic on the staged genome (1020-nt pieces per record, trailing short piece kept, ``frag%05d``
+  numbered across records from 1).
+* :func:`parse_result` -- the 3-tuple of ``anib.parse_blast_tab`` (anib.py:667) from one result struct.
+* :func:`calculate_anib` / :func:`fill_aniresults` -- ``anib.process_blast`` (anib.py:496-565): lengths, identity
+  (= 0.01 * mean_pid) and coverage (= aln_length / query genome length) fill the ``[query, subject]`` cell only;
+  similarity errors are written symmetrically (anib.py:562).
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .anim import ANIResults
+from .engine import Engine
+
+FRAGSIZE = 1020  # pyani_config.FRAGSIZE (pyani_config.py:95)
+
+
+def fragment_lengths(record_lengths: Sequence[int], fragsize: int = FRAGSIZE) -> Dict[str, int]:
+    """{fragment id: length} exactly as anib.fragment_fasta_files numbers and cuts them (anib.py:192-200)."""
+    out, idx = {}, 0
+    for L in record_lengths:
+        pos = 0
+        while pos < L:
+            idx += 1
+            out["frag%05d" % idx] = min(fragsize, L - pos)
+            pos += fragsize
+    return out
+
+
+def get_fraglength_dict(fastafiles: Sequence[Path], fragsize: int = FRAGSIZE) -> Dict[str, Dict[str, int]]:
+    """anib.get_fraglength_dict (anib.py:207-221) for original (unfragmented) FASTA files."""
+    from .fasta import read_fasta
+
+    out = {}
+    for f in fastafiles:
+        _, off, _ = read_fasta(f)
+        out[Path(f).stem] = fragment_lengths(np.diff(off.astype(np.int64)).tolist(), fragsize)
+    return out
+
+
+def parse_result(res) -> Tuple[int, int, float]:
+    """``(aln_length, sim_errors, mean_pid)`` as anib.parse_blast_tab (anib.py:661-667); (0, 0, 0) if nothing passes."""
+    n = int(res["n_pass"])
+    mean_pid = (int(res["pid_milli_sum"]) / n / 1000.0) if n else 0.0
+    return int(res["aln_length"]), int(res["sim_errs"]), mean_pid
+
+
+def fill_aniresults(org_lengths: Dict[str, int], tuples: Dict[Tuple[str, str], Tuple[int, int, float]], mode: str = "ANIb") -> ANIResults:
+    """anib.process_blast (anib.py:496-565) given the per-file 3-tuples instead of .blast_tab files."""
+    results = ANIResults(list(org_lengths.keys()), mode)
+    for org, length in org_lengths.items():
+        results.alignment_lengths.loc[org, org] = length
+    # files are visited in sorted(<q>_vs_<s>.blast_tab) order (pyani_files.get_input_files, pyani_files.py:124);
+    # add_sim_errors is called with its default sym=True (anib.py:562), so that table is symmetric and the later
+    # file wins, while lengths, identity and coverage only fill the [query, subject] cell
+    for (qname, sname) in sorted(tuples, key=lambda k: f"{k[0]}_vs_{k[1]}.blast_tab"):
+        if qname not in org_lengths or sname not in org_lengths:
+            continue
+        aln, errs, pid = tuples[(qname, sname)]
+        results.add_tot_length(qname, sname, aln)
+        results.add_sim_errors(qname, sname, errs)
+        results.add_pid(qname, sname, 0.01 * pid)
+        results.add_coverage(qname, sname, float(aln) / org_lengths[qname])
+    return results
+
+
+def calculate_anib(infiles: Sequence[Path], org_lengths: Optional[Dict[str, int]] = None, engine: Optional[Engine] = None,
+                   fragsize: int = FRAGSIZE) -> ANIResults:
+    """All directed comparisons between ``infiles`` on the GPU -> ANIResults (unified_anib semantics,
+    average_nucleotide_identity.py:694-760)."""
+    eng = engine or Engine(0)
+    files = sorted(Path(f) for f in infiles)
+    gids = {f.stem: eng.add_fasta(f) for f in files}
+    stems = [f.stem for f in files]
+    if org_lengths is None:
+        org_lengths = {s: eng.genome_length(gids[s]) for s in stems}
+    pairs = [(a, b) for a in stems for b in stems if a != b]
+    res = eng.anib(np.array([[gids[a], gids[b]] for a, b in pairs], dtype=np.int32), fragsize=fragsize)
+    return fill_aniresults(org_lengths, {p: parse_result(r) for p, r in zip(pairs, res)})

@@ -32,6 +32,10 @@ struct PairDesc {
     int32_t r_npos, q_npos;
     uint32_t r_ncontigs, q_ncontigs, r_table_bits;
     int32_t mirror;  // index (in the batch) of the opposite-direction pair fed from this pair's seeds, or -1
+    // ANIb only: fragments of the query genome (record c holds fragments q_fbase[c] .. q_fbase[c+1]-1)
+    const uint32_t *q_fbase;
+    int32_t fragsize;  // 0 = ANIm (no fragments)
+    uint32_t q_nfrags;
 };
 
 __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
@@ -105,12 +109,22 @@ __device__ __forceinline__ uint32_t contig_of(const uint64_t *__restrict__ goff,
     return lo;
 }
 
+// scoring models: 0 = ANIm (nucmer-like), 1 = ANIb (blastn-like, linear gaps)
+template <int MODEL> struct Scoring;
+template <> struct Scoring<0> { static constexpr int match = AN_MATCH, mismatch = AN_MISMATCH, gapopen = AN_GAPOPEN, gapext = AN_GAPEXT; };
+template <> struct Scoring<1> { static constexpr int match = AB_MATCH, mismatch = AB_MISMATCH, gapopen = AB_GAP, gapext = AB_GAP; };
+
 __device__ __forceinline__ int pack_score(int v) { return (v + AN_PACK - 1) >> 12; }
 __device__ __forceinline__ int pack_errs(int v) { return pack_score(v) * AN_PACK - v; }
 
 // anchor key/value encoding (sorted by key, ties by value)
-//   key = pair_local << 32 | strand << 31 | r      val = q << 32 | len
-__device__ __forceinline__ uint32_t key_pair(uint64_t k) { return (uint32_t)(k >> 32); }
+//   key = pair_local << 46 | fragment << 32 | strand << 31 | r      val = q << 32 | len      (fragment = 0 for ANIm)
+constexpr int KEY_PAIR_SHIFT = 46;
+__device__ __forceinline__ uint64_t make_key(int pair, uint32_t frag, int strand, int64_t r) {
+    return ((uint64_t)pair << KEY_PAIR_SHIFT) | ((uint64_t)frag << 32) | ((uint64_t)strand << 31) | (uint64_t)r;
+}
+__device__ __forceinline__ uint32_t key_pair(uint64_t k) { return (uint32_t)(k >> KEY_PAIR_SHIFT); }
+__device__ __forceinline__ uint32_t key_frag(uint64_t k) { return (uint32_t)(k >> 32) & 0x3fffu; }
 __device__ __forceinline__ int key_strand(uint64_t k) { return (int)((k >> 31) & 1); }
 __device__ __forceinline__ int key_r(uint64_t k) { return (int)(k & 0x7fffffffu); }
 __device__ __forceinline__ int val_q(uint64_t v) { return (int)(v >> 32); }

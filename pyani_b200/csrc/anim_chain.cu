@@ -56,7 +56,8 @@ __global__ void link_validate_kernel(ChainArrays A, unsigned long long *__restri
 }
 
 // trivial links are scored here; the others become DP tasks (sort key = rows, descending)
-__global__ void gap_task_kernel(ChainArrays A, uint32_t *__restrict__ task_key, uint32_t *__restrict__ task_idx, unsigned long long *__restrict__ n_tasks) {
+__global__ void gap_task_kernel(ChainArrays A, uint32_t *__restrict__ task_key, uint32_t *__restrict__ task_idx, unsigned long long *__restrict__ n_tasks,
+                                int gapopen, int gapext) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n || A.pred[i] < 0) return;
     int64_t rej, qej;
@@ -65,7 +66,7 @@ __global__ void gap_task_kernel(ChainArrays A, uint32_t *__restrict__ task_key, 
     if (lr == 0 && lq == 0) { A.gval[i] = 0; return; }
     if (lr == 0 || lq == 0) {
         int L = lr + lq;
-        A.gval[i] = -((AN_GAPOPEN + (L - 1) * AN_GAPEXT) * AN_PACK + L);
+        A.gval[i] = -((gapopen + (L - 1) * gapext) * AN_PACK + L);
         return;
     }
     unsigned long long s = atomicAdd(n_tasks, 1ull);
@@ -105,11 +106,11 @@ __global__ void cluster_weight_kernel(ChainArrays A) {
     atomicAdd(&A.cw[A.chead[i]], val_len(A.vals[i]) - A.trim[i]);
 }
 
-__global__ void segment_accum_kernel(ChainArrays A) {
+__global__ void segment_accum_kernel(ChainArrays A, int min_cluster) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n) return;
     int h = A.head[i];
-    if (A.cw[A.chead[i]] >= AN_MINCLUSTER) A.strong[h] = 1;
+    if (A.cw[A.chead[i]] >= min_cluster) A.strong[h] = 1;
     atomicAdd(&A.wsum[h], val_len(A.vals[i]) - A.trim[i]);
     int g = A.gval[i];
     if (g != 0) {

@@ -74,10 +74,11 @@ __device__ __forceinline__ int add_fma(int a, int c, int one) {
     return d;
 }
 
-template <int MODE>
+template <int MODE, int MODEL>
 __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rstep, const SeqView &Q, int64_t q0, int qstep, int lr, int lq, int klo, int one) {
-    constexpr int go = AN_GAPOPEN * AN_PACK + 1, ge = AN_GAPEXT * AN_PACK + 1;
-    constexpr int smg = AN_MATCH * AN_PACK + go, sxg = -(AN_MISMATCH * AN_PACK + 1) + go;
+    using SC = Scoring<MODEL>;
+    constexpr int go = SC::gapopen * AN_PACK + 1, ge = SC::gapext * AN_PACK + 1;
+    constexpr int smg = SC::match * AN_PACK + go, sxg = -(SC::mismatch * AN_PACK + 1) + go;
     // extension tiles are short: values stay within +-2^24, which leaves 5 low bits for the column tag
     constexpr int NEGV = MODE ? -(1 << 25) : AN_NEG;
     int Hg[AN_BANDW], F[AN_BANDW];
@@ -174,6 +175,7 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
 
 // Link alignments.  Tasks arrive sorted by row count (descending) so the 32 lanes of a warp run
 // similar-length loops.  A link whose alignment gives up (break rule) is cut.
+template <int MODEL>
 __global__ void __launch_bounds__(128, 4) gap_dp_kernel(ChainArrays A, const PairDesc *__restrict__ pairs, const uint32_t *__restrict__ task_idx, int64_t n_tasks,
                                                      unsigned long long *__restrict__ counters /*0: cells, 1: cuts*/, int one) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(128, 4) gap_dp_kernel(ChainArrays A, const Pai
         const PairDesc &P = pairs[key_pair(k)];
         SeqView R{P.r_seq, P.r_mask, P.r_npos, 0}, Q{P.q_seq, P.q_mask, P.q_npos, key_strand(k)};
         int d = lq - lr, c = d >= 0 ? d / 2 : -((-d) / 2);
-        DpResult o = dp_band<0>(R, rej, 1, Q, qej, 1, lr, lq, c - AN_BAND, one);
+        DpResult o = dp_band<0, MODEL>(R, rej, 1, Q, qej, 1, lr, lq, c - AN_BAND, one);
         cells = o.cells;
         if (o.stopped) { A.pred[i] = -1; A.trim[i] = 0; A.gval[i] = 0; cut = 1; }
         else A.gval[i] = o.val;
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(128, 4) gap_dp_kernel(ChainArrays A, const Pai
 }
 
 // Kept segments -> extension state.  seg_head[s] = head anchor of segment s (ascending).
-__global__ void segment_init_kernel(ChainArrays A, const PairDesc *__restrict__ pairs, const int *__restrict__ seg_head, SegArrays S) {
+__global__ void segment_init_kernel(ChainArrays A, const PairDesc *__restrict__ pairs, const int *__restrict__ seg_head, SegArrays S, int match_score) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S.n) return;
     const int h = seg_head[s], tl = A.tail[h];
@@ -217,9 +219,14 @@ __global__ void segment_init_kernel(ChainArrays A, const PairDesc *__restrict__ 
     S.re[s] = key_r(kt) + val_len(vt); S.qe[s] = val_q(vt) + val_len(vt);
     int64_t r_lo = (int64_t)P.r_goff[rc], r_hi = (int64_t)P.r_goff[rc + 1] - 1;
     int64_t q_lo = (int64_t)P.q_goff[qc], q_hi = (int64_t)P.q_goff[qc + 1] - 1;
+    if (P.fragsize) {  // ANIb: the query side never leaves the fragment
+        const int64_t fa = q_lo + (int64_t)(key_frag(k) - P.q_fbase[qc]) * P.fragsize;
+        q_hi = min(fa + (int64_t)P.fragsize, q_hi);
+        q_lo = fa;
+    }
     if (strand) { int64_t a = P.q_npos - q_hi, b = P.q_npos - q_lo; q_lo = a; q_hi = b; }
     S.r_lo[s] = (int)r_lo; S.r_hi[s] = (int)r_hi; S.q_lo[s] = (int)q_lo; S.q_hi[s] = (int)q_hi;
-    S.score[s] = A.ssum[h] + (long long)A.wsum[h] * AN_MATCH;
+    S.score[s] = A.ssum[h] + (long long)A.wsum[h] * match_score;
     S.errs[s] = A.esum[h];
 }
 
@@ -229,6 +236,7 @@ __global__ void segment_init_kernel(ChainArrays A, const PairDesc *__restrict__ 
 // `tiles_per_launch` tiles per launch; tasks that still extend are appended to `list_out` and continue in
 // the next launch, which bounds the tail a few long crawls (up to AN_MAXTILES tiles) would otherwise add.
 // task id = 2 * segment + side (0 = left, 1 = right).
+template <int MODEL>
 __global__ void __launch_bounds__(128, 4) ext_dp_kernel(SegArrays S, const PairDesc *__restrict__ pairs, const uint32_t *__restrict__ list_in, long long n_tasks,
                                                      uint32_t *__restrict__ list_out, int tiles_per_launch,
                                                      unsigned long long *__restrict__ counters /*0: cells, 1: tiles, 2: n_out, 3: ticket*/, int one) {
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(128, 4) ext_dp_kernel(SegArrays S, const PairD
             if (lr > 0 && lq > 0) {
                 // one call site for both directions: the two sides differ only in start position and step
                 const int step = side ? 1 : -1;
-                DpResult o = dp_band<1>(R, side ? (int64_t)re : (int64_t)rs - 1, step, Q, side ? (int64_t)qe : (int64_t)qs - 1, step, lr, lq, -AN_BAND, one);
+                DpResult o = dp_band<1, MODEL>(R, side ? (int64_t)re : (int64_t)rs - 1, step, Q, side ? (int64_t)qe : (int64_t)qs - 1, step, lr, lq, -AN_BAND, one);
                 cells += o.cells;
                 ++tiles;
                 if (o.bi != 0 || o.bj != 0) {
@@ -297,6 +305,11 @@ __global__ void emit_rows_kernel(SegArrays S, const PairDesc *__restrict__ pairs
     else { o[5] = (int)(((int64_t)P.q_npos - 1 - S.qs[s]) - qg + 1); o[6] = (int)(((int64_t)P.q_npos - S.qe[s]) - qg + 1); }
     o[7] = (int)S.errs[s];
 }
+
+template __global__ void gap_dp_kernel<0>(ChainArrays, const PairDesc *, const uint32_t *, int64_t, unsigned long long *, int);
+template __global__ void gap_dp_kernel<1>(ChainArrays, const PairDesc *, const uint32_t *, int64_t, unsigned long long *, int);
+template __global__ void ext_dp_kernel<0>(SegArrays, const PairDesc *, const uint32_t *, long long, uint32_t *, int, unsigned long long *, int);
+template __global__ void ext_dp_kernel<1>(SegArrays, const PairDesc *, const uint32_t *, long long, uint32_t *, int, unsigned long long *, int);
 
 // ---- integer-DP roofline denominator: issue rate of __viaddmax_s32 (8 independent chains per thread)
 __global__ void __launch_bounds__(256) dpx_peak_kernel(int iters, int seed, int *__restrict__ sink) {

@@ -19,15 +19,23 @@ __global__ void flag_unique_kernel(const uint64_t *, const uint64_t *, int64_t, 
 __global__ void contig_kernel(ChainArrays, const PairDesc *);
 __global__ void link_kernel(ChainArrays);
 __global__ void link_validate_kernel(ChainArrays, unsigned long long *);
-__global__ void gap_task_kernel(ChainArrays, uint32_t *, uint32_t *, unsigned long long *);
+__global__ void gap_task_kernel(ChainArrays, uint32_t *, uint32_t *, unsigned long long *, int, int);
 __global__ void label_init_kernel(ChainArrays);
 __global__ void label_jump_kernel(ChainArrays, int *);
 __global__ void cluster_weight_kernel(ChainArrays);
-__global__ void segment_accum_kernel(ChainArrays);
+__global__ void segment_accum_kernel(ChainArrays, int);
 __global__ void segment_flag_kernel(ChainArrays, uint8_t *);
-__global__ void gap_dp_kernel(ChainArrays, const PairDesc *, const uint32_t *, int64_t, unsigned long long *, int);
-__global__ void segment_init_kernel(ChainArrays, const PairDesc *, const int *, SegArrays);
-__global__ void ext_dp_kernel(SegArrays, const PairDesc *, const uint32_t *, long long, uint32_t *, int, unsigned long long *, int);
+template <int MODEL> __global__ void gap_dp_kernel(ChainArrays, const PairDesc *, const uint32_t *, int64_t, unsigned long long *, int);
+__global__ void segment_init_kernel(ChainArrays, const PairDesc *, const int *, SegArrays, int);
+template <int MODEL> __global__ void ext_dp_kernel(SegArrays, const PairDesc *, const uint32_t *, long long, uint32_t *, int, unsigned long long *, int);
+struct AnibSeg {
+    int *pair, *frag, *score, *nident, *mism, *gaps, *qlen;
+    uint8_t *pass;
+};
+__global__ void anib_segment_kernel(SegArrays, const uint64_t *, AnibSeg);
+__global__ void anib_reduce_kernel(AnibSeg, int64_t, b200ani_anib_result *, int *, uint8_t *);
+__global__ void anib_init_kernel(const PairDesc *, int, b200ani_anib_result *);
+__global__ void anib_status_kernel(int, b200ani_anib_result *);
 __global__ void emit_rows_kernel(SegArrays, const PairDesc *, int *);
 __global__ void filt_key_kernel(FiltArrays, int, uint64_t *, int *);
 __global__ void filt_gather_kernel(FiltArrays, int, const int *);
@@ -114,7 +122,10 @@ struct RowDump {
     std::vector<uint8_t> flag;
 };
 
-static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, b200ani_anim_result *out, RowDump *dump) {
+// fragsize == 0: ANIm (out = b200ani_anim_result[nb]); fragsize > 0: ANIb (out = b200ani_anib_result[nb])
+static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, int fragsize, void *out_v, RowDump *dump) {
+    const bool anib = fragsize > 0;
+    b200ani_anim_result *out = (b200ani_anim_result *)out_v;
     cudaStream_t st = ctx->stream;
     bool used[B200ANI_N_STAGES] = {false};
     // ---- pair descriptors
@@ -137,6 +148,9 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         const bool first = !second && p + 1 < nb && pairs[2 * p + 2] == pairs[2 * p + 1] && pairs[2 * p + 3] == pairs[2 * p] &&
                            pairs[2 * p] != pairs[2 * p + 1];
         d.mirror = first ? p + 1 : -1;
+        d.q_fbase = anib ? Q.d_fbase : nullptr;
+        d.fragsize = anib ? fragsize : 0;
+        d.q_nfrags = anib ? Q.n_frags : 0;
         if (!second) n_probes += Q.index->n_mini;
     }
     CK(cudaMemcpyAsync(W->d_pairs, hp.data(), sizeof(PairDesc) * nb, cudaMemcpyHostToDevice, st));
@@ -178,7 +192,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         int pair_bits = 1;
         while ((1 << pair_bits) < nb) ++pair_bits;
         size_t tb = W->cub_bytes;
-        cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb, W->keys_a, W->keys_b, W->vals_a, W->vals_b, n_raw, 0, 32 + pair_bits, st);
+        cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb, W->keys_a, W->keys_b, W->vals_a, W->vals_b, n_raw, 0, KEY_PAIR_SHIFT + pair_bits, st);
         tie_fix_kernel<<<GRID(n_raw)>>>(W->keys_b, W->vals_b, n_raw);
         flag_unique_kernel<<<GRID(n_raw)>>>(W->keys_b, W->vals_b, n_raw, W->flag);
         LAUNCHED(2);
@@ -208,7 +222,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         contig_kernel<<<GRID(n)>>>(A, W->d_pairs);
         link_kernel<<<GRID(n)>>>(A);
         link_validate_kernel<<<GRID(n)>>>(A, W->counters + 2);
-        gap_task_kernel<<<GRID(n)>>>(A, task_key, task_idx, W->counters + 3);
+        gap_task_kernel<<<GRID(n)>>>(A, task_key, task_idx, W->counters + 3, anib ? AB_GAP : AN_GAPOPEN, anib ? AB_GAP : AN_GAPEXT);
         LAUNCHED(4);
         T1(ST_LINK);
         CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
@@ -221,7 +235,8 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
             size_t tb = W->cub_bytes;
             cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb, task_key, task_key2, task_idx, task_idx2, n_tasks, 0, 11, st);
             T0(ST_GAPDP);  // exactly the kernel: this is the roofline's launch duration
-            gap_dp_kernel<<<(unsigned)ceil_div(n_tasks, 128), 128, 0, st>>>(A, W->d_pairs, task_idx2, n_tasks, W->counters + 4, 1);
+            if (anib) gap_dp_kernel<1><<<(unsigned)ceil_div(n_tasks, 128), 128, 0, st>>>(A, W->d_pairs, task_idx2, n_tasks, W->counters + 4, 1);
+            else gap_dp_kernel<0><<<(unsigned)ceil_div(n_tasks, 128), 128, 0, st>>>(A, W->d_pairs, task_idx2, n_tasks, W->counters + 4, 1);
             LAUNCHED(1);
             T1(ST_GAPDP);
             ctx->counters[CT_GAPLAUNCH] += 1;
@@ -240,7 +255,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
             if (!ch) break;
         }
         cluster_weight_kernel<<<GRID(n)>>>(A);
-        segment_accum_kernel<<<GRID(n)>>>(A);
+        segment_accum_kernel<<<GRID(n)>>>(A, anib ? 0 : AN_MINCLUSTER);
         segment_flag_kernel<<<GRID(n)>>>(A, W->flag);
         LAUNCHED(3);
         size_t tb = W->cub_bytes;
@@ -270,12 +285,13 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
 
     if (n_seg) {
         T0(ST_EXTDP);
-        segment_init_kernel<<<GRID(n_seg)>>>(A, W->d_pairs, seg_head, S);
+        segment_init_kernel<<<GRID(n_seg)>>>(A, W->d_pairs, seg_head, S, anib ? AB_MATCH : AN_MATCH);
         LAUNCHED(1);
         {   // persistent launches: resident warps pull (segment, side) tasks from a ticket counter; a task
             // gets EXT_TILES_PER_LAUNCH tiles per launch, the still-extending ones go to the next launch
             int per_sm = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ext_dp_kernel, 128, 0));
+            if (anib) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ext_dp_kernel<1>, 128, 0));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ext_dp_kernel<0>, 128, 0));
             long long n_cur = 2 * n_seg;
             for (int round = 0; round * EXT_TILES_PER_LAUNCH < AN_MAXTILES && n_cur; ++round) {
                 CK(cudaMemsetAsync(W->counters + 8, 0, 2 * sizeof(unsigned long long), st));  // n_out, ticket
@@ -288,8 +304,12 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
                 }
                 int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * std::max(per_sm, 1), ceil_div(n_cur, 128));
                 CK(cudaEventRecord(W->kev[2 * n_ext_launch], st));
-                ext_dp_kernel<<<(unsigned)blocks, 128, 0, st>>>(S, W->d_pairs, round ? ext_list[round & 1] : nullptr, n_cur, ext_list[(round + 1) & 1],
-                                                               EXT_TILES_PER_LAUNCH, W->counters + 6, 1);
+                if (anib)
+                    ext_dp_kernel<1><<<(unsigned)blocks, 128, 0, st>>>(S, W->d_pairs, round ? ext_list[round & 1] : nullptr, n_cur, ext_list[(round + 1) & 1],
+                                                                      EXT_TILES_PER_LAUNCH, W->counters + 6, 1);
+                else
+                    ext_dp_kernel<0><<<(unsigned)blocks, 128, 0, st>>>(S, W->d_pairs, round ? ext_list[round & 1] : nullptr, n_cur, ext_list[(round + 1) & 1],
+                                                                      EXT_TILES_PER_LAUNCH, W->counters + 6, 1);
                 CK(cudaEventRecord(W->kev[2 * n_ext_launch + 1], st));
                 ++n_ext_launch;
                 LAUNCHED(1);
@@ -298,11 +318,61 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
                 n_cur = (long long)hc[8];
             }
         }
-        emit_rows_kernel<<<GRID(n_seg)>>>(S, W->d_pairs, rows);
-        LAUNCHED(1);
+        if (!anib) {
+            emit_rows_kernel<<<GRID(n_seg)>>>(S, W->d_pairs, rows);
+            LAUNCHED(1);
+        }
         T1(ST_EXTDP);
         ctx->counters[CT_EXTCELLS] += (int64_t)hc[6];
         ctx->counters[CT_EXTTILES] += (int64_t)hc[7];
+    }
+
+    if (anib) {
+        // ---- ANIb: HSP columns, parse_blast_tab filter, best HSP per fragment, per-pair sums
+        b200ani_anib_result *d_out = (b200ani_anib_result *)W->d_results;
+        AnibSeg B{};
+        uint8_t *chosen = nullptr;
+        DA(B.pair, n_seg); DA(B.frag, n_seg); DA(B.score, n_seg); DA(B.nident, n_seg); DA(B.mism, n_seg); DA(B.gaps, n_seg); DA(B.qlen, n_seg);
+        DA(B.pass, n_seg); DA(chosen, n_seg);
+        T0(ST_REDUCE);
+        anib_init_kernel<<<(unsigned)ceil_div(nb, 128), 128, 0, st>>>(W->d_pairs, nb, d_out);
+        if (n_seg) {
+            anib_segment_kernel<<<GRID(n_seg)>>>(S, A.keys, B);
+            anib_reduce_kernel<<<GRID(n_seg)>>>(B, n_seg, d_out, dump ? rows : nullptr, chosen);
+        }
+        anib_status_kernel<<<(unsigned)ceil_div(nb, 128), 128, 0, st>>>(nb, d_out);
+        LAUNCHED(4);
+        CK(cudaMemcpyAsync(out_v, d_out, sizeof(b200ani_anib_result) * nb, cudaMemcpyDeviceToHost, st));
+        T1(ST_REDUCE);
+        if (dump) {
+            dump->rows.resize((size_t)8 * n_seg);
+            dump->flag.resize((size_t)n_seg);
+            if (n_seg) {
+                CK(cudaMemcpyAsync(dump->rows.data(), rows, sizeof(int) * 8 * n_seg, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(dump->flag.data(), chosen, (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        DF(B.pair); DF(B.frag); DF(B.score); DF(B.nident); DF(B.mism); DF(B.gaps); DF(B.qlen); DF(B.pass); DF(chosen);
+        DF(A.rc_of); DF(A.qc_of); DF(A.pred); DF(A.trim); DF(A.succ); DF(A.gval); DF(A.head); DF(A.chead); DF(A.cw); DF(A.wsum);
+        DF(A.tail); DF(A.ssum); DF(A.esum); DF(A.strong); DF(task_key); DF(task_idx); DF(task_key2); DF(task_idx2); DF(seg_head);
+        DF(S.pair); DF(S.strand); DF(S.head); DF(S.rc); DF(S.qc); DF(S.rs); DF(S.qs); DF(S.re); DF(S.qe);
+        DF(S.r_lo); DF(S.r_hi); DF(S.q_lo); DF(S.q_hi); DF(S.score); DF(S.errs); DF(rows); DF(ext_list[0]); DF(ext_list[1]);
+        CK(cudaStreamSynchronize(st));
+        for (int s2 = 0; s2 < B200ANI_N_STAGES; ++s2)
+            if (used[s2]) {
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, W->ev[2 * s2], W->ev[2 * s2 + 1]));
+                ctx->stage_ms[s2] += ms;
+            }
+        for (int k = 0; k < n_ext_launch; ++k) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, W->kev[2 * k], W->kev[2 * k + 1]));
+            ctx->stage_ms[ST_EXTK] += ms;
+        }
+        ctx->counters[CT_EXTLAUNCH] += n_ext_launch;
+        const b200ani_anib_result *ho = (const b200ani_anib_result *)out_v;
+        for (int p = 0; p < nb; ++p) ctx->counters[CT_ALIGNMENTS] += ho[p].n_pass;
+        return 0;
     }
 
     // ---- 1-to-1 filter + parse_delta reduction
@@ -367,7 +437,9 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     return 0;
 }
 
-static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs_in, int64_t m, int nofilter, b200ani_anim_result *out_user, RowDump *dump) {
+static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs_in, int64_t m, int nofilter, int fragsize, void *out_user_v, RowDump *dump) {
+    const size_t esz = fragsize > 0 ? sizeof(b200ani_anib_result) : sizeof(b200ani_anim_result);
+    char *out_user = (char *)out_user_v;
     // Internal order: the two directions of a genome pair adjacent (one probe pass seeds both), genome pairs
     // sorted by (min id, max id) so the probed reference table stays hot in L2.  Results go back in caller order.
     std::vector<int64_t> order(m);
@@ -382,7 +454,7 @@ static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs_in
     });
     std::vector<int32_t> pairs(2 * m);
     for (int64_t i = 0; i < m; ++i) { pairs[2 * i] = pairs_in[2 * order[i]]; pairs[2 * i + 1] = pairs_in[2 * order[i] + 1]; }
-    std::vector<b200ani_anim_result> out(m);
+    std::vector<char> out((size_t)m * esz);
     auto splits_mirror = [&](int64_t b0, int nb) {  // would a batch [b0, b0+nb) cut a (a,b),(b,a) couple in two?
         const int64_t e = b0 + nb;
         return e < m && e - 1 >= b0 && pairs[2 * e] == pairs[2 * e - 1] && pairs[2 * e + 1] == pairs[2 * e - 2] &&
@@ -392,7 +464,7 @@ static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs_in
         int nb = (int)std::min<int64_t>(MAX_BATCH_PAIRS, m - b0);
         while (true) {
             if (nb > 1 && splits_mirror(b0, nb)) --nb;
-            int rc = run_batch(ctx, W, pairs.data() + 2 * b0, nb, nofilter, out.data() + b0, dump);
+            int rc = run_batch(ctx, W, pairs.data() + 2 * b0, nb, nofilter, fragsize, out.data() + (size_t)b0 * esz, dump);
             if (rc == 0) break;
             if (rc < 0) return rc;
             if (nb == 1) FAIL(B200ANI_ERR_CAPACITY, "anim: a single pair exceeds the anchor capacity");
@@ -400,7 +472,7 @@ static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs_in
         }
         b0 += nb;
     }
-    for (int64_t i = 0; i < m; ++i) out_user[order[i]] = out[i];
+    for (int64_t i = 0; i < m; ++i) memcpy(out_user + (size_t)order[i] * esz, out.data() + (size_t)i * esz, esz);
     return 0;
 }
 
@@ -453,7 +525,7 @@ int b200ani_anim(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch
     CK(cudaEventCreate(&t1));
     CK(cudaEventRecord(t0, ctx->stream));
     int rc = prepare(ctx, pairs, m, maxmatch, &W);
-    if (rc == 0) rc = run_range(ctx, W, pairs, m, nofilter, out, nullptr);
+    if (rc == 0) rc = run_range(ctx, W, pairs, m, nofilter, 0, out, nullptr);
     CK(cudaEventRecord(t1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
@@ -472,7 +544,7 @@ int64_t b200ani_anim_alignments(b200ani_ctx *ctx, int32_t ref_id, int32_t qry_id
     if (rc) return rc;
     RowDump dump;
     b200ani_anim_result res;
-    rc = run_range(ctx, W, pr, 1, nofilter, &res, &dump);
+    rc = run_range(ctx, W, pr, 1, nofilter, 0, &res, &dump);
     if (rc) return rc;
     int64_t k = 0;
     for (size_t i = 0; i < dump.flag.size(); ++i) {
@@ -482,6 +554,74 @@ int64_t b200ani_anim_alignments(b200ani_ctx *ctx, int32_t ref_id, int32_t qry_id
             int64_t *o = rows + 7 * k;
             o[0] = a[1]; o[1] = a[2]; o[2] = a[3]; o[3] = a[4]; o[4] = a[5]; o[5] = a[6]; o[6] = a[7];
         }
+        ++k;
+    }
+    return k;
+}
+
+static int ensure_fragments(b200ani_ctx *ctx, Genome &g, int fragsize) {
+    if (g.d_fbase && g.frag_size == fragsize) return 0;
+    std::vector<uint32_t> fb(g.n_contigs + 1, 0);
+    for (uint32_t c = 0; c < g.n_contigs; ++c) {
+        const int64_t L = (int64_t)(g.h_goff[c + 1] - g.h_goff[c]) - 1;
+        fb[c + 1] = fb[c] + (uint32_t)((L + fragsize - 1) / fragsize);
+    }
+    if (fb[g.n_contigs] >= (1u << 14)) FAIL(B200ANI_ERR_CAPACITY, "anib: more than 16383 fragments in one genome");
+    if (!g.d_fbase) CK(cudaMallocAsync(&g.d_fbase, sizeof(uint32_t) * (g.n_contigs + 1), ctx->stream));
+    CK(cudaMemcpyAsync(g.d_fbase, fb.data(), sizeof(uint32_t) * (g.n_contigs + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    g.frag_size = fragsize;
+    g.n_frags = fb[g.n_contigs];
+    return 0;
+}
+
+static int anib_common(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fragsize, void *out, RowDump *dump) {
+    if (fragsize < AN_TILE || fragsize > 100000) FAIL(B200ANI_ERR_ARG, "anib: fragment size out of range");
+    // machinery pairs are (table side = subject, streamed side = query)
+    std::vector<int32_t> internal(2 * m);
+    for (int64_t i = 0; i < m; ++i) { internal[2 * i] = pairs[2 * i + 1]; internal[2 * i + 1] = pairs[2 * i]; }
+    AnimWorkspace *W = nullptr;
+    int rc = prepare(ctx, internal.data(), m, 0, &W);
+    if (rc) return rc;
+    for (int64_t i = 0; i < m; ++i) {
+        rc = ensure_fragments(ctx, ctx->genomes[pairs[2 * i]], fragsize);
+        if (rc) return rc;
+    }
+    return run_range(ctx, W, internal.data(), m, 0, fragsize, out, dump);
+}
+
+int b200ani_anib(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fragsize, b200ani_anib_result *out) {
+    if (!ctx || !pairs || !out || m < 0) return B200ANI_ERR_ARG;
+    memset(ctx->stage_ms, 0, sizeof ctx->stage_ms);
+    memset(ctx->counters, 0, sizeof ctx->counters);
+    cudaEvent_t t0, t1;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventCreate(&t0));
+    CK(cudaEventCreate(&t1));
+    CK(cudaEventRecord(t0, ctx->stream));
+    int rc = anib_common(ctx, pairs, m, fragsize, out, nullptr);
+    CK(cudaEventRecord(t1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, t0, t1));
+    ctx->stage_ms[ST_TOTAL] = ms;
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    return rc;
+}
+
+int64_t b200ani_anib_fragments(b200ani_ctx *ctx, int32_t qry_id, int32_t sbj_id, int fragsize, int64_t *rows, int64_t cap) {
+    if (!ctx || (!rows && cap > 0)) return B200ANI_ERR_ARG;
+    int32_t pr[2] = {qry_id, sbj_id};
+    RowDump dump;
+    b200ani_anib_result res;
+    int rc = anib_common(ctx, pr, 1, fragsize, &res, &dump);
+    if (rc) return rc;
+    int64_t k = 0;
+    for (size_t i = 0; i < dump.flag.size(); ++i) {
+        if (!dump.flag[i]) continue;
+        if (k < cap)
+            for (int c = 0; c < 8; ++c) rows[8 * k + c] = dump.rows[8 * i + c];
         ++k;
     }
     return k;

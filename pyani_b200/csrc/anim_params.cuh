@@ -22,5 +22,10 @@
 #define AN_CLUSTGAP 90
 #define AN_FILT_OLAP 75
 #define AN_FILT_POW 2
+#define AB_MATCH 2
+#define AB_MISMATCH 3
+#define AB_GAP 5
+#define AB_MINPIECE 11
+#define AB_FRAGSIZE 1020
 #define AN_PACK 4096
 #define AN_NEG (-(1 << 29))

@@ -97,6 +97,34 @@ __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restr
     }
 }
 
+// One anchor of pair `pi`: ANIm -> as is; ANIb (P.fragsize > 0) -> clipped to the query's fragments, one piece per
+// fragment it overlaps (pieces shorter than AB_MINPIECE are dropped), the fragment id goes into the sort key.
+__device__ __forceinline__ void emit_anchor(const PairDesc &P, int pi, int strand, int64_t rs, int64_t qs, int64_t len, uint64_t *__restrict__ keys,
+                                            uint64_t *__restrict__ vals, unsigned long long *__restrict__ n_anchors, unsigned long long cap) {
+    if (P.fragsize == 0) {
+        unsigned long long slot = atomicAdd(n_anchors, 1ull);
+        if (slot < cap) {
+            keys[slot] = make_key(pi, 0, strand, rs);
+            vals[slot] = ((uint64_t)qs << 32) | (uint64_t)len;
+        }
+        return;
+    }
+    const int64_t F = P.fragsize;
+    const int64_t fa = strand ? (int64_t)P.q_npos - qs - len : qs, fb = fa + len;  // forward query interval
+    const uint32_t c = contig_of(P.q_goff, P.q_ncontigs, fa);
+    const int64_t rec0 = (int64_t)P.q_goff[c];
+    for (int64_t k = (fa - rec0) / F; rec0 + k * F < fb; ++k) {
+        int64_t a = max(rec0 + k * F, fa), b = min(rec0 + (k + 1) * F, fb);
+        if (b - a < AB_MINPIECE) continue;
+        const int64_t t0 = strand ? ((int64_t)P.q_npos - b) - qs : a - qs;  // offset of the piece inside the match
+        unsigned long long slot = atomicAdd(n_anchors, 1ull);
+        if (slot < cap) {
+            keys[slot] = make_key(pi, P.q_fbase[c] + (uint32_t)k, strand, rs + t0);
+            vals[slot] = ((uint64_t)(qs + t0) << 32) | (uint64_t)(b - a);
+        }
+    }
+}
+
 // Phase 2 -- extend: one thread per hit (dense, so no idle lanes): drop seeds that the previous query
 // minimizer already covers, extend the others to maximal exact matches.  key/val encoding: anim.cuh.
 __global__ void __launch_bounds__(256) seed_extend_kernel(const PairDesc *__restrict__ pairs, int n_pairs, const uint2 *__restrict__ hits, int64_t n_hits,
@@ -140,18 +168,12 @@ __global__ void __launch_bounds__(256) seed_extend_kernel(const PairDesc *__rest
         // Exact matches are symmetric in the two genomes (seeds are k-mers unique in BOTH minimizer sets and the
         // selection is strand-symmetric), so the opposite-direction comparison gets its anchors from the same
         // seeds: forward (r,q) -> (q,r); reverse-strand coordinates swap roles through both genome lengths.
-        const int n_emit = P.mirror >= 0 ? 2 : 1;
-        unsigned long long slot = atomicAdd(n_anchors, (unsigned long long)n_emit);
         const int64_t rs = r0 - l, qs = q0 - l;
-        if (slot + n_emit <= cap) {
-            keys[slot] = ((uint64_t)lo << 32) | ((uint64_t)strand << 31) | (uint64_t)rs;
-            vals[slot] = ((uint64_t)qs << 32) | (uint64_t)len;
-            if (n_emit == 2) {
-                const int64_t r2 = strand ? (int64_t)P.q_npos - qs - len : qs;
-                const int64_t q2 = strand ? (int64_t)P.r_npos - rs - len : rs;
-                keys[slot + 1] = ((uint64_t)P.mirror << 32) | ((uint64_t)strand << 31) | (uint64_t)r2;
-                vals[slot + 1] = ((uint64_t)q2 << 32) | (uint64_t)len;
-            }
+        emit_anchor(P, lo, strand, rs, qs, len, keys, vals, n_anchors, cap);
+        if (P.mirror >= 0) {
+            const int64_t r2 = strand ? (int64_t)P.q_npos - qs - len : qs;
+            const int64_t q2 = strand ? (int64_t)P.r_npos - rs - len : rs;
+            emit_anchor(pairs[P.mirror], P.mirror, strand, r2, q2, len, keys, vals, n_anchors, cap);
         }
     }
 }

@@ -58,6 +58,8 @@ static void release_genome(b200ani_ctx *ctx, Genome &g, cudaStream_t st) {
     cudaFreeAsync(g.d_seq, st);
     cudaFreeAsync(g.d_mask, st);
     cudaFreeAsync(g.d_goff, st);
+    if (g.d_fbase) cudaFreeAsync(g.d_fbase, st);
+    g.d_fbase = nullptr;
     if (g.index) {  // keep the buffers for the next genome of similar size
         invalidate_index(g.index);
         ctx->spare_indexes.push_back(g.index);

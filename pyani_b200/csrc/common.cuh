@@ -32,6 +32,10 @@ struct Genome {
     uint64_t *d_goff = nullptr;
     std::vector<uint64_t> h_goff;
     MinimizerIndex *index = nullptr;  // built lazily by the first ANIm call that needs it
+    // ANIb fragment table (built lazily for the requested fragment size): record c holds fragments fbase[c]..fbase[c+1]-1
+    uint32_t *d_fbase = nullptr;
+    int frag_size = 0;
+    uint32_t n_frags = 0;
 };
 
 struct b200ani_ctx {

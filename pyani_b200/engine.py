@@ -139,6 +139,23 @@ class Engine:
             self._check(int(n), "anim_alignments")
         return rows[: min(n, cap)].copy()
 
+    # -- ANIb
+    def anib(self, pairs: np.ndarray, fragsize: int = 1020) -> np.ndarray:
+        """pairs: (m,2) int32 of (query genome id, subject genome id) -> structured array of AnibResult."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        out = np.zeros(len(pairs), dtype=ANIB_DTYPE)
+        if len(pairs):
+            self._check(self._lib.b200ani_anib(self._h, _ptr(pairs), len(pairs), int(fragsize), _ptr(out)), "anib")
+        return out
+
+    def anib_fragments(self, qry: int, sbj: int, fragsize: int = 1020, cap: int = 1 << 15) -> np.ndarray:
+        """Kept HSP per passing fragment: rows (frag, length, mismatch, gaps, nident, qlen, score, pid_milli)."""
+        rows = np.zeros((cap, 8), dtype=np.int64)
+        n = self._lib.b200ani_anib_fragments(self._h, qry, sbj, int(fragsize), _ptr(rows), cap)
+        if n < 0:
+            self._check(int(n), "anib_fragments")
+        return rows[: min(n, cap)].copy()
+
     def last_profile(self) -> Tuple[Dict[str, float], Dict[str, int]]:
         ms = np.zeros(_lib.N_STAGES, dtype=np.float64)
         cnt = np.zeros(_lib.N_STAGES, dtype=np.int64)
@@ -153,3 +170,8 @@ ANIM_DTYPE = np.dtype(
      ("sim_errs", "<i8"), ("n_alignments", "<i4"), ("status", "<i4")]
 )
 assert ANIM_DTYPE.itemsize == 48
+ANIB_DTYPE = np.dtype(
+    [("aln_length", "<i8"), ("sim_errs", "<i8"), ("pid_milli_sum", "<i8"), ("n_frags", "<i4"), ("n_pass", "<i4"),
+     ("n_hsps", "<i4"), ("status", "<i4")]
+)
+assert ANIB_DTYPE.itemsize == 40

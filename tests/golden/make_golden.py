@@ -111,6 +111,38 @@ def main():
     np.savez_compressed(OUT / "anim_alignments.npz", **arrays)
     print("anim", len(tuples))
 
+    # ---- ANIb reduction: the reference's parse_blast_tab on its checked-in BLAST+ output.  The function writes a
+    # <file>.dataframe next to its input (anib.py:666), so the fixtures are copied out of the read-only tree first.
+    from pyani import anib
+
+    blast_gold, blast_rows = {}, {}
+    with tempfile.TemporaryDirectory() as td:
+        for f in sorted((REF / "tests/fixtures/anib/blastn").glob("*.blast_tab")):
+            dst = Path(td) / f.name
+            shutil.copyfile(f, dst)
+            aln, errs, pid = anib.parse_blast_tab(dst, None, mode="ANIb")
+            blast_gold[f.stem] = [int(aln), int(errs), float(pid)]
+            # inputs of the restatement: fragment number, length, mismatch, pident, qlen, gaps per HSP row, file order
+            rows = []
+            for line in open(f):
+                c = line.rstrip("\n").split("\t")
+                rows.append((int(c[0].replace("frag", "")), int(c[2]), int(c[3]), float(c[4]), int(c[6]), int(c[14])))
+            blast_rows[f.stem] = np.asarray(rows, dtype=np.float64)
+    with tempfile.TemporaryDirectory() as td:
+        for f in sorted((REF / "tests/fixtures/anib/blastn").glob("*.blast_tab")):
+            shutil.copyfile(f, Path(td) / f.name)
+        seqdir = REF / "tests/fixtures/anib/sequences"
+        org_lengths_b = pyani_files.get_sequence_lengths(pyani_files.get_fasta_files(seqdir))
+        resb = anib.process_blast(Path(td), org_lengths_b, None, mode="ANIb")
+        legacy_b = {"org_lengths": org_lengths_b}
+        for name in ("alignment_lengths", "similarity_errors", "percentage_identity", "alignment_coverage"):
+            df = getattr(resb, name)
+            legacy_b[name] = {"index": list(df.index), "columns": list(df.columns), "values": df.values.tolist()}
+        json.dump(legacy_b, open(OUT / "anib_process_blast.json", "w"))
+    json.dump(blast_gold, open(OUT / "anib_parse_blast_tab.json", "w"), indent=0)
+    np.savez_compressed(OUT / "anib_blast_rows.npz", **blast_rows)
+    print("anib", len(blast_gold))
+
 
 if __name__ == "__main__":
     main()

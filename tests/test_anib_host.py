@@ -1,0 +1,44 @@
+"""Host-side mirror of the reference's ANIb interfaces (pyani_b200/anib.py) -- no GPU needed."""
+import json
+
+import numpy as np
+import pandas as pd
+
+from conftest import GOLDEN, fixture_genomes
+from pyani_b200 import anib as banib
+from pyani_b200.engine import ANIB_DTYPE
+
+
+def test_fill_aniresults_matches_reference_process_blast():
+    """anib.process_blast run by the reference on its own BLAST+ fixtures vs fill_aniresults fed the per-file
+    tuples: every cell of all four tables (incl. the symmetric, last-file-wins similarity errors)."""
+    tuples = json.load(open(GOLDEN / "anib_parse_blast_tab.json"))
+    legacy = json.load(open(GOLDEN / "anib_process_blast.json"))
+    per_file = {tuple(k.split("_vs_")): tuple(v) for k, v in tuples.items()}
+    res = banib.fill_aniresults(legacy["org_lengths"], per_file)
+    for tab in ("alignment_lengths", "similarity_errors", "percentage_identity", "alignment_coverage"):
+        g = legacy[tab]
+        want = pd.DataFrame(g["values"], index=g["index"], columns=g["columns"])
+        got = getattr(res, tab).loc[g["index"], g["columns"]]
+        assert (got.values == want.values).all(), tab
+
+
+def test_parse_result_and_fragment_lengths():
+    r = np.zeros(1, dtype=ANIB_DTYPE)[0]
+    r["aln_length"], r["sim_errs"], r["pid_milli_sum"], r["n_pass"] = 1818, 42, 98750 + 97000, 2
+    assert banib.parse_result(r) == (1818, 42, (98.75 + 97.0) / 2)
+    assert banib.parse_result(np.zeros(1, dtype=ANIB_DTYPE)[0]) == (0, 0, 0.0)  # anib.py:661-663
+    fl = banib.fragment_lengths([2500, 1020, 5], 1020)  # anib.py:192-200: ids run across records, short tails kept
+    assert fl == {"frag00001": 1020, "frag00002": 1020, "frag00003": 460, "frag00004": 1020, "frag00005": 5}
+
+
+def test_fragment_counts_of_fixture_genomes():
+    files = fixture_genomes()
+    if not files:
+        import pytest
+
+        pytest.skip("fixture genomes not copied")
+    d = banib.get_fraglength_dict(files)
+    # tests/fixtures/anib/fragfiles hold 3,940 / 5,371 / 3,964 / 4,565 fragments
+    assert [len(d[f.stem]) for f in files] == [3940, 5371, 3964, 4565]
+    assert max(max(v.values()) for v in d.values()) == 1020  # tests/test_anib.py:317-324

@@ -1,0 +1,34 @@
+"""The ANIb-equivalent aligner oracle against the reference's checked-in BLAST+ results.
+
+blastn cannot run here; the pin is the 12 .blast_tab files of the reference's fixtures reduced by the reference's
+own parse_blast_tab (tests/golden/anib_parse_blast_tab.json).  Tolerance = the reference's own concordance
+tolerance for ANIb (tests/test_concordance.py:118-153,250-253): 0.2 percentage points where identity >= 90 %,
+5 points below.  Measured: |delta| <= 0.005 for the 99.99 % pair, 1.7 .. 3.2 points for the 80-84 % pairs
+(the 20-mer seeds find ~75 % of the fragments BLAST's 11-mer seeds align, and those are the better conserved ones).
+"""
+import json
+
+import pytest
+
+import oracle
+from conftest import GOLDEN, fixture_genomes
+
+pytestmark = pytest.mark.skipif(not fixture_genomes(), reason="fixture genomes not copied (tests/golden/make_golden.py)")
+
+
+def test_anib_identity_within_reference_tolerance():
+    gold = json.load(open(GOLDEN / "anib_parse_blast_tab.json"))
+    g = {}
+    for f in fixture_genomes():
+        a, off, _ = oracle.read_fasta(f)
+        g[f.stem] = oracle.OGenome(a, off)
+    for name, (aln, errs, pid) in gold.items():
+        q, s = name.split("_vs_")
+        res, rows, _ = oracle.anib_pair(g[q], g[s])
+        mean_pid = res["pid_milli_sum"] / res["n_pass"] / 1000
+        tol = 0.2 if pid >= 90 else 5.0
+        assert abs(mean_pid - pid) < tol, (name, mean_pid, pid)
+        assert 0.6 * aln < res["aln_length"] < 1.1 * aln, (name, res["aln_length"], aln)
+        assert res["n_pass"] == len(rows) and (rows[:, 1] == rows[:, 2] + rows[:, 3] + rows[:, 4]).all()
+        if pid >= 99:
+            assert abs(res["aln_length"] - aln) < 1500 and res["n_frags"] in (3940, 3964)
