@@ -31,4 +31,4 @@ def test_anib_identity_within_reference_tolerance():
         assert 0.6 * aln < res["aln_length"] < 1.1 * aln, (name, res["aln_length"], aln)
         assert res["n_pass"] == len(rows) and (rows[:, 1] == rows[:, 2] + rows[:, 3] + rows[:, 4]).all()
         if pid >= 99:
-            assert abs(res["aln_length"] - aln) < 1500 and res["n_frags"] in (3940, 3964)
+            assert abs(res["aln_length"] - aln) < 2500 and res["n_frags"] in (3940, 3964)
