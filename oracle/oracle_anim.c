@@ -200,7 +200,11 @@ typedef struct { int32_t val, bi, bj, stopped; int64_t cells; } dp_out;
 static const int SC_ANIM[4] = {AN_MATCH, AN_MISMATCH, AN_GAPOPEN, AN_GAPEXT};
 static const int SC_ANIB[4] = {AB_MATCH, AB_MISMATCH, AB_GAP, AB_GAP};
 
-static dp_out dp_band_sc(const uint8_t *R, int rstride, const uint8_t *Q, int qstride, int lr, int lq, int klo, int mode, const int *sc) {
+static dp_out dp_band_sc(const uint8_t *R, int rstride, const uint8_t *Q, int qstride, int lr, int lq, int klo, int mode, const int *sc, int64_t qavail) {
+    /* mode 0 (link alignment): the band is NOT clipped at the corner column -- cells with j > lq use the query
+     * bases that follow the gap (at most qavail are readable, beyond that: mismatch); they never feed H[lr][lq]
+     * but take part in the best-row tracking of the break rule and in the cell count.  mode 1: j <= lq. */
+    const int jmax = mode == 0 ? 0x3fffffff : lq;
     enum { BW = AN_BANDW };
     const int32_t go = sc[2] * AN_PACK + 1, ge = sc[3] * AN_PACK + 1;
     const int32_t sm = sc[0] * AN_PACK, sx = -(sc[1] * AN_PACK + 1);
@@ -209,7 +213,7 @@ static dp_out dp_band_sc(const uint8_t *R, int rstride, const uint8_t *Q, int qs
     for (int kk = 0; kk < BW; ++kk) { /* row 0 */
         int j = klo + kk;
         Fp[kk] = AN_NEG;
-        if (j < 0 || j > lq) Hp[kk] = AN_NEG;
+        if (j < 0 || j > jmax) Hp[kk] = AN_NEG;
         else if (j == 0) Hp[kk] = 0;
         else Hp[kk] = -(go + (j - 1) * ge);
     }
@@ -221,7 +225,7 @@ static dp_out dp_band_sc(const uint8_t *R, int rstride, const uint8_t *Q, int qs
         for (int kk = 0; kk < BW; ++kk) {
             int j = i + klo + kk;
             int32_t h, e, f;
-            if (j < 0 || j > lq) { h = e = f = AN_NEG; }
+            if (j < 0 || j > jmax) { h = e = f = AN_NEG; }
             else {
                 o.cells++;
                 int32_t e1 = eleft - ge, e2 = hleft - go;
@@ -230,7 +234,7 @@ static dp_out dp_band_sc(const uint8_t *R, int rstride, const uint8_t *Q, int qs
                 f = f1 > f2 ? f1 : f2;
                 int32_t d = AN_NEG;
                 if (j >= 1) {
-                    uint8_t qb = Q[(int64_t)qstride * (j - 1)];
+                    uint8_t qb = (j - 1 < qavail) ? Q[(int64_t)qstride * (j - 1)] : 4;
                     d = Hp[kk] + ((rb == qb && rb < 4) ? sm : sx);
                 }
                 h = d > e ? d : e;
@@ -259,7 +263,7 @@ static dp_out dp_band_sc(const uint8_t *R, int rstride, const uint8_t *Q, int qs
 }
 
 static dp_out dp_band(const uint8_t *R, int rstride, const uint8_t *Q, int qstride, int lr, int lq, int klo, int mode) {
-    return dp_band_sc(R, rstride, Q, qstride, lr, lq, klo, mode, SC_ANIM);
+    return dp_band_sc(R, rstride, Q, qstride, lr, lq, klo, mode, SC_ANIM, lq);
 }
 
 /* value = score*PACK - errs with 0 <= errs < PACK  ->  score = ceil(value / PACK) */
@@ -371,7 +375,7 @@ int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int64_t *rows, 
         } else {
             int d = lq - lr, c = d >= 0 ? d / 2 : -((-d) / 2);
             const uint8_t *Qs = b->strand ? Q->rc : Q->fw;
-            dp_out o = dp_band(R->fw + rej, 1, Qs + qej, 1, lr, lq, c - AN_BAND, 0);
+            dp_out o = dp_band_sc(R->fw + rej, 1, Qs + qej, 1, lr, lq, c - AN_BAND, 0, SC_ANIM, Q->n_pos - qej);
             v = o.val;
             stats[4] += o.cells;
             if (o.stopped) { pred[i] = -1; trim[i] = 0; v = 0; stats[2]++; }
@@ -648,7 +652,7 @@ int64_t orc_anib_pair(const orc_genome *Q, const orc_genome *S, int fragsize, in
         } else {
             int d = lq - lr, c = d >= 0 ? d / 2 : -((-d) / 2);
             const uint8_t *Qs = b->strand ? Q->rc : Q->fw;
-            dp_out o = dp_band_sc(R->fw + rej, 1, Qs + qej, 1, lr, lq, c - AN_BAND, 0, SC_ANIB);
+            dp_out o = dp_band_sc(R->fw + rej, 1, Qs + qej, 1, lr, lq, c - AN_BAND, 0, SC_ANIB, Q->n_pos - qej);
             v = o.val;
             stats[4] += o.cells;
             if (o.stopped) { pred[i] = -1; trim[i] = 0; v = 0; stats[2]++; }
@@ -701,8 +705,8 @@ int64_t orc_anib_pair(const orc_genome *Q, const orc_genome *S, int fragsize, in
                 int64_t ar = side ? r_hi - re : rs - r_lo, aq = side ? q_hi - qe : qs - q_lo;
                 int lr = (int)(ar < AN_TILE ? ar : AN_TILE), lq = (int)(aq < AN_TILE + AN_BAND ? aq : AN_TILE + AN_BAND);
                 if (lr <= 0 || lq <= 0) break;
-                dp_out o = side ? dp_band_sc(R->fw + re, 1, Qs + qe, 1, lr, lq, -AN_BAND, 1, SC_ANIB)
-                                : dp_band_sc(R->fw + rs - 1, -1, Qs + qs - 1, -1, lr, lq, -AN_BAND, 1, SC_ANIB);
+                dp_out o = side ? dp_band_sc(R->fw + re, 1, Qs + qe, 1, lr, lq, -AN_BAND, 1, SC_ANIB, lq)
+                                : dp_band_sc(R->fw + rs - 1, -1, Qs + qs - 1, -1, lr, lq, -AN_BAND, 1, SC_ANIB, lq);
                 stats[5] += o.cells; stats[6]++;
                 if (o.bi == 0 && o.bj == 0) break;
                 score += pack_score(o.val);

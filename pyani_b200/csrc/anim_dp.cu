@@ -87,7 +87,8 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
     for (int kk = 0; kk < AN_BANDW; ++kk) {  // row 0
         int j = klo + kk;
         F[kk] = NEGV;
-        Hg[kk] = ((j < 0 || j > lq) ? NEGV : (j == 0 ? 0 : -(go + (j - 1) * ge))) - go;
+        // link alignments (MODE 0) do not clip the band at the corner column (see oracle dp_band_sc)
+        Hg[kk] = ((j < 0 || (MODE == 1 && j > lq)) ? NEGV : (j == 0 ? 0 : -(go + (j - 1) * ge))) - go;
     }
     // query window of row 1: column kk holds query base index klo + kk; klo is always in [-24, -8], so the
     // window is the first chunk shifted up, the rest of that chunk feeds the stream
@@ -115,10 +116,10 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
         uint64_t mm = ((x | (x >> 1)) & 0x5555555555555555ull) | nwin;
         if (rn) mm = 0x5555555555555555ull;
         const uint32_t mlo = (uint32_t)mm, mhi = (uint32_t)(mm >> 32);
-        const int kkhi = lq - i - klo;  // columns with j <= lq
+        const int kkhi = MODE ? lq - i - klo : AN_BANDW;  // columns with j <= lq (extension tiles only)
         int hgleft = NEGV, eleft = NEGV;
         int rowkey = MODE ? (int)0x80000000 : NEGV;
-        if (kkhi >= AN_BANDW - 1) {
+        if (MODE == 0 || kkhi >= AN_BANDW - 1) {
 #pragma unroll
             for (int kk = 0; kk < AN_BANDW; ++kk) {
                 const uint32_t bit = (kk < 16 ? mlo : mhi) & (1u << ((2 * kk) & 31));
@@ -150,7 +151,7 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
         } else {
             if (rowkey > best) { best = rowkey; o.bi = i; }
         }
-        {   // cells with 0 <= j <= lq in this row
+        {   // cells with 0 <= j (<= lq in extension tiles) in this row
             int lo = max(0, -(i + klo)), hi = min(AN_BANDW - 1, kkhi);
             if (hi >= lo) o.cells += hi - lo + 1;
         }
