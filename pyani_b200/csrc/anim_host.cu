@@ -48,7 +48,7 @@ static const char *kStageNames[B200ANI_N_STAGES] = {"index", "seed", "sort", "li
 static const char *kCounterNames[B200ANI_N_STAGES] = {"probes", "seed_hits", "anchors", "links", "cut_links", "segments", "gap_cells", "ext_cells",
                                                       "ext_tiles", "alignments", "launches", "gap_tasks", "pairs", "ext_dp_launches", "gap_dp_launches", "seed_launches"};
 
-constexpr int MAX_BATCH_PAIRS = 512;
+constexpr int MAX_BATCH_PAIRS = 1280;
 constexpr int64_t ANCHOR_CAP = 48ll << 20;
 constexpr int64_t HIT_CAP = 192ll << 20;
 constexpr int EXT_TILES_PER_LAUNCH = 8;  // seed hits of one batch (8 B each)

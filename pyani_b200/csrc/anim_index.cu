@@ -171,7 +171,7 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo) {
         for (size_t k = 0; k < G; ++k) {
             const int64_t ns = (int64_t)h_cnt[k];
             size_t tb = cub_bytes;
-            cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, ns, 0, 64, st);
+            cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, ns, 32, 64, st);  // group equal k-mers; order inside a group is irrelevant
             if (ns) mark_unique_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(tmp[k].sorted, ns, tmp[k].flag);
             CK(cudaGetLastError());
             tb = cub_bytes;
