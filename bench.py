@@ -294,23 +294,28 @@ def main():
         "gap_dp_kernel": {"ms": stage_tot["gap_dp"] / K, "launches": counters_last["gap_dp_launches"]},
         "ext_dp_kernel": {"ms": stage_tot["ext_dp_kernel"] / K, "launches": counters_last["ext_dp_launches"]},
     }
-    dom = max(kern, key=lambda k: kern[k]["ms"])
-    if dom.startswith("seed"):
-        # algorithmic bytes: probe = 4 B k-mer streamed + one 8 B table slot per query minimizer and
-        # 8 B written per hit; extend = 8 B hit + 4 B posflag + 2 x 16 B packed sequence per hit, 16 B per anchor
-        alg = probes * 12 + hits * 8 if dom == "seed_probe_kernel" else hits * 44 + counters_last["anchors"] * 16
-        ach = alg / (kern[dom]["ms"] * 1e-3) / 1e9
-        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-                "peak_source": peak_src, "per_launch_ms": kern[dom]["ms"] / max(1, kern[dom]["launches"]),
-                "algorithmic_bytes_per_launch": alg / max(1, kern[dom]["launches"])}
-    else:
-        cells = cells_gap if dom == "gap_dp_kernel" else cells_ext
-        ach = cells * DPX_OPS_PER_CELL / (kern[dom]["ms"] * 1e-3) / 1e9
-        roof = {"kernel": dom, "bound": "alu", "achieved": ach, "peak": dpx_peak, "unit": "Gop/s (DPX-class int32 max-plus ops)",
+    n_anchors = counters_last["anchors"]
+
+    def roofline_of(name):
+        ms_k, launches = kern[name]["ms"], max(1, kern[name]["launches"])
+        if name.startswith("seed"):
+            # algorithmic bytes: probe = 4 B k-mer streamed + 4 B presence-filter word + (for the ~10 % that
+            # pass it) one 8 B table slot, 8 B written per hit; extend = 8 B hit + 4 B posflag + 2 x 16 B packed sequence
+            # per hit, 16 B per anchor written
+            alg = probes * 8 + hits * 16 if name == "seed_probe_kernel" else hits * 44 + n_anchors * 16
+            ach = alg / (ms_k * 1e-3) / 1e9
+            return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                    "peak_source": peak_src, "per_launch_ms": ms_k / launches, "algorithmic_bytes_per_launch": alg / launches}
+        cells = cells_gap if name == "gap_dp_kernel" else cells_ext
+        ach = cells * DPX_OPS_PER_CELL / (ms_k * 1e-3) / 1e9
+        return {"kernel": name, "bound": "alu", "achieved": ach, "peak": dpx_peak, "unit": "Gop/s (DPX-class int32 max-plus ops)",
                 "frac": ach / dpx_peak, "traffic": None, "peak_source": "measured live: b200ani_dpx_peak (__viaddmax_s32 issue rate)",
-                "per_launch_ms": kern[dom]["ms"] / max(1, kern[dom]["launches"]),
-                "cells_per_launch": cells / max(1, kern[dom]["launches"]), "ops_per_cell": DPX_OPS_PER_CELL,
-                "gcups": cells / (kern[dom]["ms"] * 1e-3) / 1e9}
+                "per_launch_ms": ms_k / launches, "cells_per_launch": cells / launches, "ops_per_cell": DPX_OPS_PER_CELL,
+                "gcups": cells / (ms_k * 1e-3) / 1e9}
+
+    dom = max(kern, key=lambda k: kern[k]["ms"])
+    roof = roofline_of(dom)
+    roof["all_kernels"] = {k: {kk: vv for kk, vv in roofline_of(k).items() if kk in ("bound", "achieved", "peak", "frac", "per_launch_ms", "gcups")} for k in kern}
     roof["hbm_peak_gbs"] = hbm_peak
     roof["dpx_peak_gops"] = dpx_peak
 

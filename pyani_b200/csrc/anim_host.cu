@@ -90,7 +90,7 @@ static int get_workspace(b200ani_ctx *ctx, AnimWorkspace **out) {
     CK(cudaMalloc(&w->hits, sizeof(uint2) * HIT_CAP));
     CK(cudaMalloc(&w->counters, 16 * sizeof(unsigned long long)));
     CK(cudaMalloc(&w->changed, sizeof(int)));
-    CK(cudaMalloc(&w->d_pairs, sizeof(PairDesc) * MAX_BATCH_PAIRS));
+    CK(cudaMalloc(&w->d_pairs, sizeof(PairDesc) * (MAX_BATCH_PAIRS + 1)));
     CK(cudaMalloc(&w->d_results, sizeof(b200ani_anim_result) * MAX_BATCH_PAIRS));
     size_t a = 0, b = 0, c = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, a, w->keys_a, w->keys_b, w->vals_a, w->vals_b, ANCHOR_CAP, 0, 64, ctx->stream);
@@ -129,7 +129,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     cudaStream_t st = ctx->stream;
     bool used[B200ANI_N_STAGES] = {false};
     // ---- pair descriptors
-    std::vector<PairDesc> hp(nb);
+    std::vector<PairDesc> hp(nb + 1);  // + sentinel
     int64_t n_probes = 0;
     for (int p = 0; p < nb; ++p) {
         const Genome &R = ctx->genomes[pairs[2 * p]], &Q = ctx->genomes[pairs[2 * p + 1]];
@@ -153,7 +153,10 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         d.q_nfrags = anib ? Q.n_frags : 0;
         if (!second) n_probes += Q.index->n_mini;
     }
-    CK(cudaMemcpyAsync(W->d_pairs, hp.data(), sizeof(PairDesc) * nb, cudaMemcpyHostToDevice, st));
+    hp[nb] = hp[nb - 1];
+    hp[nb].probe_base = n_probes;  // sentinel: end of the last pair's probe range
+    hp[nb].mirror = -1;
+    CK(cudaMemcpyAsync(W->d_pairs, hp.data(), sizeof(PairDesc) * (nb + 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(W->counters, 0, 16 * sizeof(unsigned long long), st));
     unsigned long long hc[16];
     ctx->counters[CT_PROBES] += n_probes;
@@ -162,7 +165,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     // ---- seeds -> anchors: probe (latency bound, uniform) then extend (one thread per hit)
     T0(ST_SEED);
     if (n_probes) {
-        int blocks = (int)std::min<int64_t>(ceil_div(n_probes, 256), (int64_t)ctx->sm_count * 8);
+        int blocks = (int)std::min<int64_t>(ceil_div(n_probes, 256 * 16), (int64_t)ctx->sm_count * 8);
         seed_probe_kernel<<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP);
         LAUNCHED(1);
         ctx->counters[CT_SEEDLAUNCH] += 1;

@@ -55,44 +55,49 @@ __device__ __forceinline__ int pair_of_probe(const PairDesc *__restrict__ pairs,
 // divergent work, so the warps in flight are all waiting on independent loads.
 __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restrict__ pairs, int n_pairs, int64_t n_probes, uint2 *__restrict__ hits,
                                                          unsigned long long *__restrict__ n_hits, unsigned long long cap) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // Each block walks contiguous chunks of PROBE_CHUNK probes; the pair a probe belongs to is searched once per
+    // chunk and then advanced linearly (pairs[n_pairs] is a sentinel with probe_base = n_probes).
+    constexpr int64_t PROBE_CHUNK = 256 * 16;
     const int lane = threadIdx.x & 31;
-    for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; g0 < n_probes; g0 += stride) {
-        const int64_t gi = g0 + lane;
-        bool hit = false;
-        uint32_t rpf = 0, qpf = 0;
-        int pair = -1;
-        if (gi < n_probes) {
-            pair = pair_of_probe(pairs, n_pairs, gi);
-            const PairDesc &P = pairs[pair];
-            const int64_t t = gi - P.probe_base;
-            const uint32_t kmer = __ldcs(P.q_kmer + t);
-            // ~90 % of the probes miss: the 4 MB presence filter (L2 resident) answers those without touching the table
-            hit = bitmap_test(P.r_bitmap, P.r_table_bits, kmer) && table_lookup(P.r_table, P.r_table_bits, kmer, rpf);
-            if (hit) qpf = __ldcs(P.q_posflag + t);
-        }
-        // A hit whose neighbouring query minimizer (previous one on the forward strand, next one on the reverse
-        // strand) hits the same diagonal with overlapping / abutting k-mers lies in the same exact match: only
-        // the first seed of such a run is passed on (the match set is unchanged, see seed_extend_kernel).
-        {
-            const int strand = (int)((rpf ^ qpf) >> 31);
-            const int r0 = (int)(rpf & 0x7fffffffu), qp = (int)(qpf & 0x7fffffffu);
-            const int key = strand ? r0 + qp : r0 - qp;  // constant along a diagonal of that strand
-            const int nb = strand ? lane + 1 : lane - 1;
-            const bool nhit = __shfl_sync(0xffffffffu, (int)hit, nb & 31) != 0;
-            const int npair = __shfl_sync(0xffffffffu, pair, nb & 31);
-            const int nstrand = __shfl_sync(0xffffffffu, strand, nb & 31);
-            const int nkey = __shfl_sync(0xffffffffu, key, nb & 31);
-            const int nqp = __shfl_sync(0xffffffffu, qp, nb & 31);
-            if (hit && nb >= 0 && nb < 32 && nhit && npair == pair && nstrand == strand && nkey == key && abs(nqp - qp) <= AN_K) hit = false;
-        }
-        const uint32_t m = __ballot_sync(0xffffffffu, hit);
-        if (m) {  // one atomic per warp
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(n_hits, (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
-            if (hit && slot < cap) hits[slot] = make_uint2((uint32_t)gi, rpf);
+    const int64_t n_chunks = (n_probes + PROBE_CHUNK - 1) / PROBE_CHUNK;
+    for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        int pair = pair_of_probe(pairs, n_pairs, ch * PROBE_CHUNK + threadIdx.x < n_probes ? ch * PROBE_CHUNK + threadIdx.x : n_probes - 1);
+        for (int it = 0; it < 16; ++it) {
+            const int64_t gi = ch * PROBE_CHUNK + (int64_t)it * 256 + threadIdx.x;
+            bool hit = false;
+            uint32_t rpf = 0, qpf = 0;
+            if (gi < n_probes) {
+                while (gi >= pairs[pair + 1].probe_base) ++pair;
+                const PairDesc &P = pairs[pair];
+                const int64_t t = gi - P.probe_base;
+                const uint32_t kmer = __ldcs(P.q_kmer + t);
+                // ~90 % of the probes miss: the 4 MB presence filter (L2 resident) answers those without touching the table
+                hit = bitmap_test(P.r_bitmap, P.r_table_bits, kmer) && table_lookup(P.r_table, P.r_table_bits, kmer, rpf);
+                if (hit) qpf = __ldcs(P.q_posflag + t);
+            }
+            // A hit whose neighbouring query minimizer (previous one on the forward strand, next one on the reverse
+            // strand) hits the same diagonal with overlapping / abutting k-mers lies in the same exact match: only
+            // the first seed of such a run is passed on (the match set is unchanged, see seed_extend_kernel).
+            {
+                const int strand = (int)((rpf ^ qpf) >> 31);
+                const int r0 = (int)(rpf & 0x7fffffffu), qp = (int)(qpf & 0x7fffffffu);
+                const int key = strand ? r0 + qp : r0 - qp;  // constant along a diagonal of that strand
+                const int nb = strand ? lane + 1 : lane - 1;
+                const bool nhit = __shfl_sync(0xffffffffu, (int)hit, nb & 31) != 0;
+                const int npair = __shfl_sync(0xffffffffu, pair, nb & 31);
+                const int nstrand = __shfl_sync(0xffffffffu, strand, nb & 31);
+                const int nkey = __shfl_sync(0xffffffffu, key, nb & 31);
+                const int nqp = __shfl_sync(0xffffffffu, qp, nb & 31);
+                if (hit && nb >= 0 && nb < 32 && nhit && npair == pair && nstrand == strand && nkey == key && abs(nqp - qp) <= AN_K) hit = false;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (m) {  // one atomic per warp
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(n_hits, (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+                if (hit && slot < cap) hits[slot] = make_uint2((uint32_t)gi, rpf);
+            }
         }
     }
 }
