@@ -117,3 +117,39 @@ def test_reference_fixture_genomes(engine):
         ident = r["sum_weighted"] / r["sum_aligned"]
         assert abs(100 * (ident - g[2])) < 0.15
         assert abs(r["ref_aln_len"] / g[0] - 1) < 0.01
+
+
+def test_degenerate_inputs(engine):
+    """Empty / tiny / all-N / zero-length-record genomes and an empty pair list must not crash (the
+    reference's edge cases are empty and ragged inputs); they yield NO_ALIGNMENT, like the oracle."""
+    u8 = lambda s: np.frombuffer(s, dtype=np.uint8)
+    rng = np.random.default_rng(5)
+    base = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 5000)]
+    cases = {
+        "tiny": (u8(b"ACGTACGTAC"), [0, 10]),
+        "alln": (u8(b"N" * 3000), [0, 3000]),
+        "ragged": (np.concatenate([base[:2000], base[2000:]]), [0, 0, 2000, 2000, 5000]),  # zero-length records
+        "normal": (base, [0, 5000]),
+        "short_records": (base[:90], [0, 30, 60, 90]),
+    }
+    gids, og = {}, {}
+    for k, (arr, off) in cases.items():
+        off = np.asarray(off, dtype=np.uint64)
+        gids[k] = engine.add_genome(arr, off, k)
+        og[k] = oracle.OGenome(arr, off)
+    names = list(cases)
+    pairs = [(a, b) for a in names for b in names]
+    res = engine.anim(np.array([[gids[a], gids[b]] for a, b in pairs], dtype=np.int32))
+    for (a, b), r in zip(pairs, res):
+        want = oracle.anim_pair(og[a], og[b])[0]
+        for f in FIELDS:
+            assert int(r[f]) == want[f], (a, b, f)
+    assert res[pairs.index(("normal", "ragged"))]["ref_aln_len"] == 5000  # same bases, different record layout
+    assert engine.anim(np.zeros((0, 2), np.int32)).shape == (0,)
+    rb = engine.anib(np.array([[gids[a], gids[b]] for a, b in pairs], dtype=np.int32))
+    for (a, b), r in zip(pairs, rb):
+        want = oracle.anib_pair(og[a], og[b])[0]
+        for f in ["aln_length", "sim_errs", "pid_milli_sum", "n_frags", "n_pass", "n_hsps", "status"]:
+            assert int(r[f]) == want[f], (a, b, f)
+    z, obs = engine.tetra_zscores([gids["tiny"], gids["alln"]])
+    assert obs[1].sum() == 0
