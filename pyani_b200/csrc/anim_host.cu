@@ -5,6 +5,7 @@
 // (anim.py:240-289,292-411; run_multiprocessing.py:113-152).
 #include <algorithm>
 #include <cub/cub.cuh>
+#include <cstdlib>
 #include <cstring>
 
 #include "anim.cuh"
@@ -57,6 +58,7 @@ struct AnimWorkspace {
     uint64_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr;
     uint8_t *flag = nullptr;
     uint2 *hits = nullptr;
+    int64_t anchor_cap = ANCHOR_CAP_DEFAULT, hit_cap = HIT_CAP_DEFAULT;
     unsigned long long *counters = nullptr;  // 16 device counters
     int *changed = nullptr;
     PairDesc *d_pairs = nullptr;
@@ -82,6 +84,9 @@ static int get_workspace(b200ani_ctx *ctx, AnimWorkspace **out) {
     if (ctx->anim_ws) { *out = (AnimWorkspace *)ctx->anim_ws; return 0; }
     AnimWorkspace *w = new AnimWorkspace();
     ctx->anim_ws = w;
+    if (const char *e = getenv("B200ANI_ANCHOR_CAP")) w->anchor_cap = std::max<int64_t>(1024, atoll(e));
+    if (const char *e = getenv("B200ANI_HIT_CAP")) w->hit_cap = std::max<int64_t>(1024, atoll(e));
+    const int64_t ANCHOR_CAP = w->anchor_cap, HIT_CAP = w->hit_cap;
     CK(cudaMalloc(&w->keys_a, sizeof(uint64_t) * ANCHOR_CAP));
     CK(cudaMalloc(&w->vals_a, sizeof(uint64_t) * ANCHOR_CAP));
     CK(cudaMalloc(&w->keys_b, sizeof(uint64_t) * ANCHOR_CAP));
@@ -125,6 +130,7 @@ struct RowDump {
 // fragsize == 0: ANIm (out = b200ani_anim_result[nb]); fragsize > 0: ANIb (out = b200ani_anib_result[nb])
 static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, int fragsize, void *out_v, RowDump *dump) {
     const bool anib = fragsize > 0;
+    const int64_t ANCHOR_CAP = W->anchor_cap, HIT_CAP = W->hit_cap;
     b200ani_anim_result *out = (b200ani_anim_result *)out_v;
     cudaStream_t st = ctx->stream;
     bool used[B200ANI_N_STAGES] = {false};

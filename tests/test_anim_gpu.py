@@ -153,3 +153,37 @@ def test_degenerate_inputs(engine):
             assert int(r[f]) == want[f], (a, b, f)
     z, obs = engine.tetra_zscores([gids["tiny"], gids["alln"]])
     assert obs[1].sum() == 0
+
+
+def test_batch_splitting_on_buffer_overflow():
+    """When a batch overflows the anchor / hit buffers the engine retries with half the pairs.  Force that with tiny
+    buffers in a fresh process (the capacities are read when the context's workspace is created)."""
+    import os
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    code = r"""
+import numpy as np, sys
+sys.path.insert(0, %r)
+import oracle, pyani_b200
+from pyani_b200 import synth
+gs = synth.make_set(2, 3, 150_000, seed=77)
+with pyani_b200.Engine(0) as eng:
+    gids = [eng.add_genome(g.residues, g.contig_off, g.name) for g in gs]
+    og = [oracle.OGenome(g.residues, g.contig_off) for g in gs]
+    pairs = synth.all_directed_pairs(len(gs))
+    res = eng.anim(np.array([[gids[a], gids[b]] for a, b in pairs], dtype=np.int32))
+    for (a, b), r in zip(pairs, res):
+        want = oracle.anim_pair(og[a], og[b])[0]
+        assert all(int(r[k]) == v for k, v in want.items()), (a, b)
+    rb = eng.anib(np.array([[gids[a], gids[b]] for a, b in pairs[:8]], dtype=np.int32))
+    for (a, b), r in zip(pairs[:8], rb):
+        want = oracle.anib_pair(og[a], og[b])[0]
+        assert all(int(r[k]) == v for k, v in want.items()), (a, b)
+print("SPLIT-OK", int(res["n_alignments"].sum()))
+""" % str(ROOT)
+    env = dict(os.environ, B200ANI_ANCHOR_CAP="9000", B200ANI_HIT_CAP="20000")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert "SPLIT-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
