@@ -50,9 +50,9 @@ static const char *kCounterNames[B200ANI_N_STAGES] = {"probes", "seed_hits", "an
                                                       "ext_tiles", "alignments", "launches", "gap_tasks", "pairs", "ext_dp_launches", "gap_dp_launches", "seed_launches"};
 
 constexpr int MAX_BATCH_PAIRS = 1280;
-constexpr int64_t ANCHOR_CAP = 48ll << 20;
-constexpr int64_t HIT_CAP = 192ll << 20;
-constexpr int EXT_TILES_PER_LAUNCH = 8;  // seed hits of one batch (8 B each)
+constexpr int64_t ANCHOR_CAP_DEFAULT = 48ll << 20;  // anchors of one batch (overridable: B200ANI_ANCHOR_CAP, used by the batch-split test)
+constexpr int64_t HIT_CAP_DEFAULT = 192ll << 20;    // seed hits of one batch, 8 B each (B200ANI_HIT_CAP)
+constexpr int EXT_TILES_PER_LAUNCH = 8;
 
 struct AnimWorkspace {
     uint64_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr;
