@@ -94,3 +94,43 @@ def test_run_dependency_graph_writes_files_parse_delta_can_read(tmp_path):
     text = open(str(out) + ".filter").read().splitlines()
     assert text[1] == "NUCMER" and text[2] == ">a1 b1 18 14" and text[3].split() == "1 10 1 11 5 5 0".split()
     assert oracle.parse_delta_reduce(d)[2] == pytest.approx(0.696969696969697)  # anim.py:343 worked example
+
+
+def test_anim_matrices_match_cellwise_fill():
+    """matrices.anim_matrices vs a literal restatement of pyani_orm.update_comparison_matrices (pyani_orm.py:618-666)."""
+    from pyani_b200 import matrices
+
+    tuples, legacy = _gold()
+    names = ["NC_014100", "NC_002696", "NC_011916", "NC_010338"]  # deliberately unsorted ids
+    lengths = [legacy["org_lengths"][n] for n in names]
+    pairs, res = [], []
+    for i, a in enumerate(names):
+        for j, b in enumerate(names):
+            if a == b:
+                continue
+            ral, qal, ident, errs = tuples[f"{a}_vs_{b}.filter"]
+            r = np.zeros(1, dtype=ANIM_DTYPE)[0]
+            # integer sums consistent with the golden identity are not recoverable from the tuple; use exact stand-ins
+            r["ref_aln_len"], r["qry_aln_len"], r["sim_errs"] = ral, qal, errs
+            r["sum_aligned"], r["sum_weighted"] = 10**9, round(ident * 10**9)
+            pairs.append((i, j)); res.append(r)
+    res = np.array(res, dtype=ANIM_DTYPE)
+    got = matrices.anim_matrices(names, lengths, np.array(pairs), res)
+    ids = sorted(names)
+    want = {k: pd.DataFrame(index=ids, columns=ids, dtype=float) for k in got}
+    for k, v in (("identity", 1.0), ("coverage", 1.0), ("sim_errors", 0.0), ("hadamard", 1.0)):
+        np.fill_diagonal(want[k].values, v)
+    for n, l in zip(names, lengths):
+        want["aln_lengths"].loc[n, n] = l
+    for (i, j), r in zip(pairs, res):
+        q, s = names[i], names[j]
+        ident = r["sum_weighted"] / r["sum_aligned"]
+        cov = r["ref_aln_len"] / lengths[i]
+        want["identity"].loc[q, s] = ident
+        want["coverage"].loc[q, s] = cov
+        want["aln_lengths"].loc[q, s] = r["ref_aln_len"]
+        want["sim_errors"].loc[q, s] = r["sim_errs"]
+        want["hadamard"].loc[q, s] = ident * cov
+    for k in got:
+        assert list(got[k].index) == ids
+        assert np.array_equal(got[k].values, want[k].values, equal_nan=True), k
