@@ -162,6 +162,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     hp[nb] = hp[nb - 1];
     hp[nb].probe_base = n_probes;  // sentinel: end of the last pair's probe range
     hp[nb].mirror = -1;
+    if (n_probes >= (1ll << 32) && nb > 1) return 1;  // probe indices are 32-bit: split the batch
     CK(cudaMemcpyAsync(W->d_pairs, hp.data(), sizeof(PairDesc) * (nb + 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(W->counters, 0, 16 * sizeof(unsigned long long), st));
     unsigned long long hc[16];
