@@ -94,11 +94,10 @@ __global__ void split_bypos_kernel(const uint64_t *__restrict__ bypos, int64_t n
 
 void free_index(MinimizerIndex *ix, cudaStream_t st) {
     if (!ix) return;
-    (void)st;
-    cudaFree(ix->d_kmer);
-    cudaFree(ix->d_posflag);
-    cudaFree(ix->d_table);
-    cudaFree(ix->d_bitmap);
+    cudaFreeAsync(ix->d_kmer, st);
+    cudaFreeAsync(ix->d_posflag, st);
+    cudaFreeAsync(ix->d_table, st);
+    cudaFreeAsync(ix->d_bitmap, st);
     delete ix;
 }
 void invalidate_index(MinimizerIndex *ix) { if (ix) ix->valid = false; }
@@ -199,13 +198,14 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo) {
             ix->n_mini = h_nu;
             ix->table_bits = bits;
             if (ix->cap_bits < bits || ix->cap_mini < h_nu + 1) {  // first build (or a bigger genome): allocate once
-                CK(cudaStreamSynchronize(st));
-                cudaFree(ix->d_table); cudaFree(ix->d_kmer); cudaFree(ix->d_posflag); cudaFree(ix->d_bitmap);
+                // stream-ordered pool allocations (a plain cudaMalloc costs milliseconds each on a busy context);
+                // index buffers live until the genome or the context goes away, so there is no alloc/free churn
+                if (ix->d_table) { cudaFreeAsync(ix->d_table, st); cudaFreeAsync(ix->d_kmer, st); cudaFreeAsync(ix->d_posflag, st); cudaFreeAsync(ix->d_bitmap, st); }
                 ix->d_table = nullptr; ix->d_kmer = nullptr; ix->d_posflag = nullptr; ix->d_bitmap = nullptr;
-                CK(cudaMalloc(&ix->d_table, sizeof(uint64_t) << bits));
-                CK(cudaMalloc(&ix->d_bitmap, sizeof(uint32_t) << (bits + 3 - 5)));
-                CK(cudaMalloc(&ix->d_kmer, sizeof(uint32_t) * (size_t)(h_nu + 1)));
-                CK(cudaMalloc(&ix->d_posflag, sizeof(uint32_t) * (size_t)(h_nu + 1)));
+                CK(cudaMallocAsync(&ix->d_table, sizeof(uint64_t) << bits, st));
+                CK(cudaMallocAsync(&ix->d_bitmap, sizeof(uint32_t) << (bits + 3 - 5), st));
+                CK(cudaMallocAsync(&ix->d_kmer, sizeof(uint32_t) * (size_t)(h_nu + 1), st));
+                CK(cudaMallocAsync(&ix->d_posflag, sizeof(uint32_t) * (size_t)(h_nu + 1), st));
                 ix->cap_bits = bits;
                 ix->cap_mini = h_nu + 1;
             }
