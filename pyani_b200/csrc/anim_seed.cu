@@ -32,11 +32,25 @@ __device__ int64_t match_right(const SeqView &R, const SeqView &Q, int64_t r, in
 __device__ int64_t match_left(const SeqView &R, const SeqView &Q, int64_t r, int64_t q) {
     int64_t l = 0;
     while (true) {
-        int64_t rr = r - l - 1, qq = q - l - 1;
-        if (rr < 0 || qq < 0) return l;
-        int a = view_code(R, rr), b = view_code(Q, qq);
-        if (a > 3 || a != b) return l;
-        ++l;
+        const int64_t rr = r - l, qq = q - l;  // bases [rr-32, rr) and [qq-32, qq) are compared from the top down
+        if (rr <= 0 || qq <= 0) return l;
+        if (rr >= 32 && qq >= 32 && rr <= R.n && qq <= Q.n) {
+            uint32_t mr, mq;
+            uint64_t a = view_chunk(R, rr - 32, mr), b = view_chunk(Q, qq - 32, mq);
+            uint64_t d = a ^ b;
+            d = (d | (d >> 1)) & 0x5555555555555555ull;
+            // highest differing base (closest to the seed) decides: matches run from base 31 downwards
+            int top = d ? 31 - (__clzll((long long)d) >> 1) : -1;
+            uint32_t mk = mr | mq;
+            int tm = mk ? 31 - __clz((int)mk) : -1;
+            top = max(top, tm);
+            if (top >= 0) return l + (31 - top);
+            l += 32;
+        } else {
+            int a = view_code(R, rr - 1), b = view_code(Q, qq - 1);
+            if (a > 3 || a != b) return l;
+            ++l;
+        }
     }
 }
 
@@ -55,48 +69,87 @@ __device__ __forceinline__ int pair_of_probe(const PairDesc *__restrict__ pairs,
 // divergent work, so the warps in flight are all waiting on independent loads.
 __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restrict__ pairs, int n_pairs, int64_t n_probes, uint2 *__restrict__ hits,
                                                          unsigned long long *__restrict__ n_hits, unsigned long long cap) {
-    // Each block walks contiguous chunks of PROBE_CHUNK probes; the pair a probe belongs to is searched once per
-    // chunk and then advanced linearly (pairs[n_pairs] is a sentinel with probe_base = n_probes).
-    constexpr int64_t PROBE_CHUNK = 256 * 16;
+    // Each block walks contiguous chunks of PROBE_CHUNK probes, PROBE_ILP probes per thread per step so that the
+    // dependent loads (k-mer -> presence word -> table slot) of several probes are in flight together.  The pair a
+    // probe belongs to is searched once per chunk and then advanced linearly; its descriptor fields stay in
+    // registers until the pair changes (pairs[n_pairs] is a sentinel with probe_base = n_probes).
+    constexpr int PROBE_ILP = 4, PROBE_STEPS = 4;
+    constexpr int64_t PROBE_CHUNK = 256 * PROBE_ILP * PROBE_STEPS;
     const int lane = threadIdx.x & 31;
     const int64_t n_chunks = (n_probes + PROBE_CHUNK - 1) / PROBE_CHUNK;
     for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
-        int pair = pair_of_probe(pairs, n_pairs, ch * PROBE_CHUNK + threadIdx.x < n_probes ? ch * PROBE_CHUNK + threadIdx.x : n_probes - 1);
-        for (int it = 0; it < 16; ++it) {
-            const int64_t gi = ch * PROBE_CHUNK + (int64_t)it * 256 + threadIdx.x;
-            bool hit = false;
-            uint32_t rpf = 0, qpf = 0;
-            if (gi < n_probes) {
-                while (gi >= pairs[pair + 1].probe_base) ++pair;
-                const PairDesc &P = pairs[pair];
-                const int64_t t = gi - P.probe_base;
-                const uint32_t kmer = __ldcs(P.q_kmer + t);
-                // ~90 % of the probes miss: the 4 MB presence filter (L2 resident) answers those without touching the table
-                hit = bitmap_test(P.r_bitmap, P.r_table_bits, kmer) && table_lookup(P.r_table, P.r_table_bits, kmer, rpf);
-                if (hit) qpf = __ldcs(P.q_posflag + t);
+        const int64_t g_first = ch * PROBE_CHUNK + threadIdx.x;
+        int pair = pair_of_probe(pairs, n_pairs, g_first < n_probes ? g_first : n_probes - 1);
+        int cached = -1;
+        const uint32_t *q_kmer = nullptr, *q_posflag = nullptr, *r_bitmap = nullptr;
+        const uint64_t *r_table = nullptr;
+        uint32_t bits = 0;
+        int64_t base = 0, next_base = 0;
+        for (int step = 0; step < PROBE_STEPS; ++step) {
+            uint32_t kmer[PROBE_ILP], rpf[PROBE_ILP], qpf[PROBE_ILP];
+            int64_t gi[PROBE_ILP];
+            int pr[PROBE_ILP];
+            bool hit[PROBE_ILP];
+#pragma unroll
+            for (int k = 0; k < PROBE_ILP; ++k) {  // phase 1: k-mers (coalesced, streaming)
+                gi[k] = ch * PROBE_CHUNK + (int64_t)(step * PROBE_ILP + k) * 256 + threadIdx.x;
+                hit[k] = false; rpf[k] = 0; qpf[k] = 0; kmer[k] = 0; pr[k] = -1;
+                if (gi[k] < n_probes) {
+                    while (gi[k] >= next_base || cached < 0) {  // (re)load the pair's fields
+                        if (cached >= 0) ++pair;
+                        while (gi[k] >= pairs[pair + 1].probe_base) ++pair;
+                        const PairDesc &P = pairs[pair];
+                        q_kmer = P.q_kmer; q_posflag = P.q_posflag; r_bitmap = P.r_bitmap; r_table = P.r_table; bits = P.r_table_bits;
+                        base = P.probe_base; next_base = pairs[pair + 1].probe_base;
+                        cached = pair;
+                    }
+                    pr[k] = pair;
+                    kmer[k] = __ldcs(q_kmer + (gi[k] - base));
+                }
             }
-            // A hit whose neighbouring query minimizer (previous one on the forward strand, next one on the reverse
-            // strand) hits the same diagonal with overlapping / abutting k-mers lies in the same exact match: only
-            // the first seed of such a run is passed on (the match set is unchanged, see seed_extend_kernel).
-            {
-                const int strand = (int)((rpf ^ qpf) >> 31);
-                const int r0 = (int)(rpf & 0x7fffffffu), qp = (int)(qpf & 0x7fffffffu);
+            // phase 2: presence filter (4 MB per reference, L2 resident) -- ~90 % of the probes end here
+            const uint32_t *bm[PROBE_ILP];
+            const uint64_t *tb[PROBE_ILP];
+            const uint32_t *pf[PROBE_ILP];
+            uint32_t tbits[PROBE_ILP];
+#pragma unroll
+            for (int k = 0; k < PROBE_ILP; ++k) {
+                // the cached fields belong to the LAST probe's pair; re-read them when an earlier probe sits in another pair
+                const bool same = pr[k] == cached;
+                const PairDesc &P = pairs[pr[k] < 0 ? 0 : pr[k]];
+                bm[k] = same ? r_bitmap : P.r_bitmap; tb[k] = same ? r_table : P.r_table; tbits[k] = same ? bits : P.r_table_bits;
+                pf[k] = (same ? q_posflag : P.q_posflag) + (gi[k] - (same ? base : P.probe_base));
+                hit[k] = pr[k] >= 0 && bitmap_test(bm[k], tbits[k], kmer[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < PROBE_ILP; ++k) {  // phase 3: table probe for the filter's positives
+                if (hit[k]) hit[k] = table_lookup(tb[k], tbits[k], kmer[k], rpf[k]);
+                if (hit[k]) qpf[k] = __ldcs(pf[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < PROBE_ILP; ++k) {
+                // A hit whose neighbouring query minimizer (previous one on the forward strand, next one on the reverse
+                // strand) hits the same diagonal with overlapping / abutting k-mers lies in the same exact match: only
+                // the first seed of such a run is passed on (the match set is unchanged, see seed_extend_kernel).
+                bool h = hit[k];
+                const int strand = (int)((rpf[k] ^ qpf[k]) >> 31);
+                const int r0 = (int)(rpf[k] & 0x7fffffffu), qp = (int)(qpf[k] & 0x7fffffffu);
                 const int key = strand ? r0 + qp : r0 - qp;  // constant along a diagonal of that strand
                 const int nb = strand ? lane + 1 : lane - 1;
-                const bool nhit = __shfl_sync(0xffffffffu, (int)hit, nb & 31) != 0;
-                const int npair = __shfl_sync(0xffffffffu, pair, nb & 31);
+                const bool nhit = __shfl_sync(0xffffffffu, (int)h, nb & 31) != 0;
+                const int npair = __shfl_sync(0xffffffffu, pr[k], nb & 31);
                 const int nstrand = __shfl_sync(0xffffffffu, strand, nb & 31);
                 const int nkey = __shfl_sync(0xffffffffu, key, nb & 31);
                 const int nqp = __shfl_sync(0xffffffffu, qp, nb & 31);
-                if (hit && nb >= 0 && nb < 32 && nhit && npair == pair && nstrand == strand && nkey == key && abs(nqp - qp) <= AN_K) hit = false;
-            }
-            const uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (m) {  // one atomic per warp
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(n_hits, (unsigned long long)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
-                if (hit && slot < cap) hits[slot] = make_uint2((uint32_t)gi, rpf);
+                if (h && nb >= 0 && nb < 32 && nhit && npair == pr[k] && nstrand == strand && nkey == key && abs(nqp - qp) <= AN_K) h = false;
+                const uint32_t m = __ballot_sync(0xffffffffu, h);
+                if (m) {  // one atomic per warp
+                    unsigned long long bslot = 0;
+                    if (lane == 0) bslot = atomicAdd(n_hits, (unsigned long long)__popc(m));
+                    bslot = __shfl_sync(0xffffffffu, bslot, 0);
+                    const unsigned long long slot = bslot + __popc(m & ((1u << lane) - 1u));
+                    if (h && slot < cap) hits[slot] = make_uint2((uint32_t)gi[k], rpf[k]);
+                }
             }
         }
     }
