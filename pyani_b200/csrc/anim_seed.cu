@@ -75,12 +75,19 @@ __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restr
     // registers until the pair changes (pairs[n_pairs] is a sentinel with probe_base = n_probes).
     constexpr int PROBE_ILP = 4, PROBE_STEPS = 4;
     constexpr int64_t PROBE_CHUNK = 256 * PROBE_ILP * PROBE_STEPS;
+    // hits of a chunk are staged in shared memory and appended with ONE global atomic per chunk: tens of millions
+    // of atomics on a single counter serialise in L2 and were the actual bound of this kernel
+    __shared__ uint2 s_hits[PROBE_CHUNK];
+    __shared__ unsigned int s_n;
+    __shared__ unsigned long long s_base;
     const int lane = threadIdx.x & 31;
     const int64_t n_chunks = (n_probes + PROBE_CHUNK - 1) / PROBE_CHUNK;
     for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
         const int64_t g_first = ch * PROBE_CHUNK + threadIdx.x;
         int pair = pair_of_probe(pairs, n_pairs, g_first < n_probes ? g_first : n_probes - 1);
         int cached = -1;
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
         const uint32_t *q_kmer = nullptr, *q_posflag = nullptr, *r_bitmap = nullptr;
         const uint64_t *r_table = nullptr;
         uint32_t bits = 0;
@@ -143,28 +150,59 @@ __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restr
                 const int nqp = __shfl_sync(0xffffffffu, qp, nb & 31);
                 if (h && nb >= 0 && nb < 32 && nhit && npair == pr[k] && nstrand == strand && nkey == key && abs(nqp - qp) <= AN_K) h = false;
                 const uint32_t m = __ballot_sync(0xffffffffu, h);
-                if (m) {  // one atomic per warp
-                    unsigned long long bslot = 0;
-                    if (lane == 0) bslot = atomicAdd(n_hits, (unsigned long long)__popc(m));
+                if (m) {  // one shared-memory atomic per warp
+                    unsigned int bslot = 0;
+                    if (lane == 0) bslot = atomicAdd(&s_n, (unsigned int)__popc(m));
                     bslot = __shfl_sync(0xffffffffu, bslot, 0);
-                    const unsigned long long slot = bslot + __popc(m & ((1u << lane) - 1u));
-                    if (h && slot < cap) hits[slot] = make_uint2((uint32_t)gi[k], rpf[k]);
+                    if (h) s_hits[bslot + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)gi[k], rpf[k]);
                 }
             }
         }
+        __syncthreads();
+        const unsigned int n_stage = s_n;
+        if (threadIdx.x == 0 && n_stage) s_base = atomicAdd(n_hits, (unsigned long long)n_stage);
+        __syncthreads();
+        for (unsigned int i = threadIdx.x; i < n_stage; i += 256)
+            if (s_base + i < cap) hits[s_base + i] = s_hits[i];
+        __syncthreads();
     }
 }
 
 // One anchor of pair `pi`: ANIm -> as is; ANIb (P.fragsize > 0) -> clipped to the query's fragments, one piece per
 // fragment it overlaps (pieces shorter than AB_MINPIECE are dropped), the fragment id goes into the sort key.
-__device__ __forceinline__ void emit_anchor(const PairDesc &P, int pi, int strand, int64_t rs, int64_t qs, int64_t len, uint64_t *__restrict__ keys,
+// Anchors are staged per block in shared memory and appended with one global atomic per block step (the same
+// single-counter serialisation as in the probe kernel); a full stage falls back to a direct append.
+constexpr int STAGE_CAP = 2048;
+struct AnchorStage {
+    uint64_t key[STAGE_CAP], val[STAGE_CAP];
+    unsigned int n;
+    unsigned long long base;
+};
+__device__ __forceinline__ void stage_anchor(AnchorStage &S, uint64_t key, uint64_t val, uint64_t *__restrict__ keys, uint64_t *__restrict__ vals,
+                                             unsigned long long *__restrict__ n_anchors, unsigned long long cap) {
+    const unsigned int slot = atomicAdd(&S.n, 1u);
+    if (slot < STAGE_CAP) { S.key[slot] = key; S.val[slot] = val; return; }
+    const unsigned long long g = atomicAdd(n_anchors, 1ull);
+    if (g < cap) { keys[g] = key; vals[g] = val; }
+}
+// all threads of the block; resets the stage
+__device__ __forceinline__ void flush_stage(AnchorStage &S, uint64_t *__restrict__ keys, uint64_t *__restrict__ vals,
+                                            unsigned long long *__restrict__ n_anchors, unsigned long long cap) {
+    __syncthreads();
+    const unsigned int n = min(S.n, (unsigned int)STAGE_CAP);
+    if (threadIdx.x == 0 && n) S.base = atomicAdd(n_anchors, (unsigned long long)n);
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i < n; i += blockDim.x)
+        if (S.base + i < cap) { keys[S.base + i] = S.key[i]; vals[S.base + i] = S.val[i]; }
+    __syncthreads();
+    if (threadIdx.x == 0) S.n = 0;
+    __syncthreads();
+}
+
+__device__ __forceinline__ void emit_anchor(AnchorStage &S, const PairDesc &P, int pi, int strand, int64_t rs, int64_t qs, int64_t len, uint64_t *__restrict__ keys,
                                             uint64_t *__restrict__ vals, unsigned long long *__restrict__ n_anchors, unsigned long long cap) {
     if (P.fragsize == 0) {
-        unsigned long long slot = atomicAdd(n_anchors, 1ull);
-        if (slot < cap) {
-            keys[slot] = make_key(pi, 0, strand, rs);
-            vals[slot] = ((uint64_t)qs << 32) | (uint64_t)len;
-        }
+        stage_anchor(S, make_key(pi, 0, strand, rs), ((uint64_t)qs << 32) | (uint64_t)len, keys, vals, n_anchors, cap);
         return;
     }
     const int64_t F = P.fragsize;
@@ -175,11 +213,7 @@ __device__ __forceinline__ void emit_anchor(const PairDesc &P, int pi, int stran
         int64_t a = max(rec0 + k * F, fa), b = min(rec0 + (k + 1) * F, fb);
         if (b - a < AB_MINPIECE) continue;
         const int64_t t0 = strand ? ((int64_t)P.q_npos - b) - qs : a - qs;  // offset of the piece inside the match
-        unsigned long long slot = atomicAdd(n_anchors, 1ull);
-        if (slot < cap) {
-            keys[slot] = make_key(pi, P.q_fbase[c] + (uint32_t)k, strand, rs + t0);
-            vals[slot] = ((uint64_t)(qs + t0) << 32) | (uint64_t)(b - a);
-        }
+        stage_anchor(S, make_key(pi, P.q_fbase[c] + (uint32_t)k, strand, rs + t0), ((uint64_t)(qs + t0) << 32) | (uint64_t)(b - a), keys, vals, n_anchors, cap);
     }
 }
 
@@ -188,8 +222,13 @@ __device__ __forceinline__ void emit_anchor(const PairDesc &P, int pi, int stran
 __global__ void __launch_bounds__(256) seed_extend_kernel(const PairDesc *__restrict__ pairs, int n_pairs, const uint2 *__restrict__ hits, int64_t n_hits,
                                                           uint64_t *__restrict__ keys, uint64_t *__restrict__ vals,
                                                           unsigned long long *__restrict__ n_anchors, unsigned long long cap) {
+    __shared__ AnchorStage stage;
+    if (threadIdx.x == 0) stage.n = 0;
+    __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t hi_ = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; hi_ < n_hits; hi_ += stride) {
+    for (int64_t h0 = (int64_t)blockIdx.x * blockDim.x; h0 < n_hits; h0 += stride) {
+      const int64_t hi_ = h0 + threadIdx.x;
+      if (hi_ < n_hits) do {
         const uint2 h = hits[hi_];
         const int64_t gi = h.x;
         const int lo = pair_of_probe(pairs, n_pairs, gi);
@@ -215,24 +254,26 @@ __global__ void __launch_bounds__(256) seed_extend_kernel(const PairDesc *__rest
                         int a = view_code(R, x + (r0 - q0)), b = view_code(Q, x);
                         same = a < 4 && a == b;
                     }
-                    if (same) continue;
+                    if (same) break;  // redundant seed
                 }
             }
         }
         int64_t l = match_left(R, Q, r0, q0);
         int64_t rr = match_right(R, Q, r0 + AN_K, q0 + AN_K);
         int64_t len = AN_K + l + rr;
-        if (len < AN_MINLEN) continue;
+        if (len < AN_MINLEN) break;
         // Exact matches are symmetric in the two genomes (seeds are k-mers unique in BOTH minimizer sets and the
         // selection is strand-symmetric), so the opposite-direction comparison gets its anchors from the same
         // seeds: forward (r,q) -> (q,r); reverse-strand coordinates swap roles through both genome lengths.
         const int64_t rs = r0 - l, qs = q0 - l;
-        emit_anchor(P, lo, strand, rs, qs, len, keys, vals, n_anchors, cap);
+        emit_anchor(stage, P, lo, strand, rs, qs, len, keys, vals, n_anchors, cap);
         if (P.mirror >= 0) {
             const int64_t r2 = strand ? (int64_t)P.q_npos - qs - len : qs;
             const int64_t q2 = strand ? (int64_t)P.r_npos - rs - len : rs;
-            emit_anchor(pairs[P.mirror], P.mirror, strand, r2, q2, len, keys, vals, n_anchors, cap);
+            emit_anchor(stage, pairs[P.mirror], P.mirror, strand, r2, q2, len, keys, vals, n_anchors, cap);
         }
+      } while (false);
+      flush_stage(stage, keys, vals, n_anchors, cap);
     }
 }
 
