@@ -80,7 +80,8 @@ typedef struct {
 
 /* All m directed pairs (pairs[2*i]=ref genome id, pairs[2*i+1]=qry genome id).  Replaces, per pair, the
  * nucmer + delta-filter subprocesses (anim.py:240-289) and anim.parse_delta (anim.py:292-411).
- * maxmatch: anim.py:276-279 (only --mum semantics, maxmatch=0, are implemented in this version).
+ * maxmatch: anim.py:276-279.  0 = --mum (seed k-mers unique in both genomes); 1 = --maxmatch (every seed k-mer with
+ * at most 16 occurrences per genome; nucmer itself has no cap).
  * nofilter: subcmd_anim.py:341-344 (skip the 1-to-1 filter stage). */
 int b200ani_anim(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch, int nofilter,
                  b200ani_anim_result *out);

@@ -147,9 +147,9 @@ ANIM_STAT_NAMES = ["anchors", "links", "cut_links", "segments", "gap_cells", "ex
 class OGenome:
     """Oracle-side genome handle (byte-per-base g-space + unique-minimizer index)."""
 
-    def __init__(self, ascii_u8: np.ndarray, contig_off: np.ndarray):
+    def __init__(self, ascii_u8: np.ndarray, contig_off: np.ndarray, maxmatch: bool = False):
         L = lib()
-        L.orc_genome_create.restype = ctypes.c_void_p
+        L.orc_genome_create_occ.restype = ctypes.c_void_p
         L.orc_genome_free.argtypes = [ctypes.c_void_p]
         L.orc_genome_n_mini.restype = ctypes.c_int64
         L.orc_genome_n_mini.argtypes = [ctypes.c_void_p]
@@ -157,7 +157,9 @@ class OGenome:
         o = np.ascontiguousarray(contig_off, dtype=np.uint64)
         self.n_bases = int(o[-1])
         self.contig_off = o
-        self._h = ctypes.c_void_p(L.orc_genome_create(_p(a, ctypes.c_uint8), _p(o, ctypes.c_uint64), ctypes.c_uint32(len(o) - 1)))
+        self.maxmatch = bool(maxmatch)
+        self._h = ctypes.c_void_p(L.orc_genome_create_occ(_p(a, ctypes.c_uint8), _p(o, ctypes.c_uint64), ctypes.c_uint32(len(o) - 1),
+                                                          ctypes.c_int(16 if maxmatch else 1)))
 
     def __del__(self):
         try:

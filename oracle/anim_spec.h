@@ -14,6 +14,7 @@
 
 #define AN_K 16          /* seed k-mer length (2-bit packed -> one u32) */
 #define AN_W 5           /* minimizer window: K+W-1 = 20 = nucmer -l 20 => every match >= 20 is seeded */
+#define AN_MAXOCC 16     /* --maxmatch: seed k-mers with more occurrences than this in a genome are ignored */
 #define AN_MINLEN 20     /* minimum maximal-exact-match length (nucmer -l 20) */
 #define AN_LOOKBACK 32   /* chaining: predecessor searched among the previous 32 anchors */
 #define AN_GAPMAX 1000   /* chaining: max gap between linked anchors on either genome */

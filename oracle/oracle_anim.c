@@ -68,7 +68,14 @@ void orc_genome_free(orc_genome *g) {
     free(g);
 }
 
+/* maxocc = 1: --mum seeds (k-mers unique among the genome's minimizers); maxocc = AN_MAXOCC: --maxmatch seeds
+ * (every k-mer with at most that many occurrences; nucmer itself has no cap, anim.py:276-279) */
+orc_genome *orc_genome_create_occ(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs, int maxocc);
 orc_genome *orc_genome_create(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs) {
+    return orc_genome_create_occ(ascii, off, n_contigs, 1);
+}
+
+orc_genome *orc_genome_create_occ(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs, int maxocc) {
     orc_genome *g = (orc_genome *)calloc(1, sizeof *g);
     g->n_contigs = n_contigs;
     g->n_bases = (int64_t)off[n_contigs];
@@ -131,7 +138,8 @@ orc_genome *orc_genome_create(const uint8_t *ascii, const uint64_t *off, uint32_
     for (int64_t i = 0; i < ns;) {
         int64_t j = i + 1;
         while (j < ns && (sel[j] >> 32) == (sel[i] >> 32)) ++j;
-        if (j - i == 1) sel[nu++] = sel[i];
+        if (j - i <= maxocc)
+            for (int64_t x = i; x < j; ++x) sel[nu++] = sel[x];
         i = j;
     }
     g->n_mini = nu;
@@ -170,6 +178,17 @@ static inline int lookup(const orc_genome *g, uint32_t kmer, uint32_t *posflag) 
     uint64_t mask = (1ull << g->table_bits) - 1, s = table_hash(kmer) >> (32 - g->table_bits);
     while (g->table[s] != ~0ull) {
         if ((uint32_t)(g->table[s] >> 32) == kmer) { *posflag = (uint32_t)g->table[s]; return 1; }
+        s = (s + 1) & mask;
+    }
+    return 0;
+}
+
+/* all table entries of a k-mer: call with *cursor = ~0 first; returns 0 when exhausted */
+static inline int lookup_next(const orc_genome *g, uint32_t kmer, uint64_t *cursor, uint32_t *posflag) {
+    uint64_t mask = (1ull << g->table_bits) - 1;
+    uint64_t s = *cursor == ~0ull ? (uint64_t)(table_hash(kmer) >> (32 - g->table_bits)) : ((*cursor + 1) & mask);
+    while (g->table[s] != ~0ull) {
+        if ((uint32_t)(g->table[s] >> 32) == kmer) { *posflag = (uint32_t)g->table[s]; *cursor = s; return 1; }
         s = (s + 1) & mask;
     }
     return 0;
@@ -295,8 +314,9 @@ int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int64_t *rows, 
     anchor *A = (anchor *)malloc(sizeof(anchor) * (size_t)acap);
     int64_t last_d[2] = {0, 0}, last_r0[2] = {-1, -1}, last_r1[2] = {-1, -1}; /* last match per strand */
     for (int64_t t = 0; t < Q->n_mini; ++t) {
-        uint32_t rpf;
-        if (!lookup(R, Q->mini_kmer[t], &rpf)) continue;
+      uint32_t rpf;
+      uint64_t cursor = ~0ull;
+      while (lookup_next(R, Q->mini_kmer[t], &cursor, &rpf)) { /* one entry for --mum indexes, up to AN_MAXOCC for --maxmatch */
         stats[7]++;
         uint32_t qpf = Q->mini_posflag[t];
         int strand = (int)((rpf ^ qpf) >> 31);
@@ -316,6 +336,7 @@ int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int64_t *rows, 
         if (na == acap) { acap *= 2; A = (anchor *)realloc(A, sizeof(anchor) * (size_t)acap); }
         A[na].strand = strand; A[na].r = (int32_t)(r0 - l); A[na].q = (int32_t)(q0 - l); A[na].len = (int32_t)len;
         ++na;
+      }
     }
     qsort(A, (size_t)na, sizeof(anchor), cmp_anchor);
     int64_t nu = 0;

@@ -9,6 +9,7 @@
 
 struct MinimizerIndex {
     bool valid = false;             // false after b200ani_reset_indexes: buffers are kept, content is rebuilt
+    int maxocc = 1;                 // 1: --mum seeds (unique k-mers); AN_MAXOCC: --maxmatch seeds
     int64_t cap_mini = 0;           // capacity of d_kmer / d_posflag
     uint32_t cap_bits = 0;          // capacity of d_table = 2^cap_bits slots
     int64_t n_mini = 0;
@@ -59,6 +60,18 @@ __device__ __forceinline__ bool table_lookup(const uint64_t *__restrict__ table,
         uint64_t e = __ldg(table + s);
         if (e == ~0ull) return false;
         if ((uint32_t)(e >> 32) == kmer) { posflag = (uint32_t)e; return true; }
+        s = (s + 1) & msk;
+    }
+}
+
+// every table entry of a k-mer (--maxmatch indexes hold up to AN_MAXOCC per k-mer): start with cursor = ~0u
+__device__ __forceinline__ bool table_next(const uint64_t *__restrict__ table, uint32_t bits, uint32_t kmer, uint32_t &cursor, uint32_t &posflag) {
+    const uint32_t msk = (1u << bits) - 1u;
+    uint32_t s = cursor == ~0u ? table_hash(kmer) >> (32 - bits) : (cursor + 1) & msk;
+    while (true) {
+        uint64_t e = __ldg(table + s);
+        if (e == ~0ull) return false;
+        if ((uint32_t)(e >> 32) == kmer) { posflag = (uint32_t)e; cursor = s; return true; }
         s = (s + 1) & msk;
     }
 }

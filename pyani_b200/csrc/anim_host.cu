@@ -10,10 +10,10 @@
 
 #include "anim.cuh"
 
-int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo);
+int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc);
 
 // kernels defined in the other translation units
-__global__ void seed_probe_kernel(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
+template <bool MAXMATCH> __global__ void seed_probe_kernel(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
 __global__ void seed_extend_kernel(const PairDesc *, int, const uint2 *, int64_t, uint64_t *, uint64_t *, unsigned long long *, unsigned long long);
 __global__ void tie_fix_kernel(uint64_t *, uint64_t *, int64_t);
 __global__ void flag_unique_kernel(const uint64_t *, const uint64_t *, int64_t, uint8_t *);
@@ -173,7 +173,10 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     T0(ST_SEED);
     if (n_probes) {
         int blocks = (int)std::min<int64_t>(ceil_div(n_probes, 256 * 16), (int64_t)ctx->sm_count * 8);
-        seed_probe_kernel<<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP);
+        if (ctx->genomes[pairs[0]].index->maxocc > 1)
+            seed_probe_kernel<true><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP);
+        else
+            seed_probe_kernel<false><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP);
         LAUNCHED(1);
         ctx->counters[CT_SEEDLAUNCH] += 1;
     }
@@ -487,7 +490,7 @@ static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs_in
 }
 
 static int prepare(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch, AnimWorkspace **W) {
-    if (maxmatch) FAIL(B200ANI_ERR_ARG, "anim: --maxmatch anchoring is not implemented in this version (only --mum semantics)");
+    const int maxocc = maxmatch ? AN_MAXOCC : 1;
     CK(cudaSetDevice(ctx->device));
     const int32_t ng = (int32_t)ctx->genomes.size();
     for (int64_t i = 0; i < 2 * m; ++i)
@@ -501,11 +504,11 @@ static int prepare(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmat
     for (int64_t i = 0; i < 2 * m; ++i) {
         Genome &g = ctx->genomes[pairs[i]];
         if (g.n_contigs >= 65535) FAIL(B200ANI_ERR_CAPACITY, "anim: genomes with >= 65535 records are not supported");
-        if (!index_valid(g.index) && !seen[pairs[i]]) { seen[pairs[i]] = 1; todo.push_back(&g); }
+        if (!index_valid(g.index, maxocc) && !seen[pairs[i]]) { seen[pairs[i]] = 1; todo.push_back(&g); }
     }
     const bool any = !todo.empty();
     CK(cudaEventRecord(e0, st));
-    rc = build_indexes(ctx, todo);
+    rc = build_indexes(ctx, todo, maxocc);
     if (rc) return rc;
     CK(cudaEventRecord(e1, st));
     CK(cudaStreamSynchronize(st));

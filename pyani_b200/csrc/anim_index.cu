@@ -62,12 +62,15 @@ __global__ void __launch_bounds__(256) minimizer_select_kernel(const uint64_t *_
     }
 }
 
-__global__ void mark_unique_kernel(const uint64_t *__restrict__ sorted, int64_t n, uint8_t *__restrict__ flag) {
+// keep the entries of k-mers that occur at most maxocc times among the selected minimizers (1 = --mum)
+__global__ void mark_unique_kernel(const uint64_t *__restrict__ sorted, int64_t n, uint8_t *__restrict__ flag, int maxocc) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t k = (uint32_t)(sorted[i] >> 32);
-    bool u = (i == 0 || (uint32_t)(sorted[i - 1] >> 32) != k) && (i + 1 == n || (uint32_t)(sorted[i + 1] >> 32) != k);
-    flag[i] = u;
+    int run = 1;
+    for (int64_t j = i - 1; j >= 0 && run <= maxocc && (uint32_t)(sorted[j] >> 32) == k; --j) ++run;
+    for (int64_t j = i + 1; j < n && run <= maxocc && (uint32_t)(sorted[j] >> 32) == k; ++j) ++run;
+    flag[i] = run <= maxocc;
 }
 
 __global__ void table_insert_kernel(const uint64_t *__restrict__ uniq, int64_t n, uint64_t *table, uint32_t *bitmap, uint32_t bits, uint64_t *__restrict__ bypos) {
@@ -101,13 +104,13 @@ void free_index(MinimizerIndex *ix, cudaStream_t st) {
     delete ix;
 }
 void invalidate_index(MinimizerIndex *ix) { if (ix) ix->valid = false; }
-bool index_valid(const MinimizerIndex *ix) { return ix && ix->valid; }
+bool index_valid(const MinimizerIndex *ix, int maxocc) { return ix && ix->valid && ix->maxocc == maxocc; }
 
 // Build (or rebuild) the indexes of many genomes.  Scratch comes from one reusable workspace and the
 // index arrays of a genome are kept across rebuilds, so steady-state builds allocate nothing; genomes are
 // processed in chunks that fit the workspace with three host synchronisations per chunk (the counts of
 // selected and of unique minimizers are needed on the host to size the sorts and the table).
-int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo) {
+int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc) {
     if (todo.empty()) return 0;
     cudaStream_t st = ctx->stream;
     auto need = [](const Genome &g) { return (size_t)(g.n_pos + 64) * 25 + 4096; };  // sel + sorted + uniq (u64) + flag (u8)
@@ -171,7 +174,7 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo) {
             const int64_t ns = (int64_t)h_cnt[k];
             size_t tb = cub_bytes;
             cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, ns, 32, 64, st);  // group equal k-mers; order inside a group is irrelevant
-            if (ns) mark_unique_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(tmp[k].sorted, ns, tmp[k].flag);
+            if (ns) mark_unique_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(tmp[k].sorted, ns, tmp[k].flag, maxocc);
             CK(cudaGetLastError());
             tb = cub_bytes;
             cub::DeviceSelect::Flagged(d_tmp, tb, tmp[k].sorted, tmp[k].flag, tmp[k].uniq, (int *)(d_cnt + 256 + k), ns, st);
@@ -221,6 +224,7 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo) {
             }
             ctx->counters[CT_LAUNCHES] += 4;
             ix->valid = true;
+            ix->maxocc = maxocc;
         }
         CK(cudaStreamSynchronize(st));  // the workspace is reused by the next chunk
         done = end;

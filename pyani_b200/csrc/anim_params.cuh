@@ -5,6 +5,7 @@
 
 #define AN_K 16
 #define AN_W 5
+#define AN_MAXOCC 16
 #define AN_MINLEN 20
 #define AN_LOOKBACK 32
 #define AN_GAPMAX 1000

@@ -67,6 +67,7 @@ __device__ __forceinline__ int pair_of_probe(const PairDesc *__restrict__ pairs,
 // (evict-first loads) through the reference's table; hits are appended as (probe index, table entry).
 // Memory-latency bound by design: one coalesced 4-byte read + one random 8-byte read per probe, no
 // divergent work, so the warps in flight are all waiting on independent loads.
+template <bool MAXMATCH>
 __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restrict__ pairs, int n_pairs, int64_t n_probes, uint2 *__restrict__ hits,
                                                          unsigned long long *__restrict__ n_hits, unsigned long long cap) {
     // Each block walks contiguous chunks of PROBE_CHUNK probes, PROBE_ILP probes per thread per step so that the
@@ -128,6 +129,23 @@ __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restr
                 pf[k] = (same ? q_posflag : P.q_posflag) + (gi[k] - (same ? base : P.probe_base));
                 hit[k] = pr[k] >= 0 && bitmap_test(bm[k], tbits[k], kmer[k]);
             }
+            if (MAXMATCH) {
+                // --maxmatch: a k-mer may sit in the table up to AN_MAXOCC times; every entry is a hit of its own and the
+                // in-warp redundancy shortcut below does not apply (duplicates are removed after the sort)
+#pragma unroll
+                for (int k = 0; k < PROBE_ILP; ++k) {
+                    uint32_t cursor = ~0u, e;
+                    while (hit[k] && table_next(tb[k], tbits[k], kmer[k], cursor, e)) {
+                        const unsigned int slot = atomicAdd(&s_n, 1u);
+                        if (slot < (unsigned int)PROBE_CHUNK) s_hits[slot] = make_uint2((uint32_t)gi[k], e);
+                        else {
+                            const unsigned long long g = atomicAdd(n_hits, 1ull);
+                            if (g < cap) hits[g] = make_uint2((uint32_t)gi[k], e);
+                        }
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int k = 0; k < PROBE_ILP; ++k) {  // phase 3: table probe for the filter's positives
                 if (hit[k]) hit[k] = table_lookup(tb[k], tbits[k], kmer[k], rpf[k]);
@@ -159,7 +177,7 @@ __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restr
             }
         }
         __syncthreads();
-        const unsigned int n_stage = s_n;
+        const unsigned int n_stage = min(s_n, (unsigned int)PROBE_CHUNK);
         if (threadIdx.x == 0 && n_stage) s_base = atomicAdd(n_hits, (unsigned long long)n_stage);
         __syncthreads();
         for (unsigned int i = threadIdx.x; i < n_stage; i += 256)
@@ -167,6 +185,9 @@ __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restr
         __syncthreads();
     }
 }
+
+template __global__ void seed_probe_kernel<false>(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
+template __global__ void seed_probe_kernel<true>(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
 
 // One anchor of pair `pi`: ANIm -> as is; ANIb (P.fragsize > 0) -> clipped to the query's fragments, one piece per
 // fragment it overlaps (pieces shorter than AB_MINPIECE are dropped), the fragment id goes into the sort key.
@@ -247,8 +268,13 @@ __global__ void __launch_bounds__(256) seed_extend_kernel(const PairDesc *__rest
             if (tn >= 0 && tn < P.q_nmini) {
                 uint32_t qpfn = P.q_posflag[tn], rpfn;
                 int64_t qn = strand ? (int64_t)P.q_npos - AN_K - (qpfn & 0x7fffffffu) : (qpfn & 0x7fffffffu);
-                if (qn < q0 && q0 - qn <= 64 && table_lookup(P.r_table, P.r_table_bits, P.q_kmer[tn], rpfn) &&
-                    (int)((rpfn ^ qpfn) >> 31) == strand && (int64_t)(rpfn & 0x7fffffffu) - qn == r0 - q0) {
+                bool nb_same_diag = false;
+                if (qn < q0 && q0 - qn <= 64) {
+                    uint32_t cursor = ~0u;
+                    while (!nb_same_diag && table_next(P.r_table, P.r_table_bits, P.q_kmer[tn], cursor, rpfn))
+                        nb_same_diag = (int)((rpfn ^ qpfn) >> 31) == strand && (int64_t)(rpfn & 0x7fffffffu) - qn == r0 - q0;
+                }
+                if (nb_same_diag) {
                     bool same = true;
                     for (int64_t x = qn + AN_K; x < q0 && same; ++x) {
                         int a = view_code(R, x + (r0 - q0)), b = view_code(Q, x);

@@ -86,5 +86,5 @@ int tetra_zscores_device(b200ani_ctx *ctx, const unsigned long long *d_tot, int 
 int tetra_corr_device(b200ani_ctx *ctx, const double *d_z, const int *d_idx, int m, int n, double *d_corr);
 void free_index(MinimizerIndex *ix, cudaStream_t st);
 void invalidate_index(MinimizerIndex *ix);
-bool index_valid(const MinimizerIndex *ix);
+bool index_valid(const MinimizerIndex *ix, int maxocc);
 void free_anim_workspace(void *ws);

@@ -187,3 +187,43 @@ print("SPLIT-OK", int(res["n_alignments"].sum()))
     env = dict(os.environ, B200ANI_ANCHOR_CAP="9000", B200ANI_HIT_CAP="20000")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert "SPLIT-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_maxmatch_with_repeats(engine):
+    """--maxmatch (anim.py:276-279): seeds may occur several times per genome.  Genomes with 10 copies of a 1.5 kb
+    element; CUDA == oracle bit-exact in both modes, and the two modes differ (the repeats only anchor with --maxmatch)."""
+    from pyani_b200 import synth
+
+    rng = np.random.default_rng(99)
+    elem = synth.random_codes(rng, 1500, 0.5)
+    def with_repeats(core, n_copies):
+        g = core
+        for _ in range(n_copies):
+            t = int(rng.integers(0, len(g)))
+            g = np.concatenate([g[:t], synth.substitute(rng, elem, 0.01), g[t:]])
+        return g
+    core = synth.random_codes(rng, 250_000, 0.5)
+    a = with_repeats(core, 10)
+    b = with_repeats(synth.indels(rng, synth.substitute(rng, core, 0.04), 0.004, 0.5), 10)
+    asc = np.frombuffer(b"ACGT", np.uint8)
+    arrs = [(asc[a], np.array([0, len(a)], np.uint64)), (asc[b], np.array([0, 120_000, len(b)], np.uint64))]
+    gids = [engine.add_genome(x, off, f"rep{i}") for i, (x, off) in enumerate(arrs)]
+    pairs = [(0, 1), (1, 0)]
+    out = {}
+    for mm in (False, True):
+        og = [oracle.OGenome(x, off, maxmatch=mm) for x, off in arrs]
+        for nofilter in (False, True):
+            res = engine.anim(np.array([[gids[r], gids[q]] for r, q in pairs], np.int32), maxmatch=mm, nofilter=nofilter)
+            for (r, q), got in zip(pairs, res):
+                want = oracle.anim_pair(og[r], og[q], nofilter=nofilter)[0]
+                for f in FIELDS:
+                    assert int(got[f]) == want[f], (mm, nofilter, r, q, f, int(got[f]), want[f])
+            out[(mm, nofilter)] = res
+        rows = engine.anim_alignments(gids[0], gids[1], maxmatch=mm, nofilter=True)
+        assert (rows == oracle.anim_pair(og[0], og[1], nofilter=True)[1]).all()
+    assert out[(True, True)][0]["n_alignments"] > out[(False, True)][0]["n_alignments"]  # repeat copies align to each other
+    # ANIb after a --maxmatch call rebuilds the --mum index and still matches the oracle
+    og = [oracle.OGenome(x, off) for x, off in arrs]
+    rb = engine.anib(np.array([[gids[0], gids[1]]], np.int32))[0]
+    want = oracle.anib_pair(og[0], og[1])[0]
+    assert all(int(rb[k]) == v for k, v in want.items())
