@@ -36,29 +36,49 @@ __device__ __forceinline__ uint64_t kmer_hash(const uint64_t *s, const uint32_t 
 
 // A position is selected iff its hash is <= every hash of at least one window of AN_W consecutive
 // k-mer starts containing it (ties select all, which keeps the selection strand-symmetric).
+// One block = one tile of SEL_TILE positions: every hash is computed once into shared memory (+ a halo of
+// AN_W-1 on both sides), the window test then reads shared memory only.
+constexpr int SEL_TILE = 2048, SEL_HALO = AN_W - 1;
 __global__ void __launch_bounds__(256) minimizer_select_kernel(const uint64_t *__restrict__ s, const uint32_t *__restrict__ m, int64_t n_pos,
                                                                uint64_t *__restrict__ out, unsigned long long *__restrict__ n_out) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pos; p += stride) {
-        uint32_t canon = 0, orient = 0, c2, o2;
-        uint64_t h = kmer_hash(s, m, p, n_pos, canon, orient);
-        bool chosen = false;
-        if (h != (1ull << 32)) {
-            uint64_t hv[2 * AN_W - 1];
+    __shared__ uint64_t hv[SEL_TILE + 2 * SEL_HALO];
+    __shared__ unsigned int s_n;
+    __shared__ unsigned long long s_base;
+    __shared__ uint64_t s_out[SEL_TILE];
+    const int64_t n_tiles = (n_pos + SEL_TILE - 1) / SEL_TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t p0 = tile * SEL_TILE;
+        if (threadIdx.x == 0) s_n = 0;
+        for (int i = threadIdx.x; i < SEL_TILE + 2 * SEL_HALO; i += 256) {
+            uint32_t c, o;
+            hv[i] = kmer_hash(s, m, p0 - SEL_HALO + i, n_pos, c, o);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < SEL_TILE; i += 256) {
+            const int64_t p = p0 + i;
+            const uint64_t h = hv[i + SEL_HALO];
+            bool chosen = false;
+            if (p < n_pos && h != (1ull << 32)) {
 #pragma unroll
-            for (int d = 0; d < 2 * AN_W - 1; ++d) hv[d] = (d == AN_W - 1) ? h : kmer_hash(s, m, p + d - (AN_W - 1), n_pos, c2, o2);
+                for (int o = 0; o < AN_W; ++o) {  // window [p-o, p-o+W-1]
+                    bool is_min = true;
 #pragma unroll
-            for (int o = 0; o < AN_W; ++o) {  // window [p-o, p-o+W-1] = hv[W-1-o .. 2W-2-o]
-                bool is_min = true;
-#pragma unroll
-                for (int x = 0; x < AN_W; ++x) is_min = is_min && !(hv[AN_W - 1 - o + x] < h);
-                chosen = chosen || is_min;
+                    for (int x = 0; x < AN_W; ++x) is_min = is_min && !(hv[i + SEL_HALO - o + x] < h);
+                    chosen = chosen || is_min;
+                }
+            }
+            if (chosen) {
+                uint32_t canon, orient;
+                kmer_hash(s, m, p, n_pos, canon, orient);
+                s_out[atomicAdd(&s_n, 1u)] = ((uint64_t)canon << 32) | (uint32_t)p | (orient << 31);
             }
         }
-        if (chosen) {
-            unsigned long long slot = atomicAdd(n_out, 1ull);
-            out[slot] = ((uint64_t)canon << 32) | (uint32_t)p | (orient << 31);
-        }
+        __syncthreads();
+        const unsigned int n = s_n;
+        if (threadIdx.x == 0 && n) s_base = atomicAdd(n_out, (unsigned long long)n);
+        __syncthreads();
+        for (unsigned int i = threadIdx.x; i < n; i += 256) out[s_base + i] = s_out[i];
+        __syncthreads();
     }
 }
 
@@ -113,6 +133,15 @@ bool index_valid(const MinimizerIndex *ix, int maxocc) { return ix && ix->valid 
 int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc) {
     if (todo.empty()) return 0;
     cudaStream_t st = ctx->stream;
+    constexpr int NS = 4;  // the per-genome sorts are too small to fill the GPU: run NS genomes side by side
+    if (!ctx->side[0]) {
+        for (auto &ss : ctx->side) CK(cudaStreamCreateWithFlags(&ss, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->side_ev, cudaEventDisableTiming));
+    }
+    auto sync_sides = [&]() -> cudaError_t {
+        for (auto &ss : ctx->side) { cudaError_t e = cudaStreamSynchronize(ss); if (e != cudaSuccess) return e; }
+        return cudaSuccess;
+    };
     auto need = [](const Genome &g) { return (size_t)(g.n_pos + 64) * 25 + 4096; };  // sel + sorted + uniq (u64) + flag (u8)
     size_t biggest = 0;
     for (Genome *g : todo) biggest = std::max(biggest, need(*g));
@@ -124,8 +153,8 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc) {
         cub::DeviceSelect::Flagged(nullptr, tb2, (uint64_t *)nullptr, (uint8_t *)nullptr, (uint64_t *)nullptr, (int *)nullptr, max_n, st);
         cub_bytes = std::max(cub_bytes, tb2) + 256;
     }
-    const size_t want = std::max<size_t>(biggest + cub_bytes + 65536, (size_t)1536 << 20);
-    if (ctx->index_ws_bytes < biggest + cub_bytes + 65536) {
+    const size_t want = std::max<size_t>(biggest + 4 * cub_bytes + 65536, (size_t)1536 << 20);
+    if (ctx->index_ws_bytes < biggest + 4 * cub_bytes + 65536) {
         CK(cudaStreamSynchronize(st));
         if (ctx->index_ws) CK(cudaFree(ctx->index_ws));
         ctx->index_ws = nullptr;
@@ -142,8 +171,9 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc) {
         size_t off = 0, end = done;
         unsigned long long *d_cnt = (unsigned long long *)base;  // [2 * 256] counters
         off = 4096;
-        void *d_tmp = base + off;
-        off += (cub_bytes + 255) & ~(size_t)255;
+        char *d_tmp_base = base + off;  // one CUB scratch region per side stream
+        const size_t cub_stride = (cub_bytes + 255) & ~(size_t)255;
+        off += cub_stride * NS;
         while (end < G_all && tmp.size() < 256) {
             const size_t n = (size_t)todo[end]->n_pos + 64;
             const size_t bytes = ((n * 25 + 4096) + 255) & ~(size_t)255;
@@ -163,7 +193,7 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc) {
         for (size_t k = 0; k < G; ++k) {
             Genome &g = *todo[done + k];
             const int64_t n = g.n_pos;
-            int blocks = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->sm_count * 16);
+            int blocks = (int)std::min<int64_t>(ceil_div(n, SEL_TILE), (int64_t)ctx->sm_count * 6);
             minimizer_select_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint64_t *>(g.d_seq), g.d_mask, n, tmp[k].sel, d_cnt + k);
             CK(cudaGetLastError());
         }
@@ -172,13 +202,16 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc) {
         CK(cudaStreamSynchronize(st));
         for (size_t k = 0; k < G; ++k) {
             const int64_t ns = (int64_t)h_cnt[k];
+            cudaStream_t ss = ctx->side[k % NS];
+            void *d_tmp = d_tmp_base + cub_stride * (k % NS);
             size_t tb = cub_bytes;
-            cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, ns, 32, 64, st);  // group equal k-mers; order inside a group is irrelevant
-            if (ns) mark_unique_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(tmp[k].sorted, ns, tmp[k].flag, maxocc);
+            cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, ns, 32, 64, ss);  // group equal k-mers; order inside a group is irrelevant
+            if (ns) mark_unique_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, ss>>>(tmp[k].sorted, ns, tmp[k].flag, maxocc);
             CK(cudaGetLastError());
             tb = cub_bytes;
-            cub::DeviceSelect::Flagged(d_tmp, tb, tmp[k].sorted, tmp[k].flag, tmp[k].uniq, (int *)(d_cnt + 256 + k), ns, st);
+            cub::DeviceSelect::Flagged(d_tmp, tb, tmp[k].sorted, tmp[k].flag, tmp[k].uniq, (int *)(d_cnt + 256 + k), ns, ss);
         }
+        CK(sync_sides());
         CK(cudaMemcpyAsync(h_cnt + 256, d_cnt + 256, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         for (size_t k = 0; k < G; ++k) {
@@ -212,20 +245,32 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc) {
                 ix->cap_bits = bits;
                 ix->cap_mini = h_nu + 1;
             }
-            CK(cudaMemsetAsync(ix->d_table, 0xff, sizeof(uint64_t) << bits, st));
-            CK(cudaMemsetAsync(ix->d_bitmap, 0, sizeof(uint32_t) << (bits + 3 - 5), st));
+        }
+        // the pool allocations above were made on the main stream: let the side streams see them, then fill
+        CK(cudaEventRecord(ctx->side_ev, st));
+        for (auto &ss : ctx->side) CK(cudaStreamWaitEvent(ss, ctx->side_ev, 0));
+        for (size_t k = 0; k < G; ++k) {
+            Genome &g = *todo[done + k];
+            MinimizerIndex *ix = g.index;
+            const int h_nu = (int)ix->n_mini;
+            const uint32_t bits = ix->table_bits;
+            cudaStream_t ss = ctx->side[k % NS];
+            void *d_tmp = d_tmp_base + cub_stride * (k % NS);
+            CK(cudaMemsetAsync(ix->d_table, 0xff, sizeof(uint64_t) << bits, ss));
+            CK(cudaMemsetAsync(ix->d_bitmap, 0, sizeof(uint32_t) << (bits + 3 - 5), ss));
             if (h_nu) {
-                table_insert_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, st>>>(tmp[k].uniq, h_nu, ix->d_table, ix->d_bitmap, bits, tmp[k].sel);
+                table_insert_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, ss>>>(tmp[k].uniq, h_nu, ix->d_table, ix->d_bitmap, bits, tmp[k].sel);
                 CK(cudaGetLastError());
                 size_t tb = cub_bytes;
-                cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, h_nu, 33, 64, st);
-                split_bypos_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, st>>>(tmp[k].sorted, h_nu, ix->d_kmer, ix->d_posflag);
+                cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, h_nu, 33, 64, ss);
+                split_bypos_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, ss>>>(tmp[k].sorted, h_nu, ix->d_kmer, ix->d_posflag);
                 CK(cudaGetLastError());
             }
             ctx->counters[CT_LAUNCHES] += 4;
             ix->valid = true;
             ix->maxocc = maxocc;
         }
+        CK(sync_sides());
         CK(cudaStreamSynchronize(st));  // the workspace is reused by the next chunk
         done = end;
     }
