@@ -41,6 +41,10 @@ sys.path.insert(0, str(ROOT))
 SEED = 20260925  # 20260924 + config index 1
 N_CLADES, PER_CLADE, GENOME_LEN = 5, 10, 5_000_000
 DPX_OPS_PER_CELL = 4  # E, F, H max-plus updates + 1 add per affine cell
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this workload
+# (profiles/r01_v13_prof_*.txt, first captured launch of each kernel); None where no capture exists
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"gap_dp_kernel": 9.763972e9 + 0.826295e9, "ext_dp_kernel": 95.096064e6 + 10.758912e6,
+                                "seed_probe_kernel": 15.358575e9 + 158.697984e6, "seed_extend_kernel": 5.661587e9 + 391.503104e6}
 
 
 def log(*a):
@@ -304,18 +308,20 @@ def main():
             # per hit, 16 B per anchor written
             alg = probes * 8 + hits * 16 if name == "seed_probe_kernel" else hits * 44 + n_anchors * 16
             ach = alg / (ms_k * 1e-3) / 1e9
-            return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(name) if not args.small else None,
                     "peak_source": peak_src, "per_launch_ms": ms_k / launches, "algorithmic_bytes_per_launch": alg / launches}
         cells = cells_gap if name == "gap_dp_kernel" else cells_ext
         ach = cells * DPX_OPS_PER_CELL / (ms_k * 1e-3) / 1e9
         return {"kernel": name, "bound": "alu", "achieved": ach, "peak": dpx_peak, "unit": "Gop/s (DPX-class int32 max-plus ops)",
-                "frac": ach / dpx_peak, "traffic": None, "peak_source": "measured live: b200ani_dpx_peak (__viaddmax_s32 issue rate)",
+                "frac": ach / dpx_peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(name) if not args.small else None,
+                "peak_source": "measured live: b200ani_dpx_peak (__viaddmax_s32 issue rate)",
                 "per_launch_ms": ms_k / launches, "cells_per_launch": cells / launches, "ops_per_cell": DPX_OPS_PER_CELL,
                 "gcups": cells / (ms_k * 1e-3) / 1e9}
 
     dom = max(kern, key=lambda k: kern[k]["ms"])
     roof = roofline_of(dom)
-    roof["all_kernels"] = {k: {kk: vv for kk, vv in roofline_of(k).items() if kk in ("bound", "achieved", "peak", "frac", "per_launch_ms", "gcups")} for k in kern}
+    roof["all_kernels"] = {k: {kk: vv for kk, vv in roofline_of(k).items() if kk in ("bound", "achieved", "peak", "frac", "per_launch_ms", "gcups", "traffic")} for k in kern}
     roof["hbm_peak_gbs"] = hbm_peak
     roof["dpx_peak_gops"] = dpx_peak
 
