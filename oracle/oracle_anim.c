@@ -215,9 +215,9 @@ static uint32_t contig_of(const uint64_t *goff, uint32_t n, int64_t pos) {
  * mode 1: extension tile over at most lr rows and lq columns; returns the best cell in bi,bj. */
 typedef struct { int32_t val, bi, bj, stopped; int64_t cells; } dp_out;
 
-/* scoring model: {match, mismatch, first gap column, further gap columns} */
-static const int SC_ANIM[4] = {AN_MATCH, AN_MISMATCH, AN_GAPOPEN, AN_GAPEXT};
-static const int SC_ANIB[4] = {AB_MATCH, AB_MISMATCH, AB_GAP, AB_GAP};
+/* scoring model: {match, mismatch, first gap column, further gap columns, break length in rows} */
+static const int SC_ANIM[5] = {AN_MATCH, AN_MISMATCH, AN_GAPOPEN, AN_GAPEXT, AN_BREAK};
+static const int SC_ANIB[5] = {AB_MATCH, AB_MISMATCH, AB_GAP, AB_GAP, AB_BREAK};
 
 static dp_out dp_band_sc(const uint8_t *R, int rstride, const uint8_t *Q, int qstride, int lr, int lq, int klo, int mode, const int *sc, int64_t qavail) {
     /* mode 0 (link alignment): the band is NOT clipped at the corner column -- cells with j > lq use the query
@@ -271,7 +271,7 @@ static dp_out dp_band_sc(const uint8_t *R, int rstride, const uint8_t *Q, int qs
         memcpy(Fp, Fc, sizeof(int32_t) * BW);
         (void)Ec;
         (void)rowmax;
-        if (i - o.bi > AN_BREAK) { o.stopped = 1; break; }
+        if (i - o.bi > sc[4]) { o.stopped = 1; break; }
     }
     if (mode == 0) {
         int kk = (lq - lr) - klo;
@@ -724,7 +724,7 @@ int64_t orc_anib_pair(const orc_genome *Q, const orc_genome *S, int fragsize, in
         for (int side = 0; side < 2; ++side) {
             for (int t = 0; t < AN_MAXTILES; ++t) {
                 int64_t ar = side ? r_hi - re : rs - r_lo, aq = side ? q_hi - qe : qs - q_lo;
-                int lr = (int)(ar < AN_TILE ? ar : AN_TILE), lq = (int)(aq < AN_TILE + AN_BAND ? aq : AN_TILE + AN_BAND);
+                int lr = (int)(ar < AB_TILE ? ar : AB_TILE), lq = (int)(aq < AB_TILE + AN_BAND ? aq : AB_TILE + AN_BAND);
                 if (lr <= 0 || lq <= 0) break;
                 dp_out o = side ? dp_band_sc(R->fw + re, 1, Qs + qe, 1, lr, lq, -AN_BAND, 1, SC_ANIB, lq)
                                 : dp_band_sc(R->fw + rs - 1, -1, Qs + qs - 1, -1, lr, lq, -AN_BAND, 1, SC_ANIB, lq);

@@ -124,8 +124,8 @@ __device__ __forceinline__ uint32_t contig_of(const uint64_t *__restrict__ goff,
 
 // scoring models: 0 = ANIm (nucmer-like), 1 = ANIb (blastn-like, linear gaps)
 template <int MODEL> struct Scoring;
-template <> struct Scoring<0> { static constexpr int match = AN_MATCH, mismatch = AN_MISMATCH, gapopen = AN_GAPOPEN, gapext = AN_GAPEXT; };
-template <> struct Scoring<1> { static constexpr int match = AB_MATCH, mismatch = AB_MISMATCH, gapopen = AB_GAP, gapext = AB_GAP; };
+template <> struct Scoring<0> { static constexpr int match = AN_MATCH, mismatch = AN_MISMATCH, gapopen = AN_GAPOPEN, gapext = AN_GAPEXT, brk = AN_BREAK, tile = AN_TILE; };
+template <> struct Scoring<1> { static constexpr int match = AB_MATCH, mismatch = AB_MISMATCH, gapopen = AB_GAP, gapext = AB_GAP, brk = AB_BREAK, tile = AB_TILE; };
 
 __device__ __forceinline__ int pack_score(int v) { return (v + AN_PACK - 1) >> 12; }
 __device__ __forceinline__ int pack_errs(int v) { return pack_score(v) * AN_PACK - v; }

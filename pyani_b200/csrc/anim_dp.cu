@@ -155,7 +155,7 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
             int lo = max(0, -(i + klo)), hi = min(AN_BANDW - 1, kkhi);
             if (hi >= lo) o.cells += hi - lo + 1;
         }
-        if (i - o.bi > AN_BREAK) { o.stopped = 1; break; }
+        if (i - o.bi > SC::brk) { o.stopped = 1; break; }
         // slide the query window: drop column 0, append the next base of the stream
         if (qs.left == 0) qs.refill(Q, qstep);
         qwin = (qwin >> 2) | ((qs.buf & 3ull) << 62);
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(128, 4) ext_dp_kernel(SegArrays S, const PairD
             const int rs = S.rs[s], qs = S.qs[s], re = S.re[s], qe = S.qe[s];
             int64_t ar = side ? S.r_hi[s] - re : rs - S.r_lo[s];
             int64_t aq = side ? S.q_hi[s] - qe : qs - S.q_lo[s];
-            int lr = (int)min(ar, (int64_t)AN_TILE), lq = (int)min(aq, (int64_t)(AN_TILE + AN_BAND));
+            int lr = (int)min(ar, (int64_t)Scoring<MODEL>::tile), lq = (int)min(aq, (int64_t)(Scoring<MODEL>::tile + AN_BAND));
             bool on = false;
             if (lr > 0 && lq > 0) {
                 // one call site for both directions: the two sides differ only in start position and step

@@ -26,6 +26,8 @@
 #define AB_MATCH 2
 #define AB_MISMATCH 3
 #define AB_GAP 5
+#define AB_BREAK 250
+#define AB_TILE 256
 #define AB_MINPIECE 11
 #define AB_FRAGSIZE 1020
 #define AN_PACK 4096
