@@ -91,6 +91,26 @@ __global__ void label_init_kernel(ChainArrays A) {
     A.cw[i] = 0; A.wsum[i] = 0; A.tail[i] = -1; A.ssum[i] = 0; A.esum[i] = 0; A.strong[i] = 0;
 }
 
+// Block-local pre-pass of the pointer jumping: chains mostly run through neighbouring anchors (pred[i] = i-1 most of the
+// time), so 10 jumps inside a 1024-anchor block in shared memory resolve everything that does not leave the block;
+// the global rounds below then only have to hop from block to block (log2(#blocks a chain spans) rounds).
+__global__ void __launch_bounds__(1024) label_local_kernel(ChainArrays A) {
+    __shared__ int sh[1024], sc[1024];
+    const int64_t b0 = (int64_t)blockIdx.x * 1024, i = b0 + threadIdx.x;
+    sh[threadIdx.x] = i < A.n ? A.head[i] : (int)i;
+    sc[threadIdx.x] = i < A.n ? A.chead[i] : (int)i;
+    __syncthreads();
+    for (int it = 0; it < 10; ++it) {
+        int h = sh[threadIdx.x], c = sc[threadIdx.x];
+        int hh = h >= b0 ? sh[h - b0] : h, cc = c >= b0 ? sc[c - b0] : c;  // pointers only go backwards (pred < i)
+        __syncthreads();
+        sh[threadIdx.x] = hh;
+        sc[threadIdx.x] = cc;
+        __syncthreads();
+    }
+    if (i < A.n) { A.head[i] = sh[threadIdx.x]; A.chead[i] = sc[threadIdx.x]; }
+}
+
 __global__ void label_jump_kernel(ChainArrays A, int *__restrict__ changed) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n) return;

@@ -22,6 +22,7 @@ __global__ void link_kernel(ChainArrays);
 __global__ void link_validate_kernel(ChainArrays, unsigned long long *);
 __global__ void gap_task_kernel(ChainArrays, uint32_t *, uint32_t *, unsigned long long *, int, int);
 __global__ void label_init_kernel(ChainArrays);
+__global__ void label_local_kernel(ChainArrays);
 __global__ void label_jump_kernel(ChainArrays, int *);
 __global__ void cluster_weight_kernel(ChainArrays);
 __global__ void segment_accum_kernel(ChainArrays, int);
@@ -257,11 +258,12 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         // ---- clusters and segments
         T0(ST_LABEL);
         label_init_kernel<<<GRID(n)>>>(A);
-        LAUNCHED(1);
+        label_local_kernel<<<(unsigned)ceil_div(n, 1024), 1024, 0, st>>>(A);
+        LAUNCHED(2);
         for (int round = 0; round < 8; ++round) {
             CK(cudaMemsetAsync(W->changed, 0, sizeof(int), st));
-            for (int k = 0; k < 4; ++k) label_jump_kernel<<<GRID(n)>>>(A, W->changed);
-            LAUNCHED(4);
+            for (int k = 0; k < 3; ++k) label_jump_kernel<<<GRID(n)>>>(A, W->changed);
+            LAUNCHED(3);
             int ch = 0;
             CK(cudaMemcpyAsync(&ch, W->changed, sizeof ch, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
