@@ -206,7 +206,17 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         int pair_bits = 1;
         while ((1 << pair_bits) < nb) ++pair_bits;
         size_t tb = W->cub_bytes;
-        cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb, W->keys_a, W->keys_b, W->vals_a, W->vals_b, n_raw, 0, KEY_PAIR_SHIFT + pair_bits, st);
+        if (anib) {
+            cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb, W->keys_a, W->keys_b, W->vals_a, W->vals_b, n_raw, 0, KEY_PAIR_SHIFT + pair_bits, st);
+        } else {
+            // ANIm keys carry no fragment id (bits 32..45 are zero): two stable LSD passes over the used bit ranges
+            // (strand + position, then pair) skip those digits; the result ends up in the *_b buffers again
+            cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb, W->keys_a, W->keys_b, W->vals_a, W->vals_b, n_raw, 0, 32, st);
+            tb = W->cub_bytes;
+            cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb, W->keys_b, W->keys_a, W->vals_b, W->vals_a, n_raw, KEY_PAIR_SHIFT, KEY_PAIR_SHIFT + pair_bits, st);
+            CK(cudaMemcpyAsync(W->keys_b, W->keys_a, sizeof(uint64_t) * n_raw, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(W->vals_b, W->vals_a, sizeof(uint64_t) * n_raw, cudaMemcpyDeviceToDevice, st));
+        }
         tie_fix_kernel<<<GRID(n_raw)>>>(W->keys_b, W->vals_b, n_raw);
         flag_unique_kernel<<<GRID(n_raw)>>>(W->keys_b, W->vals_b, n_raw, W->flag);
         LAUNCHED(2);
