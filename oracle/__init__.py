@@ -140,16 +140,17 @@ def read_fasta(path):
 
 
 # ----------------------------------------------------------------------------- ANIm aligner (oracle_anim.c)
-ANIM_NSTATS = 8
-ANIM_STAT_NAMES = ["anchors", "links", "cut_links", "segments", "gap_cells", "ext_cells", "ext_tiles", "seed_hits"]
+ANIM_NSTATS = 16
+ANIM_STAT_NAMES = ["anchors", "links", "cut_links", "segments", "gap_cells", "ext_cells", "ext_tiles", "seed_hits", "raw_anchors", "bridges",
+                   "bridge_cells", "", "", "", "", ""]
 
 
 class OGenome:
-    """Oracle-side genome handle (byte-per-base g-space + unique-minimizer index)."""
+    """Oracle-side genome handle (byte-per-base g-space + minimizer index: k-mers with <= 16 occurrences, repeats flagged)."""
 
-    def __init__(self, ascii_u8: np.ndarray, contig_off: np.ndarray, maxmatch: bool = False):
+    def __init__(self, ascii_u8: np.ndarray, contig_off: np.ndarray):
         L = lib()
-        L.orc_genome_create_occ.restype = ctypes.c_void_p
+        L.orc_genome_create.restype = ctypes.c_void_p
         L.orc_genome_free.argtypes = [ctypes.c_void_p]
         L.orc_genome_n_mini.restype = ctypes.c_int64
         L.orc_genome_n_mini.argtypes = [ctypes.c_void_p]
@@ -157,9 +158,7 @@ class OGenome:
         o = np.ascontiguousarray(contig_off, dtype=np.uint64)
         self.n_bases = int(o[-1])
         self.contig_off = o
-        self.maxmatch = bool(maxmatch)
-        self._h = ctypes.c_void_p(L.orc_genome_create_occ(_p(a, ctypes.c_uint8), _p(o, ctypes.c_uint64), ctypes.c_uint32(len(o) - 1),
-                                                          ctypes.c_int(16 if maxmatch else 1)))
+        self._h = ctypes.c_void_p(L.orc_genome_create(_p(a, ctypes.c_uint8), _p(o, ctypes.c_uint64), ctypes.c_uint32(len(o) - 1)))
 
     def __del__(self):
         try:
@@ -181,16 +180,16 @@ class OGenome:
         return k, pf
 
 
-def anim_align(R: OGenome, Q: OGenome, cap: int = 1 << 16):
+def anim_align(R: OGenome, Q: OGenome, maxmatch: bool = False, cap: int = 1 << 16):
     """Unfiltered alignments of R (nucmer reference) vs Q: rows (rc, qc, rs, re, qs, qe, errs, score) + stats dict."""
     L = lib()
     L.orc_anim_align.restype = ctypes.c_int64
-    L.orc_anim_align.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    L.orc_anim_align.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     rows = np.zeros((cap, 8), dtype=np.int64)
     stats = np.zeros(ANIM_NSTATS, dtype=np.int64)
-    n = L.orc_anim_align(R._h, Q._h, rows.ctypes.data, cap, stats.ctypes.data)
+    n = L.orc_anim_align(R._h, Q._h, int(bool(maxmatch)), rows.ctypes.data, cap, stats.ctypes.data)
     assert n <= cap, "alignment capacity exceeded"
-    return rows[:n].copy(), dict(zip(ANIM_STAT_NAMES, stats.tolist()))
+    return rows[:n].copy(), {k: v for k, v in zip(ANIM_STAT_NAMES, stats.tolist()) if k}
 
 
 def filter_1to1(rows: np.ndarray) -> np.ndarray:
@@ -205,11 +204,11 @@ def filter_1to1(rows: np.ndarray) -> np.ndarray:
     return keep.astype(bool)
 
 
-def anim_pair(R: OGenome, Q: OGenome, nofilter: bool = False):
+def anim_pair(R: OGenome, Q: OGenome, nofilter: bool = False, maxmatch: bool = False):
     """One directed comparison through the whole oracle pipeline.
 
     -> (result dict with the fields of b200ani_anim_result, kept rows (n,7), stats)."""
-    rows, stats = anim_align(R, Q)
+    rows, stats = anim_align(R, Q, maxmatch=maxmatch)
     keep = np.ones(len(rows), bool) if nofilter else filter_1to1(rows)
     kept = rows[keep][:, :7]
     out = np.zeros(5, dtype=np.int64)
@@ -259,4 +258,4 @@ def anib_pair(Q: OGenome, S: OGenome, fragsize: int = 1020, cap: int = 1 << 15):
     assert n <= cap
     res = dict(aln_length=int(out[0]), sim_errs=int(out[1]), pid_milli_sum=int(out[2]), n_frags=int(out[3]), n_pass=int(out[4]),
                n_hsps=int(out[5]), status=0 if out[4] else 1)
-    return res, rows[:n].copy(), dict(zip(ANIM_STAT_NAMES, stats.tolist()))
+    return res, rows[:n].copy(), {k: v for k, v in zip(ANIM_STAT_NAMES, stats.tolist()) if k}

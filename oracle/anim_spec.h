@@ -14,7 +14,8 @@
 
 #define AN_K 16          /* seed k-mer length (2-bit packed -> one u32) */
 #define AN_W 5           /* minimizer window: K+W-1 = 20 = nucmer -l 20 => every match >= 20 is seeded */
-#define AN_MAXOCC 16     /* --maxmatch: seed k-mers with more occurrences than this in a genome are ignored */
+#define AN_MAXOCC 16     /* seed k-mers with more occurrences than this in a genome are ignored */
+#define AN_POSBITS 30    /* minimizer entry = position (30 bits) | repeated-in-own-genome << 30 | orientation << 31 */
 #define AN_MINLEN 20     /* minimum maximal-exact-match length (nucmer -l 20) */
 #define AN_LOOKBACK 32   /* chaining: predecessor searched among the previous 32 anchors */
 #define AN_GAPMAX 1000   /* chaining: max gap between linked anchors on either genome */
@@ -27,8 +28,9 @@
 #define AN_MATCH 3       /* sw_align scores [EXT]: match 3, mismatch -7 */
 #define AN_MISMATCH 7
 #define AN_GAPOPEN 10    /* cost of the first column of a gap */
-#define AN_GAPEXT 4      /* cost of each further gap column */
-#define AN_BREAK 94      /* rows without a new best before an extension/link gives up (nucmer -b 200 anti-diagonals) */
+#define AN_GAPEXT 7      /* cost of each further gap column (error counts of nucmer's own alignments are reproduced exactly with 10/7) */
+#define AN_BREAK 104     /* rows without a new best before an extension/link gives up (nucmer -b 200 anti-diagonals) */
+#define AN_BRIDGE_DD 60   /* bridging: max |gap_q - gap_r| between two alignments that are joined (longest indel run in nucmer's fixture output: 59) */
 #define AN_CLUSTGAP 90   /* anchors closer than this on both genomes form a cluster (mgaps -s 90) */
 #define AN_FILT_OLAP 75  /* delta-filter -o 75: max overlap % of either alignment in a kept chain */
 #define AN_FILT_POW 2    /* alignment weight = length * identity^POW */

@@ -22,6 +22,9 @@
 
 #include "anim_spec.h"
 
+#define POS_MASK ((1u << AN_POSBITS) - 1u)
+#define REP_BIT (1u << AN_POSBITS)
+
 /* ------------------------------------------------------------------ genome in "g-space"
  * records back to back, one separator position (code 4) after each record; code 0..3 = ACGT,
  * 4 = anything else.  rc[] is the reverse complement of the whole g-space array. */
@@ -30,10 +33,10 @@ typedef struct {
     uint32_t n_contigs;
     uint64_t *goff; /* n_contigs+1 */
     uint8_t *fw, *rc;
-    /* index: unique canonical minimizers */
+    /* index: canonical minimizers whose k-mer occurs at most maxocc times among the genome's minimizers */
     int64_t n_mini;
     uint32_t *mini_kmer;    /* sorted by position */
-    uint32_t *mini_posflag; /* pos | orient<<31 */
+    uint32_t *mini_posflag; /* pos | repeated<<30 | orient<<31 (repeated: the k-mer occurs more than once in this genome) */
     uint64_t *table;        /* open addressing: kmer<<32 | posflag ; empty = ~0 */
     uint32_t table_bits;
 } orc_genome;
@@ -68,11 +71,11 @@ void orc_genome_free(orc_genome *g) {
     free(g);
 }
 
-/* maxocc = 1: --mum seeds (k-mers unique among the genome's minimizers); maxocc = AN_MAXOCC: --maxmatch seeds
- * (every k-mer with at most that many occurrences; nucmer itself has no cap, anim.py:276-279) */
+/* One index serves every mode: minimizers whose k-mer occurs at most AN_MAXOCC times in the genome, the repeated
+ * ones flagged (nucmer itself has no occurrence cap, anim.py:276-279).  maxocc is a parameter for experiments only. */
 orc_genome *orc_genome_create_occ(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs, int maxocc);
 orc_genome *orc_genome_create(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs) {
-    return orc_genome_create_occ(ascii, off, n_contigs, 1);
+    return orc_genome_create_occ(ascii, off, n_contigs, AN_MAXOCC);
 }
 
 orc_genome *orc_genome_create_occ(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs, int maxocc) {
@@ -132,14 +135,15 @@ orc_genome *orc_genome_create_occ(const uint8_t *ascii, const uint64_t *off, uin
         }
         if (chosen) sel[ns++] = ((uint64_t)canon[p] << 32) | (uint32_t)p | ((uint32_t)orient[p] << 31);
     }
-    /* ---- keep k-mers that occur once among the selected (--mum uniqueness, approximated on seeds) */
+    /* ---- keep k-mers that occur at most maxocc times among the selected; flag the repeated ones (the seed
+     * stage decides per mode what a repeated k-mer may do, see orc_anim_align) */
     qsort(sel, (size_t)ns, sizeof(uint64_t), cmp_u64);
     int64_t nu = 0;
     for (int64_t i = 0; i < ns;) {
         int64_t j = i + 1;
         while (j < ns && (sel[j] >> 32) == (sel[i] >> 32)) ++j;
         if (j - i <= maxocc)
-            for (int64_t x = i; x < j; ++x) sel[nu++] = sel[x];
+            for (int64_t x = i; x < j; ++x) sel[nu++] = sel[x] | (j - i > 1 ? REP_BIT : 0u);
         i = j;
     }
     g->n_mini = nu;
@@ -156,13 +160,13 @@ orc_genome *orc_genome_create_occ(const uint8_t *ascii, const uint64_t *off, uin
     }
     /* position-sorted list (what a query streams through the reference's table) */
     uint64_t *bypos = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(nu + 1));
-    for (int64_t i = 0; i < nu; ++i) bypos[i] = ((uint64_t)((uint32_t)sel[i] & 0x7fffffffu) << 33) | ((sel[i] >> 31 & 1) << 32) | (sel[i] >> 32);
+    for (int64_t i = 0; i < nu; ++i) bypos[i] = ((uint64_t)((uint32_t)sel[i] & POS_MASK) << 34) | ((sel[i] >> AN_POSBITS & 3) << 32) | (sel[i] >> 32);
     qsort(bypos, (size_t)nu, sizeof(uint64_t), cmp_u64);
     g->mini_kmer = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(nu + 1));
     g->mini_posflag = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(nu + 1));
     for (int64_t i = 0; i < nu; ++i) {
         g->mini_kmer[i] = (uint32_t)bypos[i];
-        g->mini_posflag[i] = (uint32_t)(bypos[i] >> 33) | ((uint32_t)(bypos[i] >> 32 & 1) << 31);
+        g->mini_posflag[i] = (uint32_t)(bypos[i] >> 34) | ((uint32_t)(bypos[i] >> 32 & 3) << AN_POSBITS);
     }
     free(bypos); free(sel); free(hv); free(canon); free(orient);
     return g;
@@ -289,6 +293,28 @@ static dp_out dp_band(const uint8_t *R, int rstride, const uint8_t *Q, int qstri
 static inline int32_t pack_score(int32_t v) { return (v + AN_PACK - 1) >> 12; } /* arithmetic shift = floor */
 static inline int32_t pack_errs(int32_t v) { return pack_score(v) * AN_PACK - v; }
 
+/* unbanded global affine alignment of a small rectangle (bridges, at most AN_BREAK x AN_BREAK): H[lr][lq] in the
+ * same packed units as dp_band_sc */
+static int32_t dp_full(const uint8_t *R, const uint8_t *Q, int lr, int lq) {
+    const int32_t go = AN_GAPOPEN * AN_PACK + 1, ge = AN_GAPEXT * AN_PACK + 1, sm = AN_MATCH * AN_PACK, sx = -(AN_MISMATCH * AN_PACK + 1);
+    int32_t H[AN_BREAK + 2], F[AN_BREAK + 2];
+    H[0] = 0; F[0] = AN_NEG;
+    for (int j = 1; j <= lq; ++j) { H[j] = -(go + (j - 1) * ge); F[j] = AN_NEG; }
+    for (int i = 1; i <= lr; ++i) {
+        int32_t diag = H[0], hleft = -(go + (i - 1) * ge), eleft = AN_NEG;
+        H[0] = hleft;
+        for (int j = 1; j <= lq; ++j) {
+            int32_t e1 = eleft - ge, e2 = hleft - go, e = e1 > e2 ? e1 : e2;
+            int32_t f1 = F[j] - ge, f2 = H[j] - go, f = f1 > f2 ? f1 : f2;
+            int32_t d = diag + ((R[i - 1] == Q[j - 1] && R[i - 1] < 4) ? sm : sx);
+            int32_t h = d > e ? d : e;
+            if (f > h) h = f;
+            diag = H[j]; H[j] = h; F[j] = f; hleft = h; eleft = e;
+        }
+    }
+    return H[lq];
+}
+
 /* ------------------------------------------------------------------ one directed pair */
 typedef struct { int32_t strand, r, q, len; } anchor;
 
@@ -300,14 +326,54 @@ static int cmp_anchor(const void *a, const void *b) {
     return x->len - y->len;
 }
 
-/* stats[]: 0 anchors, 1 links, 2 cut links, 3 segments kept, 4 gap cells, 5 ext cells, 6 ext tiles,
- *          7 seed hits */
-#define ORC_NSTATS 8
+/* stats[]: 0 anchors (after the cluster pre-pass), 1 links, 2 cut links, 3 segments, 4 gap cells, 5 ext cells,
+ *          6 ext tiles, 7 seed hits, 8 anchors before the pre-pass, 9 bridges, 10 bridge cells */
+#define ORC_NSTATS 16
+
+/* Linking: every anchor takes the nearest compatible predecessor among the previous AN_LOOKBACK anchors (same strand,
+ * same records, gaps <= gapmax on both genomes, diagonal drift <= AN_DMAX), then each predecessor keeps only its
+ * nearest successor.  trim = overlap of the two anchors that the link removes from the later one. */
+static void link_anchors(const anchor *A, int64_t na, const uint32_t *rc_of, const uint32_t *qc_of, int gapmax, int32_t *pred, int32_t *succ, int32_t *trim) {
+    for (int64_t i = 0; i < na; ++i) { pred[i] = -1; succ[i] = 0x7fffffff; trim[i] = 0; }
+    for (int64_t i = 0; i < na; ++i) {
+        for (int64_t j = i - 1; j >= 0 && j >= i - AN_LOOKBACK; --j) {
+            if (A[j].strand != A[i].strand) break;
+            if (rc_of[j] != rc_of[i] || qc_of[j] != qc_of[i]) continue;
+            int64_t rej = (int64_t)A[j].r + A[j].len, qej = (int64_t)A[j].q + A[j].len;
+            int64_t ov = 0;
+            if (rej - A[i].r > ov) ov = rej - A[i].r;
+            if (qej - A[i].q > ov) ov = qej - A[i].q;
+            if (ov >= A[i].len) continue;
+            int64_t gr = A[i].r + ov - rej, gq = A[i].q + ov - qej;
+            if (gr > gapmax || gq > gapmax) continue;
+            int64_t dd = gq - gr;
+            if (dd > AN_DMAX || dd < -AN_DMAX) continue;
+            pred[i] = (int32_t)j; trim[i] = (int32_t)ov;
+            break;
+        }
+    }
+    for (int64_t i = 0; i < na; ++i)
+        if (pred[i] >= 0 && succ[pred[i]] > (int32_t)i) succ[pred[i]] = (int32_t)i;
+    for (int64_t i = 0; i < na; ++i)
+        if (pred[i] >= 0 && succ[pred[i]] != (int32_t)i) { pred[i] = -1; trim[i] = 0; }
+}
+
+static void anchor_records(const orc_genome *R, const orc_genome *Q, const anchor *A, int64_t na, uint32_t *rc_of, uint32_t *qc_of) {
+    for (int64_t i = 0; i < na; ++i) {
+        rc_of[i] = contig_of(R->goff, R->n_contigs, A[i].r);
+        int64_t qf = A[i].strand ? Q->n_pos - 1 - A[i].q : A[i].q; /* any base of the anchor identifies the record */
+        qc_of[i] = contig_of(Q->goff, Q->n_contigs, qf);
+    }
+}
+
+typedef struct { int32_t strand, pred, succ, bval; uint32_t rc, qc; int64_t rs, re, qs, qe, score, errs, sdist; } seg_t;
 
 /* Alignments of R (reference = pyani query, anim.py:280) vs Q before the 1-to-1 filter.
+ * maxmatch = 0 (nucmer --mum): a seed k-mer must be unique in at least one of the two genomes;
+ * maxmatch = 1 (--maxmatch, anim.py:276-279): every k-mer with at most AN_MAXOCC occurrences per genome seeds.
  * rows: up to cap rows of 8 int64: ref_contig, qry_contig, rs, re, qs, qe, errs, score  (.delta
  * conventions: 1-based closed, reverse strand qs > qe).  Returns the number of alignments. */
-int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int64_t *rows, int64_t cap, int64_t *stats) {
+int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int maxmatch, int64_t *rows, int64_t cap, int64_t *stats) {
     memset(stats, 0, sizeof(int64_t) * ORC_NSTATS);
     /* ---- seeds -> maximal exact matches */
     int64_t acap = 1 << 16, na = 0;
@@ -316,11 +382,12 @@ int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int64_t *rows, 
     for (int64_t t = 0; t < Q->n_mini; ++t) {
       uint32_t rpf;
       uint64_t cursor = ~0ull;
-      while (lookup_next(R, Q->mini_kmer[t], &cursor, &rpf)) { /* one entry for --mum indexes, up to AN_MAXOCC for --maxmatch */
+      const uint32_t qpf = Q->mini_posflag[t];
+      while (lookup_next(R, Q->mini_kmer[t], &cursor, &rpf)) { /* up to AN_MAXOCC entries per k-mer */
+        if (!maxmatch && (rpf & REP_BIT) && (qpf & REP_BIT)) continue; /* --mum: repeated in both genomes */
         stats[7]++;
-        uint32_t qpf = Q->mini_posflag[t];
         int strand = (int)((rpf ^ qpf) >> 31);
-        int64_t r0 = rpf & 0x7fffffffu, qpos = qpf & 0x7fffffffu;
+        int64_t r0 = rpf & POS_MASK, qpos = qpf & POS_MASK;
         int64_t q0 = strand ? Q->n_pos - AN_K - qpos : qpos;
         const uint8_t *Qs = strand ? Q->rc : Q->fw;
         /* a seed inside the match found by the previous seed of this strand yields the same match
@@ -343,7 +410,7 @@ int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int64_t *rows, 
     for (int64_t i = 0; i < na; ++i)
         if (i == 0 || cmp_anchor(&A[i], &A[i - 1]) != 0) A[nu++] = A[i];
     na = nu;
-    stats[0] = na;
+    stats[8] = na;
 
     int32_t *pred = (int32_t *)malloc(sizeof(int32_t) * (size_t)(na + 1));
     int32_t *succ = (int32_t *)malloc(sizeof(int32_t) * (size_t)(na + 1));
@@ -352,37 +419,26 @@ int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int64_t *rows, 
     int32_t *head = (int32_t *)malloc(sizeof(int32_t) * (size_t)(na + 1));
     uint32_t *rc_of = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(na + 1));
     uint32_t *qc_of = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(na + 1));
+    int64_t *cw = (int64_t *)calloc((size_t)(na + 1), sizeof(int64_t));
+    /* ---- cluster pre-pass (mgaps -s 90 -l 65): clusters = chains of links whose gaps are <= AN_CLUSTGAP on both
+     * genomes; anchors of clusters with fewer than AN_MINCLUSTER matched bases are dropped -- they neither start an
+     * alignment nor serve as stepping stones between the others */
+    anchor_records(R, Q, A, na, rc_of, qc_of);
+    link_anchors(A, na, rc_of, qc_of, AN_CLUSTGAP, pred, succ, trim);
     for (int64_t i = 0; i < na; ++i) {
-        rc_of[i] = contig_of(R->goff, R->n_contigs, A[i].r);
-        int64_t qf = A[i].strand ? Q->n_pos - 1 - A[i].q : A[i].q; /* any base of the anchor identifies the record */
-        qc_of[i] = contig_of(Q->goff, Q->n_contigs, qf);
+        head[i] = pred[i] < 0 ? (int32_t)i : head[pred[i]];
+        cw[head[i]] += A[i].len - trim[i];
     }
-    /* ---- linking: nearest compatible predecessor within the lookback, then each predecessor keeps
-     * only its nearest successor */
-    for (int64_t i = 0; i < na; ++i) { pred[i] = -1; succ[i] = 0x7fffffff; }
-    for (int64_t i = 0; i < na; ++i) {
-        for (int64_t j = i - 1; j >= 0 && j >= i - AN_LOOKBACK; --j) {
-            if (A[j].strand != A[i].strand) break;
-            if (rc_of[j] != rc_of[i] || qc_of[j] != qc_of[i]) continue;
-            int64_t rej = (int64_t)A[j].r + A[j].len, qej = (int64_t)A[j].q + A[j].len;
-            int64_t ov = 0;
-            if (rej - A[i].r > ov) ov = rej - A[i].r;
-            if (qej - A[i].q > ov) ov = qej - A[i].q;
-            if (ov >= A[i].len) continue;
-            int64_t gr = A[i].r + ov - rej, gq = A[i].q + ov - qej;
-            if (gr > AN_GAPMAX || gq > AN_GAPMAX) continue;
-            int64_t dd = gq - gr;
-            if (dd > AN_DMAX || dd < -AN_DMAX) continue;
-            pred[i] = (int32_t)j; trim[i] = (int32_t)ov;
-            break;
-        }
-    }
+    nu = 0;
     for (int64_t i = 0; i < na; ++i)
-        if (pred[i] >= 0 && succ[pred[i]] > (int32_t)i) succ[pred[i]] = (int32_t)i;
-    for (int64_t i = 0; i < na; ++i)
-        if (pred[i] >= 0 && succ[pred[i]] != (int32_t)i) { pred[i] = -1; trim[i] = 0; }
-    /* ---- gap alignments of the links; cut bad links */
+        if (cw[head[i]] >= AN_MINCLUSTER) A[nu++] = A[i];
+    na = nu;
+    stats[0] = na;
+    /* ---- links between the surviving anchors, their gap alignments; cut the links whose alignment gives up */
+    anchor_records(R, Q, A, na, rc_of, qc_of);
+    link_anchors(A, na, rc_of, qc_of, AN_GAPMAX, pred, succ, trim);
     for (int64_t i = 0; i < na; ++i) {
+        gval[i] = 0;
         if (pred[i] < 0) continue;
         stats[1]++;
         const anchor *a = &A[pred[i]], *b = &A[i];
@@ -408,33 +464,19 @@ int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int64_t *rows, 
     int64_t *ssum = (int64_t *)calloc((size_t)(na + 1), sizeof(int64_t)); /* gap scores */
     int64_t *esum = (int64_t *)calloc((size_t)(na + 1), sizeof(int64_t)); /* gap errors */
     int32_t *tail = (int32_t *)malloc(sizeof(int32_t) * (size_t)(na + 1));
-    /* clusters = runs of intact links whose gaps are <= AN_CLUSTGAP on both genomes (mgaps -s 90); a
-     * segment is reported only if one of its clusters holds >= AN_MINCLUSTER matched bases (mgaps -l 65) */
-    int32_t *chead = (int32_t *)malloc(sizeof(int32_t) * (size_t)(na + 1));
-    int64_t *cw = (int64_t *)calloc((size_t)(na + 1), sizeof(int64_t));
-    uint8_t *strong = (uint8_t *)calloc((size_t)(na + 1), 1);
-    for (int64_t i = 0; i < na; ++i) {
-        chead[i] = (int32_t)i;
-        if (pred[i] >= 0) {
-            const anchor *a = &A[pred[i]], *b = &A[i];
-            int64_t gr = b->r + trim[i] - ((int64_t)a->r + a->len), gq = b->q + trim[i] - ((int64_t)a->q + a->len);
-            if (gr <= AN_CLUSTGAP && gq <= AN_CLUSTGAP) chead[i] = chead[pred[i]];
-        }
-        cw[chead[i]] += A[i].len - trim[i];
-    }
     for (int64_t i = 0; i < na; ++i) {
         head[i] = pred[i] < 0 ? (int32_t)i : head[pred[i]];
         int32_t h = head[i];
-        if (cw[chead[i]] >= AN_MINCLUSTER) strong[h] = 1;
         wsum[h] += A[i].len - trim[i];
         ssum[h] += pack_score(gval[i]);
         esum[h] += pack_errs(gval[i]);
         tail[h] = (int32_t)i;
     }
-    /* ---- extend both ends of every kept segment, emit alignments */
-    int64_t nout = 0;
+    /* ---- extend both ends of every segment */
+    seg_t *S = (seg_t *)malloc(sizeof(seg_t) * (size_t)(na + 1));
+    int64_t ns = 0;
     for (int64_t h = 0; h < na; ++h) {
-        if (head[h] != (int32_t)h || !strong[h]) continue;
+        if (head[h] != (int32_t)h) continue;
         stats[3]++;
         const anchor *f = &A[h], *l = &A[tail[h]];
         const uint8_t *Qs = f->strand ? Q->rc : Q->fw;
@@ -460,18 +502,70 @@ int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int64_t *rows, 
                 if (o.stopped) break;
             }
         }
+        seg_t *g = &S[ns++];
+        g->strand = f->strand; g->rc = rc; g->qc = qc; g->rs = rs; g->re = re; g->qs = qs; g->qe = qe;
+        g->score = score; g->errs = errs; g->pred = -1; g->succ = 0x7fffffff; g->bval = 0; g->sdist = 0;
+    }
+    /* ---- bridging: two extended alignments whose facing ends are at most AN_BREAK bases apart on both genomes (and
+     * no more than AN_BRIDGE_DD off each other's diagonal) are one alignment for nucmer -- its extension reaches the
+     * neighbouring cluster before the break length runs out.  Every alignment takes the nearest such predecessor
+     * among the previous AN_LOOKBACK alignments, every predecessor keeps its nearest successor, the residual gap is
+     * aligned globally (unbanded) and chains of bridged alignments are merged. */
+    for (int64_t b = 0; b < ns; ++b) {
+        int64_t bestd = -1;
+        for (int64_t a = b - 1; a >= 0 && a >= b - AN_LOOKBACK; --a) {
+            if (S[a].strand != S[b].strand) break;
+            if (S[a].rc != S[b].rc || S[a].qc != S[b].qc) continue;
+            int64_t gr = S[b].rs - S[a].re, gq = S[b].qs - S[a].qe;
+            if (gr < 0 || gq < 0 || gr > AN_BREAK || gq > AN_BREAK) continue;
+            int64_t dd = gq - gr;
+            if (dd > AN_BRIDGE_DD || dd < -AN_BRIDGE_DD) continue;
+            if (bestd < 0 || gr + gq < bestd) { bestd = gr + gq; S[b].pred = (int32_t)a; }
+        }
+        S[b].sdist = bestd;
+    }
+    for (int64_t b = 0; b < ns; ++b) /* ascending b: ties keep the earlier successor */
+        if (S[b].pred >= 0) {
+            seg_t *a = &S[S[b].pred];
+            if (a->succ == 0x7fffffff || S[b].sdist < S[a->succ].sdist) a->succ = (int32_t)b;
+        }
+    for (int64_t b = 0; b < ns; ++b)
+        if (S[b].pred >= 0 && S[S[b].pred].succ != (int32_t)b) S[b].pred = -1;
+    for (int64_t b = 0; b < ns; ++b) {
+        if (S[b].pred < 0) continue;
+        stats[9]++;
+        const seg_t *a = &S[S[b].pred];
+        int lr = (int)(S[b].rs - a->re), lq = (int)(S[b].qs - a->qe);
+        const uint8_t *Qs = S[b].strand ? Q->rc : Q->fw;
+        int32_t v;
+        if (lr == 0 && lq == 0) v = 0;
+        else if (lr == 0 || lq == 0) { int L = lr + lq; v = -((AN_GAPOPEN + (L - 1) * AN_GAPEXT) * AN_PACK + L); }
+        else { v = dp_full(R->fw + a->re, Qs + a->qe, lr, lq); stats[10] += (int64_t)lr * lq; }
+        S[b].bval = v;
+    }
+    /* ---- emit: one row per chain of bridged alignments */
+    int64_t nout = 0;
+    for (int64_t h = 0; h < ns; ++h) {
+        if (S[h].pred >= 0) continue;
+        int64_t re = S[h].re, qe = S[h].qe, score = S[h].score, errs = S[h].errs;
+        for (int32_t pv = (int32_t)h, n2 = S[h].succ; n2 != 0x7fffffff && S[n2].pred == pv; pv = n2, n2 = S[n2].succ) {
+            score += S[n2].score + pack_score(S[n2].bval);
+            errs += S[n2].errs + pack_errs(S[n2].bval);
+            re = S[n2].re; qe = S[n2].qe;
+        }
         if (nout < cap) {
             int64_t *o = rows + 8 * nout;
+            const uint32_t rc = S[h].rc, qc = S[h].qc;
             o[0] = rc; o[1] = qc;
-            o[2] = rs - (int64_t)R->goff[rc] + 1; o[3] = re - 1 - (int64_t)R->goff[rc] + 1;
-            if (!f->strand) { o[4] = qs - (int64_t)Q->goff[qc] + 1; o[5] = qe - 1 - (int64_t)Q->goff[qc] + 1; }
-            else { o[4] = (Q->n_pos - 1 - qs) - (int64_t)Q->goff[qc] + 1; o[5] = (Q->n_pos - qe) - (int64_t)Q->goff[qc] + 1; }
+            o[2] = S[h].rs - (int64_t)R->goff[rc] + 1; o[3] = re - 1 - (int64_t)R->goff[rc] + 1;
+            if (!S[h].strand) { o[4] = S[h].qs - (int64_t)Q->goff[qc] + 1; o[5] = qe - 1 - (int64_t)Q->goff[qc] + 1; }
+            else { o[4] = (Q->n_pos - 1 - S[h].qs) - (int64_t)Q->goff[qc] + 1; o[5] = (Q->n_pos - qe) - (int64_t)Q->goff[qc] + 1; }
             o[6] = errs; o[7] = score;
         }
         ++nout;
     }
     free(A); free(pred); free(succ); free(trim); free(gval); free(head); free(rc_of); free(qc_of);
-    free(chead); free(cw); free(strong); free(wsum); free(ssum); free(esum); free(tail);
+    free(cw); free(wsum); free(ssum); free(esum); free(tail); free(S);
     return nout;
 }
 
@@ -591,11 +685,12 @@ int64_t orc_anib_pair(const orc_genome *Q, const orc_genome *S, int fragsize, in
     int64_t last_d[2] = {0, 0}, last_r0[2] = {-1, -1}, last_r1[2] = {-1, -1};
     for (int64_t t = 0; t < Q->n_mini; ++t) {
         uint32_t rpf;
-        if (!lookup(R, Q->mini_kmer[t], &rpf)) continue;
-        stats[7]++;
         uint32_t qpf = Q->mini_posflag[t];
+        if (qpf & REP_BIT) continue; /* ANIb seeds: k-mers unique in both genomes */
+        if (!lookup(R, Q->mini_kmer[t], &rpf) || (rpf & REP_BIT)) continue;
+        stats[7]++;
         int strand = (int)((rpf ^ qpf) >> 31);
-        int64_t r0 = rpf & 0x7fffffffu, qpos = qpf & 0x7fffffffu;
+        int64_t r0 = rpf & POS_MASK, qpos = qpf & POS_MASK;
         int64_t q0 = strand ? Q->n_pos - AN_K - qpos : qpos;
         const uint8_t *Qs = strand ? Q->rc : Q->fw;
         if (r0 - q0 == last_d[strand] && r0 >= last_r0[strand] && r0 + AN_K <= last_r1[strand]) continue;

@@ -7,14 +7,17 @@
 #include "anim_params.cuh"
 #include "common.cuh"
 
+// minimizer entry (index lists and table slots): position | repeated-in-own-genome << 30 | orientation << 31
+constexpr uint32_t AN_POSMASK = (1u << AN_POSBITS) - 1u, AN_REPBIT = 1u << AN_POSBITS;
+
 struct MinimizerIndex {
     bool valid = false;             // false after b200ani_reset_indexes: buffers are kept, content is rebuilt
-    int maxocc = 1;                 // 1: --mum seeds (unique k-mers); AN_MAXOCC: --maxmatch seeds
+    int maxocc = AN_MAXOCC;         // k-mers with more occurrences in the genome are not indexed
     int64_t cap_mini = 0;           // capacity of d_kmer / d_posflag
     uint32_t cap_bits = 0;          // capacity of d_table = 2^cap_bits slots
     int64_t n_mini = 0;
-    uint32_t *d_kmer = nullptr;     // unique canonical minimizers, sorted by position
-    uint32_t *d_posflag = nullptr;  // position | orientation << 31
+    uint32_t *d_kmer = nullptr;     // canonical minimizers, sorted by position
+    uint32_t *d_posflag = nullptr;  // position | repeated << 30 | orientation << 31
     uint64_t *d_table = nullptr;    // open addressing, slot = kmer << 32 | posflag, empty = ~0
     uint32_t *d_bitmap = nullptr;   // presence filter, 2^(table_bits+3) bits: answers most misses from L2
     uint32_t table_bits = 0;
@@ -175,6 +178,11 @@ struct SegArrays {
     int *rs, *qs, *re, *qe;            // [s,e) in view coordinates (reference g-space / query view)
     int *r_lo, *r_hi, *q_lo, *q_hi;    // record bounds in the same coordinates
     long long *score, *errs;
+    // bridging (ANIm): predecessor alignment this one is joined to (-1: none), the predecessor's choice of successor
+    // (distance << 32 | index, ~0 = none), packed value of the bridge alignment, 1 = this entry is emitted as a row
+    int *bpred, *bval;
+    unsigned long long *bsucc;
+    uint8_t *alive;
 };
 
 // rows: n x 8 int32 (pair, ref record, qry record, rs, re, qs, qe, errs), grouped by pair.
@@ -193,7 +201,7 @@ struct FiltArrays {
 
 // stage / counter slots of b200ani_last_profile
 enum {
-    ST_INDEX = 0, ST_SEED, ST_SORT, ST_LINK, ST_GAPDP, ST_LABEL, ST_EXTDP, ST_FILTER, ST_REDUCE, ST_TOTAL, ST_EXTK, ST_SEEDX,
+    ST_INDEX = 0, ST_SEED, ST_SORT, ST_LINK, ST_GAPDP, ST_LABEL, ST_EXTDP, ST_FILTER, ST_REDUCE, ST_TOTAL, ST_EXTK, ST_SEEDX, ST_PREPASS, ST_BRIDGE,
     CT_PROBES = 0, CT_SEEDHITS, CT_ANCHORS, CT_LINKS, CT_CUTS, CT_SEGMENTS, CT_GAPCELLS, CT_EXTCELLS, CT_EXTTILES, CT_ALIGNMENTS, CT_LAUNCHES,
     CT_GAPTASKS, CT_PAIRS, CT_EXTLAUNCH, CT_GAPLAUNCH, CT_SEEDLAUNCH
 };

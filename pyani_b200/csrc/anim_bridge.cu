@@ -1,0 +1,108 @@
+// Bridging stage (ANIm): join extended alignments whose facing ends are close.  nucmer extends every cluster towards the
+// neighbouring one and fuses the two when the extension gets there before its break length runs out (postnuc's
+// extendForward / extendBackward "target reached", SURVEY.md 8a-M2 [EXT]); in its output no two colinear alignments
+// end closer than ~100 bases to each other.  Here: every alignment takes the nearest predecessor (among the previous
+// AN_LOOKBACK alignments of the same pair, strand and records) whose end lies at most AN_BREAK bases before its
+// start on both genomes and at most AN_BRIDGE_DD off its diagonal; every predecessor keeps its nearest successor; the
+// residual gap is aligned globally (unbanded, at most AN_BREAK x AN_BREAK cells) and chains of bridged alignments are
+// merged into one row.  Segments arrive in (pair, strand, reference start of the head anchor) order.
+#include "anim.cuh"
+
+__global__ void bridge_init_kernel(SegArrays S) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S.n) return;
+    S.bpred[s] = -1;
+    S.bval[s] = 0;
+    S.bsucc[s] = ~0ull;
+    S.alive[s] = 1;
+}
+
+__global__ void bridge_link_kernel(SegArrays S) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= S.n) return;
+    const int pair = S.pair[b], strand = S.strand[b];
+    const uint32_t rc = S.rc[b], qc = S.qc[b];
+    const int rs = S.rs[b], qs = S.qs[b];
+    int best = -1, bestd = 0;
+    for (int64_t a = b - 1; a >= 0 && a >= b - AN_LOOKBACK; --a) {
+        if (S.pair[a] != pair || S.strand[a] != strand) break;
+        if (S.rc[a] != rc || S.qc[a] != qc) continue;
+        const int gr = rs - S.re[a], gq = qs - S.qe[a];
+        if (gr < 0 || gq < 0 || gr > AN_BREAK || gq > AN_BREAK) continue;
+        const int dd = gq - gr;
+        if (dd > AN_BRIDGE_DD || dd < -AN_BRIDGE_DD) continue;
+        if (best < 0 || gr + gq < bestd) { bestd = gr + gq; best = (int)a; }
+    }
+    if (best >= 0) {
+        S.bpred[b] = best;
+        atomicMin(&S.bsucc[best], ((unsigned long long)bestd << 32) | (unsigned long long)b);  // nearest, ties: the earlier one
+    }
+}
+
+// one thread per bridge: unbanded global affine alignment of the residual gap, value = score * AN_PACK - errs
+__global__ void __launch_bounds__(64) bridge_dp_kernel(SegArrays S, const PairDesc *__restrict__ pairs, unsigned long long *__restrict__ counters /*0: bridges, 1: cells*/) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= S.n) return;
+    const int a = S.bpred[b];
+    if (a < 0) return;
+    if ((uint32_t)S.bsucc[a] != (uint32_t)b) { S.bpred[b] = -1; return; }  // the predecessor prefers another successor
+    S.alive[b] = 0;
+    const int lr = S.rs[b] - S.re[a], lq = S.qs[b] - S.qe[a];
+    constexpr int go = AN_GAPOPEN * AN_PACK + 1, ge = AN_GAPEXT * AN_PACK + 1, sm = AN_MATCH * AN_PACK, sx = -(AN_MISMATCH * AN_PACK + 1);
+    int v;
+    if (lr == 0 && lq == 0) v = 0;
+    else if (lr == 0 || lq == 0) {
+        const int L = lr + lq;
+        v = -((AN_GAPOPEN + (L - 1) * AN_GAPEXT) * AN_PACK + L);
+    } else {
+        const PairDesc &P = pairs[S.pair[b]];
+        SeqView R{P.r_seq, P.r_mask, P.r_npos, 0}, Q{P.q_seq, P.q_mask, P.q_npos, S.strand[b]};
+        const int64_t r0 = S.re[a], q0 = S.qe[a];
+        int H[AN_BREAK + 1], F[AN_BREAK + 1];
+        uint8_t qb[AN_BREAK + 1];
+        H[0] = 0; F[0] = AN_NEG;
+        for (int j = 1; j <= lq; ++j) {
+            H[j] = -(go + (j - 1) * ge);
+            F[j] = AN_NEG;
+            qb[j] = (uint8_t)view_code(Q, q0 + j - 1);
+        }
+        for (int i = 1; i <= lr; ++i) {
+            const int rb = view_code(R, r0 + i - 1);
+            int diag = H[0], hleft = -(go + (i - 1) * ge), eleft = AN_NEG;
+            H[0] = hleft;
+            for (int j = 1; j <= lq; ++j) {
+                const int e = max(eleft - ge, hleft - go);
+                const int f = max(F[j] - ge, H[j] - go);
+                const int d = diag + ((rb == qb[j] && rb < 4) ? sm : sx);
+                const int h = max(max(d, e), f);
+                diag = H[j]; H[j] = h; F[j] = f; hleft = h; eleft = e;
+            }
+        }
+        v = H[lq];
+        atomicAdd(&counters[1], (unsigned long long)lr * (unsigned long long)lq);
+    }
+    S.bval[b] = v;
+    atomicAdd(&counters[0], 1ull);
+}
+
+// one thread per chain head: fold the chain's members into the head
+__global__ void bridge_merge_kernel(SegArrays S) {
+    int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= S.n || S.bpred[h] >= 0) return;
+    int re = S.re[h], qe = S.qe[h];
+    long long score = S.score[h], errs = S.errs[h];
+    int pv = (int)h;
+    unsigned long long sc = S.bsucc[h];
+    while (sc != ~0ull) {
+        const int n2 = (int)(uint32_t)sc;
+        if (S.bpred[n2] != pv) break;
+        const int g = S.bval[n2];
+        score += S.score[n2] + pack_score(g);
+        errs += S.errs[n2] + pack_errs(g);
+        re = S.re[n2]; qe = S.qe[n2];
+        pv = n2;
+        sc = S.bsucc[n2];
+    }
+    // members are never heads, so nobody reads the fields written here
+    S.re[h] = re; S.qe[h] = qe; S.score[h] = score; S.errs[h] = errs;
+}

@@ -19,7 +19,8 @@ __global__ void contig_kernel(ChainArrays A, const PairDesc *__restrict__ pairs)
 }
 
 // nearest compatible predecessor among the previous AN_LOOKBACK anchors of the same pair and strand
-__global__ void link_kernel(ChainArrays A) {
+// (gapmax = AN_CLUSTGAP in the cluster pre-pass, AN_GAPMAX for the links proper)
+__global__ void link_kernel(ChainArrays A, int gapmax) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n) return;
     const uint64_t ki = A.keys[i], vi = A.vals[i];
@@ -35,7 +36,7 @@ __global__ void link_kernel(ChainArrays A) {
         int64_t ov = max((int64_t)0, max(rej - ri, qej - qi));
         if (ov >= leni) continue;
         int64_t gr = ri + ov - rej, gq = qi + ov - qej;
-        if (gr > AN_GAPMAX || gq > AN_GAPMAX) continue;
+        if (gr > gapmax || gq > gapmax) continue;
         int64_t dd = gq - gr;
         if (dd > AN_DMAX || dd < -AN_DMAX) continue;
         A.pred[i] = (int)j;
@@ -144,4 +145,13 @@ __global__ void segment_flag_kernel(ChainArrays A, uint8_t *__restrict__ flag) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n) return;
     flag[i] = (A.head[i] == (int)i) && A.strong[i];
+}
+
+// Cluster pre-pass (mgaps -s 90 -l 65): after linking with gapmax = AN_CLUSTGAP and labelling, an anchor survives iff its
+// cluster holds at least AN_MINCLUSTER matched bases.  Anchors of weak clusters neither start an alignment nor serve as
+// stepping stones between the others.
+__global__ void cluster_keep_kernel(ChainArrays A, uint8_t *__restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    flag[i] = A.cw[A.chead[i]] >= AN_MINCLUSTER;
 }

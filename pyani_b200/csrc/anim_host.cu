@@ -1,6 +1,6 @@
 // Host orchestration of the ANIm pipeline and its C ABI (b200ani_anim, b200ani_anim_alignments).
 // One batch = up to MAX_BATCH_PAIRS directed comparisons flowing through flat kernels together:
-//   seed -> sort/unique -> link -> link DP -> labels -> extension DP rounds -> rows -> filter -> reduce
+//   seed -> sort/unique -> cluster pre-pass -> link -> link DP -> labels -> extension DP rounds -> bridging -> rows -> filter -> reduce
 // replacing, per pair, one nucmer and one delta-filter subprocess plus anim.parse_delta
 // (anim.py:240-289,292-411; run_multiprocessing.py:113-152).
 #include <algorithm>
@@ -11,14 +11,20 @@
 #include "anim.cuh"
 
 int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc);
+enum { SEED_BOTH_UNIQUE = 0, SEED_ALL = 1, SEED_EITHER_UNIQUE = 2 };  // anim_seed.cu
 
 // kernels defined in the other translation units
-template <bool MAXMATCH> __global__ void seed_probe_kernel(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
-__global__ void seed_extend_kernel(const PairDesc *, int, const uint2 *, int64_t, uint64_t *, uint64_t *, unsigned long long *, unsigned long long);
+template <int MODE> __global__ void seed_probe_kernel(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
+__global__ void seed_extend_kernel(const PairDesc *, int, const uint2 *, int64_t, uint64_t *, uint64_t *, unsigned long long *, unsigned long long, int);
 __global__ void tie_fix_kernel(uint64_t *, uint64_t *, int64_t);
 __global__ void flag_unique_kernel(const uint64_t *, const uint64_t *, int64_t, uint8_t *);
 __global__ void contig_kernel(ChainArrays, const PairDesc *);
-__global__ void link_kernel(ChainArrays);
+__global__ void link_kernel(ChainArrays, int);
+__global__ void cluster_keep_kernel(ChainArrays, uint8_t *);
+__global__ void bridge_init_kernel(SegArrays);
+__global__ void bridge_link_kernel(SegArrays);
+__global__ void bridge_dp_kernel(SegArrays, const PairDesc *, unsigned long long *);
+__global__ void bridge_merge_kernel(SegArrays);
 __global__ void link_validate_kernel(ChainArrays, unsigned long long *);
 __global__ void gap_task_kernel(ChainArrays, uint32_t *, uint32_t *, unsigned long long *, int, int);
 __global__ void label_init_kernel(ChainArrays);
@@ -46,7 +52,7 @@ __global__ void filt_dp_kernel(FiltArrays, int, const int *, int);
 __global__ void reduce_kernel(FiltArrays, const int *, int, int, b200ani_anim_result *);
 
 static const char *kStageNames[B200ANI_N_STAGES] = {"index", "seed", "sort", "link", "gap_dp", "label", "ext_dp", "filter", "reduce", "total",
-                                                    "ext_dp_kernel", "seed_extend", "", "", "", ""};
+                                                    "ext_dp_kernel", "seed_extend", "prepass", "bridge", "", ""};
 static const char *kCounterNames[B200ANI_N_STAGES] = {"probes", "seed_hits", "anchors", "links", "cut_links", "segments", "gap_cells", "ext_cells",
                                                       "ext_tiles", "alignments", "launches", "gap_tasks", "pairs", "ext_dp_launches", "gap_dp_launches", "seed_launches"};
 
@@ -123,14 +129,16 @@ static int dalloc(b200ani_ctx *ctx, T **p, int64_t n) {
 #define T1(s) do { CK(cudaEventRecord(W->ev[2 * (s) + 1], st)); used[(s)] = true; } while (0)
 
 // rows_out (optional): host buffer receiving the batch's alignment rows (n x 8 int32) + keep flags
+struct Row8 { int v[8]; };  // one alignment row
 struct RowDump {
     std::vector<int> rows;
     std::vector<uint8_t> flag;
 };
 
 // fragsize == 0: ANIm (out = b200ani_anim_result[nb]); fragsize > 0: ANIb (out = b200ani_anib_result[nb])
-static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, int fragsize, void *out_v, RowDump *dump) {
+static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, int fragsize, int maxmatch, void *out_v, RowDump *dump) {
     const bool anib = fragsize > 0;
+    const int seedmode = anib ? SEED_BOTH_UNIQUE : (maxmatch ? SEED_ALL : SEED_EITHER_UNIQUE);
     const int64_t ANCHOR_CAP = W->anchor_cap, HIT_CAP = W->hit_cap;
     b200ani_anim_result *out = (b200ani_anim_result *)out_v;
     cudaStream_t st = ctx->stream;
@@ -174,10 +182,12 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     T0(ST_SEED);
     if (n_probes) {
         int blocks = (int)std::min<int64_t>(ceil_div(n_probes, 256 * 16), (int64_t)ctx->sm_count * 8);
-        if (ctx->genomes[pairs[0]].index->maxocc > 1)
-            seed_probe_kernel<true><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP);
+        if (seedmode == SEED_BOTH_UNIQUE)
+            seed_probe_kernel<SEED_BOTH_UNIQUE><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP);
+        else if (seedmode == SEED_ALL)
+            seed_probe_kernel<SEED_ALL><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP);
         else
-            seed_probe_kernel<false><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP);
+            seed_probe_kernel<SEED_EITHER_UNIQUE><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP);
         LAUNCHED(1);
         ctx->counters[CT_SEEDLAUNCH] += 1;
     }
@@ -190,7 +200,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     T0(ST_SEEDX);
     if (n_hits) {
         int blocks = (int)std::min<int64_t>(ceil_div(n_hits, 256), (int64_t)ctx->sm_count * 8);
-        seed_extend_kernel<<<blocks, 256, 0, st>>>(W->d_pairs, nb, W->hits, n_hits, W->keys_a, W->vals_a, W->counters, (unsigned long long)ANCHOR_CAP);
+        seed_extend_kernel<<<blocks, 256, 0, st>>>(W->d_pairs, nb, W->hits, n_hits, W->keys_a, W->vals_a, W->counters, (unsigned long long)ANCHOR_CAP, seedmode);
         LAUNCHED(1);
     }
     T1(ST_SEEDX);
@@ -230,7 +240,6 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         n = hn;
     }
     T1(ST_SORT);
-    ctx->counters[CT_ANCHORS] += n;
 
     // ---- chain arrays
     ChainArrays A{};
@@ -240,11 +249,50 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     DA(A.rc_of, n); DA(A.qc_of, n); DA(A.pred, n); DA(A.trim, n); DA(A.succ, n); DA(A.gval, n);
     DA(A.head, n); DA(A.chead, n); DA(A.cw, n); DA(A.wsum, n); DA(A.tail, n); DA(A.ssum, n); DA(A.esum, n); DA(A.strong, n);
     DA(task_key, n); DA(task_idx, n); DA(task_key2, n); DA(task_idx2, n); DA(seg_head, n);
+    // chain / cluster labels of the current links by pointer jumping (block-local pre-pass, then global rounds)
+    auto run_labels = [&]() -> int {
+        label_init_kernel<<<GRID(A.n)>>>(A);
+        label_local_kernel<<<(unsigned)ceil_div(A.n, 1024), 1024, 0, st>>>(A);
+        LAUNCHED(2);
+        for (int round = 0; round < 8; ++round) {
+            CK(cudaMemsetAsync(W->changed, 0, sizeof(int), st));
+            for (int k = 0; k < 3; ++k) label_jump_kernel<<<GRID(A.n)>>>(A, W->changed);
+            LAUNCHED(3);
+            int ch = 0;
+            CK(cudaMemcpyAsync(&ch, W->changed, sizeof ch, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (!ch) break;
+        }
+        return 0;
+    };
+    if (n && !anib) {
+        // ---- cluster pre-pass: drop the anchors of clusters with fewer than AN_MINCLUSTER matched bases
+        T0(ST_PREPASS);
+        contig_kernel<<<GRID(n)>>>(A, W->d_pairs);
+        link_kernel<<<GRID(n)>>>(A, AN_CLUSTGAP);
+        link_validate_kernel<<<GRID(n)>>>(A, W->counters + 12);
+        LAUNCHED(3);
+        if (int rc = run_labels()) return rc;
+        cluster_weight_kernel<<<GRID(n)>>>(A);
+        cluster_keep_kernel<<<GRID(n)>>>(A, W->flag);
+        LAUNCHED(2);
+        size_t tb = W->cub_bytes;
+        cub::DeviceSelect::Flagged(W->cub_tmp, tb, W->keys_a, W->flag, W->keys_b, W->changed, n, st);
+        tb = W->cub_bytes;
+        cub::DeviceSelect::Flagged(W->cub_tmp, tb, W->vals_a, W->flag, W->vals_b, W->changed, n, st);
+        int hn = 0;
+        CK(cudaMemcpyAsync(&hn, W->changed, sizeof hn, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        T1(ST_PREPASS);
+        n = hn;
+        A.keys = W->keys_b; A.vals = W->vals_b; A.n = n;
+    }
+    ctx->counters[CT_ANCHORS] += n;
     int64_t n_seg = 0;
     if (n) {
         T0(ST_LINK);
         contig_kernel<<<GRID(n)>>>(A, W->d_pairs);
-        link_kernel<<<GRID(n)>>>(A);
+        link_kernel<<<GRID(n)>>>(A, AN_GAPMAX);
         link_validate_kernel<<<GRID(n)>>>(A, W->counters + 2);
         gap_task_kernel<<<GRID(n)>>>(A, task_key, task_idx, W->counters + 3, anib ? AB_GAP : AN_GAPOPEN, anib ? AB_GAP : AN_GAPEXT);
         LAUNCHED(4);
@@ -267,20 +315,9 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         }
         // ---- clusters and segments
         T0(ST_LABEL);
-        label_init_kernel<<<GRID(n)>>>(A);
-        label_local_kernel<<<(unsigned)ceil_div(n, 1024), 1024, 0, st>>>(A);
-        LAUNCHED(2);
-        for (int round = 0; round < 8; ++round) {
-            CK(cudaMemsetAsync(W->changed, 0, sizeof(int), st));
-            for (int k = 0; k < 3; ++k) label_jump_kernel<<<GRID(n)>>>(A, W->changed);
-            LAUNCHED(3);
-            int ch = 0;
-            CK(cudaMemcpyAsync(&ch, W->changed, sizeof ch, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            if (!ch) break;
-        }
+        if (int rc = run_labels()) return rc;
         cluster_weight_kernel<<<GRID(n)>>>(A);
-        segment_accum_kernel<<<GRID(n)>>>(A, anib ? 0 : AN_MINCLUSTER);
+        segment_accum_kernel<<<GRID(n)>>>(A, 0);  // anchors of weak clusters are already gone (pre-pass): every chain is reported
         segment_flag_kernel<<<GRID(n)>>>(A, W->flag);
         LAUNCHED(3);
         size_t tb = W->cub_bytes;
@@ -305,6 +342,10 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     DA(S.rs, n_seg); DA(S.qs, n_seg); DA(S.re, n_seg); DA(S.qe, n_seg);
     DA(S.r_lo, n_seg); DA(S.r_hi, n_seg); DA(S.q_lo, n_seg); DA(S.q_hi, n_seg);
     DA(S.score, n_seg); DA(S.errs, n_seg); DA(rows, 8 * n_seg);
+    DA(S.bpred, n_seg); DA(S.bval, n_seg); DA(S.bsucc, n_seg); DA(S.alive, n_seg);
+    int *rows_all = nullptr;
+    DA(rows_all, 8 * n_seg);
+    int64_t n_rows = n_seg;
     uint32_t *ext_list[2] = {nullptr, nullptr};
     DA(ext_list[0], 2 * n_seg); DA(ext_list[1], 2 * n_seg);
 
@@ -343,13 +384,26 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
                 n_cur = (long long)hc[8];
             }
         }
-        if (!anib) {
-            emit_rows_kernel<<<GRID(n_seg)>>>(S, W->d_pairs, rows);
-            LAUNCHED(1);
-        }
         T1(ST_EXTDP);
         ctx->counters[CT_EXTCELLS] += (int64_t)hc[6];
         ctx->counters[CT_EXTTILES] += (int64_t)hc[7];
+        if (!anib) {
+            // ---- bridging: join alignments whose facing ends are close, then one row per chain of joined alignments
+            T0(ST_BRIDGE);
+            bridge_init_kernel<<<GRID(n_seg)>>>(S);
+            bridge_link_kernel<<<GRID(n_seg)>>>(S);
+            bridge_dp_kernel<<<(unsigned)ceil_div(n_seg, 64), 64, 0, st>>>(S, W->d_pairs, W->counters + 10);
+            bridge_merge_kernel<<<GRID(n_seg)>>>(S);
+            emit_rows_kernel<<<GRID(n_seg)>>>(S, W->d_pairs, rows_all);
+            LAUNCHED(5);
+            size_t tb = W->cub_bytes;
+            cub::DeviceSelect::Flagged(W->cub_tmp, tb, (const Row8 *)rows_all, S.alive, (Row8 *)rows, W->changed, n_seg, st);
+            int hr = 0;
+            CK(cudaMemcpyAsync(&hr, W->changed, sizeof hr, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            T1(ST_BRIDGE);
+            n_rows = hr;
+        }
     }
 
     if (anib) {
@@ -382,6 +436,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         DF(A.tail); DF(A.ssum); DF(A.esum); DF(A.strong); DF(task_key); DF(task_idx); DF(task_key2); DF(task_idx2); DF(seg_head);
         DF(S.pair); DF(S.strand); DF(S.head); DF(S.rc); DF(S.qc); DF(S.rs); DF(S.qs); DF(S.re); DF(S.qe);
         DF(S.r_lo); DF(S.r_hi); DF(S.q_lo); DF(S.q_hi); DF(S.score); DF(S.errs); DF(rows); DF(ext_list[0]); DF(ext_list[1]);
+    DF(S.bpred); DF(S.bval); DF(S.bsucc); DF(S.alive); DF(rows_all);
         CK(cudaStreamSynchronize(st));
         for (int s2 = 0; s2 < B200ANI_N_STAGES; ++s2)
             if (used[s2]) {
@@ -402,20 +457,20 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
 
     // ---- 1-to-1 filter + parse_delta reduction
     FiltArrays F{};
-    F.rows = rows; F.n = n_seg;
+    F.rows = rows; F.n = n_rows;
     uint64_t *fkey = nullptr, *fkey2 = nullptr;
     int *fidx = nullptr, *fidx2 = nullptr, *pair_start = nullptr;
-    for (int a = 0; a < 2; ++a) { DA(F.sidx[a], n_seg); DA(F.slo[a], n_seg); DA(F.shi[a], n_seg); DA(F.sseq[a], n_seg); }
-    DA(F.best, n_seg); DA(F.from, n_seg); DA(F.unit, n_seg); DA(F.flag, n_seg);
-    DA(fkey, n_seg); DA(fkey2, n_seg); DA(fidx, n_seg); DA(fidx2, n_seg); DA(pair_start, nb + 2);
+    for (int a = 0; a < 2; ++a) { DA(F.sidx[a], n_rows); DA(F.slo[a], n_rows); DA(F.shi[a], n_rows); DA(F.sseq[a], n_rows); }
+    DA(F.best, n_rows); DA(F.from, n_rows); DA(F.unit, n_rows); DA(F.flag, n_rows);
+    DA(fkey, n_rows); DA(fkey2, n_rows); DA(fidx, n_rows); DA(fidx2, n_rows); DA(pair_start, nb + 2);
     T0(ST_FILTER);
-    pair_range_kernel<<<(unsigned)ceil_div(nb + 1, 128), 128, 0, st>>>(rows, n_seg, nb, pair_start);
+    pair_range_kernel<<<(unsigned)ceil_div(nb + 1, 128), 128, 0, st>>>(rows, n_rows, nb, pair_start);
     LAUNCHED(1);
-    for (int axis = 0; axis < 2 && n_seg; ++axis) {
-        filt_key_kernel<<<GRID(n_seg)>>>(F, axis, fkey, fidx);
+    for (int axis = 0; axis < 2 && n_rows; ++axis) {
+        filt_key_kernel<<<GRID(n_rows)>>>(F, axis, fkey, fidx);
         size_t tb = W->cub_bytes;
-        cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb, fkey, fkey2, fidx, fidx2, n_seg, 0, 64, st);
-        filt_gather_kernel<<<GRID(n_seg)>>>(F, axis, fidx2);
+        cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb, fkey, fkey2, fidx, fidx2, n_rows, 0, 64, st);
+        filt_gather_kernel<<<GRID(n_rows)>>>(F, axis, fidx2);
         LAUNCHED(2);
         if (!nofilter) {
             filt_dp_kernel<<<nb, 256, 0, st>>>(F, axis, pair_start, nb);
@@ -429,11 +484,11 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     CK(cudaMemcpyAsync(out, W->d_results, sizeof(b200ani_anim_result) * nb, cudaMemcpyDeviceToHost, st));
     T1(ST_REDUCE);
     if (dump) {
-        dump->rows.resize((size_t)8 * n_seg);
-        dump->flag.resize((size_t)n_seg);
-        if (n_seg) {
-            CK(cudaMemcpyAsync(dump->rows.data(), rows, sizeof(int) * 8 * n_seg, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(dump->flag.data(), F.flag, (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+        dump->rows.resize((size_t)8 * n_rows);
+        dump->flag.resize((size_t)n_rows);
+        if (n_rows) {
+            CK(cudaMemcpyAsync(dump->rows.data(), rows, sizeof(int) * 8 * n_rows, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(dump->flag.data(), F.flag, (size_t)n_rows, cudaMemcpyDeviceToHost, st));
         }
     }
     // ---- release
@@ -441,6 +496,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     DF(A.tail); DF(A.ssum); DF(A.esum); DF(A.strong); DF(task_key); DF(task_idx); DF(task_key2); DF(task_idx2); DF(seg_head);
     DF(S.pair); DF(S.strand); DF(S.head); DF(S.rc); DF(S.qc); DF(S.rs); DF(S.qs); DF(S.re); DF(S.qe);
     DF(S.r_lo); DF(S.r_hi); DF(S.q_lo); DF(S.q_hi); DF(S.score); DF(S.errs); DF(rows); DF(ext_list[0]); DF(ext_list[1]);
+    DF(S.bpred); DF(S.bval); DF(S.bsucc); DF(S.alive); DF(rows_all);
     for (int a = 0; a < 2; ++a) { DF(F.sidx[a]); DF(F.slo[a]); DF(F.shi[a]); DF(F.sseq[a]); }
     DF(F.best); DF(F.from); DF(F.unit); DF(F.flag); DF(fkey); DF(fkey2); DF(fidx); DF(fidx2); DF(pair_start);
     CK(cudaStreamSynchronize(st));
@@ -462,7 +518,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     return 0;
 }
 
-static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs_in, int64_t m, int nofilter, int fragsize, void *out_user_v, RowDump *dump) {
+static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs_in, int64_t m, int nofilter, int fragsize, int maxmatch, void *out_user_v, RowDump *dump) {
     const size_t esz = fragsize > 0 ? sizeof(b200ani_anib_result) : sizeof(b200ani_anim_result);
     char *out_user = (char *)out_user_v;
     // Internal order: the two directions of a genome pair adjacent (one probe pass seeds both), genome pairs
@@ -489,7 +545,7 @@ static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs_in
         int nb = (int)std::min<int64_t>(MAX_BATCH_PAIRS, m - b0);
         while (true) {
             if (nb > 1 && splits_mirror(b0, nb)) --nb;
-            int rc = run_batch(ctx, W, pairs.data() + 2 * b0, nb, nofilter, fragsize, out.data() + (size_t)b0 * esz, dump);
+            int rc = run_batch(ctx, W, pairs.data() + 2 * b0, nb, nofilter, fragsize, maxmatch, out.data() + (size_t)b0 * esz, dump);
             if (rc == 0) break;
             if (rc < 0) return rc;
             if (nb == 1) FAIL(B200ANI_ERR_CAPACITY, "anim: a single pair exceeds the anchor capacity");
@@ -501,8 +557,8 @@ static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs_in
     return 0;
 }
 
-static int prepare(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch, AnimWorkspace **W) {
-    const int maxocc = maxmatch ? AN_MAXOCC : 1;
+static int prepare(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, AnimWorkspace **W) {
+    const int maxocc = AN_MAXOCC;  // one index serves --mum, --maxmatch and ANIb (the seed stage filters per mode)
     CK(cudaSetDevice(ctx->device));
     const int32_t ng = (int32_t)ctx->genomes.size();
     for (int64_t i = 0; i < 2 * m; ++i)
@@ -549,8 +605,8 @@ int b200ani_anim(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch
     CK(cudaEventCreate(&t0));
     CK(cudaEventCreate(&t1));
     CK(cudaEventRecord(t0, ctx->stream));
-    int rc = prepare(ctx, pairs, m, maxmatch, &W);
-    if (rc == 0) rc = run_range(ctx, W, pairs, m, nofilter, 0, out, nullptr);
+    int rc = prepare(ctx, pairs, m, &W);
+    if (rc == 0) rc = run_range(ctx, W, pairs, m, nofilter, 0, maxmatch, out, nullptr);
     CK(cudaEventRecord(t1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
@@ -565,11 +621,11 @@ int64_t b200ani_anim_alignments(b200ani_ctx *ctx, int32_t ref_id, int32_t qry_id
     if (!ctx || (!rows && cap > 0)) return B200ANI_ERR_ARG;
     int32_t pr[2] = {ref_id, qry_id};
     AnimWorkspace *W = nullptr;
-    int rc = prepare(ctx, pr, 1, maxmatch, &W);
+    int rc = prepare(ctx, pr, 1, &W);
     if (rc) return rc;
     RowDump dump;
     b200ani_anim_result res;
-    rc = run_range(ctx, W, pr, 1, nofilter, 0, &res, &dump);
+    rc = run_range(ctx, W, pr, 1, nofilter, 0, maxmatch, &res, &dump);
     if (rc) return rc;
     int64_t k = 0;
     for (size_t i = 0; i < dump.flag.size(); ++i) {
@@ -606,13 +662,13 @@ static int anib_common(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fr
     std::vector<int32_t> internal(2 * m);
     for (int64_t i = 0; i < m; ++i) { internal[2 * i] = pairs[2 * i + 1]; internal[2 * i + 1] = pairs[2 * i]; }
     AnimWorkspace *W = nullptr;
-    int rc = prepare(ctx, internal.data(), m, 0, &W);
+    int rc = prepare(ctx, internal.data(), m, &W);
     if (rc) return rc;
     for (int64_t i = 0; i < m; ++i) {
         rc = ensure_fragments(ctx, ctx->genomes[pairs[2 * i]], fragsize);
         if (rc) return rc;
     }
-    return run_range(ctx, W, internal.data(), m, 0, fragsize, out, dump);
+    return run_range(ctx, W, internal.data(), m, 0, fragsize, 0, out, dump);
 }
 
 int b200ani_anib(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fragsize, b200ani_anib_result *out) {

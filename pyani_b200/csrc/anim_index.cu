@@ -1,4 +1,6 @@
-// Per-genome seed index: canonical (w=5,k=16) minimizers that are unique within the genome.
+// Per-genome seed index: canonical (w=5,k=16) minimizers whose k-mer occurs at most AN_MAXOCC times in the genome,
+// the repeated ones flagged (entry = position | repeated << 30 | orientation << 31); the seed stage decides per mode
+// (--mum, --maxmatch, ANIb) what a repeated k-mer may seed.
 // Built once per genome and reused by every comparison the genome takes part in -- nucmer instead
 // rebuilds its suffix tree for each of the N-1 runs a genome is the reference of.
 #include <cub/cub.cuh>
@@ -82,8 +84,9 @@ __global__ void __launch_bounds__(256) minimizer_select_kernel(const uint64_t *_
     }
 }
 
-// keep the entries of k-mers that occur at most maxocc times among the selected minimizers (1 = --mum)
-__global__ void mark_unique_kernel(const uint64_t *__restrict__ sorted, int64_t n, uint8_t *__restrict__ flag, int maxocc) {
+// keep the entries of k-mers that occur at most maxocc times among the selected minimizers; entries of k-mers that
+// occur more than once get the "repeated" flag
+__global__ void mark_unique_kernel(uint64_t *__restrict__ sorted, int64_t n, uint8_t *__restrict__ flag, int maxocc) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t k = (uint32_t)(sorted[i] >> 32);
@@ -91,6 +94,7 @@ __global__ void mark_unique_kernel(const uint64_t *__restrict__ sorted, int64_t 
     for (int64_t j = i - 1; j >= 0 && run <= maxocc && (uint32_t)(sorted[j] >> 32) == k; --j) ++run;
     for (int64_t j = i + 1; j < n && run <= maxocc && (uint32_t)(sorted[j] >> 32) == k; ++j) ++run;
     flag[i] = run <= maxocc;
+    if (run > 1) sorted[i] |= (uint64_t)AN_REPBIT;  // neighbours only read the k-mer half of the word
 }
 
 __global__ void table_insert_kernel(const uint64_t *__restrict__ uniq, int64_t n, uint64_t *table, uint32_t *bitmap, uint32_t bits, uint64_t *__restrict__ bypos) {
@@ -102,9 +106,9 @@ __global__ void table_insert_kernel(const uint64_t *__restrict__ uniq, int64_t n
     while (atomicCAS((unsigned long long *)&table[s], ~0ull, (unsigned long long)e) != ~0ull) s = (s + 1) & msk;
     const uint32_t bh = bitmap_hash(k, bits);
     atomicOr(&bitmap[bh >> 5], 1u << (bh & 31));
-    // key for the by-position order: pos << 33 | orient << 32 | kmer
+    // key for the by-position order: pos << 34 | flags << 32 | kmer
     uint32_t pf = (uint32_t)e;
-    bypos[i] = ((uint64_t)(pf & 0x7fffffffu) << 33) | ((uint64_t)(pf >> 31) << 32) | k;
+    bypos[i] = ((uint64_t)(pf & AN_POSMASK) << 34) | ((uint64_t)(pf >> AN_POSBITS) << 32) | k;
 }
 
 __global__ void split_bypos_kernel(const uint64_t *__restrict__ bypos, int64_t n, uint32_t *__restrict__ kmer, uint32_t *__restrict__ posflag) {
@@ -112,7 +116,7 @@ __global__ void split_bypos_kernel(const uint64_t *__restrict__ bypos, int64_t n
     if (i >= n) return;
     uint64_t b = bypos[i];
     kmer[i] = (uint32_t)b;
-    posflag[i] = (uint32_t)(b >> 33) | ((uint32_t)((b >> 32) & 1) << 31);
+    posflag[i] = (uint32_t)(b >> 34) | ((uint32_t)((b >> 32) & 3) << AN_POSBITS);
 }
 
 void free_index(MinimizerIndex *ix, cudaStream_t st) {
@@ -262,7 +266,7 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc) {
                 table_insert_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, ss>>>(tmp[k].uniq, h_nu, ix->d_table, ix->d_bitmap, bits, tmp[k].sel);
                 CK(cudaGetLastError());
                 size_t tb = cub_bytes;
-                cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, h_nu, 33, 64, ss);
+                cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, h_nu, 34, 64, ss);
                 split_bypos_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, ss>>>(tmp[k].sorted, h_nu, ix->d_kmer, ix->d_posflag);
                 CK(cudaGetLastError());
             }

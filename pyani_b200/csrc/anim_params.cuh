@@ -6,6 +6,7 @@
 #define AN_K 16
 #define AN_W 5
 #define AN_MAXOCC 16
+#define AN_POSBITS 30
 #define AN_MINLEN 20
 #define AN_LOOKBACK 32
 #define AN_GAPMAX 1000
@@ -18,8 +19,9 @@
 #define AN_MATCH 3
 #define AN_MISMATCH 7
 #define AN_GAPOPEN 10
-#define AN_GAPEXT 4
-#define AN_BREAK 94
+#define AN_GAPEXT 7
+#define AN_BREAK 104
+#define AN_BRIDGE_DD 60
 #define AN_CLUSTGAP 90
 #define AN_FILT_OLAP 75
 #define AN_FILT_POW 2

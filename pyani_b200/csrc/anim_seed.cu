@@ -63,11 +63,22 @@ __device__ __forceinline__ int pair_of_probe(const PairDesc *__restrict__ pairs,
     return lo;
 }
 
+// Which table entries a query minimizer may seed with (entries carry "repeated in the reference" in bit 30, query
+// minimizers carry "repeated in the query"):
+//   SEED_BOTH_UNIQUE   ANIb: the k-mer is unique in both genomes
+//   SEED_ALL           --maxmatch: every entry (up to AN_MAXOCC per k-mer)
+//   SEED_EITHER_UNIQUE --mum: the k-mer is unique in at least one of the two genomes
+enum { SEED_BOTH_UNIQUE = 0, SEED_ALL = 1, SEED_EITHER_UNIQUE = 2 };
+__device__ __forceinline__ bool seed_ok(int mode, uint32_t rpf, uint32_t qpf) {
+    const bool rr = rpf & AN_REPBIT, qr = qpf & AN_REPBIT;
+    return mode == SEED_ALL || (mode == SEED_BOTH_UNIQUE ? !(rr || qr) : !(rr && qr));
+}
+
 // Phase 1 -- probe: one thread per (pair, query minimizer): stream the query's minimizer list
 // (evict-first loads) through the reference's table; hits are appended as (probe index, table entry).
 // Memory-latency bound by design: one coalesced 4-byte read + one random 8-byte read per probe, no
 // divergent work, so the warps in flight are all waiting on independent loads.
-template <bool MAXMATCH>
+template <int MODE>
 __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restrict__ pairs, int n_pairs, int64_t n_probes, uint2 *__restrict__ hits,
                                                          unsigned long long *__restrict__ n_hits, unsigned long long cap) {
     // Each block walks contiguous chunks of PROBE_CHUNK probes, PROBE_ILP probes per thread per step so that the
@@ -94,14 +105,14 @@ __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restr
         uint32_t bits = 0;
         int64_t base = 0, next_base = 0;
         for (int step = 0; step < PROBE_STEPS; ++step) {
-            uint32_t kmer[PROBE_ILP], rpf[PROBE_ILP], qpf[PROBE_ILP];
+            uint32_t kmer[PROBE_ILP], rpf[PROBE_ILP], qpf[PROBE_ILP], cur[PROBE_ILP];
             int64_t gi[PROBE_ILP];
             int pr[PROBE_ILP];
-            bool hit[PROBE_ILP];
+            bool hit[PROBE_ILP], more[PROBE_ILP];
 #pragma unroll
             for (int k = 0; k < PROBE_ILP; ++k) {  // phase 1: k-mers (coalesced, streaming)
                 gi[k] = ch * PROBE_CHUNK + (int64_t)(step * PROBE_ILP + k) * 256 + threadIdx.x;
-                hit[k] = false; rpf[k] = 0; qpf[k] = 0; kmer[k] = 0; pr[k] = -1;
+                hit[k] = false; more[k] = false; rpf[k] = 0; qpf[k] = 0; kmer[k] = 0; pr[k] = -1; cur[k] = ~0u;
                 if (gi[k] < n_probes) {
                     while (gi[k] >= next_base || cached < 0) {  // (re)load the pair's fields
                         if (cached >= 0) ++pair;
@@ -129,27 +140,15 @@ __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restr
                 pf[k] = (same ? q_posflag : P.q_posflag) + (gi[k] - (same ? base : P.probe_base));
                 hit[k] = pr[k] >= 0 && bitmap_test(bm[k], tbits[k], kmer[k]);
             }
-            if (MAXMATCH) {
-                // --maxmatch: a k-mer may sit in the table up to AN_MAXOCC times; every entry is a hit of its own and the
-                // in-warp redundancy shortcut below does not apply (duplicates are removed after the sort)
 #pragma unroll
-                for (int k = 0; k < PROBE_ILP; ++k) {
-                    uint32_t cursor = ~0u, e;
-                    while (hit[k] && table_next(tb[k], tbits[k], kmer[k], cursor, e)) {
-                        const unsigned int slot = atomicAdd(&s_n, 1u);
-                        if (slot < (unsigned int)PROBE_CHUNK) s_hits[slot] = make_uint2((uint32_t)gi[k], e);
-                        else {
-                            const unsigned long long g = atomicAdd(n_hits, 1ull);
-                            if (g < cap) hits[g] = make_uint2((uint32_t)gi[k], e);
-                        }
-                    }
+            for (int k = 0; k < PROBE_ILP; ++k) {  // phase 3: first table entry of the filter's positives
+                if (hit[k]) hit[k] = table_next(tb[k], tbits[k], kmer[k], cur[k], rpf[k]);
+                if (hit[k]) {
+                    qpf[k] = __ldcs(pf[k]);
+                    // a repeated k-mer has further entries; they can only qualify if the query side allows it
+                    more[k] = (rpf[k] & AN_REPBIT) && (MODE == SEED_ALL || (MODE == SEED_EITHER_UNIQUE && !(qpf[k] & AN_REPBIT)));
+                    hit[k] = seed_ok(MODE, rpf[k], qpf[k]);
                 }
-                continue;
-            }
-#pragma unroll
-            for (int k = 0; k < PROBE_ILP; ++k) {  // phase 3: table probe for the filter's positives
-                if (hit[k]) hit[k] = table_lookup(tb[k], tbits[k], kmer[k], rpf[k]);
-                if (hit[k]) qpf[k] = __ldcs(pf[k]);
             }
 #pragma unroll
             for (int k = 0; k < PROBE_ILP; ++k) {
@@ -158,7 +157,7 @@ __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restr
                 // the first seed of such a run is passed on (the match set is unchanged, see seed_extend_kernel).
                 bool h = hit[k];
                 const int strand = (int)((rpf[k] ^ qpf[k]) >> 31);
-                const int r0 = (int)(rpf[k] & 0x7fffffffu), qp = (int)(qpf[k] & 0x7fffffffu);
+                const int r0 = (int)(rpf[k] & AN_POSMASK), qp = (int)(qpf[k] & AN_POSMASK);
                 const int key = strand ? r0 + qp : r0 - qp;  // constant along a diagonal of that strand
                 const int nb = strand ? lane + 1 : lane - 1;
                 const bool nhit = __shfl_sync(0xffffffffu, (int)h, nb & 31) != 0;
@@ -172,7 +171,30 @@ __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restr
                     unsigned int bslot = 0;
                     if (lane == 0) bslot = atomicAdd(&s_n, (unsigned int)__popc(m));
                     bslot = __shfl_sync(0xffffffffu, bslot, 0);
-                    if (h) s_hits[bslot + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)gi[k], rpf[k]);
+                    if (h) {
+                        const unsigned int slot = bslot + __popc(m & ((1u << lane) - 1u));
+                        if (slot < (unsigned int)PROBE_CHUNK) s_hits[slot] = make_uint2((uint32_t)gi[k], rpf[k]);
+                        else {
+                            const unsigned long long g = atomicAdd(n_hits, 1ull);
+                            if (g < cap) hits[g] = make_uint2((uint32_t)gi[k], rpf[k]);
+                        }
+                    }
+                }
+            }
+            if (MODE != SEED_BOTH_UNIQUE) {
+                // the other entries of repeated k-mers (rare): every entry is a hit of its own, duplicates of a match
+                // are removed after the sort
+#pragma unroll
+                for (int k = 0; k < PROBE_ILP; ++k) {
+                    uint32_t e;
+                    while (more[k] && table_next(tb[k], tbits[k], kmer[k], cur[k], e)) {
+                        const unsigned int slot = atomicAdd(&s_n, 1u);
+                        if (slot < (unsigned int)PROBE_CHUNK) s_hits[slot] = make_uint2((uint32_t)gi[k], e);
+                        else {
+                            const unsigned long long g = atomicAdd(n_hits, 1ull);
+                            if (g < cap) hits[g] = make_uint2((uint32_t)gi[k], e);
+                        }
+                    }
                 }
             }
         }
@@ -186,8 +208,9 @@ __global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restr
     }
 }
 
-template __global__ void seed_probe_kernel<false>(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
-template __global__ void seed_probe_kernel<true>(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
+template __global__ void seed_probe_kernel<SEED_BOTH_UNIQUE>(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
+template __global__ void seed_probe_kernel<SEED_ALL>(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
+template __global__ void seed_probe_kernel<SEED_EITHER_UNIQUE>(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
 
 // One anchor of pair `pi`: ANIm -> as is; ANIb (P.fragsize > 0) -> clipped to the query's fragments, one piece per
 // fragment it overlaps (pieces shorter than AB_MINPIECE are dropped), the fragment id goes into the sort key.
@@ -242,7 +265,7 @@ __device__ __forceinline__ void emit_anchor(AnchorStage &S, const PairDesc &P, i
 // minimizer already covers, extend the others to maximal exact matches.  key/val encoding: anim.cuh.
 __global__ void __launch_bounds__(256) seed_extend_kernel(const PairDesc *__restrict__ pairs, int n_pairs, const uint2 *__restrict__ hits, int64_t n_hits,
                                                           uint64_t *__restrict__ keys, uint64_t *__restrict__ vals,
-                                                          unsigned long long *__restrict__ n_anchors, unsigned long long cap) {
+                                                          unsigned long long *__restrict__ n_anchors, unsigned long long cap, int mode) {
     __shared__ AnchorStage stage;
     if (threadIdx.x == 0) stage.n = 0;
     __syncthreads();
@@ -258,7 +281,7 @@ __global__ void __launch_bounds__(256) seed_extend_kernel(const PairDesc *__rest
         const uint32_t rpf = h.y;
         const uint32_t qpf = P.q_posflag[t];
         const int strand = (int)((rpf ^ qpf) >> 31);
-        const int64_t r0 = rpf & 0x7fffffffu, qpos = qpf & 0x7fffffffu;
+        const int64_t r0 = rpf & AN_POSMASK, qpos = qpf & AN_POSMASK;
         const int64_t q0 = strand ? (int64_t)P.q_npos - AN_K - qpos : qpos;
         SeqView R{P.r_seq, P.r_mask, P.r_npos, 0}, Q{P.q_seq, P.q_mask, P.q_npos, strand};
         // redundancy: the minimizer just before this one in view order seeds the same match if it hits the
@@ -267,12 +290,12 @@ __global__ void __launch_bounds__(256) seed_extend_kernel(const PairDesc *__rest
             int64_t tn = strand ? t + 1 : t - 1;
             if (tn >= 0 && tn < P.q_nmini) {
                 uint32_t qpfn = P.q_posflag[tn], rpfn;
-                int64_t qn = strand ? (int64_t)P.q_npos - AN_K - (qpfn & 0x7fffffffu) : (qpfn & 0x7fffffffu);
+                int64_t qn = strand ? (int64_t)P.q_npos - AN_K - (qpfn & AN_POSMASK) : (qpfn & AN_POSMASK);
                 bool nb_same_diag = false;
                 if (qn < q0 && q0 - qn <= 64) {
                     uint32_t cursor = ~0u;
                     while (!nb_same_diag && table_next(P.r_table, P.r_table_bits, P.q_kmer[tn], cursor, rpfn))
-                        nb_same_diag = (int)((rpfn ^ qpfn) >> 31) == strand && (int64_t)(rpfn & 0x7fffffffu) - qn == r0 - q0;
+                        nb_same_diag = seed_ok(mode, rpfn, qpfn) && (int)((rpfn ^ qpfn) >> 31) == strand && (int64_t)(rpfn & AN_POSMASK) - qn == r0 - q0;
                 }
                 if (nb_same_diag) {
                     bool same = true;
@@ -288,8 +311,8 @@ __global__ void __launch_bounds__(256) seed_extend_kernel(const PairDesc *__rest
         int64_t rr = match_right(R, Q, r0 + AN_K, q0 + AN_K);
         int64_t len = AN_K + l + rr;
         if (len < AN_MINLEN) break;
-        // Exact matches are symmetric in the two genomes (seeds are k-mers unique in BOTH minimizer sets and the
-        // selection is strand-symmetric), so the opposite-direction comparison gets its anchors from the same
+        // Exact matches are symmetric in the two genomes (every seed rule above is symmetric in the two genomes and
+        // the minimizer selection is strand-symmetric), so the opposite-direction comparison gets its anchors from the same
         // seeds: forward (r,q) -> (q,r); reverse-strand coordinates swap roles through both genome lengths.
         const int64_t rs = r0 - l, qs = q0 - l;
         emit_anchor(stage, P, lo, strand, rs, qs, len, keys, vals, n_anchors, cap);

@@ -2,6 +2,7 @@
 // The ANIm entry points live in anim_host.cu.
 #include <cstring>
 
+#include "anim_params.cuh"
 #include "common.cuh"
 
 static const char *kVersion = "b200ani 0.1.0 (sm_100a)";
@@ -102,7 +103,7 @@ int b200ani_add_genome(b200ani_ctx *ctx, const uint8_t *ascii, const uint64_t *c
         if (contig_off[c + 1] < contig_off[c]) FAIL(B200ANI_ERR_ARG, "add_genome: record offsets must be non-decreasing");
     const int64_t n_bases = (int64_t)contig_off[n_contigs];
     if (n_bases > 0 && !ascii) FAIL(B200ANI_ERR_ARG, "add_genome: null residues");
-    if (n_bases + n_contigs >= (1ll << 31) - 1024) FAIL(B200ANI_ERR_CAPACITY, "add_genome: genome exceeds 2^31 positions");
+    if (n_bases + n_contigs >= (1ll << AN_POSBITS) - 1024) FAIL(B200ANI_ERR_CAPACITY, "add_genome: genome exceeds 2^30 positions");
     CK(cudaSetDevice(ctx->device));
     Genome g;
     g.n_bases = n_bases;

@@ -47,14 +47,37 @@ def rand_fasta(seed, n_rec, length, p_n=0.002):
     return "".join(out)
 
 
+def jspecies_tables(path):
+    """tests/fixtures/concordance/jspecies_output.tab -> {"Tetra" | "ANIb" | "ANIm": {"names": [...], "values": [[...]]}}
+    (row = first column label, column = header label; '---' on the diagonal -> None).  The targets of the reference's
+    own concordance tests (tests/test_concordance.py:169-302)."""
+    out, cur, names = {}, None, None
+    for raw in list(open(path)) + [""]:
+        line = raw.strip()
+        if line in ("Tetra", "ANIb", "ANIm"):
+            cur, names = line, None
+            out[cur] = {"names": [], "rows": [], "values": []}
+        elif cur and names is None and line:
+            names = [c for c in line.split("\t") if c]
+            out[cur]["names"] = names
+        elif cur and line:
+            cells = [c for c in line.split("\t") if c]
+            out[cur]["rows"].append(cells[0])
+            out[cur]["values"].append([None if c == "---" else float(c) for c in cells[1:]])
+        elif cur and not line and names is not None:
+            cur = None
+    return out
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     FIX.mkdir(parents=True, exist_ok=True)
+    json.dump(jspecies_tables(REF / "tests/fixtures/concordance/jspecies_output.tab"), open(OUT / "jspecies_concordance.json", "w"), indent=1)
     EDGE_FASTAS["edge_rand3x4k"] = rand_fasta(11, 3, 4000)
     EDGE_FASTAS["edge_rand1x20k"] = rand_fasta(12, 1, 20000, p_n=0.0)
 
     # ---- fixture genomes for the GPU box
-    for sub in ("fixtures/sequences", "test_targets/legacy_scripts/C_blochmannia"):
+    for sub in ("fixtures/sequences", "test_targets/legacy_scripts/C_blochmannia", "fixtures/concordance"):
         dst = FIX / Path(sub).name
         dst.mkdir(exist_ok=True)
         for f in sorted((REF / "tests" / sub).glob("*.fna")):

@@ -115,8 +115,8 @@ def test_reference_fixture_genomes(engine):
     for (i, j), r in zip(pairs, res):
         g = gold[f"{files[i].stem}_vs_{files[j].stem}.filter"]
         ident = r["sum_weighted"] / r["sum_aligned"]
-        assert abs(100 * (ident - g[2])) < 0.15
-        assert abs(r["ref_aln_len"] / g[0] - 1) < 0.01
+        assert abs(100 * (ident - g[2])) < 0.1  # the reference's own ANIm tolerance (tests/test_concordance.py:157-159)
+        assert abs(r["ref_aln_len"] / g[0] - 1) < 0.015
 
 
 def test_degenerate_inputs(engine):
@@ -210,20 +210,19 @@ def test_maxmatch_with_repeats(engine):
     gids = [engine.add_genome(x, off, f"rep{i}") for i, (x, off) in enumerate(arrs)]
     pairs = [(0, 1), (1, 0)]
     out = {}
+    og = [oracle.OGenome(x, off) for x, off in arrs]
     for mm in (False, True):
-        og = [oracle.OGenome(x, off, maxmatch=mm) for x, off in arrs]
         for nofilter in (False, True):
             res = engine.anim(np.array([[gids[r], gids[q]] for r, q in pairs], np.int32), maxmatch=mm, nofilter=nofilter)
             for (r, q), got in zip(pairs, res):
-                want = oracle.anim_pair(og[r], og[q], nofilter=nofilter)[0]
+                want = oracle.anim_pair(og[r], og[q], nofilter=nofilter, maxmatch=mm)[0]
                 for f in FIELDS:
                     assert int(got[f]) == want[f], (mm, nofilter, r, q, f, int(got[f]), want[f])
             out[(mm, nofilter)] = res
         rows = engine.anim_alignments(gids[0], gids[1], maxmatch=mm, nofilter=True)
-        assert (rows == oracle.anim_pair(og[0], og[1], nofilter=True)[1]).all()
+        assert (rows == oracle.anim_pair(og[0], og[1], nofilter=True, maxmatch=mm)[1]).all()
     assert out[(True, True)][0]["n_alignments"] > out[(False, True)][0]["n_alignments"]  # repeat copies align to each other
-    # ANIb after a --maxmatch call rebuilds the --mum index and still matches the oracle
-    og = [oracle.OGenome(x, off) for x, off in arrs]
+    # ANIb shares the index (seeds unique in both genomes) and still matches the oracle
     rb = engine.anib(np.array([[gids[0], gids[1]]], np.int32))[0]
     want = oracle.anib_pair(og[0], og[1])[0]
     assert all(int(rb[k]) == v for k, v in want.items())
