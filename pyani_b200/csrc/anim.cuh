@@ -194,6 +194,8 @@ struct FiltArrays {
     int *slo[2], *shi[2], *sseq[2];
     long long *best;   // scratch, sorted order
     int *from;         // scratch
+    long long *pmax;   // scratch: prefix maximum of best[] within the record group ...
+    int *pmaxj, *phi;  // ... its (smallest) argmax, and the running maximum of hi
     long long *unit;   // per alignment (input order), identity^2 in Q16
     uint8_t *flag;     // per alignment: bit a set = kept on axis a
 };

@@ -39,50 +39,77 @@ __global__ void bridge_link_kernel(SegArrays S) {
     }
 }
 
-// one thread per bridge: unbanded global affine alignment of the residual gap, value = score * AN_PACK - errs
-__global__ void __launch_bounds__(64) bridge_dp_kernel(SegArrays S, const PairDesc *__restrict__ pairs, unsigned long long *__restrict__ counters /*0: bridges, 1: cells*/) {
+// settle the links (a predecessor keeps one successor) and list the bridges that need a DP
+__global__ void bridge_validate_kernel(SegArrays S, uint32_t *__restrict__ tasks, uint32_t *__restrict__ task_key,
+                                       unsigned long long *__restrict__ counters /*0: bridges, 1: cells, 2: tasks*/) {
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= S.n) return;
-    const int a = S.bpred[b];
-    if (a < 0) return;
-    if ((uint32_t)S.bsucc[a] != (uint32_t)b) { S.bpred[b] = -1; return; }  // the predecessor prefers another successor
-    S.alive[b] = 0;
-    const int lr = S.rs[b] - S.re[a], lq = S.qs[b] - S.qe[a];
-    constexpr int go = AN_GAPOPEN * AN_PACK + 1, ge = AN_GAPEXT * AN_PACK + 1, sm = AN_MATCH * AN_PACK, sx = -(AN_MISMATCH * AN_PACK + 1);
-    int v;
-    if (lr == 0 && lq == 0) v = 0;
-    else if (lr == 0 || lq == 0) {
-        const int L = lr + lq;
-        v = -((AN_GAPOPEN + (L - 1) * AN_GAPEXT) * AN_PACK + L);
-    } else {
-        const PairDesc &P = pairs[S.pair[b]];
-        SeqView R{P.r_seq, P.r_mask, P.r_npos, 0}, Q{P.q_seq, P.q_mask, P.q_npos, S.strand[b]};
-        const int64_t r0 = S.re[a], q0 = S.qe[a];
-        int H[AN_BREAK + 1], F[AN_BREAK + 1];
-        uint8_t qb[AN_BREAK + 1];
-        H[0] = 0; F[0] = AN_NEG;
-        for (int j = 1; j <= lq; ++j) {
-            H[j] = -(go + (j - 1) * ge);
-            F[j] = AN_NEG;
-            qb[j] = (uint8_t)view_code(Q, q0 + j - 1);
-        }
-        for (int i = 1; i <= lr; ++i) {
-            const int rb = view_code(R, r0 + i - 1);
-            int diag = H[0], hleft = -(go + (i - 1) * ge), eleft = AN_NEG;
-            H[0] = hleft;
-            for (int j = 1; j <= lq; ++j) {
-                const int e = max(eleft - ge, hleft - go);
-                const int f = max(F[j] - ge, H[j] - go);
-                const int d = diag + ((rb == qb[j] && rb < 4) ? sm : sx);
-                const int h = max(max(d, e), f);
-                diag = H[j]; H[j] = h; F[j] = f; hleft = h; eleft = e;
+    bool task = false;
+    int cells = 0;
+    if (b < S.n) {
+        const int a = S.bpred[b];
+        if (a >= 0) {
+            if ((uint32_t)S.bsucc[a] != (uint32_t)b) S.bpred[b] = -1;  // the predecessor prefers another successor
+            else {
+                S.alive[b] = 0;
+                const int lr = S.rs[b] - S.re[a], lq = S.qs[b] - S.qe[a];
+                if (lr == 0 && lq == 0) S.bval[b] = 0;
+                else if (lr == 0 || lq == 0) {
+                    const int L = lr + lq;
+                    S.bval[b] = -((AN_GAPOPEN + (L - 1) * AN_GAPEXT) * AN_PACK + L);
+                } else { task = true; cells = lr * lq; }
             }
         }
-        v = H[lq];
-        atomicAdd(&counters[1], (unsigned long long)lr * (unsigned long long)lq);
     }
-    S.bval[b] = v;
-    atomicAdd(&counters[0], 1ull);
+    const uint32_t m = __ballot_sync(0xffffffffu, task);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&counters[2], (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (task) {
+            const unsigned long long s = base + __popc(m & ((1u << lane) - 1u));
+            tasks[s] = (uint32_t)b;
+            task_key[s] = (uint32_t)(AN_BREAK * AN_BREAK - cells) >> 6;  // sort key: big rectangles first, 64-cell buckets
+        }
+    }
+    const uint32_t mb = __ballot_sync(0xffffffffu, b < S.n && S.bpred[b] >= 0);
+    if (mb && (threadIdx.x & 31) == 0) atomicAdd(&counters[0], (unsigned long long)__popc(mb));
+}
+
+// one thread per listed bridge: unbanded global affine alignment of the residual gap, value = score * AN_PACK - errs
+__global__ void __launch_bounds__(64) bridge_dp_kernel(SegArrays S, const PairDesc *__restrict__ pairs, const uint32_t *__restrict__ tasks, int64_t n_tasks,
+                                                      unsigned long long *__restrict__ counters) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tasks) return;
+    const int64_t b = tasks[t];
+    const int a = S.bpred[b];
+    const int lr = S.rs[b] - S.re[a], lq = S.qs[b] - S.qe[a];
+    constexpr int go = AN_GAPOPEN * AN_PACK + 1, ge = AN_GAPEXT * AN_PACK + 1, sm = AN_MATCH * AN_PACK, sx = -(AN_MISMATCH * AN_PACK + 1);
+    const PairDesc &P = pairs[S.pair[b]];
+    SeqView R{P.r_seq, P.r_mask, P.r_npos, 0}, Q{P.q_seq, P.q_mask, P.q_npos, S.strand[b]};
+    const int64_t r0 = S.re[a], q0 = S.qe[a];
+    int H[AN_BREAK + 1], F[AN_BREAK + 1];
+    uint8_t qb[AN_BREAK + 1];
+    H[0] = 0; F[0] = AN_NEG;
+    for (int j = 1; j <= lq; ++j) {
+        H[j] = -(go + (j - 1) * ge);
+        F[j] = AN_NEG;
+        qb[j] = (uint8_t)view_code(Q, q0 + j - 1);
+    }
+    for (int i = 1; i <= lr; ++i) {
+        const int rb = view_code(R, r0 + i - 1);
+        int diag = H[0], hleft = -(go + (i - 1) * ge), eleft = AN_NEG;
+        H[0] = hleft;
+        for (int j = 1; j <= lq; ++j) {
+            const int e = max(eleft - ge, hleft - go);
+            const int f = max(F[j] - ge, H[j] - go);
+            const int d = diag + ((rb == qb[j] && rb < 4) ? sm : sx);
+            const int h = max(max(d, e), f);
+            diag = H[j]; H[j] = h; F[j] = f; hleft = h; eleft = e;
+        }
+    }
+    S.bval[b] = H[lq];
+    atomicAdd(&counters[1], (unsigned long long)lr * (unsigned long long)lq);
 }
 
 // one thread per chain head: fold the chain's members into the head

@@ -19,19 +19,33 @@ __global__ void contig_kernel(ChainArrays A, const PairDesc *__restrict__ pairs)
 }
 
 // nearest compatible predecessor among the previous AN_LOOKBACK anchors of the same pair and strand
-// (gapmax = AN_CLUSTGAP in the cluster pre-pass, AN_GAPMAX for the links proper)
-__global__ void link_kernel(ChainArrays A, int gapmax) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// (gapmax = AN_CLUSTGAP in the cluster pre-pass, AN_GAPMAX for the links proper).  A block stages its 256 anchors and
+// the AN_LOOKBACK before them in shared memory: the backward scan is a chain of dependent reads.
+__global__ void __launch_bounds__(256) link_kernel(ChainArrays A, int gapmax) {
+    __shared__ uint64_t sk[256 + AN_LOOKBACK], sv[256 + AN_LOOKBACK];
+    __shared__ uint32_t src[256 + AN_LOOKBACK], sqc[256 + AN_LOOKBACK];
+    const int64_t b0 = (int64_t)blockIdx.x * 256 - AN_LOOKBACK;
+    for (int t = threadIdx.x; t < 256 + AN_LOOKBACK; t += 256) {
+        const int64_t g = b0 + t;
+        const bool ok = g >= 0 && g < A.n;
+        sk[t] = ok ? A.keys[g] : ~0ull;
+        sv[t] = ok ? A.vals[g] : 0ull;
+        src[t] = ok ? A.rc_of[g] : 0u;
+        sqc[t] = ok ? A.qc_of[g] : 0u;
+    }
+    __syncthreads();
+    const int li = threadIdx.x + AN_LOOKBACK;
+    const int64_t i = b0 + li;
     if (i >= A.n) return;
-    const uint64_t ki = A.keys[i], vi = A.vals[i];
+    const uint64_t ki = sk[li], vi = sv[li];
     const uint64_t group = ki >> 31;  // pair + strand
     const int ri = key_r(ki), qi = val_q(vi), leni = val_len(vi);
-    const uint32_t rci = A.rc_of[i], qci = A.qc_of[i];
-    for (int64_t j = i - 1; j >= 0 && j >= i - AN_LOOKBACK; --j) {
-        const uint64_t kj = A.keys[j];
+    const uint32_t rci = src[li], qci = sqc[li];
+    for (int lj = li - 1; lj >= li - AN_LOOKBACK && b0 + lj >= 0; --lj) {
+        const uint64_t kj = sk[lj];
         if ((kj >> 31) != group) break;
-        if (A.rc_of[j] != rci || A.qc_of[j] != qci) continue;
-        const uint64_t vj = A.vals[j];
+        if (src[lj] != rci || sqc[lj] != qci) continue;
+        const uint64_t vj = sv[lj];
         int64_t rej = (int64_t)key_r(kj) + val_len(vj), qej = (int64_t)val_q(vj) + val_len(vj);
         int64_t ov = max((int64_t)0, max(rej - ri, qej - qi));
         if (ov >= leni) continue;
@@ -39,40 +53,55 @@ __global__ void link_kernel(ChainArrays A, int gapmax) {
         if (gr > gapmax || gq > gapmax) continue;
         int64_t dd = gq - gr;
         if (dd > AN_DMAX || dd < -AN_DMAX) continue;
-        A.pred[i] = (int)j;
+        A.pred[i] = (int)(b0 + lj);
         A.trim[i] = (int)ov;
-        atomicMin(&A.succ[j], (int)i);
+        atomicMin(&A.succ[b0 + lj], (int)i);
         break;
     }
 }
 
 // a predecessor keeps only its nearest successor; links that lose become chain heads
+// (counters are bumped once per warp: tens of millions of atomics on one address serialise in L2)
 __global__ void link_validate_kernel(ChainArrays A, unsigned long long *__restrict__ n_links) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.n) return;
-    int p = A.pred[i];
-    if (p < 0) return;
-    if (A.succ[p] != (int)i) { A.pred[i] = -1; A.trim[i] = 0; }
-    else atomicAdd(n_links, 1ull);
+    bool kept = false;
+    if (i < A.n) {
+        int p = A.pred[i];
+        if (p >= 0) {
+            if (A.succ[p] != (int)i) { A.pred[i] = -1; A.trim[i] = 0; }
+            else kept = true;
+        }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, kept);
+    if (m && (threadIdx.x & 31) == 0) atomicAdd(n_links, (unsigned long long)__popc(m));
 }
 
 // trivial links are scored here; the others become DP tasks (sort key = rows, descending)
 __global__ void gap_task_kernel(ChainArrays A, uint32_t *__restrict__ task_key, uint32_t *__restrict__ task_idx, unsigned long long *__restrict__ n_tasks,
                                 int gapopen, int gapext) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.n || A.pred[i] < 0) return;
-    int64_t rej, qej;
-    int lr, lq;
-    link_box(A, i, rej, qej, lr, lq);
-    if (lr == 0 && lq == 0) { A.gval[i] = 0; return; }
-    if (lr == 0 || lq == 0) {
-        int L = lr + lq;
-        A.gval[i] = -((gapopen + (L - 1) * gapext) * AN_PACK + L);
-        return;
+    bool task = false;
+    int lr = 0, lq = 0;
+    if (i < A.n && A.pred[i] >= 0) {
+        int64_t rej, qej;
+        link_box(A, i, rej, qej, lr, lq);
+        if (lr == 0 && lq == 0) A.gval[i] = 0;
+        else if (lr == 0 || lq == 0) {
+            int L = lr + lq;
+            A.gval[i] = -((gapopen + (L - 1) * gapext) * AN_PACK + L);
+        } else task = true;
     }
-    unsigned long long s = atomicAdd(n_tasks, 1ull);
-    task_key[s] = (uint32_t)(AN_GAPMAX + 1 - lr);
-    task_idx[s] = (uint32_t)i;
+    const uint32_t m = __ballot_sync(0xffffffffu, task);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(n_tasks, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (task) {
+        const unsigned long long s = base + __popc(m & ((1u << lane) - 1u));
+        task_key[s] = (uint32_t)(AN_GAPMAX + 1 - lr);
+        task_idx[s] = (uint32_t)i;
+    }
 }
 
 // ---- labels by pointer jumping ------------------------------------------------------------------

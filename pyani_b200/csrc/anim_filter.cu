@@ -44,16 +44,15 @@ __global__ void pair_range_kernel(const int *__restrict__ rows, int64_t n, int n
     pair_start[p] = (int)lo;
 }
 
-// Weighted chain DP of one axis: one block per pair, i sequential, j across the block's threads.
+// Weighted chain DP of one axis: one warp per pair, i sequential.
 //   best[i] = w_i + max(0, max_{j<i same record, overlap <= 75 % of len_j} best[j] - overlap * unit_i)
 // The chain ending at the (first) best score of each record is kept.
-constexpr int FD_THREADS = 256;
+// Alignments are sorted by lo, so all j before the first one whose running-maximum end reaches lo_i cannot overlap i:
+// their contribution is a prefix maximum of best[] (ties: smallest j), found by a binary search on the running
+// maximum of hi; only the few j after that point are scanned (across the lanes).  Exactly the full scan's result.
+constexpr int FD_THREADS = 128;
 __global__ void __launch_bounds__(FD_THREADS) filt_dp_kernel(FiltArrays A, int axis, const int *__restrict__ pair_start, int n_pairs) {
-    __shared__ long long w_sc[FD_THREADS / 32];
-    __shared__ int w_j[FD_THREADS / 32];
-    __shared__ long long r_sc;
-    __shared__ int r_j;
-    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int pair = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (pair >= n_pairs) return;
     const int s0 = pair_start[pair], e0 = pair_start[pair + 1];
     const int *slo = A.slo[axis], *shi = A.shi[axis], *sseq = A.sseq[axis], *sidx = A.sidx[axis];
@@ -62,46 +61,51 @@ __global__ void __launch_bounds__(FD_THREADS) filt_dp_kernel(FiltArrays A, int a
     int arg = -1;
     for (int i = s0; i <= e0; ++i) {
         if (i == e0 || (i > gs && sseq[i] != sseq[gs])) {  // close the group [gs, i)
-            if (tid == 0)
+            if (lane == 0)
                 for (int x = arg; x >= 0; x = A.from[x]) A.flag[sidx[x]] |= (uint8_t)(1 << axis);
             gs = i; top = -1; arg = -1;
             if (i == e0) break;
         }
-        const long long leni = shi[i] - slo[i] + 1, ui = A.unit[sidx[i]];
-        const int loi = slo[i];
+        const int hii = shi[i], loi = slo[i];
+        const long long leni = hii - loi + 1, ui = A.unit[sidx[i]];
+        // first j in [gs, i) whose running-maximum end reaches lo_i
+        int f = gs, hi_ = i;
+        while (f < hi_) {
+            const int mid = (f + hi_) >> 1;
+            if (A.phi[mid] < loi) f = mid + 1; else hi_ = mid;
+        }
         long long lsc = -1;
         int lj = 0x7fffffff;
-        for (int j = gs + tid; j < i; j += FD_THREADS) {
+        for (int j = f + lane; j < i; j += 32) {
             long long hj = shi[j];
             long long ol = hj - loi + 1, lenj = hj - slo[j] + 1;
             if (ol < 0) ol = 0;
             if (ol * 100 > (long long)AN_FILT_OLAP * lenj) continue;
-            long long sc = __ldcg(&A.best[j]) + (leni - ol) * ui;
+            long long sc = A.best[j] + (leni - ol) * ui;
             if (sc > lsc) { lsc = sc; lj = j; }
         }
-        for (int off = 16; off; off >>= 1) {  // max score, ties -> smallest j
+        for (int off = 16; off; off >>= 1) {  // max score, ties -> smallest j; every lane ends up with the result
             long long osc = __shfl_xor_sync(0xffffffffu, lsc, off);
             int oj = __shfl_xor_sync(0xffffffffu, lj, off);
             if (osc > lsc || (osc == lsc && oj < lj)) { lsc = osc; lj = oj; }
         }
-        if (lane == 0) { w_sc[wid] = lsc; w_j[wid] = lj; }
-        __syncthreads();
-        if (tid == 0) {
-            long long bsc = leni * ui;  // starting a new chain
-            int bj = -1;
-            long long msc = -1;
-            int mj = 0x7fffffff;
-            for (int w = 0; w < FD_THREADS / 32; ++w)
-                if (w_sc[w] > msc || (w_sc[w] == msc && w_j[w] < mj)) { msc = w_sc[w]; mj = w_j[w]; }
-            if (msc > bsc) { bsc = msc; bj = mj; }
-            A.best[i] = bsc;
-            A.from[i] = bj;
-            r_sc = bsc;
-            r_j = bj;
-            __threadfence_block();
+        if (f > gs) {  // the non-overlapping prefix [gs, f): its j are all smaller than the scanned ones, so it wins ties
+            const long long psc = A.pmax[f - 1] + leni * ui;
+            if (psc >= lsc) { lsc = psc; lj = A.pmaxj[f - 1]; }
         }
-        __syncthreads();
-        if (r_sc > top) { top = r_sc; arg = i; }
+        long long bsc = leni * ui;  // starting a new chain
+        int bj = -1;
+        if (lsc > bsc) { bsc = lsc; bj = lj; }
+        if (lane == 0) {
+            A.best[i] = bsc; A.from[i] = bj;
+            const bool first = i == gs;
+            A.phi[i] = first ? hii : max(A.phi[i - 1], hii);
+            const bool better = first || bsc > A.pmax[i - 1];
+            A.pmax[i] = better ? bsc : A.pmax[i - 1];
+            A.pmaxj[i] = better ? i : A.pmaxj[i - 1];
+        }
+        __syncwarp();  // lane 0's stores are visible to the warp from here on
+        if (bsc > top) { top = bsc; arg = i; }
     }
 }
 

@@ -23,7 +23,8 @@ __global__ void link_kernel(ChainArrays, int);
 __global__ void cluster_keep_kernel(ChainArrays, uint8_t *);
 __global__ void bridge_init_kernel(SegArrays);
 __global__ void bridge_link_kernel(SegArrays);
-__global__ void bridge_dp_kernel(SegArrays, const PairDesc *, unsigned long long *);
+__global__ void bridge_validate_kernel(SegArrays, uint32_t *, uint32_t *, unsigned long long *);
+__global__ void bridge_dp_kernel(SegArrays, const PairDesc *, const uint32_t *, int64_t, unsigned long long *);
 __global__ void bridge_merge_kernel(SegArrays);
 __global__ void link_validate_kernel(ChainArrays, unsigned long long *);
 __global__ void gap_task_kernel(ChainArrays, uint32_t *, uint32_t *, unsigned long long *, int, int);
@@ -270,7 +271,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         T0(ST_PREPASS);
         contig_kernel<<<GRID(n)>>>(A, W->d_pairs);
         link_kernel<<<GRID(n)>>>(A, AN_CLUSTGAP);
-        link_validate_kernel<<<GRID(n)>>>(A, W->counters + 12);
+        link_validate_kernel<<<GRID(n)>>>(A, W->counters + 13);
         LAUNCHED(3);
         if (int rc = run_labels()) return rc;
         cluster_weight_kernel<<<GRID(n)>>>(A);
@@ -392,7 +393,15 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
             T0(ST_BRIDGE);
             bridge_init_kernel<<<GRID(n_seg)>>>(S);
             bridge_link_kernel<<<GRID(n_seg)>>>(S);
-            bridge_dp_kernel<<<(unsigned)ceil_div(n_seg, 64), 64, 0, st>>>(S, W->d_pairs, W->counters + 10);
+            bridge_validate_kernel<<<GRID(n_seg)>>>(S, task_idx, task_key, W->counters + 10);  // the link stage's task arrays are free again
+            CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const int64_t n_btasks = (int64_t)hc[12];
+            if (n_btasks) {  // similar-sized rectangles side by side in a warp
+                size_t tb2 = W->cub_bytes;
+                cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb2, task_key, task_key2, task_idx, task_idx2, n_btasks, 0, 8, st);
+                bridge_dp_kernel<<<(unsigned)ceil_div(n_btasks, 64), 64, 0, st>>>(S, W->d_pairs, task_idx2, n_btasks, W->counters + 10);
+            }
             bridge_merge_kernel<<<GRID(n_seg)>>>(S);
             emit_rows_kernel<<<GRID(n_seg)>>>(S, W->d_pairs, rows_all);
             LAUNCHED(5);
@@ -462,6 +471,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     int *fidx = nullptr, *fidx2 = nullptr, *pair_start = nullptr;
     for (int a = 0; a < 2; ++a) { DA(F.sidx[a], n_rows); DA(F.slo[a], n_rows); DA(F.shi[a], n_rows); DA(F.sseq[a], n_rows); }
     DA(F.best, n_rows); DA(F.from, n_rows); DA(F.unit, n_rows); DA(F.flag, n_rows);
+    DA(F.pmax, n_rows); DA(F.pmaxj, n_rows); DA(F.phi, n_rows);
     DA(fkey, n_rows); DA(fkey2, n_rows); DA(fidx, n_rows); DA(fidx2, n_rows); DA(pair_start, nb + 2);
     T0(ST_FILTER);
     pair_range_kernel<<<(unsigned)ceil_div(nb + 1, 128), 128, 0, st>>>(rows, n_rows, nb, pair_start);
@@ -473,7 +483,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         filt_gather_kernel<<<GRID(n_rows)>>>(F, axis, fidx2);
         LAUNCHED(2);
         if (!nofilter) {
-            filt_dp_kernel<<<nb, 256, 0, st>>>(F, axis, pair_start, nb);
+            filt_dp_kernel<<<(unsigned)ceil_div((int64_t)nb * 32, 128), 128, 0, st>>>(F, axis, pair_start, nb);
             LAUNCHED(1);
         }
     }
@@ -498,7 +508,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     DF(S.r_lo); DF(S.r_hi); DF(S.q_lo); DF(S.q_hi); DF(S.score); DF(S.errs); DF(rows); DF(ext_list[0]); DF(ext_list[1]);
     DF(S.bpred); DF(S.bval); DF(S.bsucc); DF(S.alive); DF(rows_all);
     for (int a = 0; a < 2; ++a) { DF(F.sidx[a]); DF(F.slo[a]); DF(F.shi[a]); DF(F.sseq[a]); }
-    DF(F.best); DF(F.from); DF(F.unit); DF(F.flag); DF(fkey); DF(fkey2); DF(fidx); DF(fidx2); DF(pair_start);
+    DF(F.best); DF(F.from); DF(F.unit); DF(F.flag); DF(F.pmax); DF(F.pmaxj); DF(F.phi); DF(fkey); DF(fkey2); DF(fidx); DF(fidx2); DF(pair_start);
     CK(cudaStreamSynchronize(st));
     for (int s = 0; s < B200ANI_N_STAGES; ++s)
         if (used[s]) {

@@ -79,7 +79,7 @@ __device__ __forceinline__ bool seed_ok(int mode, uint32_t rpf, uint32_t qpf) {
 // Memory-latency bound by design: one coalesced 4-byte read + one random 8-byte read per probe, no
 // divergent work, so the warps in flight are all waiting on independent loads.
 template <int MODE>
-__global__ void __launch_bounds__(256) seed_probe_kernel(const PairDesc *__restrict__ pairs, int n_pairs, int64_t n_probes, uint2 *__restrict__ hits,
+__global__ void __launch_bounds__(256, 4) seed_probe_kernel(const PairDesc *__restrict__ pairs, int n_pairs, int64_t n_probes, uint2 *__restrict__ hits,
                                                          unsigned long long *__restrict__ n_hits, unsigned long long cap) {
     // Each block walks contiguous chunks of PROBE_CHUNK probes, PROBE_ILP probes per thread per step so that the
     // dependent loads (k-mer -> presence word -> table slot) of several probes are in flight together.  The pair a
