@@ -105,30 +105,27 @@ __global__ void gap_task_kernel(ChainArrays A, uint32_t *__restrict__ task_key, 
 }
 
 // ---- labels by pointer jumping ------------------------------------------------------------------
-__global__ void label_init_kernel(ChainArrays A) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.n) return;
-    int p = A.pred[i];
-    A.head[i] = p >= 0 ? p : (int)i;
-    int c = (int)i;
-    if (p >= 0) {
-        int64_t rej, qej;
-        int lr, lq;
-        link_box(A, i, rej, qej, lr, lq);
-        if (lr <= AN_CLUSTGAP && lq <= AN_CLUSTGAP) c = p;
-    }
-    A.chead[i] = c;
-    A.cw[i] = 0; A.wsum[i] = 0; A.tail[i] = -1; A.ssum[i] = 0; A.esum[i] = 0; A.strong[i] = 0;
-}
-
-// Block-local pre-pass of the pointer jumping: chains mostly run through neighbouring anchors (pred[i] = i-1 most of the
-// time), so 10 jumps inside a 1024-anchor block in shared memory resolve everything that does not leave the block;
-// the global rounds below then only have to hop from block to block (log2(#blocks a chain spans) rounds).
+// Initial pointers (head: predecessor, chead: predecessor if the link stays inside a cluster) and a block-local
+// pre-pass of the pointer jumping in one kernel: chains mostly run through neighbouring anchors (pred[i] = i-1 most
+// of the time), so 10 jumps inside a 1024-anchor block in shared memory resolve everything that does not leave the
+// block; the global rounds below then only have to hop from block to block (log2(#blocks a chain spans) rounds).
 __global__ void __launch_bounds__(1024) label_local_kernel(ChainArrays A) {
     __shared__ int sh[1024], sc[1024];
     const int64_t b0 = (int64_t)blockIdx.x * 1024, i = b0 + threadIdx.x;
-    sh[threadIdx.x] = i < A.n ? A.head[i] : (int)i;
-    sc[threadIdx.x] = i < A.n ? A.chead[i] : (int)i;
+    int h0 = (int)i, c0 = (int)i;
+    if (i < A.n) {
+        const int p = A.pred[i];
+        if (p >= 0) {
+            h0 = p;
+            int64_t rej, qej;
+            int lr, lq;
+            link_box(A, i, rej, qej, lr, lq);
+            if (lr <= AN_CLUSTGAP && lq <= AN_CLUSTGAP) c0 = p;
+        }
+        A.cw[i] = 0; A.wsum[i] = 0; A.tail[i] = -1; A.ssum[i] = 0; A.esum[i] = 0; A.strong[i] = 0;
+    }
+    sh[threadIdx.x] = h0;
+    sc[threadIdx.x] = c0;
     __syncthreads();
     for (int it = 0; it < 10; ++it) {
         int h = sh[threadIdx.x], c = sc[threadIdx.x];

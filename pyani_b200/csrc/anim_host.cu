@@ -28,7 +28,6 @@ __global__ void bridge_dp_kernel(SegArrays, const PairDesc *, const uint32_t *, 
 __global__ void bridge_merge_kernel(SegArrays);
 __global__ void link_validate_kernel(ChainArrays, unsigned long long *);
 __global__ void gap_task_kernel(ChainArrays, uint32_t *, uint32_t *, unsigned long long *, int, int);
-__global__ void label_init_kernel(ChainArrays);
 __global__ void label_local_kernel(ChainArrays);
 __global__ void label_jump_kernel(ChainArrays, int *);
 __global__ void cluster_weight_kernel(ChainArrays);
@@ -252,9 +251,8 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     DA(task_key, n); DA(task_idx, n); DA(task_key2, n); DA(task_idx2, n); DA(seg_head, n);
     // chain / cluster labels of the current links by pointer jumping (block-local pre-pass, then global rounds)
     auto run_labels = [&]() -> int {
-        label_init_kernel<<<GRID(A.n)>>>(A);
         label_local_kernel<<<(unsigned)ceil_div(A.n, 1024), 1024, 0, st>>>(A);
-        LAUNCHED(2);
+        LAUNCHED(1);
         for (int round = 0; round < 8; ++round) {
             CK(cudaMemsetAsync(W->changed, 0, sizeof(int), st));
             for (int k = 0; k < 3; ++k) label_jump_kernel<<<GRID(A.n)>>>(A, W->changed);

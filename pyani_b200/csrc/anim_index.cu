@@ -36,20 +36,41 @@ __device__ __forceinline__ uint64_t kmer_hash(const uint64_t *s, const uint32_t 
     return fmix32(canon);
 }
 
+// One genome of a batched index build, as the kernels see it.
+struct GenomeDesc {
+    const uint64_t *seq;
+    const uint32_t *mask;
+    int64_t n_pos;
+    int64_t tile0;       // first selection tile of this genome in the batch-wide tile numbering
+    uint64_t *table;     // filled in after the counts are known
+    uint32_t *bitmap;
+    uint32_t *kmer_out, *posflag_out;
+    int64_t out0;        // index of this genome's first entry in the batch-wide by-position order
+    uint32_t bits;
+};
+
 // A position is selected iff its hash is <= every hash of at least one window of AN_W consecutive
 // k-mer starts containing it (ties select all, which keeps the selection strand-symmetric).
-// One block = one tile of SEL_TILE positions: every hash is computed once into shared memory (+ a halo of
-// AN_W-1 on both sides), the window test then reads shared memory only.
+// One block = one tile of SEL_TILE positions of one genome: every hash is computed once into shared memory (+ a
+// halo of AN_W-1 on both sides), the window test then reads shared memory only.  All genomes of a batch go through
+// one launch and into one array: key = genome << 32 | canonical k-mer, value = position | orientation << 31.
 constexpr int SEL_TILE = 2048, SEL_HALO = AN_W - 1;
-__global__ void __launch_bounds__(256) minimizer_select_kernel(const uint64_t *__restrict__ s, const uint32_t *__restrict__ m, int64_t n_pos,
-                                                               uint64_t *__restrict__ out, unsigned long long *__restrict__ n_out) {
+__global__ void __launch_bounds__(256) minimizer_select_kernel(const GenomeDesc *__restrict__ gd, int n_genomes, int64_t n_tiles, uint64_t *__restrict__ keys,
+                                                               uint32_t *__restrict__ vals, unsigned long long *__restrict__ n_out, unsigned long long cap) {
     __shared__ uint64_t hv[SEL_TILE + 2 * SEL_HALO];
     __shared__ unsigned int s_n;
     __shared__ unsigned long long s_base;
-    __shared__ uint64_t s_out[SEL_TILE];
-    const int64_t n_tiles = (n_pos + SEL_TILE - 1) / SEL_TILE;
+    __shared__ uint32_t s_kmer[SEL_TILE], s_val[SEL_TILE];
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t p0 = tile * SEL_TILE;
+        int lo = 0, hi = n_genomes;  // genome of this tile
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (gd[mid].tile0 <= tile) lo = mid; else hi = mid;
+        }
+        const uint64_t *s = gd[lo].seq;
+        const uint32_t *m = gd[lo].mask;
+        const int64_t n_pos = gd[lo].n_pos;
+        const int64_t p0 = (tile - gd[lo].tile0) * SEL_TILE;
         if (threadIdx.x == 0) s_n = 0;
         for (int i = threadIdx.x; i < SEL_TILE + 2 * SEL_HALO; i += 256) {
             uint32_t c, o;
@@ -72,51 +93,74 @@ __global__ void __launch_bounds__(256) minimizer_select_kernel(const uint64_t *_
             if (chosen) {
                 uint32_t canon, orient;
                 kmer_hash(s, m, p, n_pos, canon, orient);
-                s_out[atomicAdd(&s_n, 1u)] = ((uint64_t)canon << 32) | (uint32_t)p | (orient << 31);
+                const unsigned int slot = atomicAdd(&s_n, 1u);
+                s_kmer[slot] = canon;
+                s_val[slot] = (uint32_t)p | (orient << 31);
             }
         }
         __syncthreads();
         const unsigned int n = s_n;
         if (threadIdx.x == 0 && n) s_base = atomicAdd(n_out, (unsigned long long)n);
         __syncthreads();
-        for (unsigned int i = threadIdx.x; i < n; i += 256) out[s_base + i] = s_out[i];
+        for (unsigned int i = threadIdx.x; i < n; i += 256)
+            if (s_base + i < cap) {
+                keys[s_base + i] = ((uint64_t)lo << 32) | s_kmer[i];
+                vals[s_base + i] = s_val[i];
+            }
         __syncthreads();
     }
 }
 
-// keep the entries of k-mers that occur at most maxocc times among the selected minimizers; entries of k-mers that
-// occur more than once get the "repeated" flag
-__global__ void mark_unique_kernel(uint64_t *__restrict__ sorted, int64_t n, uint8_t *__restrict__ flag, int maxocc) {
+// After the sort by (genome, k-mer): entries of k-mers that occur at most maxocc times in their genome are kept, the
+// repeated ones get the "repeated" flag.  Emits the key of the second sort (genome << 30 | position; dropped entries
+// get ~0 and end up behind everything) and counts the kept entries per genome.
+__global__ void __launch_bounds__(256) mark_kernel(const uint64_t *__restrict__ sorted, uint32_t *__restrict__ vals, int64_t n, uint64_t *__restrict__ key2,
+                                                   uint32_t *__restrict__ idx, unsigned long long *__restrict__ counts, int maxocc) {
+    __shared__ unsigned int s_cnt[256];
+    s_cnt[threadIdx.x] = 0;
+    __syncthreads();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t k = (uint32_t)(sorted[i] >> 32);
-    int run = 1;
-    for (int64_t j = i - 1; j >= 0 && run <= maxocc && (uint32_t)(sorted[j] >> 32) == k; --j) ++run;
-    for (int64_t j = i + 1; j < n && run <= maxocc && (uint32_t)(sorted[j] >> 32) == k; ++j) ++run;
-    flag[i] = run <= maxocc;
-    if (run > 1) sorted[i] |= (uint64_t)AN_REPBIT;  // neighbours only read the k-mer half of the word
+    if (i < n) {
+        const uint64_t k = sorted[i];
+        int run = 1;
+        for (int64_t j = i - 1; j >= 0 && run <= maxocc && sorted[j] == k; --j) ++run;
+        for (int64_t j = i + 1; j < n && run <= maxocc && sorted[j] == k; ++j) ++run;
+        const uint32_t gid = (uint32_t)(k >> 32);
+        uint32_t v = vals[i];
+        if (run > 1) { v |= AN_REPBIT; vals[i] = v; }
+        const bool kept = run <= maxocc;
+        key2[i] = kept ? ((uint64_t)gid << AN_POSBITS) | (v & AN_POSMASK) : ~0ull;
+        idx[i] = (uint32_t)i;
+        if (kept) atomicAdd(&s_cnt[gid & 255], 1u);
+    }
+    __syncthreads();
+    if (s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
 }
 
-__global__ void table_insert_kernel(const uint64_t *__restrict__ uniq, int64_t n, uint64_t *table, uint32_t *bitmap, uint32_t bits, uint64_t *__restrict__ bypos) {
+__global__ void table_insert_kernel(const uint64_t *__restrict__ sorted, const uint32_t *__restrict__ vals, const uint64_t *__restrict__ key2, int64_t n,
+                                    const GenomeDesc *__restrict__ gd) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t e = uniq[i];
-    uint32_t k = (uint32_t)(e >> 32), msk = (1u << bits) - 1u;
+    if (i >= n || key2[i] == ~0ull) return;
+    const uint64_t sk = sorted[i];
+    const GenomeDesc &g = gd[sk >> 32];
+    const uint32_t k = (uint32_t)sk, bits = g.bits, msk = (1u << bits) - 1u;
+    const uint64_t e = ((uint64_t)k << 32) | vals[i];
     uint32_t s = table_hash(k) >> (32 - bits);
-    while (atomicCAS((unsigned long long *)&table[s], ~0ull, (unsigned long long)e) != ~0ull) s = (s + 1) & msk;
+    while (atomicCAS((unsigned long long *)&g.table[s], ~0ull, (unsigned long long)e) != ~0ull) s = (s + 1) & msk;
     const uint32_t bh = bitmap_hash(k, bits);
-    atomicOr(&bitmap[bh >> 5], 1u << (bh & 31));
-    // key for the by-position order: pos << 34 | flags << 32 | kmer
-    uint32_t pf = (uint32_t)e;
-    bypos[i] = ((uint64_t)(pf & AN_POSMASK) << 34) | ((uint64_t)(pf >> AN_POSBITS) << 32) | k;
+    atomicOr(&g.bitmap[bh >> 5], 1u << (bh & 31));
 }
 
-__global__ void split_bypos_kernel(const uint64_t *__restrict__ bypos, int64_t n, uint32_t *__restrict__ kmer, uint32_t *__restrict__ posflag) {
+// after the sort by (genome, position): write each genome's by-position lists
+__global__ void split_bypos_kernel(const uint64_t *__restrict__ key2s, const uint32_t *__restrict__ idxs, int64_t n_kept, const uint64_t *__restrict__ sorted,
+                                   const uint32_t *__restrict__ vals, const GenomeDesc *__restrict__ gd) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t b = bypos[i];
-    kmer[i] = (uint32_t)b;
-    posflag[i] = (uint32_t)(b >> 34) | ((uint32_t)((b >> 32) & 3) << AN_POSBITS);
+    if (i >= n_kept) return;
+    const GenomeDesc &g = gd[key2s[i] >> AN_POSBITS];
+    const uint32_t src = idxs[i];
+    const int64_t o = i - g.out0;
+    g.kmer_out[o] = (uint32_t)sorted[src];
+    g.posflag_out[o] = vals[src];
 }
 
 void free_index(MinimizerIndex *ix, cudaStream_t st) {
@@ -130,97 +174,95 @@ void free_index(MinimizerIndex *ix, cudaStream_t st) {
 void invalidate_index(MinimizerIndex *ix) { if (ix) ix->valid = false; }
 bool index_valid(const MinimizerIndex *ix, int maxocc) { return ix && ix->valid && ix->maxocc == maxocc; }
 
-// Build (or rebuild) the indexes of many genomes.  Scratch comes from one reusable workspace and the
-// index arrays of a genome are kept across rebuilds, so steady-state builds allocate nothing; genomes are
-// processed in chunks that fit the workspace with three host synchronisations per chunk (the counts of
-// selected and of unique minimizers are needed on the host to size the sorts and the table).
+// Build (or rebuild) the indexes of many genomes.  The genomes go through the pipeline together -- one selection
+// launch, one radix sort by (genome, k-mer), one marking pass, one table-insert launch, one radix sort by (genome,
+// position), one split -- instead of a dozen small launches per genome; scratch comes from one reusable workspace
+// and a genome's index arrays are kept across rebuilds, so steady-state builds allocate nothing.  Two host
+// synchronisations per chunk (number of selected minimizers, kept entries per genome).
 int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc) {
     if (todo.empty()) return 0;
     cudaStream_t st = ctx->stream;
-    constexpr int NS = 4;  // the per-genome sorts are too small to fill the GPU: run NS genomes side by side
-    if (!ctx->side[0]) {
-        for (auto &ss : ctx->side) CK(cudaStreamCreateWithFlags(&ss, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&ctx->side_ev, cudaEventDisableTiming));
-    }
-    auto sync_sides = [&]() -> cudaError_t {
-        for (auto &ss : ctx->side) { cudaError_t e = cudaStreamSynchronize(ss); if (e != cudaSuccess) return e; }
-        return cudaSuccess;
-    };
-    auto need = [](const Genome &g) { return (size_t)(g.n_pos + 64) * 25 + 4096; };  // sel + sorted + uniq (u64) + flag (u8)
-    size_t biggest = 0;
-    for (Genome *g : todo) biggest = std::max(biggest, need(*g));
-    size_t cub_bytes = 0, tb2 = 0;
-    {
-        int64_t max_n = 0;
-        for (Genome *g : todo) max_n = std::max(max_n, g->n_pos);
-        cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (uint64_t *)nullptr, (uint64_t *)nullptr, max_n, 0, 64, st);
-        cub::DeviceSelect::Flagged(nullptr, tb2, (uint64_t *)nullptr, (uint8_t *)nullptr, (uint64_t *)nullptr, (int *)nullptr, max_n, st);
-        cub_bytes = std::max(cub_bytes, tb2) + 256;
-    }
-    const size_t want = std::max<size_t>(biggest + 4 * cub_bytes + 65536, (size_t)1536 << 20);
-    if (ctx->index_ws_bytes < biggest + 4 * cub_bytes + 65536) {
-        CK(cudaStreamSynchronize(st));
-        if (ctx->index_ws) CK(cudaFree(ctx->index_ws));
-        ctx->index_ws = nullptr;
-        CK(cudaMalloc(&ctx->index_ws, want));
-        ctx->index_ws_bytes = want;
-    }
-    char *base = (char *)ctx->index_ws;
+    constexpr size_t PER_ENTRY = 36;      // keys, keys2, key4 (u64) + vals, vals2, idx2 (u32); key3 / idx reuse keys / vals
+    constexpr int MAX_CHUNK = 256;        // genomes per chunk (mark_kernel's shared counters, 8 bits of genome id)
     const size_t G_all = todo.size();
     size_t done = 0;
+    double fill = 0.5;                    // selected minimizers per position the scratch is sized for (w = 5: ~0.36)
     while (done < G_all) {
-        // ---- chunk [done, end): carve the workspace
-        struct Tmp { uint64_t *sel, *sorted, *uniq; uint8_t *flag; };
-        std::vector<Tmp> tmp;
-        size_t off = 0, end = done;
-        unsigned long long *d_cnt = (unsigned long long *)base;  // [2 * 256] counters
-        off = 4096;
-        char *d_tmp_base = base + off;  // one CUB scratch region per side stream
-        const size_t cub_stride = (cub_bytes + 255) & ~(size_t)255;
-        off += cub_stride * NS;
-        while (end < G_all && tmp.size() < 256) {
-            const size_t n = (size_t)todo[end]->n_pos + 64;
-            const size_t bytes = ((n * 25 + 4096) + 255) & ~(size_t)255;
-            if (off + bytes > ctx->index_ws_bytes) break;
-            Tmp t;
-            t.sel = (uint64_t *)(base + off);
-            t.sorted = t.sel + n;
-            t.uniq = t.sorted + n;
-            t.flag = (uint8_t *)(t.uniq + n);
-            tmp.push_back(t);
-            off += bytes;
+        // ---- chunk [done, end): as many genomes as fit a workspace of at most WS_MAX bytes
+        constexpr size_t WS_MAX = (size_t)12 << 30;
+        size_t end = done;
+        int64_t cap = 0, n_tiles = 0, max_pos = 0;
+        std::vector<GenomeDesc> hd;
+        while (end < G_all && hd.size() < (size_t)MAX_CHUNK) {
+            const Genome &g = *todo[end];
+            const int64_t c = (int64_t)((double)g.n_pos * fill) + 4096;
+            if (!hd.empty() && (size_t)(cap + c) * PER_ENTRY > WS_MAX) break;
+            GenomeDesc d{};
+            d.seq = reinterpret_cast<const uint64_t *>(g.d_seq); d.mask = g.d_mask; d.n_pos = g.n_pos; d.tile0 = n_tiles;
+            hd.push_back(d);
+            cap += c;
+            n_tiles += ceil_div(g.n_pos, SEL_TILE);
+            max_pos = std::max(max_pos, g.n_pos);
             ++end;
         }
-        const size_t G = end - done;
-        if (G == 0) FAIL(B200ANI_ERR_NOMEM, "index workspace too small");
-        CK(cudaMemsetAsync(d_cnt, 0, 2 * 256 * sizeof(unsigned long long), st));
-        for (size_t k = 0; k < G; ++k) {
-            Genome &g = *todo[done + k];
-            const int64_t n = g.n_pos;
-            int blocks = (int)std::min<int64_t>(ceil_div(n, SEL_TILE), (int64_t)ctx->sm_count * 6);
-            minimizer_select_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint64_t *>(g.d_seq), g.d_mask, n, tmp[k].sel, d_cnt + k);
+        const int G = (int)hd.size();
+        int gid_bits = 1;
+        while ((1 << gid_bits) < G) ++gid_bits;
+        size_t cub_a = 0, cub_b = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, cub_a, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, cap, 0, 64, st);
+        cub_b = cub_a;
+        const size_t cub_bytes = std::max(cub_a, cub_b) + 256;
+        const size_t head = 8192 + sizeof(GenomeDesc) * MAX_CHUNK;
+        const size_t want = head + cub_bytes + (size_t)cap * PER_ENTRY + 1024;
+        if (ctx->index_ws_bytes < want) {
+            CK(cudaStreamSynchronize(st));
+            if (ctx->index_ws) CK(cudaFree(ctx->index_ws));
+            ctx->index_ws = nullptr;
+            ctx->index_ws_bytes = 0;
+            CK(cudaMalloc(&ctx->index_ws, want));
+            ctx->index_ws_bytes = want;
+        }
+        char *base = (char *)ctx->index_ws;
+        unsigned long long *d_cnt = (unsigned long long *)base;  // [0]: selected, [1 + g]: kept per genome (256 slots)
+        GenomeDesc *d_gd = (GenomeDesc *)(base + 8192);
+        char *d_tmp = base + head;
+        char *q = d_tmp + ((cub_bytes + 255) & ~(size_t)255);
+        uint64_t *keys = (uint64_t *)q;   q += sizeof(uint64_t) * cap;
+        uint64_t *keys2 = (uint64_t *)q;  q += sizeof(uint64_t) * cap;
+        uint64_t *key4 = (uint64_t *)q;   q += sizeof(uint64_t) * cap;
+        uint32_t *vals = (uint32_t *)q;   q += sizeof(uint32_t) * cap;
+        uint32_t *vals2 = (uint32_t *)q;  q += sizeof(uint32_t) * cap;
+        uint32_t *idx2 = (uint32_t *)q;
+        CK(cudaMemsetAsync(d_cnt, 0, 8192, st));
+        CK(cudaMemcpyAsync(d_gd, hd.data(), sizeof(GenomeDesc) * G, cudaMemcpyHostToDevice, st));
+        {
+            int blocks = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 6);
+            minimizer_select_kernel<<<blocks, 256, 0, st>>>(d_gd, G, n_tiles, keys, vals, d_cnt, (unsigned long long)cap);
             CK(cudaGetLastError());
         }
-        unsigned long long h_cnt[512];
-        CK(cudaMemcpyAsync(h_cnt, d_cnt, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        unsigned long long h_cnt[1 + MAX_CHUNK];
+        CK(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        for (size_t k = 0; k < G; ++k) {
-            const int64_t ns = (int64_t)h_cnt[k];
-            cudaStream_t ss = ctx->side[k % NS];
-            void *d_tmp = d_tmp_base + cub_stride * (k % NS);
+        const int64_t ns = (int64_t)h_cnt[0];
+        if (ns > cap) {  // denser than the scratch was sized for (low-complexity sequence): redo the chunk with room for every position
+            if (fill >= 1.0) FAIL(B200ANI_ERR_NOMEM, "index scratch too small");
+            fill = 1.0;
+            continue;
+        }
+        uint64_t *key3 = keys;  // free again after the first sort
+        uint32_t *idx = vals;
+        if (ns) {
             size_t tb = cub_bytes;
-            cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, ns, 32, 64, ss);  // group equal k-mers; order inside a group is irrelevant
-            if (ns) mark_unique_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, ss>>>(tmp[k].sorted, ns, tmp[k].flag, maxocc);
+            cub::DeviceRadixSort::SortPairs(d_tmp, tb, keys, keys2, vals, vals2, ns, 0, 32 + gid_bits, st);
+            mark_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(keys2, vals2, ns, key3, idx, d_cnt + 1, maxocc);
             CK(cudaGetLastError());
-            tb = cub_bytes;
-            cub::DeviceSelect::Flagged(d_tmp, tb, tmp[k].sorted, tmp[k].flag, tmp[k].uniq, (int *)(d_cnt + 256 + k), ns, ss);
         }
-        CK(sync_sides());
-        CK(cudaMemcpyAsync(h_cnt + 256, d_cnt + 256, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_cnt + 1, d_cnt + 1, sizeof(unsigned long long) * MAX_CHUNK, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        for (size_t k = 0; k < G; ++k) {
+        int64_t n_kept = 0;
+        for (int k = 0; k < G; ++k) {
             Genome &g = *todo[done + k];
-            const int h_nu = (int)(h_cnt[256 + k] & 0xffffffffu);
+            const int h_nu = (int)h_cnt[1 + k];
             uint32_t bits = 4;
             while ((1ll << bits) < 2ll * h_nu) ++bits;
             if (!g.index) {  // prefer the buffers of a released genome that are large enough
@@ -249,33 +291,25 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc) {
                 ix->cap_bits = bits;
                 ix->cap_mini = h_nu + 1;
             }
-        }
-        // the pool allocations above were made on the main stream: let the side streams see them, then fill
-        CK(cudaEventRecord(ctx->side_ev, st));
-        for (auto &ss : ctx->side) CK(cudaStreamWaitEvent(ss, ctx->side_ev, 0));
-        for (size_t k = 0; k < G; ++k) {
-            Genome &g = *todo[done + k];
-            MinimizerIndex *ix = g.index;
-            const int h_nu = (int)ix->n_mini;
-            const uint32_t bits = ix->table_bits;
-            cudaStream_t ss = ctx->side[k % NS];
-            void *d_tmp = d_tmp_base + cub_stride * (k % NS);
-            CK(cudaMemsetAsync(ix->d_table, 0xff, sizeof(uint64_t) << bits, ss));
-            CK(cudaMemsetAsync(ix->d_bitmap, 0, sizeof(uint32_t) << (bits + 3 - 5), ss));
-            if (h_nu) {
-                table_insert_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, ss>>>(tmp[k].uniq, h_nu, ix->d_table, ix->d_bitmap, bits, tmp[k].sel);
-                CK(cudaGetLastError());
-                size_t tb = cub_bytes;
-                cub::DeviceRadixSort::SortKeys(d_tmp, tb, tmp[k].sel, tmp[k].sorted, h_nu, 34, 64, ss);
-                split_bypos_kernel<<<(unsigned)ceil_div(h_nu, 256), 256, 0, ss>>>(tmp[k].sorted, h_nu, ix->d_kmer, ix->d_posflag);
-                CK(cudaGetLastError());
-            }
-            ctx->counters[CT_LAUNCHES] += 4;
+            CK(cudaMemsetAsync(ix->d_table, 0xff, sizeof(uint64_t) << bits, st));
+            CK(cudaMemsetAsync(ix->d_bitmap, 0, sizeof(uint32_t) << (bits + 3 - 5), st));
+            hd[k].table = ix->d_table; hd[k].bitmap = ix->d_bitmap; hd[k].kmer_out = ix->d_kmer; hd[k].posflag_out = ix->d_posflag;
+            hd[k].bits = bits; hd[k].out0 = n_kept;
+            n_kept += h_nu;
             ix->valid = true;
             ix->maxocc = maxocc;
         }
-        CK(sync_sides());
-        CK(cudaStreamSynchronize(st));  // the workspace is reused by the next chunk
+        CK(cudaMemcpyAsync(d_gd, hd.data(), sizeof(GenomeDesc) * G, cudaMemcpyHostToDevice, st));
+        if (ns) {
+            table_insert_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(keys2, vals2, key3, ns, d_gd);
+            CK(cudaGetLastError());
+            size_t tb = cub_bytes;
+            cub::DeviceRadixSort::SortPairs(d_tmp, tb, key3, key4, idx, idx2, ns, 0, AN_POSBITS + gid_bits, st);
+            if (n_kept) split_bypos_kernel<<<(unsigned)ceil_div(n_kept, 256), 256, 0, st>>>(key4, idx2, n_kept, keys2, vals2, d_gd);
+            CK(cudaGetLastError());
+        }
+        ctx->counters[CT_LAUNCHES] += 5;
+        CK(cudaStreamSynchronize(st));  // the workspace (and the host-side descriptor array) is reused by the next chunk
         done = end;
     }
     return 0;
