@@ -120,6 +120,7 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
         int hgleft = NEGV, eleft = NEGV;
         int rowkey = MODE ? (int)0x80000000 : NEGV;
         if (MODE == 0 || kkhi >= AN_BANDW - 1) {
+            int key_even = 0;
 #pragma unroll
             for (int kk = 0; kk < AN_BANDW; ++kk) {
                 const uint32_t bit = (kk < 16 ? mlo : mhi) & (1u << ((2 * kk) & 31));
@@ -130,7 +131,10 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
                 Hg[kk] = hgleft;
                 F[kk] = f;
                 eleft = e;
-                rowkey = MODE ? max(rowkey, add_fma(h, 31 - kk, one << 5)) : max(rowkey, h);
+                // row maximum: two cells per 3-input max (the max-plus instructions are what the ALU pipe is full of)
+                const int key = MODE ? add_fma(h, 31 - kk, one << 5) : h;
+                if (kk & 1) rowkey = __vimax3_s32(rowkey, key_even, key);
+                else key_even = key;
             }
         } else {
 #pragma unroll
