@@ -40,6 +40,8 @@
 #define AB_GAP 5         /* ... and 5 per gap column (linear; blastn: 5 + 2 per column) */
 #define AB_BREAK 250     /* ANIb: rows without a new best before giving up (blastn's gapped X-drop is far more lenient than nucmer's break) */
 #define AB_TILE 256      /* ANIb: extension tile rows (a tile that brings no new best ends the extension, so this is the effective break) */
+#define AB_BRIDGE_GAP 250 /* ANIb bridging: max distance between two candidate HSPs of a fragment that are joined ... */
+#define AB_BRIDGE_DD 120  /* ... and max diagonal offset between them (blastn's gapped extension is not banded) */
 #define AB_MINPIECE 11   /* shortest anchor piece kept after clipping to a fragment (blastn word size) */
 #define AB_FRAGSIZE 1020 /* pyani_config.FRAGSIZE (pyani_config.py:95) */
 #define AN_PACK 4096     /* DP value = score*PACK - errs */

@@ -297,11 +297,12 @@ static dp_out dp_band(const uint8_t *R, int rstride, const uint8_t *Q, int qstri
 static inline int32_t pack_score(int32_t v) { return (v + AN_PACK - 1) >> 12; } /* arithmetic shift = floor */
 static inline int32_t pack_errs(int32_t v) { return pack_score(v) * AN_PACK - v; }
 
-/* unbanded global affine alignment of a small rectangle (bridges, at most AN_BREAK x AN_BREAK): H[lr][lq] in the
- * same packed units as dp_band_sc */
-static int32_t dp_full(const uint8_t *R, const uint8_t *Q, int lr, int lq) {
-    const int32_t go = AN_GAPOPEN * AN_PACK + 1, ge = AN_GAPEXT * AN_PACK + 1, sm = AN_MATCH * AN_PACK, sx = -(AN_MISMATCH * AN_PACK + 1);
-    int32_t H[AN_BREAK + 2], F[AN_BREAK + 2];
+/* unbanded global affine alignment of a small rectangle (bridges: at most BRIDGE_CAP x BRIDGE_CAP cells): H[lr][lq] in
+ * the same packed units as dp_band_sc; sc = {match, mismatch, first gap column, further gap columns} */
+#define BRIDGE_CAP (AN_BREAK > AB_BRIDGE_GAP ? AN_BREAK : AB_BRIDGE_GAP)
+static int32_t dp_full(const uint8_t *R, const uint8_t *Q, int lr, int lq, const int *sc) {
+    const int32_t go = sc[2] * AN_PACK + 1, ge = sc[3] * AN_PACK + 1, sm = sc[0] * AN_PACK, sx = -(sc[1] * AN_PACK + 1);
+    int32_t H[BRIDGE_CAP + 2], F[BRIDGE_CAP + 2];
     H[0] = 0; F[0] = AN_NEG;
     for (int j = 1; j <= lq; ++j) { H[j] = -(go + (j - 1) * ge); F[j] = AN_NEG; }
     for (int i = 1; i <= lr; ++i) {
@@ -544,7 +545,7 @@ int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int maxmatch, i
         int32_t v;
         if (lr == 0 && lq == 0) v = 0;
         else if (lr == 0 || lq == 0) { int L = lr + lq; v = -((AN_GAPOPEN + (L - 1) * AN_GAPEXT) * AN_PACK + L); }
-        else { v = dp_full(R->fw + a->re, Qs + a->qe, lr, lq); stats[10] += (int64_t)lr * lq; }
+        else { v = dp_full(R->fw + a->re, Qs + a->qe, lr, lq, SC_ANIM); stats[10] += (int64_t)lr * lq; }
         S[b].bval = v;
     }
     /* ---- emit: one row per chain of bridged alignments */
@@ -787,23 +788,12 @@ int64_t orc_anib_pair(const orc_genome *Q, const orc_genome *S, int fragsize, in
         esum[h] += pack_errs(gval[i]);
         tail[h] = (int32_t)i;
     }
-    /* ---- every chain is a candidate HSP: extend inside the fragment, score, filter, best per fragment */
-    int64_t best_frag = -1, best_score = 0, best_row[8] = {0}, n_rows = 0;
-    for (int64_t h = 0; h <= na; ++h) {
-        int is_seg = h < na && head[h] == (int32_t)h;
-        if (h == na || (is_seg && A[h].frag != best_frag)) { /* close the previous fragment */
-            if (best_frag >= 0 && best_score > 0) {
-                out[0] += best_row[4] + best_row[2]; /* ani_alnlen = nident + mismatch */
-                out[1] += best_row[2] + best_row[3];
-                out[2] += best_row[7];
-                out[4] += 1;
-                if (frag_rows && n_rows < cap_rows) memcpy(frag_rows + 8 * n_rows, best_row, sizeof best_row);
-                ++n_rows;
-            }
-            best_score = 0;
-            best_frag = h < na ? A[h].frag : -1;
-        }
-        if (!is_seg) continue;
+    /* ---- every chain is a candidate HSP: extend it inside the fragment */
+    typedef struct { int32_t frag, strand, pred, succ, bval; uint32_t rc; int64_t rs, re, qs, qe, score, errs, qlen, sdist; } cand_t;
+    cand_t *C = (cand_t *)malloc(sizeof(cand_t) * (size_t)(na + 1));
+    int64_t nc = 0;
+    for (int64_t h = 0; h < na; ++h) {
+        if (head[h] != (int32_t)h) continue;
         stats[3]++;
         out[5] += 1;
         const fanchor *f = &A[h], *l = &A[tail[h]];
@@ -835,6 +825,72 @@ int64_t orc_anib_pair(const orc_genome *Q, const orc_genome *S, int fragsize, in
                 if (o.stopped) break;
             }
         }
+        cand_t *c = &C[nc++];
+        c->frag = f->frag; c->strand = f->strand; c->rc = rc; c->rs = rs; c->re = re; c->qs = qs; c->qe = qe;
+        c->score = score; c->errs = errs; c->qlen = qlen; c->pred = -1; c->succ = 0x7fffffff; c->bval = 0; c->sdist = 0;
+    }
+    /* ---- bridging inside a fragment: blastn's gapped extension is not banded, so where two candidates of one
+     * fragment are separated by an indel or a stretch the banded extension cannot cross, BLAST reports one HSP.  A
+     * candidate takes the nearest earlier one (same fragment, strand and subject record) that ends at most
+     * AB_BRIDGE_GAP bases before its start on both sequences and at most AB_BRIDGE_DD off its diagonal; the residual gap
+     * is aligned globally (unbanded); a local aligner joins two pieces only if the joint alignment outscores both. */
+    for (int64_t b = 0; b < nc; ++b) {
+        int64_t bestd = -1;
+        for (int64_t a = b - 1; a >= 0 && a >= b - AN_LOOKBACK; --a) {
+            if (C[a].frag != C[b].frag || C[a].strand != C[b].strand) break;
+            if (C[a].rc != C[b].rc) continue;
+            int64_t gr = C[b].rs - C[a].re, gq = C[b].qs - C[a].qe;
+            if (gr < 0 || gq < 0 || gr > AB_BRIDGE_GAP || gq > AB_BRIDGE_GAP) continue;
+            int64_t dd = gq - gr;
+            if (dd > AB_BRIDGE_DD || dd < -AB_BRIDGE_DD) continue;
+            if (bestd < 0 || gr + gq < bestd) { bestd = gr + gq; C[b].pred = (int32_t)a; }
+        }
+        C[b].sdist = bestd;
+    }
+    for (int64_t b = 0; b < nc; ++b)
+        if (C[b].pred >= 0) {
+            cand_t *a = &C[C[b].pred];
+            if (a->succ == 0x7fffffff || C[b].sdist < C[a->succ].sdist) a->succ = (int32_t)b;
+        }
+    for (int64_t b = 0; b < nc; ++b)
+        if (C[b].pred >= 0 && C[C[b].pred].succ != (int32_t)b) C[b].pred = -1;
+    for (int64_t b = 0; b < nc; ++b) {
+        if (C[b].pred < 0) continue;
+        const cand_t *a = &C[C[b].pred];
+        int lr = (int)(C[b].rs - a->re), lq = (int)(C[b].qs - a->qe);
+        const uint8_t *Qs = C[b].strand ? Q->rc : Q->fw;
+        int32_t v;
+        if (lr == 0 && lq == 0) v = 0;
+        else if (lr == 0 || lq == 0) { int L = lr + lq; v = -((AB_GAP + (L - 1) * AB_GAP) * AN_PACK + L); }
+        else { v = dp_full(R->fw + a->re, Qs + a->qe, lr, lq, SC_ANIB); stats[10] += (int64_t)lr * lq; }
+        int64_t mn = a->score < C[b].score ? a->score : C[b].score;
+        if (pack_score(v) + mn <= 0) { C[b].pred = -1; continue; }
+        C[b].bval = v;
+        stats[9]++;
+    }
+    /* ---- (merged) candidates -> BLAST columns, parse_blast_tab filter, best per fragment */
+    int64_t best_frag = -1, best_score = 0, best_row[8] = {0}, n_rows = 0;
+    for (int64_t h = 0; h <= nc; ++h) {
+        int is_head = h < nc && C[h].pred < 0;
+        if (h == nc || (is_head && C[h].frag != best_frag)) { /* close the previous fragment */
+            if (best_frag >= 0 && best_score > 0) {
+                out[0] += best_row[4] + best_row[2]; /* ani_alnlen = nident + mismatch */
+                out[1] += best_row[2] + best_row[3];
+                out[2] += best_row[7];
+                out[4] += 1;
+                if (frag_rows && n_rows < cap_rows) memcpy(frag_rows + 8 * n_rows, best_row, sizeof best_row);
+                ++n_rows;
+            }
+            best_score = 0;
+            best_frag = h < nc ? C[h].frag : -1;
+        }
+        if (!is_head) continue;
+        int64_t rs = C[h].rs, qs = C[h].qs, re = C[h].re, qe = C[h].qe, score = C[h].score, errs = C[h].errs, qlen = C[h].qlen;
+        for (int32_t pv = (int32_t)h, n2 = C[h].succ; n2 != 0x7fffffff && C[n2].pred == pv; pv = n2, n2 = C[n2].succ) {
+            score += C[n2].score + pack_score(C[n2].bval);
+            errs += C[n2].errs + pack_errs(C[n2].bval);
+            re = C[n2].re; qe = C[n2].qe;
+        }
         /* columns: L = consumed bases, G = L - 5E - score, X = E - G, M = (L - G)/2 - X */
         int64_t L = (re - rs) + (qe - qs);
         int64_t G = L - 5 * errs - score; /* score = L - 5E - G for (+2, -3, 5 per gap column) */
@@ -843,10 +899,11 @@ int64_t orc_anib_pair(const orc_genome *Q, const orc_genome *S, int fragsize, in
         if (!(10 * (M + X) > 7 * qlen && 10 * M > 3 * qlen)) continue; /* anib.py:646, strict */
         if (score > best_score) {
             best_score = score;
-            best_row[0] = f->frag; best_row[1] = length; best_row[2] = X; best_row[3] = G; best_row[4] = M;
+            best_row[0] = C[h].frag; best_row[1] = length; best_row[2] = X; best_row[3] = G; best_row[4] = M;
             best_row[5] = qlen; best_row[6] = score; best_row[7] = (100000 * M + length / 2) / length;
         }
     }
+    free(C);
     free(A); free(pred); free(succ); free(trim); free(gval); free(head); free(tail); free(rc_of);
     free(wsum); free(ssum); free(esum); free(fbase);
     return n_rows;

@@ -21,9 +21,10 @@ __global__ void anib_segment_kernel(SegArrays S, const uint64_t *__restrict__ ke
     const long long G = L - 5 * E - score, X = E - G, M = (L - G) / 2 - X, length = M + X + G;
     const long long qlen = S.q_hi[s] - S.q_lo[s];
     B.pair[s] = S.pair[s];
-    B.frag[s] = (int)key_frag(keys[S.head[s]]);
+    B.frag[s] = S.frag[s];
     B.score[s] = (int)score; B.nident[s] = (int)M; B.mism[s] = (int)X; B.gaps[s] = (int)G; B.qlen[s] = (int)qlen;
-    B.pass[s] = !(G < 0 || X < 0 || M < 0 || length <= 0) && 10 * (M + X) > 7 * qlen && 10 * M > 3 * qlen && score > 0;
+    // entries folded into a bridged neighbour (alive = 0) are no candidates of their own
+    B.pass[s] = S.alive[s] && !(G < 0 || X < 0 || M < 0 || length <= 0) && 10 * (M + X) > 7 * qlen && 10 * M > 3 * qlen && score > 0;
 }
 
 // Best passing HSP of each fragment (highest score, first in order on ties) -> per-pair sums.  Segments are in

@@ -173,7 +173,7 @@ __device__ __forceinline__ void link_box(const ChainArrays &A, int64_t i, int64_
 // One alignment under construction (a kept segment = chain of intact links), extended tile by tile.
 struct SegArrays {
     int64_t n;
-    int *pair, *strand, *head;
+    int *pair, *strand, *head, *frag;  // frag: ANIb fragment id (0 for ANIm)
     uint32_t *rc, *qc;                 // record indices
     int *rs, *qs, *re, *qe;            // [s,e) in view coordinates (reference g-space / query view)
     int *r_lo, *r_hi, *q_lo, *q_hi;    // record bounds in the same coordinates
@@ -186,6 +186,13 @@ struct SegArrays {
 };
 
 // rows: n x 8 int32 (pair, ref record, qry record, rs, re, qs, qe, errs), grouped by pair.
+// Bridging rules of the two aligners (anim_bridge.cu)
+struct BridgeParams {
+    int gapmax, ddmax;                       // facing ends at most gapmax apart on both sequences, at most ddmax off the diagonal
+    int match, mismatch, gapopen, gapext;    // scoring of the residual alignment
+    int need_gain;                           // 1: a bridge is kept only if the joint alignment outscores both pieces (local aligner)
+};
+
 struct FiltArrays {
     const int *rows;
     int64_t n;

@@ -219,7 +219,7 @@ __global__ void segment_init_kernel(ChainArrays A, const PairDesc *__restrict__ 
     const PairDesc &P = pairs[key_pair(k)];
     const int strand = key_strand(k);
     const uint32_t rc = A.rc_of[h], qc = A.qc_of[h];
-    S.pair[s] = (int)key_pair(k); S.strand[s] = strand; S.head[s] = h; S.rc[s] = rc; S.qc[s] = qc;
+    S.pair[s] = (int)key_pair(k); S.strand[s] = strand; S.head[s] = h; S.frag[s] = (int)key_frag(k); S.rc[s] = rc; S.qc[s] = qc;
     S.rs[s] = key_r(k); S.qs[s] = val_q(A.vals[h]);
     S.re[s] = key_r(kt) + val_len(vt); S.qe[s] = val_q(vt) + val_len(vt);
     int64_t r_lo = (int64_t)P.r_goff[rc], r_hi = (int64_t)P.r_goff[rc + 1] - 1;

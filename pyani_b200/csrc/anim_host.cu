@@ -22,9 +22,10 @@ __global__ void contig_kernel(ChainArrays, const PairDesc *);
 __global__ void link_kernel(ChainArrays, int);
 __global__ void cluster_keep_kernel(ChainArrays, uint8_t *);
 __global__ void bridge_init_kernel(SegArrays);
-__global__ void bridge_link_kernel(SegArrays);
-__global__ void bridge_validate_kernel(SegArrays, uint32_t *, uint32_t *, unsigned long long *);
-__global__ void bridge_dp_kernel(SegArrays, const PairDesc *, const uint32_t *, int64_t, unsigned long long *);
+__global__ void bridge_link_kernel(SegArrays, BridgeParams);
+__global__ void bridge_validate_kernel(SegArrays, BridgeParams, uint32_t *, uint32_t *, unsigned long long *);
+template <int CAP> __global__ void bridge_dp_kernel(SegArrays, BridgeParams, const PairDesc *, const uint32_t *, int64_t, unsigned long long *);
+__global__ void bridge_accept_kernel(SegArrays, BridgeParams, unsigned long long *);
 __global__ void bridge_merge_kernel(SegArrays);
 __global__ void link_validate_kernel(ChainArrays, unsigned long long *);
 __global__ void gap_task_kernel(ChainArrays, uint32_t *, uint32_t *, unsigned long long *, int, int);
@@ -337,7 +338,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     S.n = n_seg;
     int n_ext_launch = 0;
     int *rows = nullptr;
-    DA(S.pair, n_seg); DA(S.strand, n_seg); DA(S.head, n_seg); DA(S.rc, n_seg); DA(S.qc, n_seg);
+    DA(S.pair, n_seg); DA(S.strand, n_seg); DA(S.head, n_seg); DA(S.frag, n_seg); DA(S.rc, n_seg); DA(S.qc, n_seg);
     DA(S.rs, n_seg); DA(S.qs, n_seg); DA(S.re, n_seg); DA(S.qe, n_seg);
     DA(S.r_lo, n_seg); DA(S.r_hi, n_seg); DA(S.q_lo, n_seg); DA(S.q_hi, n_seg);
     DA(S.score, n_seg); DA(S.errs, n_seg); DA(rows, 8 * n_seg);
@@ -386,30 +387,38 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         T1(ST_EXTDP);
         ctx->counters[CT_EXTCELLS] += (int64_t)hc[6];
         ctx->counters[CT_EXTTILES] += (int64_t)hc[7];
-        if (!anib) {
-            // ---- bridging: join alignments whose facing ends are close, then one row per chain of joined alignments
+        {
+            // ---- bridging: join alignments whose facing ends are close (ANIm: one row per chain of joined alignments;
+            // ANIb: candidate HSPs of one fragment)
+            const BridgeParams BP = anib ? BridgeParams{AB_BRIDGE_GAP, AB_BRIDGE_DD, AB_MATCH, AB_MISMATCH, AB_GAP, AB_GAP, 1}
+                                         : BridgeParams{AN_BREAK, AN_BRIDGE_DD, AN_MATCH, AN_MISMATCH, AN_GAPOPEN, AN_GAPEXT, 0};
             T0(ST_BRIDGE);
             bridge_init_kernel<<<GRID(n_seg)>>>(S);
-            bridge_link_kernel<<<GRID(n_seg)>>>(S);
-            bridge_validate_kernel<<<GRID(n_seg)>>>(S, task_idx, task_key, W->counters + 10);  // the link stage's task arrays are free again
+            bridge_link_kernel<<<GRID(n_seg)>>>(S, BP);
+            bridge_validate_kernel<<<GRID(n_seg)>>>(S, BP, task_idx, task_key, W->counters + 10);  // the link stage's task arrays are free again
             CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             const int64_t n_btasks = (int64_t)hc[12];
             if (n_btasks) {  // similar-sized rectangles side by side in a warp
                 size_t tb2 = W->cub_bytes;
                 cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb2, task_key, task_key2, task_idx, task_idx2, n_btasks, 0, 8, st);
-                bridge_dp_kernel<<<(unsigned)ceil_div(n_btasks, 64), 64, 0, st>>>(S, W->d_pairs, task_idx2, n_btasks, W->counters + 10);
+                if (anib) bridge_dp_kernel<AB_BRIDGE_GAP><<<(unsigned)ceil_div(n_btasks, 64), 64, 0, st>>>(S, BP, W->d_pairs, task_idx2, n_btasks, W->counters + 10);
+                else bridge_dp_kernel<AN_BREAK><<<(unsigned)ceil_div(n_btasks, 64), 64, 0, st>>>(S, BP, W->d_pairs, task_idx2, n_btasks, W->counters + 10);
             }
+            bridge_accept_kernel<<<GRID(n_seg)>>>(S, BP, W->counters + 10);
             bridge_merge_kernel<<<GRID(n_seg)>>>(S);
-            emit_rows_kernel<<<GRID(n_seg)>>>(S, W->d_pairs, rows_all);
-            LAUNCHED(5);
-            size_t tb = W->cub_bytes;
-            cub::DeviceSelect::Flagged(W->cub_tmp, tb, (const Row8 *)rows_all, S.alive, (Row8 *)rows, W->changed, n_seg, st);
-            int hr = 0;
-            CK(cudaMemcpyAsync(&hr, W->changed, sizeof hr, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+            LAUNCHED(6);
+            if (!anib) {
+                emit_rows_kernel<<<GRID(n_seg)>>>(S, W->d_pairs, rows_all);
+                LAUNCHED(1);
+                size_t tb = W->cub_bytes;
+                cub::DeviceSelect::Flagged(W->cub_tmp, tb, (const Row8 *)rows_all, S.alive, (Row8 *)rows, W->changed, n_seg, st);
+                int hr = 0;
+                CK(cudaMemcpyAsync(&hr, W->changed, sizeof hr, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                n_rows = hr;
+            }
             T1(ST_BRIDGE);
-            n_rows = hr;
         }
     }
 
@@ -443,7 +452,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         DF(A.tail); DF(A.ssum); DF(A.esum); DF(A.strong); DF(task_key); DF(task_idx); DF(task_key2); DF(task_idx2); DF(seg_head);
         DF(S.pair); DF(S.strand); DF(S.head); DF(S.rc); DF(S.qc); DF(S.rs); DF(S.qs); DF(S.re); DF(S.qe);
         DF(S.r_lo); DF(S.r_hi); DF(S.q_lo); DF(S.q_hi); DF(S.score); DF(S.errs); DF(rows); DF(ext_list[0]); DF(ext_list[1]);
-    DF(S.bpred); DF(S.bval); DF(S.bsucc); DF(S.alive); DF(rows_all);
+    DF(S.bpred); DF(S.bval); DF(S.bsucc); DF(S.alive); DF(S.frag); DF(rows_all);
         CK(cudaStreamSynchronize(st));
         for (int s2 = 0; s2 < B200ANI_N_STAGES; ++s2)
             if (used[s2]) {
@@ -504,7 +513,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     DF(A.tail); DF(A.ssum); DF(A.esum); DF(A.strong); DF(task_key); DF(task_idx); DF(task_key2); DF(task_idx2); DF(seg_head);
     DF(S.pair); DF(S.strand); DF(S.head); DF(S.rc); DF(S.qc); DF(S.rs); DF(S.qs); DF(S.re); DF(S.qe);
     DF(S.r_lo); DF(S.r_hi); DF(S.q_lo); DF(S.q_hi); DF(S.score); DF(S.errs); DF(rows); DF(ext_list[0]); DF(ext_list[1]);
-    DF(S.bpred); DF(S.bval); DF(S.bsucc); DF(S.alive); DF(rows_all);
+    DF(S.bpred); DF(S.bval); DF(S.bsucc); DF(S.alive); DF(S.frag); DF(rows_all);
     for (int a = 0; a < 2; ++a) { DF(F.sidx[a]); DF(F.slo[a]); DF(F.shi[a]); DF(F.sseq[a]); }
     DF(F.best); DF(F.from); DF(F.unit); DF(F.flag); DF(F.pmax); DF(F.pmaxj); DF(F.phi); DF(fkey); DF(fkey2); DF(fidx); DF(fidx2); DF(pair_start);
     CK(cudaStreamSynchronize(st));

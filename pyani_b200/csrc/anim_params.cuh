@@ -30,6 +30,8 @@
 #define AB_GAP 5
 #define AB_BREAK 250
 #define AB_TILE 256
+#define AB_BRIDGE_GAP 250
+#define AB_BRIDGE_DD 120
 #define AB_MINPIECE 11
 #define AB_FRAGSIZE 1020
 #define AN_PACK 4096
