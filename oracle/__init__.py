@@ -158,13 +158,27 @@ class OGenome:
         o = np.ascontiguousarray(contig_off, dtype=np.uint64)
         self.n_bases = int(o[-1])
         self.contig_off = o
+        self._args = (a, o)
         self._h = ctypes.c_void_p(L.orc_genome_create(_p(a, ctypes.c_uint8), _p(o, ctypes.c_uint64), ctypes.c_uint32(len(o) - 1)))
+        self._hb = None  # ANIb index (shorter seeds), built on first use
+
+    @property
+    def anib_handle(self):
+        if self._hb is None:
+            L = lib()
+            L.orc_genome_create_anib.restype = ctypes.c_void_p
+            a, o = self._args
+            self._hb = ctypes.c_void_p(L.orc_genome_create_anib(_p(a, ctypes.c_uint8), _p(o, ctypes.c_uint64), ctypes.c_uint32(len(o) - 1)))
+        return self._hb
 
     def __del__(self):
         try:
             if self._h:
                 lib().orc_genome_free(self._h)
                 self._h = None
+            if self._hb:
+                lib().orc_genome_free(self._hb)
+                self._hb = None
         except Exception:
             pass
 
@@ -254,8 +268,8 @@ def anib_pair(Q: OGenome, S: OGenome, fragsize: int = 1020, cap: int = 1 << 15):
     out = np.zeros(6, dtype=np.int64)
     rows = np.zeros((cap, 8), dtype=np.int64)
     stats = np.zeros(ANIM_NSTATS, dtype=np.int64)
-    n = L.orc_anib_pair(Q._h, S._h, int(fragsize), out.ctypes.data, rows.ctypes.data, cap, stats.ctypes.data)
-    assert n <= cap
+    n = L.orc_anib_pair(Q.anib_handle, S.anib_handle, int(fragsize), out.ctypes.data, rows.ctypes.data, cap, stats.ctypes.data)
+    assert 0 <= n <= cap
     res = dict(aln_length=int(out[0]), sim_errs=int(out[1]), pid_milli_sum=int(out[2]), n_frags=int(out[3]), n_pass=int(out[4]),
                n_hsps=int(out[5]), status=0 if out[4] else 1)
     return res, rows[:n].copy(), {k: v for k, v in zip(ANIM_STAT_NAMES, stats.tolist()) if k}

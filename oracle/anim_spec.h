@@ -40,6 +40,9 @@
 #define AB_GAP 5         /* ... and 5 per gap column (linear; blastn: 5 + 2 per column) */
 #define AB_BREAK 250     /* ANIb: rows without a new best before giving up (blastn's gapped X-drop is far more lenient than nucmer's break) */
 #define AB_TILE 256      /* ANIb: extension tile rows (a tile that brings no new best ends the extension, so this is the effective break) */
+#define AB_K 13          /* ANIb seed k-mer length ... */
+#define AB_W 2           /* ... and minimizer window: every exact match >= AB_K + AB_W - 1 = 14 is seeded */
+#define AB_MINLEN 14     /* ANIb minimum exact-match length (blastn words are 11; shorter seeds stop paying: k-mers must stay unique) */
 #define AB_BRIDGE_GAP 250 /* ANIb bridging: max distance between two candidate HSPs of a fragment that are joined ... */
 #define AB_BRIDGE_DD 120  /* ... and max diagonal offset between them (blastn's gapped extension is not banded) */
 #define AB_MINPIECE 11   /* shortest anchor piece kept after clipping to a fragment (blastn word size) */

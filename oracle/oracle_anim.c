@@ -43,6 +43,7 @@ typedef struct {
     uint32_t *mini_posflag; /* pos | repeated<<30 | orient<<31 (repeated: the k-mer occurs more than once in this genome) */
     uint64_t *table;        /* open addressing: kmer<<32 | posflag ; empty = ~0 */
     uint32_t table_bits;
+    int k, w;               /* seed length and minimizer window of this index (ANIm: AN_K / AN_W, ANIb: AB_K / AB_W) */
 } orc_genome;
 
 static inline int base_code(uint8_t c) {
@@ -75,15 +76,23 @@ void orc_genome_free(orc_genome *g) {
     free(g);
 }
 
-/* One index serves every mode: minimizers whose k-mer occurs at most AN_MAXOCC times in the genome, the repeated
- * ones flagged (nucmer itself has no occurrence cap, anim.py:276-279).  maxocc is a parameter for experiments only. */
-orc_genome *orc_genome_create_occ(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs, int maxocc);
+/* The ANIm index (k = AN_K, w = AN_W) serves --mum and --maxmatch: minimizers whose k-mer occurs at most AN_MAXOCC times
+ * in the genome, the repeated ones flagged (nucmer itself has no occurrence cap, anim.py:276-279).  ANIb uses a second
+ * index of the same kind with shorter seeds (AB_K, AB_W): blastn's 11-mer words find homology that 20-mers miss. */
+orc_genome *orc_genome_create_kw(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs, int maxocc, int k, int w);
 orc_genome *orc_genome_create(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs) {
-    return orc_genome_create_occ(ascii, off, n_contigs, AN_MAXOCC);
+    return orc_genome_create_kw(ascii, off, n_contigs, AN_MAXOCC, AN_K, AN_W);
+}
+orc_genome *orc_genome_create_anib(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs) {
+    return orc_genome_create_kw(ascii, off, n_contigs, AN_MAXOCC, AB_K, AB_W);
+}
+orc_genome *orc_genome_create_occ(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs, int maxocc) {
+    return orc_genome_create_kw(ascii, off, n_contigs, maxocc, AN_K, AN_W);
 }
 
-orc_genome *orc_genome_create_occ(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs, int maxocc) {
+orc_genome *orc_genome_create_kw(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs, int maxocc, int k, int w) {
     orc_genome *g = (orc_genome *)calloc(1, sizeof *g);
+    g->k = k; g->w = w;
     g->n_contigs = n_contigs;
     g->n_bases = (int64_t)off[n_contigs];
     g->n_pos = g->n_bases + n_contigs;
@@ -101,7 +110,7 @@ orc_genome *orc_genome_create_occ(const uint8_t *ascii, const uint64_t *off, uin
         g->rc[i] = (uint8_t)(b < 4 ? 3 - b : 4);
     }
     /* ---- minimizer selection: position p is selected iff its canonical-k-mer hash is <= every hash in
-     * at least one window of AN_W consecutive k-mer start positions containing p (ties select all). */
+     * at least one window of w consecutive k-mer start positions containing p (ties select all). */
     int64_t n = g->n_pos;
     uint64_t *hv = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(n + 1));
     uint32_t *canon = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n + 1));
@@ -109,10 +118,10 @@ orc_genome *orc_genome_create_occ(const uint8_t *ascii, const uint64_t *off, uin
     const uint64_t INF = 1ull << 32;
     for (int64_t p = 0; p < n; ++p) {
         hv[p] = INF;
-        if (p + AN_K > n) continue;
+        if (p + k > n) continue;
         uint32_t f = 0, r = 0;
         int ok = 1;
-        for (int i = 0; i < AN_K; ++i) {
+        for (int i = 0; i < k; ++i) {
             uint8_t b = g->fw[p + i];
             if (b > 3) { ok = 0; break; }
             f = (f << 2) | b;                                  /* first base most significant */
@@ -128,8 +137,8 @@ orc_genome *orc_genome_create_occ(const uint8_t *ascii, const uint64_t *off, uin
     for (int64_t p = 0; p < n; ++p) {
         if (hv[p] == INF) continue;
         int chosen = 0;
-        for (int o = 0; o < AN_W && !chosen; ++o) { /* window [p-o, p-o+W-1] */
-            int64_t lo = p - o, hi = lo + AN_W - 1;
+        for (int o = 0; o < w && !chosen; ++o) { /* window [p-o, p-o+W-1] */
+            int64_t lo = p - o, hi = lo + w - 1;
             int is_min = 1;
             for (int64_t x = lo; x <= hi; ++x) {
                 uint64_t h = (x < 0 || x >= n) ? INF : hv[x];
@@ -380,6 +389,8 @@ typedef struct { int32_t strand, pred, succ, bval; uint32_t rc, qc; int64_t rs, 
  * conventions: 1-based closed, reverse strand qs > qe).  Returns the number of alignments. */
 int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int maxmatch, int64_t *rows, int64_t cap, int64_t *stats) {
     memset(stats, 0, sizeof(int64_t) * ORC_NSTATS);
+    const int K = R->k; /* both genomes carry the same kind of index */
+    if (Q->k != K || Q->w != R->w) return -1;
     /* ---- seeds -> maximal exact matches */
     int64_t acap = 1 << 16, na = 0;
     anchor *A = (anchor *)malloc(sizeof(anchor) * (size_t)acap);
@@ -393,16 +404,16 @@ int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int maxmatch, i
         stats[7]++;
         int strand = (int)((rpf ^ qpf) >> 31);
         int64_t r0 = rpf & POS_MASK, qpos = qpf & POS_MASK;
-        int64_t q0 = strand ? Q->n_pos - AN_K - qpos : qpos;
+        int64_t q0 = strand ? Q->n_pos - K - qpos : qpos;
         const uint8_t *Qs = strand ? Q->rc : Q->fw;
         /* a seed inside the match found by the previous seed of this strand yields the same match
          * (pure speed-up: the anchor list is a set, see the sort + unique below) */
-        if (r0 - q0 == last_d[strand] && r0 >= last_r0[strand] && r0 + AN_K <= last_r1[strand]) continue;
+        if (r0 - q0 == last_d[strand] && r0 >= last_r0[strand] && r0 + K <= last_r1[strand]) continue;
         int64_t l = 0, rr = 0;
         while (r0 - l - 1 >= 0 && q0 - l - 1 >= 0 && R->fw[r0 - l - 1] < 4 && R->fw[r0 - l - 1] == Qs[q0 - l - 1]) ++l;
-        while (r0 + AN_K + rr < R->n_pos && q0 + AN_K + rr < Q->n_pos && R->fw[r0 + AN_K + rr] < 4 &&
-               R->fw[r0 + AN_K + rr] == Qs[q0 + AN_K + rr]) ++rr;
-        int64_t len = AN_K + l + rr;
+        while (r0 + K + rr < R->n_pos && q0 + K + rr < Q->n_pos && R->fw[r0 + K + rr] < 4 &&
+               R->fw[r0 + K + rr] == Qs[q0 + K + rr]) ++rr;
+        int64_t len = K + l + rr;
         last_d[strand] = r0 - q0; last_r0[strand] = r0 - l; last_r1[strand] = r0 - l + len;
         if (len < AN_MINLEN) continue;
         if (na == acap) { acap *= 2; A = (anchor *)realloc(A, sizeof(anchor) * (size_t)acap); }
@@ -674,6 +685,8 @@ static int cmp_fanchor(const void *a, const void *b) {
 int64_t orc_anib_pair(const orc_genome *Q, const orc_genome *S, int fragsize, int64_t *out, int64_t *frag_rows, int64_t cap_rows, int64_t *stats) {
     memset(stats, 0, sizeof(int64_t) * ORC_NSTATS);
     memset(out, 0, sizeof(int64_t) * 6);
+    const int K = S->k;
+    if (Q->k != K || Q->w != S->w) return -1;
     const orc_genome *R = S; /* the subject plays nucmer's reference role: its table is probed */
     /* fragment table of the query: record c holds ceil(len/fragsize) fragments, ids are global */
     uint32_t *fbase = (uint32_t *)malloc(sizeof(uint32_t) * (Q->n_contigs + 1));
@@ -696,16 +709,16 @@ int64_t orc_anib_pair(const orc_genome *Q, const orc_genome *S, int fragsize, in
         stats[7]++;
         int strand = (int)((rpf ^ qpf) >> 31);
         int64_t r0 = rpf & POS_MASK, qpos = qpf & POS_MASK;
-        int64_t q0 = strand ? Q->n_pos - AN_K - qpos : qpos;
+        int64_t q0 = strand ? Q->n_pos - K - qpos : qpos;
         const uint8_t *Qs = strand ? Q->rc : Q->fw;
-        if (r0 - q0 == last_d[strand] && r0 >= last_r0[strand] && r0 + AN_K <= last_r1[strand]) continue;
+        if (r0 - q0 == last_d[strand] && r0 >= last_r0[strand] && r0 + K <= last_r1[strand]) continue;
         int64_t l = 0, rr = 0;
         while (r0 - l - 1 >= 0 && q0 - l - 1 >= 0 && R->fw[r0 - l - 1] < 4 && R->fw[r0 - l - 1] == Qs[q0 - l - 1]) ++l;
-        while (r0 + AN_K + rr < R->n_pos && q0 + AN_K + rr < Q->n_pos && R->fw[r0 + AN_K + rr] < 4 &&
-               R->fw[r0 + AN_K + rr] == Qs[q0 + AN_K + rr]) ++rr;
-        int64_t len = AN_K + l + rr, rs = r0 - l, qs = q0 - l;
+        while (r0 + K + rr < R->n_pos && q0 + K + rr < Q->n_pos && R->fw[r0 + K + rr] < 4 &&
+               R->fw[r0 + K + rr] == Qs[q0 + K + rr]) ++rr;
+        int64_t len = K + l + rr, rs = r0 - l, qs = q0 - l;
         last_d[strand] = r0 - q0; last_r0[strand] = rs; last_r1[strand] = rs + len;
-        if (len < AN_MINLEN) continue;
+        if (len < AB_MINLEN) continue;
         /* forward query interval of the match and the record it lies in */
         int64_t fa = strand ? Q->n_pos - qs - len : qs, fb = fa + len;
         uint32_t c = contig_of(Q->goff, Q->n_contigs, fa);

@@ -13,6 +13,7 @@ constexpr uint32_t AN_POSMASK = (1u << AN_POSBITS) - 1u, AN_REPBIT = 1u << AN_PO
 struct MinimizerIndex {
     bool valid = false;             // false after b200ani_reset_indexes: buffers are kept, content is rebuilt
     int maxocc = AN_MAXOCC;         // k-mers with more occurrences in the genome are not indexed
+    int k = AN_K, w = AN_W;         // seed length / minimizer window (ANIm: AN_K / AN_W; ANIb: AB_K / AB_W)
     int64_t cap_mini = 0;           // capacity of d_kmer / d_posflag
     uint32_t cap_bits = 0;          // capacity of d_table = 2^cap_bits slots
     int64_t n_mini = 0;

@@ -10,12 +10,12 @@
 
 #include "anim.cuh"
 
-int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc);
+int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc, bool anib);
 enum { SEED_BOTH_UNIQUE = 0, SEED_ALL = 1, SEED_EITHER_UNIQUE = 2 };  // anim_seed.cu
 
 // kernels defined in the other translation units
-template <int MODE> __global__ void seed_probe_kernel(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
-__global__ void seed_extend_kernel(const PairDesc *, int, const uint2 *, int64_t, uint64_t *, uint64_t *, unsigned long long *, unsigned long long, int);
+template <int MODE> __global__ void seed_probe_kernel(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long, int);
+__global__ void seed_extend_kernel(const PairDesc *, int, const uint2 *, int64_t, uint64_t *, uint64_t *, unsigned long long *, unsigned long long, int, int, int);
 __global__ void tie_fix_kernel(uint64_t *, uint64_t *, int64_t);
 __global__ void flag_unique_kernel(const uint64_t *, const uint64_t *, int64_t, uint8_t *);
 __global__ void contig_kernel(ChainArrays, const PairDesc *);
@@ -140,6 +140,7 @@ struct RowDump {
 static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, int fragsize, int maxmatch, void *out_v, RowDump *dump) {
     const bool anib = fragsize > 0;
     const int seedmode = anib ? SEED_BOTH_UNIQUE : (maxmatch ? SEED_ALL : SEED_EITHER_UNIQUE);
+    const int seed_k = anib ? AB_K : AN_K, min_len = anib ? AB_MINLEN : AN_MINLEN;
     const int64_t ANCHOR_CAP = W->anchor_cap, HIT_CAP = W->hit_cap;
     b200ani_anim_result *out = (b200ani_anim_result *)out_v;
     cudaStream_t st = ctx->stream;
@@ -149,12 +150,13 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     int64_t n_probes = 0;
     for (int p = 0; p < nb; ++p) {
         const Genome &R = ctx->genomes[pairs[2 * p]], &Q = ctx->genomes[pairs[2 * p + 1]];
+        const MinimizerIndex *Ri = anib ? R.index_b : R.index, *Qi = anib ? Q.index_b : Q.index;
         PairDesc &d = hp[p];
         d.r_seq = (const uint64_t *)R.d_seq; d.q_seq = (const uint64_t *)Q.d_seq;
         d.r_mask = R.d_mask; d.q_mask = Q.d_mask;
         d.r_goff = R.d_goff; d.q_goff = Q.d_goff;
-        d.r_table = R.index->d_table; d.r_table_bits = R.index->table_bits; d.r_bitmap = R.index->d_bitmap;
-        d.q_kmer = Q.index->d_kmer; d.q_posflag = Q.index->d_posflag; d.q_nmini = Q.index->n_mini;
+        d.r_table = Ri->d_table; d.r_table_bits = Ri->table_bits; d.r_bitmap = Ri->d_bitmap;
+        d.q_kmer = Qi->d_kmer; d.q_posflag = Qi->d_posflag; d.q_nmini = Qi->n_mini;
         d.probe_base = n_probes;
         d.r_npos = (int32_t)R.n_pos; d.q_npos = (int32_t)Q.n_pos;
         d.r_ncontigs = R.n_contigs; d.q_ncontigs = Q.n_contigs;
@@ -167,7 +169,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         d.q_fbase = anib ? Q.d_fbase : nullptr;
         d.fragsize = anib ? fragsize : 0;
         d.q_nfrags = anib ? Q.n_frags : 0;
-        if (!second) n_probes += Q.index->n_mini;
+        if (!second) n_probes += Qi->n_mini;
     }
     hp[nb] = hp[nb - 1];
     hp[nb].probe_base = n_probes;  // sentinel: end of the last pair's probe range
@@ -184,11 +186,11 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     if (n_probes) {
         int blocks = (int)std::min<int64_t>(ceil_div(n_probes, 256 * 16), (int64_t)ctx->sm_count * 8);
         if (seedmode == SEED_BOTH_UNIQUE)
-            seed_probe_kernel<SEED_BOTH_UNIQUE><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP);
+            seed_probe_kernel<SEED_BOTH_UNIQUE><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP, seed_k);
         else if (seedmode == SEED_ALL)
-            seed_probe_kernel<SEED_ALL><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP);
+            seed_probe_kernel<SEED_ALL><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP, seed_k);
         else
-            seed_probe_kernel<SEED_EITHER_UNIQUE><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP);
+            seed_probe_kernel<SEED_EITHER_UNIQUE><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP, seed_k);
         LAUNCHED(1);
         ctx->counters[CT_SEEDLAUNCH] += 1;
     }
@@ -201,7 +203,7 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     T0(ST_SEEDX);
     if (n_hits) {
         int blocks = (int)std::min<int64_t>(ceil_div(n_hits, 256), (int64_t)ctx->sm_count * 8);
-        seed_extend_kernel<<<blocks, 256, 0, st>>>(W->d_pairs, nb, W->hits, n_hits, W->keys_a, W->vals_a, W->counters, (unsigned long long)ANCHOR_CAP, seedmode);
+        seed_extend_kernel<<<blocks, 256, 0, st>>>(W->d_pairs, nb, W->hits, n_hits, W->keys_a, W->vals_a, W->counters, (unsigned long long)ANCHOR_CAP, seedmode, seed_k, min_len);
         LAUNCHED(1);
     }
     T1(ST_SEEDX);
@@ -574,8 +576,8 @@ static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs_in
     return 0;
 }
 
-static int prepare(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, AnimWorkspace **W) {
-    const int maxocc = AN_MAXOCC;  // one index serves --mum, --maxmatch and ANIb (the seed stage filters per mode)
+static int prepare(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, AnimWorkspace **W, bool anib) {
+    const int maxocc = AN_MAXOCC;  // the seed stage filters the repeated k-mers per mode; ANIb has its own index (shorter seeds)
     CK(cudaSetDevice(ctx->device));
     const int32_t ng = (int32_t)ctx->genomes.size();
     for (int64_t i = 0; i < 2 * m; ++i)
@@ -589,11 +591,11 @@ static int prepare(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, AnimWorksp
     for (int64_t i = 0; i < 2 * m; ++i) {
         Genome &g = ctx->genomes[pairs[i]];
         if (g.n_contigs >= 65535) FAIL(B200ANI_ERR_CAPACITY, "anim: genomes with >= 65535 records are not supported");
-        if (!index_valid(g.index, maxocc) && !seen[pairs[i]]) { seen[pairs[i]] = 1; todo.push_back(&g); }
+        if (!index_valid(anib ? g.index_b : g.index, maxocc) && !seen[pairs[i]]) { seen[pairs[i]] = 1; todo.push_back(&g); }
     }
     const bool any = !todo.empty();
     CK(cudaEventRecord(e0, st));
-    rc = build_indexes(ctx, todo, maxocc);
+    rc = build_indexes(ctx, todo, maxocc, anib);
     if (rc) return rc;
     CK(cudaEventRecord(e1, st));
     CK(cudaStreamSynchronize(st));
@@ -622,7 +624,7 @@ int b200ani_anim(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch
     CK(cudaEventCreate(&t0));
     CK(cudaEventCreate(&t1));
     CK(cudaEventRecord(t0, ctx->stream));
-    int rc = prepare(ctx, pairs, m, &W);
+    int rc = prepare(ctx, pairs, m, &W, false);
     if (rc == 0) rc = run_range(ctx, W, pairs, m, nofilter, 0, maxmatch, out, nullptr);
     CK(cudaEventRecord(t1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -638,7 +640,7 @@ int64_t b200ani_anim_alignments(b200ani_ctx *ctx, int32_t ref_id, int32_t qry_id
     if (!ctx || (!rows && cap > 0)) return B200ANI_ERR_ARG;
     int32_t pr[2] = {ref_id, qry_id};
     AnimWorkspace *W = nullptr;
-    int rc = prepare(ctx, pr, 1, &W);
+    int rc = prepare(ctx, pr, 1, &W, false);
     if (rc) return rc;
     RowDump dump;
     b200ani_anim_result res;
@@ -679,7 +681,7 @@ static int anib_common(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fr
     std::vector<int32_t> internal(2 * m);
     for (int64_t i = 0; i < m; ++i) { internal[2 * i] = pairs[2 * i + 1]; internal[2 * i + 1] = pairs[2 * i]; }
     AnimWorkspace *W = nullptr;
-    int rc = prepare(ctx, internal.data(), m, &W);
+    int rc = prepare(ctx, internal.data(), m, &W, true);
     if (rc) return rc;
     for (int64_t i = 0; i < m; ++i) {
         rc = ensure_fragments(ctx, ctx->genomes[pairs[2 * i]], fragsize);

@@ -8,28 +8,29 @@
 
 #include "anim.cuh"
 
-// k-mer at position p in little-endian packed form (first base in the low bits) + "all 16 bases clean".
-__device__ __forceinline__ bool kmer_at(const uint64_t *__restrict__ s, const uint32_t *__restrict__ m, int64_t p, int64_t n_pos, uint32_t &g) {
-    if (p < 0 || p + AN_K > n_pos) return false;
+// k-mer (k <= 16) at position p in little-endian packed form (first base in the low bits) + "all k bases clean".
+__device__ __forceinline__ bool kmer_at(const uint64_t *__restrict__ s, const uint32_t *__restrict__ m, int64_t p, int64_t n_pos, int k, uint32_t &g) {
+    if (p < 0 || p + k > n_pos) return false;
     int64_t w = p >> 5;
     int sh = (int)(p & 31);
     uint64_t a = s[w] >> (2 * sh);
     uint64_t ma = (uint64_t)m[w] >> sh;
-    if (sh > 16) {
+    if (sh + k > 32) {
         a |= s[w + 1] << (64 - 2 * sh);
         ma |= (uint64_t)m[w + 1] << (32 - sh);
     }
-    g = (uint32_t)a;
-    return (ma & 0xffffu) == 0;
+    const uint32_t kmask = k == 16 ? 0xffffffffu : (1u << (2 * k)) - 1u;
+    g = (uint32_t)a & kmask;
+    return (ma & ((1ull << k) - 1ull)) == 0;
 }
 
 // hash of the canonical k-mer, or 2^32 if the position carries no usable k-mer (masked or palindrome)
-__device__ __forceinline__ uint64_t kmer_hash(const uint64_t *s, const uint32_t *m, int64_t p, int64_t n_pos, uint32_t &canon, uint32_t &orient) {
+__device__ __forceinline__ uint64_t kmer_hash(const uint64_t *s, const uint32_t *m, int64_t p, int64_t n_pos, int k, uint32_t &canon, uint32_t &orient) {
     uint32_t g;
-    if (!kmer_at(s, m, p, n_pos, g)) return 1ull << 32;
+    if (!kmer_at(s, m, p, n_pos, k, g)) return 1ull << 32;
     uint32_t y = __brev(g);
-    uint32_t f = ((y & 0x55555555u) << 1) | ((y >> 1) & 0x55555555u);  // first base most significant
-    uint32_t r = ~g;                                                    // reverse complement, same convention
+    uint32_t f = (((y & 0x55555555u) << 1) | ((y >> 1) & 0x55555555u)) >> (32 - 2 * k);  // first base most significant
+    uint32_t r = ~g & (k == 16 ? 0xffffffffu : (1u << (2 * k)) - 1u);                     // reverse complement, same convention
     if (f == r) return 1ull << 32;
     canon = f < r ? f : r;
     orient = r < f;
@@ -56,7 +57,7 @@ struct GenomeDesc {
 // one launch and into one array: key = genome << 32 | canonical k-mer, value = position | orientation << 31.
 constexpr int SEL_TILE = 2048, SEL_HALO = AN_W - 1;
 __global__ void __launch_bounds__(256) minimizer_select_kernel(const GenomeDesc *__restrict__ gd, int n_genomes, int64_t n_tiles, uint64_t *__restrict__ keys,
-                                                               uint32_t *__restrict__ vals, unsigned long long *__restrict__ n_out, unsigned long long cap) {
+                                                               uint32_t *__restrict__ vals, unsigned long long *__restrict__ n_out, unsigned long long cap, int k, int w) {
     __shared__ uint64_t hv[SEL_TILE + 2 * SEL_HALO];
     __shared__ unsigned int s_n;
     __shared__ unsigned long long s_base;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256) minimizer_select_kernel(const GenomeDesc 
         if (threadIdx.x == 0) s_n = 0;
         for (int i = threadIdx.x; i < SEL_TILE + 2 * SEL_HALO; i += 256) {
             uint32_t c, o;
-            hv[i] = kmer_hash(s, m, p0 - SEL_HALO + i, n_pos, c, o);
+            hv[i] = kmer_hash(s, m, p0 - SEL_HALO + i, n_pos, k, c, o);
         }
         __syncthreads();
         for (int i = threadIdx.x; i < SEL_TILE; i += 256) {
@@ -83,16 +84,16 @@ __global__ void __launch_bounds__(256) minimizer_select_kernel(const GenomeDesc 
             bool chosen = false;
             if (p < n_pos && h != (1ull << 32)) {
 #pragma unroll
-                for (int o = 0; o < AN_W; ++o) {  // window [p-o, p-o+W-1]
-                    bool is_min = true;
+                for (int o = 0; o < AN_W; ++o) {  // window [p-o, p-o+w-1], w <= AN_W
+                    bool is_min = o < w;
 #pragma unroll
-                    for (int x = 0; x < AN_W; ++x) is_min = is_min && !(hv[i + SEL_HALO - o + x] < h);
+                    for (int x = 0; x < AN_W; ++x) is_min = is_min && (x >= w || !(hv[i + SEL_HALO - o + x] < h));
                     chosen = chosen || is_min;
                 }
             }
             if (chosen) {
                 uint32_t canon, orient;
-                kmer_hash(s, m, p, n_pos, canon, orient);
+                kmer_hash(s, m, p, n_pos, k, canon, orient);
                 const unsigned int slot = atomicAdd(&s_n, 1u);
                 s_kmer[slot] = canon;
                 s_val[slot] = (uint32_t)p | (orient << 31);
@@ -173,20 +174,22 @@ void free_index(MinimizerIndex *ix, cudaStream_t st) {
 }
 void invalidate_index(MinimizerIndex *ix) { if (ix) ix->valid = false; }
 bool index_valid(const MinimizerIndex *ix, int maxocc) { return ix && ix->valid && ix->maxocc == maxocc; }
+static_assert(AB_K <= 16 && AN_K <= 16 && AB_W <= AN_W, "k-mers are packed into 32 bits; the selection tile's halo is AN_W - 1");
 
 // Build (or rebuild) the indexes of many genomes.  The genomes go through the pipeline together -- one selection
 // launch, one radix sort by (genome, k-mer), one marking pass, one table-insert launch, one radix sort by (genome,
 // position), one split -- instead of a dozen small launches per genome; scratch comes from one reusable workspace
 // and a genome's index arrays are kept across rebuilds, so steady-state builds allocate nothing.  Two host
 // synchronisations per chunk (number of selected minimizers, kept entries per genome).
-int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc) {
+int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc, bool anib) {
+    const int k = anib ? AB_K : AN_K, w = anib ? AB_W : AN_W;
     if (todo.empty()) return 0;
     cudaStream_t st = ctx->stream;
     constexpr size_t PER_ENTRY = 36;      // keys, keys2, key4 (u64) + vals, vals2, idx2 (u32); key3 / idx reuse keys / vals
     constexpr int MAX_CHUNK = 256;        // genomes per chunk (mark_kernel's shared counters, 8 bits of genome id)
     const size_t G_all = todo.size();
     size_t done = 0;
-    double fill = 0.5;                    // selected minimizers per position the scratch is sized for (w = 5: ~0.36)
+    double fill = anib ? 0.8 : 0.5;       // selected minimizers per position the scratch is sized for (w = 5: ~0.36, w = 2: ~0.7)
     while (done < G_all) {
         // ---- chunk [done, end): as many genomes as fit a workspace of at most WS_MAX bytes
         constexpr size_t WS_MAX = (size_t)12 << 30;
@@ -237,7 +240,7 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc) {
         CK(cudaMemcpyAsync(d_gd, hd.data(), sizeof(GenomeDesc) * G, cudaMemcpyHostToDevice, st));
         {
             int blocks = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 6);
-            minimizer_select_kernel<<<blocks, 256, 0, st>>>(d_gd, G, n_tiles, keys, vals, d_cnt, (unsigned long long)cap);
+            minimizer_select_kernel<<<blocks, 256, 0, st>>>(d_gd, G, n_tiles, keys, vals, d_cnt, (unsigned long long)cap, k, w);
             CK(cudaGetLastError());
         }
         unsigned long long h_cnt[1 + MAX_CHUNK];
@@ -265,18 +268,19 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc) {
             const int h_nu = (int)h_cnt[1 + k];
             uint32_t bits = 4;
             while ((1ll << bits) < 2ll * h_nu) ++bits;
-            if (!g.index) {  // prefer the buffers of a released genome that are large enough
+            MinimizerIndex *&slot = anib ? g.index_b : g.index;
+            if (!slot) {  // prefer the buffers of a released genome that are large enough
                 for (size_t x = 0; x < ctx->spare_indexes.size(); ++x) {
                     MinimizerIndex *sp = ctx->spare_indexes[x];
                     if (sp->cap_bits >= bits && sp->cap_mini >= h_nu + 1) {
-                        g.index = sp;
+                        slot = sp;
                         ctx->spare_indexes.erase(ctx->spare_indexes.begin() + x);
                         break;
                     }
                 }
             }
-            MinimizerIndex *ix = g.index ? g.index : new MinimizerIndex();
-            g.index = ix;
+            MinimizerIndex *ix = slot ? slot : new MinimizerIndex();
+            slot = ix;
             ix->n_mini = h_nu;
             ix->table_bits = bits;
             if (ix->cap_bits < bits || ix->cap_mini < h_nu + 1) {  // first build (or a bigger genome): allocate once
@@ -298,6 +302,7 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc) {
             n_kept += h_nu;
             ix->valid = true;
             ix->maxocc = maxocc;
+            ix->k = k; ix->w = w;
         }
         CK(cudaMemcpyAsync(d_gd, hd.data(), sizeof(GenomeDesc) * G, cudaMemcpyHostToDevice, st));
         if (ns) {

@@ -30,6 +30,9 @@
 #define AB_GAP 5
 #define AB_BREAK 250
 #define AB_TILE 256
+#define AB_K 13
+#define AB_W 2
+#define AB_MINLEN 14
 #define AB_BRIDGE_GAP 250
 #define AB_BRIDGE_DD 120
 #define AB_MINPIECE 11

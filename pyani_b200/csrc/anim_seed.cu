@@ -80,7 +80,7 @@ __device__ __forceinline__ bool seed_ok(int mode, uint32_t rpf, uint32_t qpf) {
 // divergent work, so the warps in flight are all waiting on independent loads.
 template <int MODE>
 __global__ void __launch_bounds__(256, 4) seed_probe_kernel(const PairDesc *__restrict__ pairs, int n_pairs, int64_t n_probes, uint2 *__restrict__ hits,
-                                                         unsigned long long *__restrict__ n_hits, unsigned long long cap) {
+                                                         unsigned long long *__restrict__ n_hits, unsigned long long cap, int seed_k) {
     // Each block walks contiguous chunks of PROBE_CHUNK probes, PROBE_ILP probes per thread per step so that the
     // dependent loads (k-mer -> presence word -> table slot) of several probes are in flight together.  The pair a
     // probe belongs to is searched once per chunk and then advanced linearly; its descriptor fields stay in
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256, 4) seed_probe_kernel(const PairDesc *__re
                 const int nstrand = __shfl_sync(0xffffffffu, strand, nb & 31);
                 const int nkey = __shfl_sync(0xffffffffu, key, nb & 31);
                 const int nqp = __shfl_sync(0xffffffffu, qp, nb & 31);
-                if (h && nb >= 0 && nb < 32 && nhit && npair == pr[k] && nstrand == strand && nkey == key && abs(nqp - qp) <= AN_K) h = false;
+                if (h && nb >= 0 && nb < 32 && nhit && npair == pr[k] && nstrand == strand && nkey == key && abs(nqp - qp) <= seed_k) h = false;
                 const uint32_t m = __ballot_sync(0xffffffffu, h);
                 if (m) {  // one shared-memory atomic per warp
                     unsigned int bslot = 0;
@@ -208,9 +208,9 @@ __global__ void __launch_bounds__(256, 4) seed_probe_kernel(const PairDesc *__re
     }
 }
 
-template __global__ void seed_probe_kernel<SEED_BOTH_UNIQUE>(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
-template __global__ void seed_probe_kernel<SEED_ALL>(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
-template __global__ void seed_probe_kernel<SEED_EITHER_UNIQUE>(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long);
+template __global__ void seed_probe_kernel<SEED_BOTH_UNIQUE>(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long, int);
+template __global__ void seed_probe_kernel<SEED_ALL>(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long, int);
+template __global__ void seed_probe_kernel<SEED_EITHER_UNIQUE>(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long, int);
 
 // One anchor of pair `pi`: ANIm -> as is; ANIb (P.fragsize > 0) -> clipped to the query's fragments, one piece per
 // fragment it overlaps (pieces shorter than AB_MINPIECE are dropped), the fragment id goes into the sort key.
@@ -265,7 +265,7 @@ __device__ __forceinline__ void emit_anchor(AnchorStage &S, const PairDesc &P, i
 // minimizer already covers, extend the others to maximal exact matches.  key/val encoding: anim.cuh.
 __global__ void __launch_bounds__(256) seed_extend_kernel(const PairDesc *__restrict__ pairs, int n_pairs, const uint2 *__restrict__ hits, int64_t n_hits,
                                                           uint64_t *__restrict__ keys, uint64_t *__restrict__ vals,
-                                                          unsigned long long *__restrict__ n_anchors, unsigned long long cap, int mode) {
+                                                          unsigned long long *__restrict__ n_anchors, unsigned long long cap, int mode, int seed_k, int min_len) {
     __shared__ AnchorStage stage;
     if (threadIdx.x == 0) stage.n = 0;
     __syncthreads();
@@ -282,35 +282,38 @@ __global__ void __launch_bounds__(256) seed_extend_kernel(const PairDesc *__rest
         const uint32_t qpf = P.q_posflag[t];
         const int strand = (int)((rpf ^ qpf) >> 31);
         const int64_t r0 = rpf & AN_POSMASK, qpos = qpf & AN_POSMASK;
-        const int64_t q0 = strand ? (int64_t)P.q_npos - AN_K - qpos : qpos;
+        const int64_t q0 = strand ? (int64_t)P.q_npos - seed_k - qpos : qpos;
         SeqView R{P.r_seq, P.r_mask, P.r_npos, 0}, Q{P.q_seq, P.q_mask, P.q_npos, strand};
-        // redundancy: the minimizer just before this one in view order seeds the same match if it hits the
-        // same diagonal and everything in between matches -> let that one report it
+        // redundancy: an earlier minimizer (in view order) that lies in the same exact match and qualifies as a seed on
+        // this diagonal reports the match -> walk back through the query's minimizers while the bases keep matching;
+        // the walk passes over minimizers that do not qualify (repeated k-mers), so only the leftmost qualifying seed of
+        // a match extends and emits it (a 500 kb match holds 10^5 seeds; ANIb clips it into hundreds of pieces)
         {
-            int64_t tn = strand ? t + 1 : t - 1;
-            if (tn >= 0 && tn < P.q_nmini) {
-                uint32_t qpfn = P.q_posflag[tn], rpfn;
-                int64_t qn = strand ? (int64_t)P.q_npos - AN_K - (qpfn & AN_POSMASK) : (qpfn & AN_POSMASK);
-                bool nb_same_diag = false;
-                if (qn < q0 && q0 - qn <= 64) {
-                    uint32_t cursor = ~0u;
-                    while (!nb_same_diag && table_next(P.r_table, P.r_table_bits, P.q_kmer[tn], cursor, rpfn))
-                        nb_same_diag = seed_ok(mode, rpfn, qpfn) && (int)((rpfn ^ qpfn) >> 31) == strand && (int64_t)(rpfn & AN_POSMASK) - qn == r0 - q0;
+            bool redundant = false;
+            int64_t covered = q0;  // view positions [covered, q0 + k) match on the diagonal
+            for (int step = 1; step <= 32 && !redundant; ++step) {
+                const int64_t tn = strand ? t + step : t - step;
+                if (tn < 0 || tn >= P.q_nmini) break;
+                const uint32_t qpfn = P.q_posflag[tn];
+                const int64_t qn = strand ? (int64_t)P.q_npos - seed_k - (qpfn & AN_POSMASK) : (qpfn & AN_POSMASK);
+                if (qn >= covered || covered - qn > 64) break;
+                bool same = true;
+                for (int64_t x = qn; x < covered && same; ++x) {
+                    int a = view_code(R, x + (r0 - q0)), b = view_code(Q, x);
+                    same = a < 4 && a == b;
                 }
-                if (nb_same_diag) {
-                    bool same = true;
-                    for (int64_t x = qn + AN_K; x < q0 && same; ++x) {
-                        int a = view_code(R, x + (r0 - q0)), b = view_code(Q, x);
-                        same = a < 4 && a == b;
-                    }
-                    if (same) break;  // redundant seed
-                }
+                if (!same) break;  // the match starts after qn: no earlier seed in it
+                covered = qn;
+                uint32_t cursor = ~0u, rpfn;
+                while (!redundant && table_next(P.r_table, P.r_table_bits, P.q_kmer[tn], cursor, rpfn))
+                    redundant = seed_ok(mode, rpfn, qpfn) && (int)((rpfn ^ qpfn) >> 31) == strand && (int64_t)(rpfn & AN_POSMASK) - qn == r0 - q0;
             }
+            if (redundant) break;
         }
         int64_t l = match_left(R, Q, r0, q0);
-        int64_t rr = match_right(R, Q, r0 + AN_K, q0 + AN_K);
-        int64_t len = AN_K + l + rr;
-        if (len < AN_MINLEN) break;
+        int64_t rr = match_right(R, Q, r0 + seed_k, q0 + seed_k);
+        int64_t len = seed_k + l + rr;
+        if (len < min_len) break;
         // Exact matches are symmetric in the two genomes (every seed rule above is symmetric in the two genomes and
         // the minimizer selection is strand-symmetric), so the opposite-direction comparison gets its anchors from the same
         // seeds: forward (r,q) -> (q,r); reverse-strand coordinates swap roles through both genome lengths.

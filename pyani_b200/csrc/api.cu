@@ -63,11 +63,13 @@ static void release_genome(b200ani_ctx *ctx, Genome &g, cudaStream_t st) {
     cudaFreeAsync(g.d_goff, st);
     if (g.d_fbase) cudaFreeAsync(g.d_fbase, st);
     g.d_fbase = nullptr;
-    if (g.index) {  // keep the buffers for the next genome of similar size
-        invalidate_index(g.index);
-        ctx->spare_indexes.push_back(g.index);
+    for (MinimizerIndex **slot : {&g.index, &g.index_b}) {
+        if (*slot) {  // keep the buffers for the next genome of similar size
+            invalidate_index(*slot);
+            ctx->spare_indexes.push_back(*slot);
+        }
+        *slot = nullptr;
     }
-    g.index = nullptr;
 }
 extern "C" {
 
@@ -84,7 +86,7 @@ int b200ani_reset_indexes(b200ani_ctx *ctx) {
     if (!ctx) return B200ANI_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (auto &g : ctx->genomes) invalidate_index(g.index);  // buffers stay, content is rebuilt on demand
+    for (auto &g : ctx->genomes) { invalidate_index(g.index); invalidate_index(g.index_b); }  // buffers stay, content is rebuilt on demand
     return B200ANI_OK;
 }
 

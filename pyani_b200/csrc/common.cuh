@@ -31,7 +31,8 @@ struct Genome {
     uint32_t *d_mask = nullptr;
     uint64_t *d_goff = nullptr;
     std::vector<uint64_t> h_goff;
-    MinimizerIndex *index = nullptr;  // built lazily by the first ANIm call that needs it
+    MinimizerIndex *index = nullptr;    // ANIm seed index, built lazily by the first ANIm call that needs it
+    MinimizerIndex *index_b = nullptr;  // ANIb seed index (shorter seeds), built lazily by the first ANIb call
     // ANIb fragment table (built lazily for the requested fragment size): record c holds fragments fbase[c]..fbase[c+1]-1
     uint32_t *d_fbase = nullptr;
     int frag_size = 0;

@@ -3,8 +3,8 @@
 blastn cannot run here; the pin is the 12 .blast_tab files of the reference's fixtures reduced by the reference's
 own parse_blast_tab (tests/golden/anib_parse_blast_tab.json).  Tolerance = the reference's own concordance
 tolerance for ANIb (tests/test_concordance.py:118-153,250-253): 0.2 percentage points where identity >= 90 %,
-5 points below.  Measured: |delta| <= 0.005 for the 99.99 % pair, +0.9 .. +1.6 points for the 80-84 % pairs, aligned
-length 6-13 % below BLAST's there (fragments at ~74 % identity with ~50 gap columns that BLAST still aligns end to end).
+5 points below.  Measured: |delta| <= 0.005 for the 99.99 % pair, +0.7 .. +1.3 points for the 80-84 % pairs, aligned
+length 4-10 % below BLAST's there (fragments at ~74 % identity with ~50 gap columns that BLAST still aligns end to end).
 """
 import json
 
@@ -28,8 +28,8 @@ def test_anib_identity_within_reference_tolerance():
         mean_pid = res["pid_milli_sum"] / res["n_pass"] / 1000
         tol = 0.2 if pid >= 90 else 5.0
         assert abs(mean_pid - pid) < tol, (name, mean_pid, pid)
-        assert 0.85 * aln < res["aln_length"] < 1.05 * aln, (name, res["aln_length"], aln)
-        assert abs(mean_pid - pid) < 1.8
+        assert 0.88 * aln < res["aln_length"] < 1.05 * aln, (name, res["aln_length"], aln)
+        assert abs(mean_pid - pid) < 1.5
         assert res["n_pass"] == len(rows) and (rows[:, 1] == rows[:, 2] + rows[:, 3] + rows[:, 4]).all()
         if pid >= 99:
             assert abs(res["aln_length"] - aln) < 2500 and res["n_frags"] in (3940, 3964)
