@@ -83,6 +83,17 @@ class Engine:
         arr, off, ids = read_fasta(path)
         return self.add_genome(arr, off, Path(path).stem, ids)
 
+    def add_fasta_many(self, paths, threads: int = 0) -> List[int]:
+        """Ingest many FASTA files with a thread pool (parse + md5 in parallel), stage them in input order.
+        The per-file records (md5, length, ...) are kept in ``self.ingested`` for the caller's bookkeeping
+        (pyani indexes genomes by md5, `pyani_orm.py:194,572`)."""
+        from .fasta import ingest
+
+        recs = ingest(paths, threads)
+        gids = [self.add_genome(r["residues"], r["offsets"], r["stem"], r["ids"]) for r in recs]
+        self.ingested = [{k: v for k, v in r.items() if k not in ("residues", "offsets")} for r in recs]
+        return gids
+
     def clear(self):
         """Drop all staged genomes (ids restart at 0)."""
         self._check(self._lib.b200ani_clear(self._h), "clear")

@@ -136,3 +136,29 @@ def test_anim_matrices_match_cellwise_fill():
     for k in got:
         assert list(got[k].index) == ids
         assert np.array_equal(got[k].values, want[k].values, equal_nan=True), k
+
+
+def test_parallel_fasta_ingest(tmp_path):
+    """f3: threaded ingest returns, per file, what the reference derives in three Biopython passes + one md5 pass."""
+    import hashlib
+
+    from pyani_b200 import fasta
+
+    files = []
+    rng = np.random.default_rng(5)
+    for i in range(6):
+        recs = [rng.choice(list("ACGTN"), size=int(rng.integers(50, 400))) for _ in range(int(rng.integers(1, 4)))]
+        p = tmp_path / f"g{i}.fna"
+        with open(p, "w") as fh:
+            for j, r in enumerate(recs):
+                s = "".join(r)
+                fh.write(f">rec{j} some description\n" + "\n".join(s[k:k + 60] for k in range(0, len(s), 60)) + "\n")
+        files.append((p, recs))
+    out = fasta.ingest([p for p, _ in files], threads=4)
+    assert [o["stem"] for o in out] == [p.stem for p, _ in files]  # input order kept
+    for o, (p, recs) in zip(out, files):
+        assert o["md5"] == hashlib.md5(p.read_bytes()).hexdigest()
+        assert o["length"] == sum(len(r) for r in recs) and o["ids"] == [f"rec{j}" for j in range(len(recs))]
+        assert bytes(o["residues"]).decode() == "".join("".join(r) for r in recs)
+        a, off, ids = fasta.read_fasta(p)
+        assert (a == o["residues"]).all() and (off == o["offsets"]).all()
