@@ -43,6 +43,10 @@
 #define AB_K 13          /* ANIb seed k-mer length ... */
 #define AB_W 2           /* ... and minimizer window: every exact match >= AB_K + AB_W - 1 = 14 is seeded */
 #define AB_MINLEN 14     /* ANIb minimum exact-match length (blastn words are 11; shorter seeds stop paying: k-mers must stay unique) */
+#define AB_SCREEN_W 28   /* ANIb screen: chains with fewer matched bases than this must pass the ungapped test ... */
+#define AB_SCREEN_MIN 12 /* ... minimum summed score of the two ungapped end extensions (+2 / -3) ... */
+#define AB_SCREEN_LEN 64 /* ... over at most this many bases per end ... */
+#define AB_SCREEN_DROP 20 /* ... each stopping once it falls this far below its best (X-drop) */
 #define AB_BRIDGE_GAP 250 /* ANIb bridging: max distance between two candidate HSPs of a fragment that are joined ... */
 #define AB_BRIDGE_DD 120  /* ... and max diagonal offset between them (blastn's gapped extension is not banded) */
 #define AB_MINPIECE 11   /* shortest anchor piece kept after clipping to a fragment (blastn word size) */

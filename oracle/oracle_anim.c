@@ -807,8 +807,6 @@ int64_t orc_anib_pair(const orc_genome *Q, const orc_genome *S, int fragsize, in
     int64_t nc = 0;
     for (int64_t h = 0; h < na; ++h) {
         if (head[h] != (int32_t)h) continue;
-        stats[3]++;
-        out[5] += 1;
         const fanchor *f = &A[h], *l = &A[tail[h]];
         const uint8_t *Qs = f->strand ? Q->rc : Q->fw;
         uint32_t rc = rc_of[h];
@@ -823,6 +821,27 @@ int64_t orc_anib_pair(const orc_genome *Q, const orc_genome *S, int fragsize, in
         int64_t q_lo = f->strand ? Q->n_pos - fb : fa, q_hi = f->strand ? Q->n_pos - fa : fb;
         int64_t rs = f->r, qs = f->q, re = (int64_t)l->r + l->len, qe = (int64_t)l->q + l->len;
         int64_t score = ssum[h] + wsum[h] * AB_MATCH, errs = esum[h];
+        /* screen (what blastn's ungapped extension does before the gapped one): a chain with fewer than AB_SCREEN_W matched
+         * bases -- in practice a lone 14..27-mer, mostly chance matches -- is a candidate only if the ungapped X-drop
+         * extensions of its two ends score at least AB_SCREEN_MIN together */
+        if (wsum[h] < AB_SCREEN_W) {
+            int tot = 0;
+            for (int side = 0; side < 2; ++side) {
+                int best = 0, cur = 0;
+                for (int x = 0; x < AB_SCREEN_LEN; ++x) {
+                    int64_t rp = side ? re + x : rs - 1 - x, qp = side ? qe + x : qs - 1 - x;
+                    if (rp < r_lo || rp >= r_hi || qp < q_lo || qp >= q_hi) break;
+                    uint8_t a = R->fw[rp], b = Qs[qp];
+                    cur += (a == b && a < 4) ? AB_MATCH : -AB_MISMATCH;
+                    if (cur > best) best = cur;
+                    if (best - cur > AB_SCREEN_DROP) break;
+                }
+                tot += best;
+            }
+            if (tot < AB_SCREEN_MIN) continue;
+        }
+        stats[3]++;
+        out[5] += 1;
         for (int side = 0; side < 2; ++side) {
             for (int t = 0; t < AN_MAXTILES; ++t) {
                 int64_t ar = side ? r_hi - re : rs - r_lo, aq = side ? q_hi - qe : qs - q_lo;

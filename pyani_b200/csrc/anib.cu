@@ -4,6 +4,34 @@
 // this file only turns finished segments into BLAST-like columns and reduces them.
 #include "anim.cuh"
 
+// Screen before the gapped extension (what blastn's ungapped extension does): a chain with fewer than AB_SCREEN_W
+// matched bases -- in practice a lone 14..27-mer, mostly chance matches -- stays a candidate only if the ungapped X-drop
+// extensions of its two ends (+2 / -3, at most AB_SCREEN_LEN bases each, inside the record and the fragment) score at
+// least AB_SCREEN_MIN together.  Takes out ~95 % of the candidates of a distant pair before any DP cell is computed.
+__global__ void anib_screen_kernel(SegArrays S, ChainArrays A, const PairDesc *__restrict__ pairs, uint8_t *__restrict__ keep) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S.n) return;
+    if (A.wsum[S.head[s]] >= AB_SCREEN_W) { keep[s] = 1; return; }
+    const PairDesc &P = pairs[S.pair[s]];
+    SeqView R{P.r_seq, P.r_mask, P.r_npos, 0}, Q{P.q_seq, P.q_mask, P.q_npos, S.strand[s]};
+    const int rs = S.rs[s], re = S.re[s], qs = S.qs[s], qe = S.qe[s];
+    const int r_lo = S.r_lo[s], r_hi = S.r_hi[s], q_lo = S.q_lo[s], q_hi = S.q_hi[s];
+    int tot = 0;
+    for (int side = 0; side < 2; ++side) {
+        int best = 0, cur = 0;
+        for (int x = 0; x < AB_SCREEN_LEN; ++x) {
+            const int rp = side ? re + x : rs - 1 - x, qp = side ? qe + x : qs - 1 - x;
+            if (rp < r_lo || rp >= r_hi || qp < q_lo || qp >= q_hi) break;
+            const int a = view_code(R, rp), b = view_code(Q, qp);
+            cur += (a == b && a < 4) ? AB_MATCH : -AB_MISMATCH;
+            best = max(best, cur);
+            if (best - cur > AB_SCREEN_DROP) break;
+        }
+        tot += best;
+    }
+    keep[s] = tot >= AB_SCREEN_MIN;
+}
+
 struct AnibSeg {
     int *pair, *frag, *score, *nident, *mism, *gaps, *qlen;
     uint8_t *pass;

@@ -41,6 +41,7 @@ struct AnibSeg {
     int *pair, *frag, *score, *nident, *mism, *gaps, *qlen;
     uint8_t *pass;
 };
+__global__ void anib_screen_kernel(SegArrays, ChainArrays, const PairDesc *, uint8_t *);
 __global__ void anib_segment_kernel(SegArrays, const uint64_t *, AnibSeg);
 __global__ void anib_reduce_kernel(AnibSeg, int64_t, b200ani_anib_result *, int *, uint8_t *);
 __global__ void anib_init_kernel(const PairDesc *, int, b200ani_anib_result *);
@@ -351,6 +352,21 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     uint32_t *ext_list[2] = {nullptr, nullptr};
     DA(ext_list[0], 2 * n_seg); DA(ext_list[1], 2 * n_seg);
 
+    if (n_seg && anib) {
+        // ---- ANIb: screen the weak candidates (ungapped end extensions) before any gapped DP; survivors are re-listed
+        segment_init_kernel<<<GRID(n_seg)>>>(A, W->d_pairs, seg_head, S, AB_MATCH);
+        anib_screen_kernel<<<GRID(n_seg)>>>(S, A, W->d_pairs, W->flag);
+        LAUNCHED(2);
+        size_t tb = W->cub_bytes;
+        cub::DeviceSelect::Flagged(W->cub_tmp, tb, seg_head, W->flag, (int *)task_idx2, W->changed, n_seg, st);
+        int hk = 0;
+        CK(cudaMemcpyAsync(&hk, W->changed, sizeof hk, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(seg_head, task_idx2, sizeof(int) * n_seg, cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->counters[CT_SEGMENTS] -= n_seg - hk;
+        n_seg = hk;
+        S.n = n_seg;
+    }
     if (n_seg) {
         T0(ST_EXTDP);
         segment_init_kernel<<<GRID(n_seg)>>>(A, W->d_pairs, seg_head, S, anib ? AB_MATCH : AN_MATCH);

@@ -33,6 +33,10 @@
 #define AB_K 13
 #define AB_W 2
 #define AB_MINLEN 14
+#define AB_SCREEN_W 28
+#define AB_SCREEN_MIN 12
+#define AB_SCREEN_LEN 64
+#define AB_SCREEN_DROP 20
 #define AB_BRIDGE_GAP 250
 #define AB_BRIDGE_DD 120
 #define AB_MINPIECE 11
