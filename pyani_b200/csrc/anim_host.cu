@@ -58,8 +58,8 @@ static const char *kStageNames[B200ANI_N_STAGES] = {"index", "seed", "sort", "li
 static const char *kCounterNames[B200ANI_N_STAGES] = {"probes", "seed_hits", "anchors", "links", "cut_links", "segments", "gap_cells", "ext_cells",
                                                       "ext_tiles", "alignments", "launches", "gap_tasks", "pairs", "ext_dp_launches", "gap_dp_launches", "seed_launches"};
 
-constexpr int MAX_BATCH_PAIRS = 1280;
-constexpr int64_t ANCHOR_CAP_DEFAULT = 48ll << 20;  // anchors of one batch (overridable: B200ANI_ANCHOR_CAP, used by the batch-split test)
+constexpr int MAX_BATCH_PAIRS = 2560;
+constexpr int64_t ANCHOR_CAP_DEFAULT = 96ll << 20;  // anchors of one batch (overridable: B200ANI_ANCHOR_CAP, used by the batch-split test)
 constexpr int64_t HIT_CAP_DEFAULT = 192ll << 20;    // seed hits of one batch, 8 B each (B200ANI_HIT_CAP)
 constexpr int EXT_TILES_PER_LAUNCH = 8;
 
@@ -185,7 +185,13 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     // ---- seeds -> anchors: probe (latency bound, uniform) then extend (one thread per hit)
     T0(ST_SEED);
     if (n_probes) {
-        int blocks = (int)std::min<int64_t>(ceil_div(n_probes, 256 * 16), (int64_t)ctx->sm_count * 8);
+        // one resident wave: every block walks its chunks in a grid-stride loop, so more blocks than fit at once would only
+        // sweep the pairs (and their reference tables) a second time
+        int per_sm = 0;
+        if (seedmode == SEED_BOTH_UNIQUE) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_probe_kernel<SEED_BOTH_UNIQUE>, 256, 0));
+        else if (seedmode == SEED_ALL) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_probe_kernel<SEED_ALL>, 256, 0));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_probe_kernel<SEED_EITHER_UNIQUE>, 256, 0));
+        int blocks = (int)std::min<int64_t>(ceil_div(n_probes, 256 * 16), (int64_t)ctx->sm_count * std::max(per_sm, 1));
         if (seedmode == SEED_BOTH_UNIQUE)
             seed_probe_kernel<SEED_BOTH_UNIQUE><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP, seed_k);
         else if (seedmode == SEED_ALL)
