@@ -113,10 +113,10 @@ __global__ void __launch_bounds__(256) minimizer_select_kernel(const GenomeDesc 
 }
 
 // After the sort by (genome, k-mer): entries of k-mers that occur at most maxocc times in their genome are kept, the
-// repeated ones get the "repeated" flag.  Emits the key of the second sort (genome << 30 | position; dropped entries
+// repeated ones get the "repeated" flag.  Emits the key of the second sort (genome << posbits | position; dropped entries
 // get ~0 and end up behind everything) and counts the kept entries per genome.
 __global__ void __launch_bounds__(256) mark_kernel(const uint64_t *__restrict__ sorted, uint32_t *__restrict__ vals, int64_t n, uint64_t *__restrict__ key2,
-                                                   uint32_t *__restrict__ idx, unsigned long long *__restrict__ counts, int maxocc) {
+                                                   uint32_t *__restrict__ idx, unsigned long long *__restrict__ counts, int maxocc, int posbits) {
     __shared__ unsigned int s_cnt[256];
     s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) mark_kernel(const uint64_t *__restrict__ 
         uint32_t v = vals[i];
         if (run > 1) { v |= AN_REPBIT; vals[i] = v; }
         const bool kept = run <= maxocc;
-        key2[i] = kept ? ((uint64_t)gid << AN_POSBITS) | (v & AN_POSMASK) : ~0ull;
+        key2[i] = kept ? ((uint64_t)gid << posbits) | (v & AN_POSMASK) : ~0ull;
         idx[i] = (uint32_t)i;
         if (kept) atomicAdd(&s_cnt[gid & 255], 1u);
     }
@@ -154,10 +154,10 @@ __global__ void table_insert_kernel(const uint64_t *__restrict__ sorted, const u
 
 // after the sort by (genome, position): write each genome's by-position lists
 __global__ void split_bypos_kernel(const uint64_t *__restrict__ key2s, const uint32_t *__restrict__ idxs, int64_t n_kept, const uint64_t *__restrict__ sorted,
-                                   const uint32_t *__restrict__ vals, const GenomeDesc *__restrict__ gd) {
+                                   const uint32_t *__restrict__ vals, const GenomeDesc *__restrict__ gd, int posbits) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_kept) return;
-    const GenomeDesc &g = gd[key2s[i] >> AN_POSBITS];
+    const GenomeDesc &g = gd[key2s[i] >> posbits];
     const uint32_t src = idxs[i];
     const int64_t o = i - g.out0;
     g.kmer_out[o] = (uint32_t)sorted[src];
@@ -209,8 +209,9 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc, boo
             ++end;
         }
         const int G = (int)hd.size();
-        int gid_bits = 1;
+        int gid_bits = 1, posbits = 1;
         while ((1 << gid_bits) < G) ++gid_bits;
+        while ((1ll << posbits) < max_pos + 1) ++posbits;  // the second sort only looks at the bits positions really use
         size_t cub_a = 0, cub_b = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, cub_a, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, cap, 0, 64, st);
         cub_b = cub_a;
@@ -257,7 +258,7 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc, boo
         if (ns) {
             size_t tb = cub_bytes;
             cub::DeviceRadixSort::SortPairs(d_tmp, tb, keys, keys2, vals, vals2, ns, 0, 32 + gid_bits, st);
-            mark_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(keys2, vals2, ns, key3, idx, d_cnt + 1, maxocc);
+            mark_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(keys2, vals2, ns, key3, idx, d_cnt + 1, maxocc, posbits);
             CK(cudaGetLastError());
         }
         CK(cudaMemcpyAsync(h_cnt + 1, d_cnt + 1, sizeof(unsigned long long) * MAX_CHUNK, cudaMemcpyDeviceToHost, st));
@@ -309,8 +310,8 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc, boo
             table_insert_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(keys2, vals2, key3, ns, d_gd);
             CK(cudaGetLastError());
             size_t tb = cub_bytes;
-            cub::DeviceRadixSort::SortPairs(d_tmp, tb, key3, key4, idx, idx2, ns, 0, AN_POSBITS + gid_bits, st);
-            if (n_kept) split_bypos_kernel<<<(unsigned)ceil_div(n_kept, 256), 256, 0, st>>>(key4, idx2, n_kept, keys2, vals2, d_gd);
+            cub::DeviceRadixSort::SortPairs(d_tmp, tb, key3, key4, idx, idx2, ns, 0, posbits + gid_bits, st);
+            if (n_kept) split_bypos_kernel<<<(unsigned)ceil_div(n_kept, 256), 256, 0, st>>>(key4, idx2, n_kept, keys2, vals2, d_gd, posbits);
             CK(cudaGetLastError());
         }
         ctx->counters[CT_LAUNCHES] += 5;
