@@ -61,7 +61,7 @@ static const char *kCounterNames[B200ANI_N_STAGES] = {"probes", "seed_hits", "an
 constexpr int MAX_BATCH_PAIRS = 2560;
 constexpr int64_t ANCHOR_CAP_DEFAULT = 96ll << 20;  // anchors of one batch (overridable: B200ANI_ANCHOR_CAP, used by the batch-split test)
 constexpr int64_t HIT_CAP_DEFAULT = 192ll << 20;    // seed hits of one batch, 8 B each (B200ANI_HIT_CAP)
-constexpr int EXT_TILES_PER_LAUNCH = 8;
+constexpr int EXT_TILES_PER_LAUNCH = 8, EXT_SHORT_ROUNDS = 8;  // a single long last launch (4 short rounds + 1) measured 1 ms slower
 
 struct AnimWorkspace {
     uint64_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr;
@@ -383,7 +383,11 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
             if (anib) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ext_dp_kernel<1>, 128, 0));
             else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ext_dp_kernel<0>, 128, 0));
             long long n_cur = 2 * n_seg;
-            for (int round = 0; round * EXT_TILES_PER_LAUNCH < AN_MAXTILES && n_cur; ++round) {
+            // the first EXT_SHORT_ROUNDS launches hand out EXT_TILES_PER_LAUNCH tiles per task; by then only a few long crawls
+            // are left whose launches are pure latency (8 tiles in sequence), so one last launch lets them run to the tile cap
+            int tiles_done = 0;
+            for (int round = 0; tiles_done < AN_MAXTILES && n_cur; ++round) {
+                const int tiles_now = round < EXT_SHORT_ROUNDS ? EXT_TILES_PER_LAUNCH : AN_MAXTILES - tiles_done;
                 CK(cudaMemsetAsync(W->counters + 8, 0, 2 * sizeof(unsigned long long), st));  // n_out, ticket
                 if ((size_t)(2 * n_ext_launch + 2) > W->kev.size()) {
                     cudaEvent_t a, b;
@@ -396,16 +400,17 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
                 CK(cudaEventRecord(W->kev[2 * n_ext_launch], st));
                 if (anib)
                     ext_dp_kernel<1><<<(unsigned)blocks, 128, 0, st>>>(S, W->d_pairs, round ? ext_list[round & 1] : nullptr, n_cur, ext_list[(round + 1) & 1],
-                                                                      EXT_TILES_PER_LAUNCH, W->counters + 6, 1);
+                                                                      tiles_now, W->counters + 6, 1);
                 else
                     ext_dp_kernel<0><<<(unsigned)blocks, 128, 0, st>>>(S, W->d_pairs, round ? ext_list[round & 1] : nullptr, n_cur, ext_list[(round + 1) & 1],
-                                                                      EXT_TILES_PER_LAUNCH, W->counters + 6, 1);
+                                                                      tiles_now, W->counters + 6, 1);
                 CK(cudaEventRecord(W->kev[2 * n_ext_launch + 1], st));
                 ++n_ext_launch;
                 LAUNCHED(1);
                 CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
                 n_cur = (long long)hc[8];
+                tiles_done += tiles_now;
             }
         }
         T1(ST_EXTDP);
