@@ -50,11 +50,18 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
 // table addressing must be independent of the selection hash (minimizers are the k-mers with small fmix32)
 __device__ __forceinline__ uint32_t table_hash(uint32_t kmer) { return fmix32(kmer ^ 0x5bd1e995u); }
 
-// presence filter: one bit per key at a hash independent of both the selection and the table hash
-__device__ __forceinline__ uint32_t bitmap_hash(uint32_t kmer, uint32_t table_bits) { return fmix32(kmer ^ 0x9e3779b9u) >> (32 - (table_bits + 3)); }
+// presence filter: two bits per key inside ONE 32-bit word (a 2-hash Bloom filter that still costs one load), at a hash
+// independent of both the selection and the table hash.  8 filter bits per table slot at load <= 0.5: ~1 % false positives
+// (one bit per key: ~5 %), and every false positive is a random 8-byte table read.
+__device__ __forceinline__ void bitmap_slot(uint32_t kmer, uint32_t table_bits, uint32_t &word, uint32_t &mask) {
+    const uint32_t h = fmix32(kmer ^ 0x9e3779b9u);
+    word = h >> (32 - (table_bits + 3 - 5));           // word index: table_bits - 2 bits
+    mask = (1u << (h & 31u)) | (1u << ((h >> 5) & 31u));  // two bit positions from the low hash bits
+}
 __device__ __forceinline__ bool bitmap_test(const uint32_t *__restrict__ bm, uint32_t table_bits, uint32_t kmer) {
-    const uint32_t h = bitmap_hash(kmer, table_bits);
-    return (__ldg(bm + (h >> 5)) >> (h & 31)) & 1u;
+    uint32_t w, m;
+    bitmap_slot(kmer, table_bits, w, m);
+    return (__ldg(bm + w) & m) == m;
 }
 
 __device__ __forceinline__ bool table_lookup(const uint64_t *__restrict__ table, uint32_t bits, uint32_t kmer, uint32_t &posflag) {

@@ -148,8 +148,9 @@ __global__ void table_insert_kernel(const uint64_t *__restrict__ sorted, const u
     const uint64_t e = ((uint64_t)k << 32) | vals[i];
     uint32_t s = table_hash(k) >> (32 - bits);
     while (atomicCAS((unsigned long long *)&g.table[s], ~0ull, (unsigned long long)e) != ~0ull) s = (s + 1) & msk;
-    const uint32_t bh = bitmap_hash(k, bits);
-    atomicOr(&g.bitmap[bh >> 5], 1u << (bh & 31));
+    uint32_t bw, bm;
+    bitmap_slot(k, bits, bw, bm);
+    atomicOr(&g.bitmap[bw], bm);
 }
 
 // after the sort by (genome, position): write each genome's by-position lists
