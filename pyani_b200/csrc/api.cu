@@ -50,8 +50,6 @@ void b200ani_destroy(b200ani_ctx *ctx) {
     for (auto *ix : ctx->spare_indexes) free_index(ix, ctx->stream);
     free_anim_workspace(ctx->anim_ws);
     cudaFree(ctx->index_ws);
-    for (auto &ss : ctx->side) if (ss) cudaStreamDestroy(ss);
-    if (ctx->side_ev) cudaEventDestroy(ctx->side_ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

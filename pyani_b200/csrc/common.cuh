@@ -49,8 +49,6 @@ struct b200ani_ctx {
     int64_t counters[B200ANI_N_STAGES] = {0};
     void *anim_ws = nullptr;  // AnimWorkspace (anim_host.cu), reused between calls
     std::vector<MinimizerIndex *> spare_indexes;  // index buffers of released genomes, reused by later builds
-    cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};  // index builds of different genomes run side by side
-    cudaEvent_t side_ev = nullptr;
     void *index_ws = nullptr;      // scratch of build_indexes (anim_index.cu), grown on demand, reused
     size_t index_ws_bytes = 0;
 };
