@@ -73,6 +73,14 @@ def main():
     OUT.mkdir(parents=True, exist_ok=True)
     FIX.mkdir(parents=True, exist_ok=True)
     json.dump(jspecies_tables(REF / "tests/fixtures/concordance/jspecies_output.tab"), open(OUT / "jspecies_concordance.json", "w"), indent=1)
+    # JSpecies 1.2.1 on the four Caulobacter fixture genomes (tests/test_JSpecies/README.md) and the nucmer deltas JSpecies
+    # wrote for an independent pair of draft genomes (Group_2): never used to calibrate anything here
+    json.dump(jspecies_tables(REF / "tests/test_JSpecies/jspecies_results.tab"), open(OUT / "jspecies_caulobacter.json", "w"), indent=1)
+    g2 = FIX / "jspecies_group2"
+    g2.mkdir(exist_ok=True)
+    for f in sorted((REF / "tests/test_JSpecies/Group_2").glob("TS*")):
+        if f.suffix in (".fna", ".delta"):
+            shutil.copyfile(f, g2 / f.name)
     EDGE_FASTAS["edge_rand3x4k"] = rand_fasta(11, 3, 4000)
     EDGE_FASTAS["edge_rand1x20k"] = rand_fasta(12, 1, 20000, p_n=0.0)
 

@@ -84,3 +84,27 @@ def test_alignments_reproduce_nucmer_rows(genomes):
             total += len(nuc)
     assert same_rows >= 0.80 * total
     assert same_rows >= 0.975 * same_coords  # where the coordinates agree, so does the error count
+
+
+def test_independent_pair_against_nucmer():
+    """tests/test_JSpecies/Group_2: two draft genomes (1.2 / 1.7 Mb, 2 + 1 records, 99.7 % identity) with the nucmer
+    .delta files JSpecies wrote for them -- a pair no constant of the aligner was fitted to.  JSpecies does not run
+    delta-filter, so the comparison is on unfiltered alignments."""
+    d = FIXTURES / "jspecies_group2"
+    if not (d / "TS32_31.fna").exists():
+        pytest.skip("Group_2 fixtures not copied (tests/golden/make_golden.py)")
+    g = {}
+    for n in ("TS32_31", "TS43_20"):
+        a, off, _ = oracle.read_fasta(d / f"{n}.fna")
+        g[n] = oracle.OGenome(a, off)
+    for r, q in (("TS32_31", "TS43_20"), ("TS43_20", "TS32_31")):
+        nd = oracle.parse_delta_text(d / f"{r}.fna_vs_{q}.fna.delta")
+        n_ral, n_qal, n_idy, _ = oracle.parse_delta_reduce(nd[:, :7])
+        res, kept, _ = oracle.anim_pair(g[r], g[q], nofilter=True)
+        idy = res["sum_weighted"] / res["sum_aligned"]
+        assert abs(100 * (idy - n_idy)) < 0.02, (r, q, idy, n_idy)              # measured: +0.004 / +0.015
+        # measured: 1,140,630 vs 1,140,614 on TS32_31; 1,149,872 vs 1,139,819 on TS43_20 (a 10 kb repeat copy aligned twice)
+        assert abs(res["ref_aln_len"] / n_ral - 1) < 0.01 and abs(res["qry_aln_len"] / n_qal - 1) < 0.01, (r, q, res, n_ral, n_qal)
+        assert abs(len(kept) - len(nd)) <= 1
+        same = set(map(tuple, kept[:, 2:7].tolist())) & set(map(tuple, nd[:, 2:7].tolist()))
+        assert len(same) >= 0.4 * len(nd)                                       # measured: 16 / 32 and 14 / 31 rows identical

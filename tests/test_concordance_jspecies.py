@@ -158,3 +158,43 @@ def test_concordance_gpu(engine, arrays, ogenomes, gids):
             assert int(x[f]) == want[f], (q, s, f)
     hi, lo = anib_devs(lambda q, s: pid[(q, s)])
     assert max(hi.values()) < 0.2 and max(lo.values()) < 5.0
+
+
+# ------------------------------------------------------------------------------------------ second JSpecies table
+# tests/test_JSpecies/jspecies_results.tab: JSpecies 1.2.1 on the four Caulobacter genomes of the reference's ANIm / ANIb
+# fixtures (tests/test_JSpecies/README.md).  Here every tolerance of the reference's concordance tests is met:
+# ANIm within 0.0993 (0.1), ANIb 0.008 above 90 % (0.2) and 2.9 below (5), TETRA 5e-6 (0.1).
+JS4 = json.load(open(GOLDEN / "jspecies_caulobacter.json"))
+CAULO = fixture_genomes()
+
+
+def target4(method, a, b):
+    t = JS4[method]
+    return t["values"][t["rows"].index(a)][t["names"].index(b)], t["values"][t["rows"].index(b)][t["names"].index(a)]
+
+
+@pytest.mark.skipif(len(CAULO) != 4, reason="fixture genomes not copied (tests/golden/make_golden.py)")
+def test_caulobacter_table_oracle():
+    arrays = {f.name: oracle.read_fasta(f)[:2] for f in CAULO}
+    og = {n: oracle.OGenome(a, off) for n, (a, off) in arrays.items()}
+    names = list(arrays)
+    z = np.array([oracle.tetra_zscores(*oracle.tetra_counts(*arrays[n]))[0] for n in names])
+    corr = oracle.tetra_corr(z)
+    worst = {"anim": 0.0, "anib_hi": 0.0, "anib_lo": 0.0, "tetra": 0.0}
+    for i, a in enumerate(names):
+        for j, b in enumerate(names):
+            if a == b:
+                continue
+            res, _, _ = oracle.anim_pair(og[a], og[b])
+            idy = 100 * res["sum_weighted"] / res["sum_aligned"]
+            worst["anim"] = max(worst["anim"], max(abs(idy - x) for x in target4("ANIm", a, b)))
+            rb, _, _ = oracle.anib_pair(og[a], og[b])
+            pid = rb["pid_milli_sum"] / rb["n_pass"] / 1000
+            tb = target4("ANIb", a, b)
+            k = "anib_hi" if min(tb) > 90 else "anib_lo"
+            worst[k] = max(worst[k], max(abs(pid - x) for x in tb))
+            worst["tetra"] = max(worst["tetra"], max(abs(corr[i, j] - x) for x in target4("Tetra", a, b)))
+    assert worst["anim"] < 0.1, worst     # tests/test_concordance.py:157-159
+    assert worst["anib_hi"] < 0.2, worst  # :131-141
+    assert worst["anib_lo"] < 5.0, worst  # :143-154
+    assert worst["tetra"] < 1e-4, worst   # :163-165 allows 0.1
