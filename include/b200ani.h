@@ -80,8 +80,8 @@ typedef struct {
 
 /* All m directed pairs (pairs[2*i]=ref genome id, pairs[2*i+1]=qry genome id).  Replaces, per pair, the
  * nucmer + delta-filter subprocesses (anim.py:240-289) and anim.parse_delta (anim.py:292-411).
- * maxmatch: anim.py:276-279.  0 = --mum (seed k-mers unique in both genomes); 1 = --maxmatch (every seed k-mer with
- * at most 16 occurrences per genome; nucmer itself has no cap).
+ * maxmatch: anim.py:276-279.  0 = --mum (seed k-mers unique in at least one of the two genomes, at most 16 occurrences
+ * in the other); 1 = --maxmatch (every seed k-mer with at most 16 occurrences per genome; nucmer itself has no cap).
  * nofilter: subcmd_anim.py:341-344 (skip the 1-to-1 filter stage). */
 int b200ani_anim(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch, int nofilter,
                  b200ani_anim_result *out);
@@ -105,7 +105,7 @@ typedef struct {
     int64_t pid_milli_sum;  /* sum over kept fragments of round(1e5 * nident / length) */
     int32_t n_frags;        /* fragments of the query genome (anib.fragment_fasta_files, anib.py:164-203) */
     int32_t n_pass;         /* fragments with an HSP passing coverage > 0.7 and identity > 0.3 (anib.py:646) */
-    int32_t n_hsps;         /* candidate HSPs examined */
+    int32_t n_hsps;         /* candidate HSPs examined (after the ungapped screen, before bridging) */
     int32_t status;         /* B200ANI_STATUS_* */
 } b200ani_anib_result;      /* 40 bytes */
 
