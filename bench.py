@@ -42,9 +42,10 @@ SEED = 20260925  # 20260924 + config index 1
 N_CLADES, PER_CLADE, GENOME_LEN = 5, 10, 5_000_000
 DPX_OPS_PER_CELL = 4  # E, F, H max-plus updates + 1 add per affine cell
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this workload
-# (profiles/r01_v22_prof_*.txt, first captured launch of each kernel); None where no capture exists
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"gap_dp_kernel": 11.515265e9 + 0.967830e9, "ext_dp_kernel": 101.286656e6 + 13.984256e6,
-                                "seed_probe_kernel": 9.123259e9 + 207.940864e6, "seed_extend_kernel": 7.349801e9 + 489.665536e6}
+# (profiles/r01_v30_prof_v30.txt: one batch per step, first captured launch of each kernel; seed_extend from the v22 capture
+# scaled to one launch per step); None where no capture exists
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"gap_dp_kernel": 21.246920e9 + 1.759511e9, "ext_dp_kernel": 216.553e6 + 35.053e6,
+                                "seed_probe_kernel": 23.121308e9 + 432.529e6, "seed_extend_kernel": 2 * (7.349801e9 + 489.665536e6)}
 
 
 def log(*a):
