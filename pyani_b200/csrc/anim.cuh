@@ -64,18 +64,7 @@ __device__ __forceinline__ bool bitmap_test(const uint32_t *__restrict__ bm, uin
     return (__ldg(bm + w) & m) == m;
 }
 
-__device__ __forceinline__ bool table_lookup(const uint64_t *__restrict__ table, uint32_t bits, uint32_t kmer, uint32_t &posflag) {
-    const uint32_t msk = (1u << bits) - 1u;
-    uint32_t s = table_hash(kmer) >> (32 - bits);
-    while (true) {
-        uint64_t e = __ldg(table + s);
-        if (e == ~0ull) return false;
-        if ((uint32_t)(e >> 32) == kmer) { posflag = (uint32_t)e; return true; }
-        s = (s + 1) & msk;
-    }
-}
-
-// every table entry of a k-mer (--maxmatch indexes hold up to AN_MAXOCC per k-mer): start with cursor = ~0u
+// every table entry of a k-mer (up to AN_MAXOCC per k-mer): start with cursor = ~0u
 __device__ __forceinline__ bool table_next(const uint64_t *__restrict__ table, uint32_t bits, uint32_t kmer, uint32_t &cursor, uint32_t &posflag) {
     const uint32_t msk = (1u << bits) - 1u;
     uint32_t s = cursor == ~0u ? table_hash(kmer) >> (32 - bits) : (cursor + 1) & msk;
@@ -132,6 +121,9 @@ __device__ __forceinline__ uint32_t contig_of(const uint64_t *__restrict__ goff,
     }
     return lo;
 }
+
+// Which table entries a query minimizer may seed with (anim_seed.cu)
+enum { SEED_BOTH_UNIQUE = 0, SEED_ALL = 1, SEED_EITHER_UNIQUE = 2 };
 
 // scoring models: 0 = ANIm (nucmer-like), 1 = ANIb (blastn-like, linear gaps)
 template <int MODEL> struct Scoring;

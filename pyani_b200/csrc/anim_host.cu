@@ -11,7 +11,6 @@
 #include "anim.cuh"
 
 int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc, bool anib);
-enum { SEED_BOTH_UNIQUE = 0, SEED_ALL = 1, SEED_EITHER_UNIQUE = 2 };  // anim_seed.cu
 
 // kernels defined in the other translation units
 template <int MODE> __global__ void seed_probe_kernel(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long, int);

@@ -68,7 +68,6 @@ __device__ __forceinline__ int pair_of_probe(const PairDesc *__restrict__ pairs,
 //   SEED_BOTH_UNIQUE   ANIb: the k-mer is unique in both genomes
 //   SEED_ALL           --maxmatch: every entry (up to AN_MAXOCC per k-mer)
 //   SEED_EITHER_UNIQUE --mum: the k-mer is unique in at least one of the two genomes
-enum { SEED_BOTH_UNIQUE = 0, SEED_ALL = 1, SEED_EITHER_UNIQUE = 2 };
 __device__ __forceinline__ bool seed_ok(int mode, uint32_t rpf, uint32_t qpf) {
     const bool rr = rpf & AN_REPBIT, qr = qpf & AN_REPBIT;
     return mode == SEED_ALL || (mode == SEED_BOTH_UNIQUE ? !(rr || qr) : !(rr && qr));
