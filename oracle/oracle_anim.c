@@ -8,7 +8,7 @@
  *
  * PARITY STATUS: "unpinned" against nucmer on arbitrary genomes (no binary, no source).  Pinned only
  *  (a) against the reference's checked-in nucmer 3.1 output for the four Caulobacter fixture genomes
- *      (tests/test_anim_oracle_fixtures.py): identity of all 12 directed pairs within 0.09 %-points (the
+ *      (tests/test_anim_oracle_fixtures.py): identity of all 12 directed pairs within 0.06 %-points (the
  *      reference's own JSpecies tolerance is +-0.1, tests/test_concordance.py:157-159,203), 81 % of nucmer's
  *      alignments reproduced row for row (coordinates and error count); every rule of the specification
  *      (gap scoring, cluster pre-pass, bridging, seed uniqueness) was derived from those .delta files,

@@ -6,7 +6,7 @@ nucmer/delta-filter cannot run here, so the ONLY pin on the aligner half of the 
    .filter selection (it does, up to a handful of near-tie duplicate repeats);
  * the whole pipeline (seed -> chain -> DP -> filter -> parse_delta reduction) must land within the
    reference's own concordance tolerance for ANIm, +-0.1 percentage points of identity
-   (tests/test_concordance.py:157-159,203).  Measured: all 12 directed pairs within 0.088; aligned
+   (tests/test_concordance.py:157-159,203).  Measured: all 12 directed pairs within 0.057; aligned
    lengths within 1.3 % (10 of 12 within 0.2 %);
  * alignment by alignment: >= 80 % of the alignments in nucmer's .delta files are reproduced with
    identical coordinates AND identical error counts (the DP scoring 3/-7/-10/-7 reproduces nucmer's
@@ -59,7 +59,7 @@ def test_pipeline_within_reference_tolerance(genomes):
             g_ral, g_qal, g_ident, g_errs = gold[f"{r}_vs_{q}.filter"]
             devs.append(100 * (ident - g_ident))
             assert abs(ral / g_ral - 1) < 0.015 and abs(qal / g_qal - 1) < 0.015, (r, q, ral, g_ral)
-            assert abs(devs[-1]) < 0.1, (r, q, ident, g_ident)  # the reference's own tolerance (test_concordance.py:157-159)
+            assert abs(devs[-1]) < 0.08, (r, q, ident, g_ident)  # measured 0.057; the reference's own tolerance is 0.1 (test_concordance.py:157-159)
     assert abs(np.mean(devs)) < 0.06
     # the near-identical pair reproduces nucmer's aligned lengths exactly
     rows, _ = oracle.anim_align(genomes["NC_002696"], genomes["NC_011916"])

@@ -163,7 +163,7 @@ def test_concordance_gpu(engine, arrays, ogenomes, gids):
 # ------------------------------------------------------------------------------------------ second JSpecies table
 # tests/test_JSpecies/jspecies_results.tab: JSpecies 1.2.1 on the four Caulobacter genomes of the reference's ANIm / ANIb
 # fixtures (tests/test_JSpecies/README.md).  Here every tolerance of the reference's concordance tests is met:
-# ANIm within 0.0993 (0.1), ANIb 0.008 above 90 % (0.2) and 2.9 below (5), TETRA 5e-6 (0.1).
+# ANIm within 0.068 (0.1), ANIb 0.008 above 90 % (0.2) and 2.9 below (5), TETRA 5e-6 (0.1).
 JS4 = json.load(open(GOLDEN / "jspecies_caulobacter.json"))
 CAULO = fixture_genomes()
 
@@ -194,7 +194,7 @@ def test_caulobacter_table_oracle():
             k = "anib_hi" if min(tb) > 90 else "anib_lo"
             worst[k] = max(worst[k], max(abs(pid - x) for x in tb))
             worst["tetra"] = max(worst["tetra"], max(abs(corr[i, j] - x) for x in target4("Tetra", a, b)))
-    assert worst["anim"] < 0.1, worst     # tests/test_concordance.py:157-159
+    assert worst["anim"] < 0.08, worst    # measured 0.068; tests/test_concordance.py:157-159 allows 0.1
     assert worst["anib_hi"] < 0.2, worst  # :131-141
     assert worst["anib_lo"] < 5.0, worst  # :143-154
     assert worst["tetra"] < 1e-4, worst   # :163-165 allows 0.1
