@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .engine import ANIM_DTYPE
+from .engine import ANIB_DTYPE, ANIM_DTYPE
 
 
 def pair_costs(pairs: np.ndarray, genome_lengths: Sequence[int]) -> np.ndarray:
@@ -39,8 +39,9 @@ def partition(costs: np.ndarray, world: int) -> List[Tuple[int, int]]:
     return [(int(bounds[r]), int(bounds[r + 1])) for r in range(world)]
 
 
-def all_gather_results(local: np.ndarray, blocks: List[Tuple[int, int]], device=None, group=None) -> np.ndarray:
+def all_gather_results(local: np.ndarray, blocks: List[Tuple[int, int]], device=None, group=None, dtype=ANIM_DTYPE) -> np.ndarray:
     """One all-gather of the per-rank result arrays (padded to the largest block) -> full array, every rank.
+    ``dtype``: the result struct (ANIM_DTYPE 48 B, ANIB_DTYPE 40 B).
 
     Works with the ``nccl`` backend (tensors on ``device``) and with ``gloo`` (CPU tensors, used by the
     world_size-2 CPU tests)."""
@@ -50,7 +51,7 @@ def all_gather_results(local: np.ndarray, blocks: List[Tuple[int, int]], device=
     world = dist.get_world_size(group)
     assert len(blocks) == world
     pad = max(e - s for s, e in blocks)
-    item = ANIM_DTYPE.itemsize
+    item = dtype.itemsize
     buf = np.zeros(pad * item, dtype=np.uint8)
     raw = np.ascontiguousarray(local).view(np.uint8).reshape(-1)
     buf[: len(raw)] = raw
@@ -60,8 +61,8 @@ def all_gather_results(local: np.ndarray, blocks: List[Tuple[int, int]], device=
     out = torch.empty(world * pad * item, dtype=torch.uint8, device=t.device)
     dist.all_gather_into_tensor(out, t, group=group)
     flat = out.cpu().numpy().reshape(world, pad * item)
-    parts = [flat[r, : (e - s) * item].copy().view(ANIM_DTYPE) for r, (s, e) in enumerate(blocks)]
-    return np.concatenate(parts) if parts else np.zeros(0, dtype=ANIM_DTYPE)
+    parts = [flat[r, : (e - s) * item].copy().view(dtype) for r, (s, e) in enumerate(blocks)]
+    return np.concatenate(parts) if parts else np.zeros(0, dtype=dtype)
 
 
 def anim_sharded(engine, pairs: np.ndarray, genome_lengths: Sequence[int], rank: int, world: int, *, maxmatch=False,
@@ -77,3 +78,17 @@ def anim_sharded(engine, pairs: np.ndarray, genome_lengths: Sequence[int], rank:
     if world == 1:
         return local
     return all_gather_results(local, blocks, device=device, group=group)
+
+
+def anib_sharded(engine, pairs: np.ndarray, genome_lengths: Sequence[int], rank: int, world: int, *, fragsize: int = 1020,
+                 device=None, group=None, compute=None) -> np.ndarray:
+    """ANIb counterpart of :func:`anim_sharded`: pairs are (query, subject); the cost model is the same (the query's
+    fragments stream through the subject's table), the gathered structs are the 40-byte ANIb results."""
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    blocks = partition(pair_costs(pairs, genome_lengths), world)
+    s, e = blocks[rank]
+    fn = compute if compute is not None else (lambda p: engine.anib(p, fragsize=fragsize))
+    local = fn(pairs[s:e]) if e > s else np.zeros(0, dtype=ANIB_DTYPE)
+    if world == 1:
+        return local
+    return all_gather_results(local, blocks, device=device, group=group, dtype=ANIB_DTYPE)

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from pyani_b200 import dist as pdist
-from pyani_b200.engine import ANIM_DTYPE
+from pyani_b200.engine import ANIB_DTYPE, ANIM_DTYPE
 
 
 def test_partition_is_contiguous_covering_and_balanced():
@@ -30,6 +30,15 @@ def _fake_compute(pairs):
     return out
 
 
+def _fake_compute_b(pairs):
+    out = np.zeros(len(pairs), dtype=ANIB_DTYPE)
+    out["aln_length"] = pairs[:, 0] * 1000 + pairs[:, 1]
+    out["pid_milli_sum"] = 7 * out["aln_length"]
+    out["n_frags"] = pairs[:, 0] + 1
+    out["n_pass"] = pairs[:, 1]
+    return out
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
 
@@ -40,7 +49,8 @@ def _worker(rank, world, port, q):
     pairs = synth.all_directed_pairs(7)
     lengths = [5, 1, 9, 3, 3, 7, 2]
     full = pdist.anim_sharded(None, pairs, lengths, rank, world, compute=_fake_compute)
-    q.put((rank, full.tobytes()))
+    fullb = pdist.anib_sharded(None, pairs, lengths, rank, world, compute=_fake_compute_b)
+    q.put((rank, full.tobytes() + fullb.tobytes()))
     dist.destroy_process_group()
 
 
@@ -61,5 +71,5 @@ def test_two_rank_gloo_all_gather_assembles_full_result():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    want = _fake_compute(synth.all_directed_pairs(7)).tobytes()
+    want = _fake_compute(synth.all_directed_pairs(7)).tobytes() + _fake_compute_b(synth.all_directed_pairs(7)).tobytes()
     assert got[0] == want and got[1] == want  # every rank holds the full, correctly ordered array
