@@ -92,3 +92,40 @@ def anib_sharded(engine, pairs: np.ndarray, genome_lengths: Sequence[int], rank:
     if world == 1:
         return local
     return all_gather_results(local, blocks, device=device, group=group, dtype=ANIB_DTYPE)
+
+
+def tetra_sharded(engine, genome_ids: Sequence[int], genome_lengths: Sequence[int], rank: int, world: int, *, device=None, group=None,
+                  compute=None) -> Tuple[np.ndarray, np.ndarray]:
+    """TETRA across ranks: every rank counts and scores a contiguous, length-balanced block of the genomes,
+    one all-gather of the 256 fp64 Z-scores + 256 "observed" flags per genome gives every rank the full Z matrix; the
+    N x N correlation (a few ms for N = 1000) is then computed wherever it is needed with ``engine.tetra_corr``.
+
+    -> (z[n][256], observed[n][256]) in the order of ``genome_ids``.  ``compute`` (tests only) replaces
+    ``engine.tetra_zscores``."""
+    import torch
+    import torch.distributed as dist
+
+    ids = np.ascontiguousarray(genome_ids, dtype=np.int32)
+    blocks = partition(np.asarray([genome_lengths[i] for i in ids], dtype=np.float64), world)
+    s, e = blocks[rank]
+    fn = compute if compute is not None else engine.tetra_zscores
+    if e > s:
+        z, obs = fn(ids[s:e])
+    else:
+        z, obs = np.zeros((0, 256), np.float64), np.zeros((0, 256), np.uint8)
+    if world == 1:
+        return z, obs
+    pad = max(b - a for a, b in blocks)
+    row = 256 * 8 + 256  # bytes per genome: Z-scores then flags
+    buf = np.zeros((pad, row), dtype=np.uint8)
+    buf[: e - s, : 256 * 8] = np.ascontiguousarray(z, dtype=np.float64).view(np.uint8).reshape(e - s, 256 * 8)
+    buf[: e - s, 256 * 8:] = np.ascontiguousarray(obs, dtype=np.uint8)
+    t = torch.from_numpy(buf.reshape(-1))
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty(world * pad * row, dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    flat = out.cpu().numpy().reshape(world, pad, row)
+    zs = [flat[r, : b - a, : 256 * 8].copy().view(np.float64).reshape(b - a, 256) for r, (a, b) in enumerate(blocks)]
+    os_ = [flat[r, : b - a, 256 * 8:].copy() for r, (a, b) in enumerate(blocks)]
+    return np.concatenate(zs), np.concatenate(os_)

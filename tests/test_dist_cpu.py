@@ -39,6 +39,13 @@ def _fake_compute_b(pairs):
     return out
 
 
+def _fake_tetra(ids):
+    ids = np.asarray(ids)
+    z = (ids[:, None] * 1000.0 + np.arange(256)[None, :]) / 7.0
+    obs = ((ids[:, None] + np.arange(256)[None, :]) % 3 != 0).astype(np.uint8)
+    return z, obs
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
 
@@ -50,7 +57,8 @@ def _worker(rank, world, port, q):
     lengths = [5, 1, 9, 3, 3, 7, 2]
     full = pdist.anim_sharded(None, pairs, lengths, rank, world, compute=_fake_compute)
     fullb = pdist.anib_sharded(None, pairs, lengths, rank, world, compute=_fake_compute_b)
-    q.put((rank, full.tobytes() + fullb.tobytes()))
+    z, obs = pdist.tetra_sharded(None, list(range(7)), lengths, rank, world, compute=_fake_tetra)
+    q.put((rank, full.tobytes() + fullb.tobytes() + z.tobytes() + obs.tobytes()))
     dist.destroy_process_group()
 
 
@@ -71,5 +79,6 @@ def test_two_rank_gloo_all_gather_assembles_full_result():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    want = _fake_compute(synth.all_directed_pairs(7)).tobytes() + _fake_compute_b(synth.all_directed_pairs(7)).tobytes()
+    zw, ow = _fake_tetra(list(range(7)))
+    want = _fake_compute(synth.all_directed_pairs(7)).tobytes() + _fake_compute_b(synth.all_directed_pairs(7)).tobytes() + zw.tobytes() + ow.tobytes()
     assert got[0] == want and got[1] == want  # every rank holds the full, correctly ordered array
