@@ -84,3 +84,18 @@ def calculate_anib(infiles: Sequence[Path], org_lengths: Optional[Dict[str, int]
     pairs = [(a, b) for a in stems for b in stems if a != b]
     res = eng.anib(np.array([[gids[a], gids[b]] for a, b in pairs], dtype=np.int32), fragsize=fragsize)
     return fill_aniresults(org_lengths, {p: parse_result(r) for p, r in zip(pairs, res)})
+
+
+def write_minimal_blast_tab(path: Path, sname: str, rows: np.ndarray, slen: int = 0) -> None:
+    """A ``.blast_tab`` file holding what ``anib.parse_blast_tab`` reads (anib.py:609-665): one line per kept HSP with the
+    15 columns of the reference's ``-outfmt`` (anib.py:468-469): qseqid sseqid length mismatch pident nident qlen slen
+    qstart qend sstart send positive ppos gaps.  rows: ``Engine.anib_fragments`` output (fragment index, length, mismatch,
+    gaps, nident, qlen, score, round(1e5 * nident / length)).  Fragment ids follow ``anib.fragment_fasta_files``
+    (``frag%05d``, numbered from 1 across the records of the file, anib.py:192-200); the coordinate columns, which the
+    reference never reads, are written as 0."""
+    path = Path(path)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    with open(path, "w") as fh:
+        for frag, length, mism, gaps, nident, qlen, _score, pid_milli in np.asarray(rows, dtype=np.int64).reshape(-1, 8):
+            pid = f"{pid_milli / 1000:.3f}"
+            fh.write("\t".join(str(x) for x in (f"frag{frag + 1:05d}", sname, length, mism, pid, nident, qlen, slen, 0, 0, 0, 0, nident, pid, gaps)) + "\n")

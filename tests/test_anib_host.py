@@ -4,6 +4,7 @@ import json
 import numpy as np
 import pandas as pd
 
+import oracle
 from conftest import GOLDEN, fixture_genomes
 from pyani_b200 import anib as banib
 from pyani_b200.engine import ANIB_DTYPE
@@ -42,3 +43,29 @@ def test_fragment_counts_of_fixture_genomes():
     # tests/fixtures/anib/fragfiles hold 3,940 / 5,371 / 3,964 / 4,565 fragments
     assert [len(d[f.stem]) for f in files] == [3940, 5371, 3964, 4565]
     assert max(max(v.values()) for v in d.values()) == 1020  # tests/test_anib.py:317-324
+
+
+def test_minimal_blast_tab_round_trip(tmp_path):
+    """f1: a .blast_tab written from the engine's per-fragment rows reduces (anib.parse_blast_tab restatement, pinned to the
+    reference's fixtures in test_oracle_anib_reduce) to the sums the engine reports for the pair."""
+    from pyani_b200 import anib as banib
+
+    rng = np.random.default_rng(3)
+    n = 40
+    qlen = np.full(n, 1020)
+    gaps = rng.integers(0, 30, n)
+    mism = rng.integers(0, 150, n)
+    nident = rng.integers(800, 1000, n)
+    length = nident + mism + gaps
+    rows = np.stack([np.arange(n) * 2, length, mism, gaps, nident, qlen, 2 * nident, (100000 * nident + length // 2) // length], axis=1)
+    f = tmp_path / "q_vs_s.blast_tab"
+    banib.write_minimal_blast_tab(f, "subject", rows, slen=4_000_000)
+    parsed = []
+    for line in open(f):
+        c = line.rstrip("\n").split("\t")
+        assert len(c) == 15 and c[0].startswith("frag") and c[1] == "subject"
+        parsed.append((int(c[0][4:]), int(c[2]), int(c[3]), float(c[4]), int(c[6]), int(c[14])))
+    aln, errs, pid = oracle.parse_blast_tab_reduce(np.asarray(parsed, dtype=np.float64))
+    keep = ((length - gaps) / qlen > 0.7) & ((length - gaps - mism) / qlen > 0.3)
+    assert aln == int((length - gaps)[keep].sum()) and errs == int((mism + gaps)[keep].sum())
+    assert abs(pid - np.mean(np.round(rows[keep, 7] / 1000, 3))) < 1e-9
