@@ -11,6 +11,7 @@
 """
 from __future__ import annotations
 
+import re
 from pathlib import Path
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -99,3 +100,54 @@ def write_minimal_blast_tab(path: Path, sname: str, rows: np.ndarray, slen: int 
         for frag, length, mism, gaps, nident, qlen, _score, pid_milli in np.asarray(rows, dtype=np.int64).reshape(-1, 8):
             pid = f"{pid_milli / 1000:.3f}"
             fh.write("\t".join(str(x) for x in (f"frag{frag + 1:05d}", sname, length, mism, pid, nident, qlen, slen, 0, 0, 0, 0, nident, pid, gaps)) + "\n")
+
+
+_BLASTN_RE = re.compile(r"-out\s+(\S+)\s+-query\s+(\S+)\s+-db\s+(\S+)\s.*-task\s+blastn\s*$")
+_MAKEDB_RE = re.compile(r"-dbtype\s+nucl\s+-in\s+(\S+)\s+-title\s+\S+\s+-out\s+(\S+)\s*$")
+
+
+def run_dependency_graph(jobgraph, workers: Optional[int] = None, logger=None, engine: Optional[Engine] = None, fragsize: int = FRAGSIZE) -> int:
+    """GPU stand-in for ``run_multiprocessing.run_dependency_graph`` on an ANIb job graph (``anib.make_job_graph``,
+    anib.py:296-347): the ``blastn`` jobs (command lines of ``construct_blastn_cmdline``, anib.py:451-471) are run on the
+    engine and their ``.blast_tab`` files written where BLAST+ would have put them; the ``makeblastdb`` dependencies
+    (``construct_makeblastdb_cmd``, anib.py:378-391) are only read for the database-name -> input-FASTA mapping.  The query
+    genome is fragmented on the device, so the ``-fragments`` FASTA named by ``-query`` is not read either.
+    Returns 0 on success, the number of failed comparisons otherwise (a summed return code)."""
+    from .anim import _iter_jobs
+    from .fasta import read_fasta
+
+    eng = engine or Engine(0)
+    db_to_fasta: Dict[str, str] = {}
+    todo = []
+    for job in _iter_jobs(jobgraph):
+        cmd = getattr(job, "command", None) or getattr(job, "script", "")
+        m = _MAKEDB_RE.search(cmd)
+        if m:
+            db_to_fasta[m.group(2)] = m.group(1)
+            continue
+        m = _BLASTN_RE.search(cmd)
+        if m:
+            todo.append((m.group(1), m.group(2), m.group(3)))
+    if not todo:
+        return 0
+    by_name = {Path(db).name: fa for db, fa in db_to_fasta.items()}
+    cache: Dict[str, int] = {}
+
+    def stage(fasta: str) -> int:
+        if fasta not in cache:
+            arr, off, ids = read_fasta(fasta)
+            cache[fasta] = eng.add_genome(arr, off, Path(fasta).stem, ids)
+        return cache[fasta]
+
+    rc = 0
+    for out, query, db in todo:
+        try:
+            sfasta = db_to_fasta[db]
+            qfasta = by_name[Path(query).name.replace("-fragments", "")]
+            rows = eng.anib_fragments(stage(qfasta), stage(sfasta), fragsize=fragsize)
+            write_minimal_blast_tab(Path(out), Path(sfasta).stem, rows, slen=eng.genome_length(stage(sfasta)))
+        except Exception as exc:  # mirrors a non-zero subprocess return code
+            if logger:
+                logger.error("b200ani ANIb comparison %s vs %s failed: %s", query, db, exc)
+            rc += 1
+    return rc

@@ -2,6 +2,7 @@
 import json
 
 import numpy as np
+import pytest
 import pandas as pd
 
 import oracle
@@ -69,3 +70,51 @@ def test_minimal_blast_tab_round_trip(tmp_path):
     keep = ((length - gaps) / qlen > 0.7) & ((length - gaps - mism) / qlen > 0.3)
     assert aln == int((length - gaps)[keep].sum()) and errs == int((mism + gaps)[keep].sum())
     assert abs(pid - np.mean(np.round(rows[keep, 7] / 1000, 3))) < 1e-9
+
+
+class _Job:
+    def __init__(self, name, command):
+        self.name, self.command, self.dependencies = name, command, []
+
+    def add_dependency(self, job):
+        self.dependencies.append(job)
+
+
+class _FakeEngine:
+    def __init__(self):
+        self.names, self.calls = [], []
+
+    def add_genome(self, arr, off, name, ids=None):
+        self.names.append((name, int(off[-1])))
+        return len(self.names) - 1
+
+    def genome_length(self, gid):
+        return self.names[gid][1]
+
+    def anib_fragments(self, q, s, fragsize=1020):
+        self.calls.append((self.names[q][0], self.names[s][0], fragsize))
+        return np.array([[0, 1000, 50, 10, 940, 1020, 1700, 94000], [1, 400, 10, 0, 390, 412, 750, 97500]])
+
+
+def test_anib_job_graph_backend_writes_blast_tab(tmp_path):
+    """f1: the ANIb job graph of anib.make_job_graph (anib.py:296-347), command lines as construct_makeblastdb_cmd
+    (anib.py:378-391) and construct_blastn_cmdline (anib.py:451-471) build them."""
+    fa, fb = tmp_path / "A.fna", tmp_path / "B.fna"
+    fa.write_text(">a1 d\nACGTACGTAC\nGTACGTAC\n")
+    fb.write_text(">b1 d\nACGTACGTACGTAC\n")
+    out = tmp_path / "blastn_output"
+    fmt = "'6 qseqid sseqid length mismatch pident nident qlen slen qstart qend sstart send positive ppos gaps'"
+    dbs = {n: _Job(f"db_{n}", f"makeblastdb -dbtype nucl -in {f} -title {n} -out {out / f.name}") for n, f in (("A", fa), ("B", fb))}
+    jobs = []
+    for q, s in (("A", "B"), ("B", "A")):
+        j = _Job(f"exe_{q}{s}", f"blastn -out {out}/{q}_vs_{s}.blast_tab -query {out}/{q}-fragments.fna -db {out}/{s}.fna "
+                                f"-xdrop_gap_final 150 -dust no -evalue 1e-15 -max_target_seqs 1 -outfmt {fmt} -task blastn")
+        j.add_dependency(dbs[s])
+        jobs.append(j)
+    eng = _FakeEngine()
+    assert banib.run_dependency_graph(jobs, workers=8, engine=eng) == 0
+    assert sorted(eng.calls) == [("A", "B", 1020), ("B", "A", 1020)]
+    lines = open(out / "A_vs_B.blast_tab").read().splitlines()
+    assert len(lines) == 2 and lines[0].split("\t") == ["frag00001", "B", "1000", "50", "94.000", "940", "1020", "14", "0", "0", "0", "0", "940", "94.000", "10"]
+    rows = [(int(c[0][4:]), int(c[2]), int(c[3]), float(c[4]), int(c[6]), int(c[14])) for c in (l.split("\t") for l in lines)]
+    assert oracle.parse_blast_tab_reduce(np.asarray(rows, dtype=np.float64)) == (990 + 400, 60 + 10, pytest.approx((94.0 + 97.5) / 2))
