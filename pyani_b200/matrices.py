@@ -40,3 +40,25 @@ def anim_matrices(genome_ids: Sequence, lengths: Sequence[int], pairs: np.ndarra
     mats["sim_errors"][q, s] = results["sim_errs"][ok]
     mats["hadamard"][q, s] = ident * cov
     return {k: pd.DataFrame(v, index=ids, columns=ids, dtype=float) for k, v in mats.items()}
+
+
+def comparison_rows(genome_ids: Sequence, lengths: Sequence[int], pairs: np.ndarray, results: np.ndarray, version: str,
+                    maxmatch: bool = False) -> list:
+    """One dict per directed comparison with the columns of ``pyani_orm.Comparison`` (pyani_orm.py:262-322), valued as
+    ``subcmd_anim.update_comparison_results`` values them (subcmd_anim.py:438-455): ``aln_length`` = aligned length on the
+    query (= nucmer reference), ``cov_query`` / ``cov_subject`` = aligned length over genome length, ``identity`` =
+    sum_weighted / sum_aligned, ``program = "b200ani"`` (a cache key of its own in ``filter_existing_comparisons``,
+    pyani_orm.py:416-491).  Ready for ``session.bulk_insert_mappings(Comparison, rows)``; pairs without
+    any alignment are left out (the reference aborts on them, anim.py:396,481-486)."""
+    p = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+    L = np.asarray(lengths, dtype=np.float64)
+    rows = []
+    for (q, s), r in zip(p, results):
+        if int(r["sum_aligned"]) <= 0:
+            continue
+        rows.append({"query_id": genome_ids[q], "subject_id": genome_ids[s], "aln_length": int(r["ref_aln_len"]),
+                     "sim_errs": int(r["sim_errs"]), "identity": int(r["sum_weighted"]) / int(r["sum_aligned"]),
+                     "cov_query": int(r["ref_aln_len"]) / L[q], "cov_subject": int(r["qry_aln_len"]) / L[s],
+                     "program": "b200ani", "version": version, "fragsize": None, "maxmatch": bool(maxmatch),
+                     "kmersize": None, "minmatch": None})
+    return rows

@@ -162,3 +162,19 @@ def test_parallel_fasta_ingest(tmp_path):
         assert bytes(o["residues"]).decode() == "".join("".join(r) for r in recs)
         a, off, ids = fasta.read_fasta(p)
         assert (a == o["residues"]).all() and (off == o["offsets"]).all()
+
+
+def test_comparison_rows_follow_update_comparison_results():
+    """f2: Comparison columns exactly as subcmd_anim.update_comparison_results derives them (subcmd_anim.py:438-455)."""
+    from pyani_b200 import matrices
+
+    res = np.zeros(3, dtype=ANIM_DTYPE)
+    res["ref_aln_len"], res["qry_aln_len"] = [900, 0, 500], [950, 0, 400]
+    res["sum_aligned"], res["sum_weighted"], res["sim_errs"] = [2000, 0, 1000], [1800, 0, 990], [100, 0, 5]
+    rows = matrices.comparison_rows([11, 22, 33], [1000, 2000, 4000], np.array([[0, 1], [1, 2], [2, 0]]), res, "b200ani 0.1.0", maxmatch=True)
+    assert len(rows) == 2  # the alignment-free pair is left out
+    a, b = rows
+    assert (a["query_id"], a["subject_id"], a["aln_length"], a["sim_errs"]) == (11, 22, 900, 100)
+    assert a["identity"] == 0.9 and a["cov_query"] == 0.9 and a["cov_subject"] == 950 / 2000
+    assert (b["query_id"], b["subject_id"]) == (33, 11) and b["cov_query"] == 500 / 4000 and b["cov_subject"] == 400 / 1000
+    assert a["program"] == "b200ani" and a["version"] == "b200ani 0.1.0" and a["maxmatch"] is True and a["fragsize"] is None
