@@ -17,7 +17,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .anim import ANIResults
+from .results import ANIResults
 from .engine import Engine
 
 FRAGSIZE = 1020  # pyani_config.FRAGSIZE (pyani_config.py:95)
@@ -57,7 +57,7 @@ def fill_aniresults(org_lengths: Dict[str, int], tuples: Dict[Tuple[str, str], T
     """anib.process_blast (anib.py:496-565) given the per-file 3-tuples instead of .blast_tab files."""
     results = ANIResults(list(org_lengths.keys()), mode)
     for org, length in org_lengths.items():
-        results.alignment_lengths.loc[org, org] = length
+        results.add_tot_length(org, org, length)
     # files are visited in sorted(<q>_vs_<s>.blast_tab) order (pyani_files.get_input_files, pyani_files.py:124);
     # add_sim_errors is called with its default sym=True (anib.py:562), so that table is symmetric and the later
     # file wins, while lengths, identity and coverage only fill the [query, subject] cell
@@ -77,13 +77,17 @@ def calculate_anib(infiles: Sequence[Path], org_lengths: Optional[Dict[str, int]
     """All directed comparisons between ``infiles`` on the GPU -> ANIResults (unified_anib semantics,
     average_nucleotide_identity.py:694-760)."""
     eng = engine or Engine(0)
-    files = sorted(Path(f) for f in infiles)
-    gids = {f.stem: eng.add_fasta(f) for f in files}
-    stems = [f.stem for f in files]
-    if org_lengths is None:
-        org_lengths = {s: eng.genome_length(gids[s]) for s in stems}
-    pairs = [(a, b) for a in stems for b in stems if a != b]
-    res = eng.anib(np.array([[gids[a], gids[b]] for a, b in pairs], dtype=np.int32), fragsize=fragsize)
+    try:
+        files = sorted(Path(f) for f in infiles)
+        gids = {f.stem: eng.add_fasta(f) for f in files}
+        stems = [f.stem for f in files]
+        if org_lengths is None:
+            org_lengths = {s: eng.genome_length(gids[s]) for s in stems}
+        pairs = [(a, b) for a in stems for b in stems if a != b]
+        res = eng.anib(np.array([[gids[a], gids[b]] for a, b in pairs], dtype=np.int32), fragsize=fragsize)
+    finally:
+        if engine is None:
+            eng.close()
     return fill_aniresults(org_lengths, {p: parse_result(r) for p, r in zip(pairs, res)})
 
 

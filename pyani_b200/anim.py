@@ -21,6 +21,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from .engine import Engine
+from .results import ANIResults  # noqa: F401  (re-exported: the sink type of this module's functions)
 from .fasta import read_fasta
 
 
@@ -39,42 +40,6 @@ def parse_result(res) -> Tuple[int, int, float, int]:
     return (int(res["ref_aln_len"]), int(res["qry_aln_len"]), int(res["sum_weighted"]) / int(res["sum_aligned"]), int(res["sim_errs"]))
 
 
-class ANIResults:
-    """Same five tables and fill semantics as ``pyani_tools.ANIResults`` (pyani_tools.py:85-196)."""
-
-    def __init__(self, labels: List[str], mode: str = "ANIm") -> None:
-        import pandas as pd
-
-        self.alignment_lengths = pd.DataFrame(index=labels, columns=labels, dtype=float)
-        self.similarity_errors = pd.DataFrame(index=labels, columns=labels, dtype=float).fillna(0)
-        self.percentage_identity = pd.DataFrame(index=labels, columns=labels, dtype=float).fillna(1.0)
-        self.alignment_coverage = pd.DataFrame(index=labels, columns=labels, dtype=float).fillna(1.0)
-        self.zero_error = False
-        self.mode = mode
-
-    def add_tot_length(self, qname, sname, query_alignment_length, subject_alignment_length=None):
-        self.alignment_lengths.loc[qname, sname] = query_alignment_length
-        if subject_alignment_length:
-            self.alignment_lengths.loc[sname, qname] = subject_alignment_length
-
-    def add_sim_errors(self, qname, sname, value, sym=True):
-        self.similarity_errors.loc[qname, sname] = value
-        if sym:
-            self.similarity_errors.loc[sname, qname] = value
-
-    def add_pid(self, qname, sname, perc_id):
-        self.percentage_identity.loc[qname, sname] = perc_id
-
-    def add_coverage(self, qname, sname, qcover, scover=None):
-        self.alignment_coverage.loc[qname, sname] = qcover
-        if scover:
-            self.alignment_coverage.loc[sname, qname] = scover
-
-    @property
-    def hadamard(self):
-        return self.percentage_identity * self.alignment_coverage
-
-
 def fill_aniresults(org_lengths: Dict[str, int], tuples: Dict[Tuple[str, str], Tuple[int, int, float, int]]) -> ANIResults:
     """``process_deltadir`` (anim.py:415-497) given the per-file 4-tuples instead of files.
 
@@ -84,8 +49,10 @@ def fill_aniresults(org_lengths: Dict[str, int], tuples: Dict[Tuple[str, str], T
     file wins."""
     results = ANIResults(list(org_lengths.keys()), "ANIm")
     for org, length in org_lengths.items():
-        results.alignment_lengths.loc[org, org] = length
-    for qname, sname in sorted(tuples, key=lambda k: f"{k[0]}/{k[0]}_vs_{k[1]}.filter"):
+        results.add_tot_length(org, org, length)
+    # Path objects compare component-wise (directory name first, then file name), which differs from comparing the
+    # joined string whenever one stem is a prefix of another followed by a character below '/'
+    for qname, sname in sorted(tuples, key=lambda k: (k[0], f"{k[0]}_vs_{k[1]}.filter")):
         if qname not in org_lengths or sname not in org_lengths:
             continue
         q_len, s_len, ident, errs = tuples[(qname, sname)]
@@ -103,13 +70,17 @@ def calculate_anim(infiles: Sequence[Path], org_lengths: Optional[Dict[str, int]
     """All directed comparisons between ``infiles`` on the GPU -> ANIResults (legacy driver semantics,
     average_nucleotide_identity.py:489-575)."""
     eng = engine or Engine(0)
-    files = sorted(Path(f) for f in infiles)  # anim.py:217: sorted file list, both directions
-    gids = {f.stem: eng.add_fasta(f) for f in files}
-    stems = [f.stem for f in files]
-    if org_lengths is None:
-        org_lengths = {s: eng.genome_length(gids[s]) for s in stems}
-    pairs = [(a, b) for a in stems for b in stems if a != b]
-    res = eng.anim(np.array([[gids[a], gids[b]] for a, b in pairs], dtype=np.int32), maxmatch=maxmatch, nofilter=nofilter)
+    try:
+        files = sorted(Path(f) for f in infiles)  # anim.py:217: sorted file list, both directions
+        gids = {f.stem: eng.add_fasta(f) for f in files}
+        stems = [f.stem for f in files]
+        if org_lengths is None:
+            org_lengths = {s: eng.genome_length(gids[s]) for s in stems}
+        pairs = [(a, b) for a in stems for b in stems if a != b]
+        res = eng.anim(np.array([[gids[a], gids[b]] for a, b in pairs], dtype=np.int32), maxmatch=maxmatch, nofilter=nofilter)
+    finally:
+        if engine is None:  # an engine created here is not the caller's to clean up
+            eng.close()
     tuples = {}
     for (a, b), r in zip(pairs, res):
         tuples[(a, b)] = parse_result(r)

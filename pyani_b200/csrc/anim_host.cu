@@ -73,7 +73,7 @@ struct AnimWorkspace {
     b200ani_anim_result *d_results = nullptr;
     void *cub_tmp = nullptr;
     size_t cub_bytes = 0;
-    cudaEvent_t ev[2 * B200ANI_N_STAGES];
+    cudaEvent_t ev[2 * B200ANI_N_STAGES] = {};
     std::vector<cudaEvent_t> kev;  // per-launch event pairs of the extension rounds
     bool ok = false;
 };
@@ -83,7 +83,7 @@ void free_anim_workspace(void *p) {
     if (!w) return;
     cudaFree(w->keys_a); cudaFree(w->vals_a); cudaFree(w->keys_b); cudaFree(w->vals_b); cudaFree(w->flag); cudaFree(w->hits);
     cudaFree(w->counters); cudaFree(w->changed); cudaFree(w->d_pairs); cudaFree(w->d_results); cudaFree(w->cub_tmp);
-    if (w->ok) for (auto &e : w->ev) cudaEventDestroy(e);
+    for (auto &e : w->ev) if (e) cudaEventDestroy(e);
     for (auto &e : w->kev) cudaEventDestroy(e);
     delete w;
 }
@@ -91,7 +91,8 @@ void free_anim_workspace(void *p) {
 static int get_workspace(b200ani_ctx *ctx, AnimWorkspace **out) {
     if (ctx->anim_ws) { *out = (AnimWorkspace *)ctx->anim_ws; return 0; }
     AnimWorkspace *w = new AnimWorkspace();
-    ctx->anim_ws = w;
+    // cached in the context only once every allocation succeeded: a half-built workspace must never be reused
+    struct Guard { AnimWorkspace *w; ~Guard() { if (w) free_anim_workspace(w); } } guard{w};
     if (const char *e = getenv("B200ANI_ANCHOR_CAP")) w->anchor_cap = std::max<int64_t>(1024, atoll(e));
     if (const char *e = getenv("B200ANI_HIT_CAP")) w->hit_cap = std::max<int64_t>(1024, atoll(e));
     const int64_t ANCHOR_CAP = w->anchor_cap, HIT_CAP = w->hit_cap;
@@ -113,6 +114,8 @@ static int get_workspace(b200ani_ctx *ctx, AnimWorkspace **out) {
     CK(cudaMalloc(&w->cub_tmp, w->cub_bytes));
     for (auto &e : w->ev) CK(cudaEventCreate(&e));
     w->ok = true;
+    guard.w = nullptr;
+    ctx->anim_ws = w;
     *out = w;
     return 0;
 }

@@ -9,6 +9,19 @@ static const char *kVersion = "b200ani 0.1.0 (sm_100a)";
 
 static void release_genome(b200ani_ctx *ctx, Genome &g, cudaStream_t st);
 
+// stream-ordered scratch that is released on every exit path of an entry point
+struct Scratch {
+    cudaStream_t st;
+    std::vector<void *> ptrs;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    ~Scratch() { for (void *p : ptrs) cudaFreeAsync(p, st); }
+    template <typename T> cudaError_t get(T **p, size_t bytes) {
+        cudaError_t e = cudaMallocAsync((void **)p, bytes ? bytes : 1, st);
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+};
+
 extern "C" {
 
 const char *b200ani_version(void) { return kVersion; }
@@ -145,11 +158,11 @@ int b200ani_tetra_counts(b200ani_ctx *ctx, int32_t id, int64_t *c2, int64_t *c3,
     if (!ctx || !c2 || !c3 || !c4) return B200ANI_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     unsigned long long *d_tot = nullptr, h[336];
-    CK(cudaMallocAsync(&d_tot, sizeof h, ctx->stream));
+    Scratch tmp(ctx->stream);
+    CK(tmp.get(&d_tot, sizeof h));
     int rc = tetra_totals_for(ctx, &id, 1, d_tot);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h, d_tot, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaFreeAsync(d_tot, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 16; ++i) c2[i] = (int64_t)h[i];
     for (int i = 0; i < 64; ++i) c3[i] = (int64_t)h[16 + i];
@@ -163,18 +176,16 @@ int b200ani_tetra_zscores(b200ani_ctx *ctx, const int32_t *ids, int n, double *z
     unsigned long long *d_tot = nullptr;
     double *d_z = nullptr;
     uint8_t *d_obs = nullptr;
-    CK(cudaMallocAsync(&d_tot, sizeof(unsigned long long) * 336 * (size_t)n, ctx->stream));
-    CK(cudaMallocAsync(&d_z, sizeof(double) * 256 * (size_t)n, ctx->stream));
-    CK(cudaMallocAsync(&d_obs, 256 * (size_t)n, ctx->stream));
+    Scratch tmp(ctx->stream);
+    CK(tmp.get(&d_tot, sizeof(unsigned long long) * 336 * (size_t)n));
+    CK(tmp.get(&d_z, sizeof(double) * 256 * (size_t)n));
+    CK(tmp.get(&d_obs, 256 * (size_t)n));
     int rc = tetra_totals_for(ctx, ids, n, d_tot);
     if (rc) return rc;
     rc = tetra_zscores_device(ctx, d_tot, n, d_z, d_obs);
     if (rc) return rc;
     CK(cudaMemcpyAsync(z, d_z, sizeof(double) * 256 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(observed, d_obs, 256 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaFreeAsync(d_tot, ctx->stream));
-    CK(cudaFreeAsync(d_z, ctx->stream));
-    CK(cudaFreeAsync(d_obs, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return B200ANI_OK;
 }
@@ -188,17 +199,15 @@ int b200ani_tetra_corr(b200ani_ctx *ctx, const double *z, const uint8_t *mask, i
     if (m == 0) FAIL(B200ANI_ERR_ARG, "tetra_corr: empty tetramer mask");
     double *d_z = nullptr, *d_corr = nullptr;
     int *d_idx = nullptr;
-    CK(cudaMallocAsync(&d_z, sizeof(double) * 256 * (size_t)n, ctx->stream));
-    CK(cudaMallocAsync(&d_corr, sizeof(double) * (size_t)n * n, ctx->stream));
-    CK(cudaMallocAsync(&d_idx, sizeof idx, ctx->stream));
+    Scratch tmp(ctx->stream);
+    CK(tmp.get(&d_z, sizeof(double) * 256 * (size_t)n));
+    CK(tmp.get(&d_corr, sizeof(double) * (size_t)n * n));
+    CK(tmp.get(&d_idx, sizeof idx));
     CK(cudaMemcpyAsync(d_z, z, sizeof(double) * 256 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_idx, idx, sizeof idx, cudaMemcpyHostToDevice, ctx->stream));
     int rc = tetra_corr_device(ctx, d_z, d_idx, m, n, d_corr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(corr, d_corr, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaFreeAsync(d_z, ctx->stream));
-    CK(cudaFreeAsync(d_corr, ctx->stream));
-    CK(cudaFreeAsync(d_idx, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return B200ANI_OK;
 }

@@ -144,11 +144,14 @@ class Engine:
         return out
 
     def anim_alignments(self, ref: int, qry: int, maxmatch: bool = False, nofilter: bool = False, cap: int = 1 << 16) -> np.ndarray:
-        rows = np.zeros((cap, 7), dtype=np.int64)
-        n = self._lib.b200ani_anim_alignments(self._h, ref, qry, int(maxmatch), int(nofilter), _ptr(rows), cap)
-        if n < 0:
-            self._check(int(n), "anim_alignments")
-        return rows[: min(n, cap)].copy()
+        while True:
+            rows = np.zeros((cap, 7), dtype=np.int64)
+            n = self._lib.b200ani_anim_alignments(self._h, ref, qry, int(maxmatch), int(nofilter), _ptr(rows), cap)
+            if n < 0:
+                self._check(int(n), "anim_alignments")
+            if n <= cap:  # never hand back a truncated list: a short .delta would parse to wrong lengths silently
+                return rows[:n].copy()
+            cap = int(n)
 
     # -- ANIb
     def anib(self, pairs: np.ndarray, fragsize: int = 1020) -> np.ndarray:
@@ -161,11 +164,14 @@ class Engine:
 
     def anib_fragments(self, qry: int, sbj: int, fragsize: int = 1020, cap: int = 1 << 15) -> np.ndarray:
         """Kept HSP per passing fragment: rows (frag, length, mismatch, gaps, nident, qlen, score, pid_milli)."""
-        rows = np.zeros((cap, 8), dtype=np.int64)
-        n = self._lib.b200ani_anib_fragments(self._h, qry, sbj, int(fragsize), _ptr(rows), cap)
-        if n < 0:
-            self._check(int(n), "anib_fragments")
-        return rows[: min(n, cap)].copy()
+        while True:
+            rows = np.zeros((cap, 8), dtype=np.int64)
+            n = self._lib.b200ani_anib_fragments(self._h, qry, sbj, int(fragsize), _ptr(rows), cap)
+            if n < 0:
+                self._check(int(n), "anib_fragments")
+            if n <= cap:
+                return rows[:n].copy()
+            cap = int(n)
 
     def last_profile(self) -> Tuple[Dict[str, float], Dict[str, int]]:
         ms = np.zeros(_lib.N_STAGES, dtype=np.float64)

@@ -23,7 +23,10 @@ def _parse(data: bytes, path="<bytes>") -> Tuple[np.ndarray, np.ndarray, List[st
     ids: List[str] = []
     parts: List[bytes] = []
     lens: List[int] = []
-    for block in data.split(b">")[1:]:
+    # records start at a LINE-INITIAL '>' only (Bio.SeqIO's FASTA model): a '>' inside a description is header text
+    if data.startswith(b">"):
+        data = b"\n" + data
+    for block in data.split(b"\n>")[1:]:
         nl = block.find(b"\n")
         header = block if nl < 0 else block[:nl]
         body = b"" if nl < 0 else block[nl + 1 :]

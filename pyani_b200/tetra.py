@@ -35,7 +35,11 @@ def calculate_tetra_zscore(filename: Path, engine: Optional[Engine] = None) -> D
     """tetra.py:78 -- Z-scores of one FASTA file, as {tetramer: z}."""
     eng = _engine(engine)
     gid = eng.add_fasta(filename)
-    z, obs = eng.tetra_zscores([gid])
+    try:
+        z, obs = eng.tetra_zscores([gid])
+    finally:
+        if engine is None:  # the shared default engine never hands genome ids out: drop what this call staged
+            eng.clear()
     return _to_dict(z[0], obs[0])
 
 
@@ -43,8 +47,12 @@ def calculate_tetra_zscores(infilenames: Iterable, engine: Optional[Engine] = No
     """tetra.py:66 -- {file stem: {tetramer: z}}; one batched device call for all files."""
     eng = _engine(engine)
     files = [Path(f) for f in infilenames]
-    gids = [eng.add_fasta(f) for f in files]
-    z, obs = eng.tetra_zscores(gids)
+    try:
+        gids = [eng.add_fasta(f) for f in files]
+        z, obs = eng.tetra_zscores(gids)
+    finally:
+        if engine is None:
+            eng.clear()
     return {f.stem: _to_dict(z[i], obs[i]) for i, f in enumerate(files)}
 
 

@@ -178,3 +178,43 @@ def test_comparison_rows_follow_update_comparison_results():
     assert a["identity"] == 0.9 and a["cov_query"] == 0.9 and a["cov_subject"] == 950 / 2000
     assert (b["query_id"], b["subject_id"]) == (33, 11) and b["cov_query"] == 500 / 4000 and b["cov_subject"] == 400 / 1000
     assert a["program"] == "b200ani" and a["version"] == "b200ani 0.1.0" and a["maxmatch"] is True and a["fragsize"] is None
+
+
+def test_fasta_gt_inside_description():
+    """Only a line-initial '>' starts a record (Bio.SeqIO's model, pyani_files.py:141): a '>' in the description is text."""
+    from pyani_b200.fasta import _parse
+
+    arr, off, ids = _parse(b">s1 desc a->b\nACGT\nAC\n>s2\nGG\n")
+    assert ids == ["s1", "s2"] and off.tolist() == [0, 6, 8] and bytes(arr) == b"ACGTACGG"
+    arr, off, ids = _parse(b"\n>only\nAC\r\nGT\r\n")
+    assert ids == ["only"] and bytes(arr) == b"ACGT"
+
+
+def test_fill_order_is_path_order_not_string_order():
+    """process_deltadir visits sorted(Path) (anim.py:438): component-wise, so 'a/...' < 'a-b/...' although '-' < '/'.
+    The later file wins the symmetric cells."""
+    from pathlib import PurePosixPath
+
+    names = ["a", "a-b"]
+    files = sorted(PurePosixPath(f"{q}/{q}_vs_{s}.filter") for q in names for s in names if q != s)
+    assert [f.parts[0] for f in files] == ["a", "a-b"]  # string order of the joined path would be the reverse
+    tuples = {("a", "a-b"): (10, 20, 0.9, 1), ("a-b", "a"): (30, 40, 0.8, 2)}
+    res = banim.fill_aniresults({"a": 100, "a-b": 100}, tuples)
+    # last visited = a-b_vs_a: its q_len lands in [a-b, a], its s_len in [a, a-b]
+    assert res.alignment_lengths.loc["a", "a-b"] == 40 and res.alignment_lengths.loc["a-b", "a"] == 30
+    assert res.similarity_errors.loc["a", "a-b"] == 2
+
+
+def test_aniresults_data_property():
+    """The legacy driver iterates ANIResults.data to write its tables (average_nucleotide_identity.py:789)."""
+    from pyani_b200.results import _ArrayResults
+
+    for cls in {banim.ANIResults, _ArrayResults}:
+        r = cls(["x", "y"], "ANIm")
+        r.add_pid("x", "y", 0.5)
+        r.add_coverage("x", "y", 0.5, 0.25)
+        stems = [stem for _, stem in r.data]
+        assert stems == ["ANIm_alignment_lengths", "ANIm_percentage_identity", "ANIm_alignment_coverage", "ANIm_similarity_errors",
+                         "ANIm_hadamard"]
+        had = dict((stem, df) for df, stem in r.data)["ANIm_hadamard"]
+        assert had.loc["x", "y"] == 0.25 and had.loc["y", "x"] == 0.25
