@@ -148,7 +148,8 @@ ANIM_STAT_NAMES = ["anchors", "links", "cut_links", "segments", "gap_cells", "ex
 class OGenome:
     """Oracle-side genome handle (byte-per-base g-space + minimizer index: k-mers with <= 16 occurrences, repeats flagged)."""
 
-    def __init__(self, ascii_u8: np.ndarray, contig_off: np.ndarray):
+    def __init__(self, ascii_u8: np.ndarray, contig_off: np.ndarray, anim_index: bool = True):
+        """anim_index=False: skip the ANIm seed index (callers that only run ANIb; the ANIb index is built on first use)."""
         L = lib()
         L.orc_genome_create.restype = ctypes.c_void_p
         L.orc_genome_free.argtypes = [ctypes.c_void_p]
@@ -159,7 +160,7 @@ class OGenome:
         self.n_bases = int(o[-1])
         self.contig_off = o
         self._args = (a, o)
-        self._h = ctypes.c_void_p(L.orc_genome_create(_p(a, ctypes.c_uint8), _p(o, ctypes.c_uint64), ctypes.c_uint32(len(o) - 1)))
+        self._h = ctypes.c_void_p(L.orc_genome_create(_p(a, ctypes.c_uint8), _p(o, ctypes.c_uint64), ctypes.c_uint32(len(o) - 1))) if anim_index else None
         self._hb = None  # ANIb index (shorter seeds), built on first use
 
     @property

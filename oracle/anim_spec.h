@@ -30,8 +30,9 @@
 #define AN_MISMATCH 7
 #define AN_GAPOPEN 10    /* cost of the first column of a gap */
 #define AN_GAPEXT 7      /* cost of each further gap column (error counts of nucmer's own alignments are reproduced exactly with 10/7) */
-#define AN_BREAK 104     /* rows without a new best before an extension/link gives up (nucmer -b 200 anti-diagonals = 100 rows; calibrated) */
-#define AN_BRIDGE_DD 100  /* bridging: max |gap_q - gap_r| between two alignments that are joined (any offset the AN_BREAK x AN_BREAK residual allows; calibrated: 60 and 100 reproduce the same nucmer rows, 100 is closer on identity) */
+#define AN_BREAK_DIAGS 200 /* ANIm break rule: anti-diagonals past the one of the best cell before an extension / link gives up (nucmer -b 200) */
+#define AN_XDROP 600     /* a join is made only if its global alignment scores at least -AN_XDROP: nucmer drops cells more than ~600 (= 3 x 200) below its high score from the band, so a costlier box is never crossed */
+#define AN_FUSE_DIAGS 198 /* two segments whose anchor-level box spans at most this many anti-diagonals (gap_r + gap_q) are always one alignment: nucmer -b 200, an alignment to a target that close cannot give up */
 #define AN_CLUSTGAP 90   /* anchors closer than this on both genomes form a cluster (mgaps -s 90) */
 #define AN_FILT_OLAP 75  /* delta-filter -o 75: max overlap % of either alignment in a kept chain */
 #define AN_FILT_POW 2    /* alignment weight = length * identity^POW */

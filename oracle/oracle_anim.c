@@ -21,6 +21,7 @@
  * callers parallelise over pairs with Python threads (ctypes releases the GIL).
  */
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -224,27 +225,29 @@ static uint32_t contig_of(const uint64_t *goff, uint32_t n, int64_t pos) {
 /* ------------------------------------------------------------------ banded affine DP
  * value = score*AN_PACK - errs ; cell (i,j): i bases of R, j bases of Q consumed; diagonal k = j - i in
  * [klo, klo+AN_BANDW-1] (AN_BANDW = 32 diagonals = one 64-bit window of 2-bit query bases).  R/Q are read as R[rs*i'] with stride rs = +1 / -1 (left extensions read
- * backwards).  Both modes track the best cell so far (row-major first maximum, starting with (0,0)=0)
- * and give up ("stopped") as soon as a row ends more than AN_BREAK rows after the best cell's row --
- * nucmer's break length: an extension must reach a new high score within -b 200 anti-diagonals
- * (~100 rows) or it is abandoned [EXT].
+ * backwards).  Both modes track the best cell so far, starting with (0,0)=0, and give up ("stopped") when the DP has moved
+ * too far past it -- nucmer's break length: an extension must reach a new high score within -b 200 anti-diagonals or it
+ * is abandoned [EXT].  ANIm: the best cell is the LAST cell with the highest score (nucmer updates its high score on >=;
+ * pinned on the fixture deltas: 7 matches + 3 mismatches score 0 and are part of nucmer's alignments) and the distance is
+ * counted in anti-diagonals; ANIb: first best cell, distance in rows (AB_BREAK).
  * mode 0: link alignment to the target corner, returns H[lr][lq] (meaningless if stopped).
  * mode 1: extension tile over at most lr rows and lq columns; returns the best cell in bi,bj. */
 typedef struct { int32_t val, bi, bj, stopped; int64_t cells; } dp_out;
 
 /* scoring model: {match, mismatch, first gap column, further gap columns, break length in rows} */
-static const int SC_ANIM[5] = {AN_MATCH, AN_MISMATCH, AN_GAPOPEN, AN_GAPEXT, AN_BREAK};
+static const int SC_ANIM[5] = {AN_MATCH, AN_MISMATCH, AN_GAPOPEN, AN_GAPEXT, 0 /* ANIm breaks on anti-diagonals: AN_BREAK_DIAGS */};
 static const int SC_ANIB[5] = {AB_MATCH, AB_MISMATCH, AB_GAP, AB_GAP, AB_BREAK};
 
+static inline int32_t pack_score(int32_t v);
 static dp_out dp_band_sc(const uint8_t *R, int rstride, const uint8_t *Q, int qstride, int lr, int lq, int klo, int mode, const int *sc, int64_t qavail) {
     /* mode 0 (link alignment): the band is NOT clipped at the corner column -- cells with j > lq use the query
      * bases that follow the gap (at most qavail are readable, beyond that: mismatch); they never feed H[lr][lq]
      * but take part in the best-row tracking of the break rule and in the cell count.  mode 1: j <= lq. */
     const int jmax = mode == 0 ? 0x3fffffff : lq;
-    enum { BW = AN_BANDW };
+    enum { BW = AN_BANDW, BWMAX = AN_BANDW };
     const int32_t go = sc[2] * AN_PACK + 1, ge = sc[3] * AN_PACK + 1;
     const int32_t sm = sc[0] * AN_PACK, sx = -(sc[1] * AN_PACK + 1);
-    int32_t Hp[BW + 2], Fp[BW + 2], Hc[BW + 2], Ec[BW + 2], Fc[BW + 2];
+    int32_t Hp[BWMAX + 2], Fp[BWMAX + 2], Hc[BWMAX + 2], Ec[BWMAX + 2], Fc[BWMAX + 2];
     dp_out o = {0, 0, 0, 0, 0};
     for (int kk = 0; kk < BW; ++kk) { /* row 0 */
         int j = klo + kk;
@@ -255,9 +258,11 @@ static dp_out dp_band_sc(const uint8_t *R, int rstride, const uint8_t *Q, int qs
     }
     Hp[BW] = Fp[BW] = AN_NEG;
     int32_t best = 0;
+    const int ties_late = sc == SC_ANIM; /* ANIm: last best cell + anti-diagonal break counter (see below); ANIb: first best cell, rows */
     for (int i = 1; i <= lr; ++i) {
         uint8_t rb = R[(int64_t)rstride * (i - 1)];
         int32_t rowmax = AN_NEG, hleft = AN_NEG, eleft = AN_NEG;
+        int rowj = 0;
         for (int kk = 0; kk < BW; ++kk) {
             int j = i + klo + kk;
             int32_t h, e, f;
@@ -278,8 +283,11 @@ static dp_out dp_band_sc(const uint8_t *R, int rstride, const uint8_t *Q, int qs
                 if (h < AN_NEG) h = AN_NEG;
                 if (e < AN_NEG) e = AN_NEG;
                 if (f < AN_NEG) f = AN_NEG;
-                if (h > rowmax) rowmax = h;
-                if (h > best) { best = h; o.bi = i; o.bj = j; }
+                if (ties_late) { if (h >= rowmax) { rowmax = h; rowj = j; } }
+                else {
+                    if (h > rowmax) rowmax = h;
+                    if (h > best) { best = h; o.bi = i; o.bj = j; }
+                }
             }
             Hc[kk] = h; Ec[kk] = e; Fc[kk] = f;
             hleft = h; eleft = e;
@@ -287,8 +295,12 @@ static dp_out dp_band_sc(const uint8_t *R, int rstride, const uint8_t *Q, int qs
         memcpy(Hp, Hc, sizeof(int32_t) * BW);
         memcpy(Fp, Fc, sizeof(int32_t) * BW);
         (void)Ec;
-        (void)rowmax;
-        if (i - o.bi > sc[4]) { o.stopped = 1; break; }
+        /* ANIm: the best cell is the LAST one with the highest score (nucmer updates its high score on >=): within a row the
+         * highest packed value (score, then fewer errors), the later column on ties; between rows the later row on equal score */
+        if (ties_late && rowmax > AN_NEG && pack_score(rowmax) >= pack_score(best)) { best = rowmax; o.bi = i; o.bj = rowj; }
+        /* break rule.  ANIm: nucmer gives up when the anti-diagonal it works on is more than -b 200 past the one of its high
+         * score; after row i the band is centred on anti-diagonal 2i + klo + BW/2.  ANIb: rows since the best row. */
+        if (ties_late ? (2 * i + klo + BW / 2 + 1 - (o.bi + o.bj) > AN_BREAK_DIAGS) : (i - o.bi > sc[4])) { o.stopped = 1; break; }
     }
     if (mode == 0) {
         int kk = (lq - lr) - klo;
@@ -308,7 +320,7 @@ static inline int32_t pack_errs(int32_t v) { return pack_score(v) * AN_PACK - v;
 
 /* unbanded global affine alignment of a small rectangle (bridges: at most BRIDGE_CAP x BRIDGE_CAP cells): H[lr][lq] in
  * the same packed units as dp_band_sc; sc = {match, mismatch, first gap column, further gap columns} */
-#define BRIDGE_CAP (AN_BREAK > AB_BRIDGE_GAP ? AN_BREAK : AB_BRIDGE_GAP)
+#define BRIDGE_CAP (AN_FUSE_DIAGS > AB_BRIDGE_GAP ? AN_FUSE_DIAGS : AB_BRIDGE_GAP)
 static int32_t dp_full(const uint8_t *R, const uint8_t *Q, int lr, int lq, const int *sc) {
     const int32_t go = sc[2] * AN_PACK + 1, ge = sc[3] * AN_PACK + 1, sm = sc[0] * AN_PACK, sx = -(sc[1] * AN_PACK + 1);
     int32_t H[BRIDGE_CAP + 2], F[BRIDGE_CAP + 2];
@@ -330,6 +342,13 @@ static int32_t dp_full(const uint8_t *R, const uint8_t *Q, int lr, int lq, const
 }
 
 /* ------------------------------------------------------------------ one directed pair */
+typedef struct { int64_t k[6], idx; } rowkey_t; /* records + coordinates of an alignment row, emission index */
+static int cmp_row_coords(const void *a, const void *b) {
+    const rowkey_t *x = (const rowkey_t *)a, *y = (const rowkey_t *)b;
+    for (int i = 0; i < 6; ++i)
+        if (x->k[i] != y->k[i]) return x->k[i] < y->k[i] ? -1 : 1;
+    return x->idx < y->idx ? -1 : x->idx > y->idx;
+}
 typedef struct { int32_t strand, r, q, len; } anchor;
 
 static int cmp_anchor(const void *a, const void *b) {
@@ -380,7 +399,17 @@ static void anchor_records(const orc_genome *R, const orc_genome *Q, const ancho
     }
 }
 
-typedef struct { int32_t strand, pred, succ, bval; uint32_t rc, qc; int64_t rs, re, qs, qe, score, errs, sdist; } seg_t;
+/* One alignment under construction.  [rs0,re0) x [qs0,qe0): the span of its anchors (first anchor start .. last anchor end,
+ * view coordinates), score0 / errs0 of that span; xs[side] / xe[side]: score and errors the extension of side 0 (left) /
+ * 1 (right) added, which moved the ends to rs / re / qs / qe.  pred / succ / bval / bmode: the junction to the previous
+ * alignment of the same row (bmode 1: fused at anchor level, the two facing extensions are dropped; 2: bridged between the
+ * extended ends). */
+typedef struct {
+    int32_t strand, pred, succ, bval, bmode, tgt, hlen, btrim; /* hlen: length of the first anchor; btrim: bases of it given up to a fused predecessor */
+    uint32_t rc, qc;
+    int64_t rs0, re0, qs0, qe0, score0, errs0;
+    int64_t rs, re, qs, qe, xs[2], xe[2], sdist;
+} seg_t;
 
 /* Alignments of R (reference = pyani query, anim.py:280) vs Q before the 1-to-1 filter.
  * maxmatch = 0 (nucmer --mum): a seed k-mer must be unique in at least one of the two genomes;
@@ -400,7 +429,7 @@ int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int maxmatch, i
       uint64_t cursor = ~0ull;
       const uint32_t qpf = Q->mini_posflag[t];
       while (lookup_next(R, Q->mini_kmer[t], &cursor, &rpf)) { /* up to AN_MAXOCC entries per k-mer */
-        if (!maxmatch && (rpf & REP_BIT) && (qpf & REP_BIT)) continue; /* --mum: repeated in both genomes */
+        if (!maxmatch && !getenv("ORC_MUM") && (rpf & REP_BIT) && (qpf & REP_BIT)) continue; /* --mum: repeated in both genomes */
         stats[7]++;
         int strand = (int)((rpf ^ qpf) >> 31);
         int64_t r0 = rpf & POS_MASK, qpos = qpf & POS_MASK;
@@ -426,6 +455,41 @@ int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int maxmatch, i
     for (int64_t i = 0; i < na; ++i)
         if (i == 0 || cmp_anchor(&A[i], &A[i - 1]) != 0) A[nu++] = A[i];
     na = nu;
+    if (!maxmatch && getenv("ORC_MUM")) {
+        /* experiment: true MUM semantics -- a maximal match is kept only if neither its reference interval nor its query
+         * interval is contained in that of another maximal match (the substring would occur twice in the other genome) */
+        uint8_t *dead = (uint8_t *)calloc((size_t)na + 1, 1);
+        for (int axis = 0; axis < 2; ++axis) {
+            int64_t *ord = (int64_t *)malloc(sizeof(int64_t) * (size_t)(na + 1));
+            int64_t *lo = (int64_t *)malloc(sizeof(int64_t) * (size_t)(na + 1)), *hi = (int64_t *)malloc(sizeof(int64_t) * (size_t)(na + 1));
+            for (int64_t i = 0; i < na; ++i) {
+                if (axis == 0) { lo[i] = A[i].r; hi[i] = (int64_t)A[i].r + A[i].len; }
+                else if (!A[i].strand) { lo[i] = A[i].q; hi[i] = (int64_t)A[i].q + A[i].len; }
+                else { lo[i] = Q->n_pos - ((int64_t)A[i].q + A[i].len); hi[i] = Q->n_pos - A[i].q; }
+                ord[i] = i;
+            }
+            /* sort by (lo asc, hi desc): simple insertion-free approach via qsort on packed keys */
+            uint64_t *key = (uint64_t *)malloc(sizeof(uint64_t) * 2 * (size_t)(na + 1));
+            for (int64_t i = 0; i < na; ++i) { key[2 * i] = ((uint64_t)lo[i] << 32) | (uint32_t)(0x7fffffff - hi[i]); key[2 * i + 1] = (uint64_t)i; }
+            /* sort pairs by key */
+            typedef struct { uint64_t k, v; } kv;
+            int cmpkv(const void *a, const void *b) { const kv *x = a, *y = b; return x->k < y->k ? -1 : x->k > y->k; }
+            qsort(key, (size_t)na, sizeof(kv), cmpkv);
+            int64_t runmax = -1, prev = -1;
+            for (int64_t t = 0; t < na; ++t) {
+                int64_t i = (int64_t)key[2 * t + 1];
+                if (runmax >= hi[i]) dead[i] |= 1;
+                if (prev >= 0 && lo[prev] == lo[i] && hi[prev] == hi[i]) dead[prev] |= 1; /* identical interval: both */
+                if (hi[i] > runmax) runmax = hi[i];
+                prev = i;
+            }
+            free(ord); free(lo); free(hi); free(key);
+        }
+        nu = 0;
+        for (int64_t i = 0; i < na; ++i) if (!dead[i]) A[nu++] = A[i];
+        na = nu;
+        free(dead);
+    }
     stats[8] = na;
 
     int32_t *pred = (int32_t *)malloc(sizeof(int32_t) * (size_t)(na + 1));
@@ -488,98 +552,185 @@ int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int maxmatch, i
         esum[h] += pack_errs(gval[i]);
         tail[h] = (int32_t)i;
     }
-    /* ---- extend both ends of every segment */
+    /* ---- segments: span, score and errors of the anchor chain */
     seg_t *S = (seg_t *)malloc(sizeof(seg_t) * (size_t)(na + 1));
     int64_t ns = 0;
     for (int64_t h = 0; h < na; ++h) {
         if (head[h] != (int32_t)h) continue;
         stats[3]++;
         const anchor *f = &A[h], *l = &A[tail[h]];
-        const uint8_t *Qs = f->strand ? Q->rc : Q->fw;
-        uint32_t rc = rc_of[h], qc = qc_of[h];
+        seg_t *g = &S[ns++];
+        memset(g, 0, sizeof *g);
+        g->strand = f->strand; g->rc = rc_of[h]; g->qc = qc_of[h];
+        g->rs0 = g->rs = f->r; g->qs0 = g->qs = f->q;
+        g->re0 = g->re = (int64_t)l->r + l->len; g->qe0 = g->qe = (int64_t)l->q + l->len;
+        g->score0 = ssum[h] + wsum[h] * AN_MATCH; g->errs0 = esum[h];
+        g->pred = -1; g->succ = 0x7fffffff; g->tgt = -1; g->hlen = f->len - trim[h];
+    }
+    /* ---- fusion at anchor level (nucmer: the forward extension of a cluster aims at the start of the next cluster, and an
+     * alignment over fewer anti-diagonals than the break length cannot give up -- it always reaches its target and the two
+     * clusters become one alignment, whatever indel separates them).  Every segment takes as target the first following
+     * segment (sorted order, next AN_LOOKBACK, same strand and records) that starts at or after its end on both genomes --
+     * after giving up the part of its first anchor that overlaps, as links do: tandem duplications make the exact matches
+     * on either side of an indel overlap on one genome -- with both gaps below AN_FUSE_DIAGS or a diagonal shift the box
+     * could pay for (10 * lesser >= 7 * greater); it is fused with its target when the box between them spans at most
+     * AN_FUSE_DIAGS anti-diagonals.  A segment that is the target of several keeps the first. */
+    for (int64_t a = 0; a < ns; ++a) {
+        for (int64_t b = a + 1; b < ns && b <= a + AN_LOOKBACK; ++b) {
+            if (S[b].strand != S[a].strand) break;
+            if (S[b].rc != S[a].rc || S[b].qc != S[a].qc) continue;
+            int64_t gr = S[b].rs0 - S[a].re0, gq = S[b].qs0 - S[a].qe0, ov = 0;
+            if (-gr > ov) ov = -gr;
+            if (-gq > ov) ov = -gq;
+            if (ov >= S[b].hlen) continue;
+            gr += ov; gq += ov;
+            int64_t gt = gr > gq ? gr : gq, ls = gr > gq ? gq : gr;
+            if (!(gt < AN_FUSE_DIAGS || 10 * ls >= 7 * gt)) continue;
+            S[a].tgt = (int32_t)b;
+            break;
+        }
+    }
+    for (int64_t a = 0; a < ns; ++a) { /* ascending a: the first claimant keeps the target */
+        int32_t b = S[a].tgt;
+        if (b < 0 || S[b].pred >= 0) continue;
+        int64_t gr = S[b].rs0 - S[a].re0, gq = S[b].qs0 - S[a].qe0, ov = 0;
+        if (-gr > ov) ov = -gr;
+        if (-gq > ov) ov = -gq;
+        if (gr + gq + 2 * ov > AN_FUSE_DIAGS) continue;
+        /* the box is short enough that the extension cannot run out of break length; it still has to arrive alive */
+        const int lr = (int)(gr + ov), lq = (int)(gq + ov);
+        const uint8_t *Qs = S[a].strand ? Q->rc : Q->fw;
+        int32_t v;
+        if (lr == 0 && lq == 0) v = 0;
+        else if (lr == 0 || lq == 0) { int L = lr + lq; v = -((AN_GAPOPEN + (L - 1) * AN_GAPEXT) * AN_PACK + L); }
+        else { v = dp_full(R->fw + S[a].re0, Qs + S[a].qe0, lr, lq, SC_ANIM); stats[10] += (int64_t)lr * lq; }
+        if (pack_score(v) < -AN_XDROP) continue;
+        S[b].pred = (int32_t)a; S[b].bmode = 1; S[b].btrim = (int32_t)ov; S[b].bval = v; S[a].succ = b;
+        stats[9]++;
+    }
+    /* ---- extend the free ends of every segment */
+    for (int64_t i = 0; i < ns; ++i) {
+        seg_t *g = &S[i];
+        const uint8_t *Qs = g->strand ? Q->rc : Q->fw;
         /* record bounds in the (possibly reversed) coordinate spaces */
-        int64_t r_lo = (int64_t)R->goff[rc], r_hi = (int64_t)R->goff[rc + 1] - 1; /* [lo,hi) bases */
-        int64_t q_lo = (int64_t)Q->goff[qc], q_hi = (int64_t)Q->goff[qc + 1] - 1;
-        if (f->strand) { int64_t a = Q->n_pos - q_hi, b = Q->n_pos - q_lo; q_lo = a; q_hi = b; }
-        int64_t rs = f->r, qs = f->q, re = (int64_t)l->r + l->len, qe = (int64_t)l->q + l->len; /* [s,e) */
-        int64_t score = ssum[h] + wsum[h] * AN_MATCH, errs = esum[h];
+        int64_t r_lo = (int64_t)R->goff[g->rc], r_hi = (int64_t)R->goff[g->rc + 1] - 1; /* [lo,hi) bases */
+        int64_t q_lo = (int64_t)Q->goff[g->qc], q_hi = (int64_t)Q->goff[g->qc + 1] - 1;
+        if (g->strand) { int64_t a = Q->n_pos - q_hi, b = Q->n_pos - q_lo; q_lo = a; q_hi = b; }
         for (int side = 0; side < 2; ++side) {
+            if (side == 0 ? (g->pred >= 0 && g->bmode == 1) : (g->succ != 0x7fffffff && S[g->succ].pred == (int32_t)i && S[g->succ].bmode == 1))
+                continue; /* fused end: nothing to extend */
             for (int t = 0; t < AN_MAXTILES; ++t) {
-                int64_t ar = side ? r_hi - re : rs - r_lo, aq = side ? q_hi - qe : qs - q_lo;
+                int64_t ar = side ? r_hi - g->re : g->rs - r_lo, aq = side ? q_hi - g->qe : g->qs - q_lo;
                 int lr = (int)(ar < AN_TILE ? ar : AN_TILE), lq = (int)(aq < AN_TILE + AN_BAND ? aq : AN_TILE + AN_BAND);
                 if (lr <= 0 || lq <= 0) break;
-                dp_out o = side ? dp_band(R->fw + re, 1, Qs + qe, 1, lr, lq, -AN_BAND, 1)
-                                : dp_band(R->fw + rs - 1, -1, Qs + qs - 1, -1, lr, lq, -AN_BAND, 1);
+                dp_out o = side ? dp_band(R->fw + g->re, 1, Qs + g->qe, 1, lr, lq, -AN_BAND, 1)
+                                : dp_band(R->fw + g->rs - 1, -1, Qs + g->qs - 1, -1, lr, lq, -AN_BAND, 1);
                 stats[5] += o.cells; stats[6]++;
                 if (o.bi == 0 && o.bj == 0) break;
-                score += pack_score(o.val);
-                errs += pack_errs(o.val);
-                if (side) { re += o.bi; qe += o.bj; } else { rs -= o.bi; qs -= o.bj; }
+                g->xs[side] += pack_score(o.val);
+                g->xe[side] += pack_errs(o.val);
+                if (side) { g->re += o.bi; g->qe += o.bj; } else { g->rs -= o.bi; g->qs -= o.bj; }
                 if (o.stopped) break;
             }
         }
-        seg_t *g = &S[ns++];
-        g->strand = f->strand; g->rc = rc; g->qc = qc; g->rs = rs; g->re = re; g->qs = qs; g->qe = qe;
-        g->score = score; g->errs = errs; g->pred = -1; g->succ = 0x7fffffff; g->bval = 0; g->sdist = 0;
     }
-    /* ---- bridging: two extended alignments whose facing ends are at most AN_BREAK bases apart on both genomes (and
-     * no more than AN_BRIDGE_DD off each other's diagonal) are one alignment for nucmer -- its extension reaches the
-     * neighbouring cluster before the break length runs out.  Every alignment takes the nearest such predecessor
-     * among the previous AN_LOOKBACK alignments, every predecessor keeps its nearest successor, the residual gap is
-     * aligned globally (unbanded) and chains of bridged alignments are merged. */
+    /* ---- bridging: two extended alignments whose facing ends leave a box of at most AN_FUSE_DIAGS anti-diagonals between
+     * them are one alignment for nucmer -- its extension reaches the neighbouring cluster before the break length runs out --
+     * provided the box can be crossed alive (global alignment score >= -AN_XDROP).  Every alignment without a fused left end takes the nearest such
+     * predecessor among the previous AN_LOOKBACK alignments (whose right end is not fused), every predecessor keeps its nearest
+     * successor, the residual gap is aligned globally (unbanded) and chains of joined alignments are merged. */
     for (int64_t b = 0; b < ns; ++b) {
         int64_t bestd = -1;
+        S[b].sdist = -1;
+        if (S[b].pred >= 0) continue;
         for (int64_t a = b - 1; a >= 0 && a >= b - AN_LOOKBACK; --a) {
             if (S[a].strand != S[b].strand) break;
             if (S[a].rc != S[b].rc || S[a].qc != S[b].qc) continue;
+            if (S[a].succ != 0x7fffffff) continue; /* right end already fused */
             int64_t gr = S[b].rs - S[a].re, gq = S[b].qs - S[a].qe;
-            if (gr < 0 || gq < 0 || gr > AN_BREAK || gq > AN_BREAK) continue;
-            int64_t dd = gq - gr;
-            if (dd > AN_BRIDGE_DD || dd < -AN_BRIDGE_DD) continue;
-            if (bestd < 0 || gr + gq < bestd) { bestd = gr + gq; S[b].pred = (int32_t)a; }
+            if (gr < 0 || gq < 0 || gr + gq > AN_FUSE_DIAGS) continue;
+            if (bestd < 0 || gr + gq < bestd) { bestd = gr + gq; S[b].pred = (int32_t)a; S[b].bmode = 2; }
         }
         S[b].sdist = bestd;
     }
     for (int64_t b = 0; b < ns; ++b) /* ascending b: ties keep the earlier successor */
-        if (S[b].pred >= 0) {
+        if (S[b].pred >= 0 && S[b].bmode == 2) {
             seg_t *a = &S[S[b].pred];
             if (a->succ == 0x7fffffff || S[b].sdist < S[a->succ].sdist) a->succ = (int32_t)b;
         }
     for (int64_t b = 0; b < ns; ++b)
-        if (S[b].pred >= 0 && S[S[b].pred].succ != (int32_t)b) S[b].pred = -1;
+        if (S[b].pred >= 0 && S[b].bmode == 2 && S[S[b].pred].succ != (int32_t)b) { S[b].pred = -1; S[b].bmode = 0; }
     for (int64_t b = 0; b < ns; ++b) {
-        if (S[b].pred < 0) continue;
+        if (S[b].pred < 0 || S[b].bmode != 2) continue;
         stats[9]++;
         const seg_t *a = &S[S[b].pred];
-        int lr = (int)(S[b].rs - a->re), lq = (int)(S[b].qs - a->qe);
+        const int64_t ar = a->re, aq = a->qe;
+        int lr = (int)(S[b].rs - ar), lq = (int)(S[b].qs - aq);
         const uint8_t *Qs = S[b].strand ? Q->rc : Q->fw;
         int32_t v;
         if (lr == 0 && lq == 0) v = 0;
         else if (lr == 0 || lq == 0) { int L = lr + lq; v = -((AN_GAPOPEN + (L - 1) * AN_GAPEXT) * AN_PACK + L); }
-        else { v = dp_full(R->fw + a->re, Qs + a->qe, lr, lq, SC_ANIM); stats[10] += (int64_t)lr * lq; }
+        else { v = dp_full(R->fw + ar, Qs + aq, lr, lq, SC_ANIM); stats[10] += (int64_t)lr * lq; }
         S[b].bval = v;
+        if (pack_score(v) < -AN_XDROP) { /* the corner is out of reach: not joined */
+            seg_t *pa = &S[S[b].pred];
+            pa->succ = 0x7fffffff; S[b].pred = -1; S[b].bmode = 0; S[b].bval = 0; stats[9]--;
+        }
     }
-    /* ---- emit: one row per chain of bridged alignments */
-    int64_t nout = 0;
+    if (getenv("ORC_DUMP_SEGS")) { /* analysis: anchor-level spans of the segments, before any fusion */
+        FILE *fh = fopen(getenv("ORC_DUMP_SEGS"), "w");
+        for (int64_t i = 0; i < ns; ++i)
+            fprintf(fh, "%d %u %u %ld %ld %ld %ld %ld %ld %ld %ld\n", S[i].strand, S[i].rc, S[i].qc, (long)S[i].rs0, (long)S[i].re0, (long)S[i].qs0, (long)S[i].qe0,
+                    (long)S[i].rs, (long)S[i].re, (long)S[i].qs, (long)S[i].qe);
+        fclose(fh);
+    }
+    if (getenv("ORC_DEBUG")) {
+        long lo = atol(getenv("ORC_DEBUG")), hi = lo + 20000;
+        for (int64_t i = 0; i < ns; ++i)
+            if (S[i].rs0 >= lo && S[i].rs0 < hi)
+                fprintf(stderr, "seg %ld st%d r0[%ld,%ld) q0[%ld,%ld) -> r[%ld,%ld) q[%ld,%ld) sc0 %ld e0 %ld xs %ld/%ld pred %d mode %d succ %d tgt %d hlen %d\n", (long)i, S[i].strand,
+                        (long)S[i].rs0, (long)S[i].re0, (long)S[i].qs0, (long)S[i].qe0, (long)S[i].rs, (long)S[i].re, (long)S[i].qs, (long)S[i].qe,
+                        (long)S[i].score0, (long)S[i].errs0, (long)S[i].xs[0], (long)S[i].xs[1], S[i].pred, S[i].bmode, S[i].succ == 0x7fffffff ? -1 : S[i].succ, S[i].tgt, S[i].hlen);
+    }
+    /* ---- emit: one row per chain of joined alignments.  Two chains that grew to the very same alignment (same records and
+     * coordinates; forks of the anchor chain re-converge when both get extended) are one alignment: the first in emission
+     * order is kept. */
+    int64_t nout = 0, nall = 0;
+    int64_t *tmp = (int64_t *)malloc(sizeof(int64_t) * 8 * (size_t)(ns + 1));
     for (int64_t h = 0; h < ns; ++h) {
         if (S[h].pred >= 0) continue;
-        int64_t re = S[h].re, qe = S[h].qe, score = S[h].score, errs = S[h].errs;
-        for (int32_t pv = (int32_t)h, n2 = S[h].succ; n2 != 0x7fffffff && S[n2].pred == pv; pv = n2, n2 = S[n2].succ) {
-            score += S[n2].score + pack_score(S[n2].bval);
-            errs += S[n2].errs + pack_errs(S[n2].bval);
-            re = S[n2].re; qe = S[n2].qe;
+        int64_t score = S[h].score0 + S[h].xs[0], errs = S[h].errs0 + S[h].xe[0];
+        int32_t last = (int32_t)h;
+        for (int32_t n2 = S[h].succ; n2 != 0x7fffffff && S[n2].pred == last; last = n2, n2 = S[n2].succ) {
+            if (S[n2].bmode == 2) { score += S[last].xs[1] + S[n2].xs[0]; errs += S[last].xe[1] + S[n2].xe[0]; }
+            score += S[n2].score0 - (int64_t)AN_MATCH * S[n2].btrim + pack_score(S[n2].bval);
+            errs += S[n2].errs0 + pack_errs(S[n2].bval);
         }
-        if (nout < cap) {
-            int64_t *o = rows + 8 * nout;
-            const uint32_t rc = S[h].rc, qc = S[h].qc;
-            o[0] = rc; o[1] = qc;
-            o[2] = S[h].rs - (int64_t)R->goff[rc] + 1; o[3] = re - 1 - (int64_t)R->goff[rc] + 1;
-            if (!S[h].strand) { o[4] = S[h].qs - (int64_t)Q->goff[qc] + 1; o[5] = qe - 1 - (int64_t)Q->goff[qc] + 1; }
-            else { o[4] = (Q->n_pos - 1 - S[h].qs) - (int64_t)Q->goff[qc] + 1; o[5] = (Q->n_pos - qe) - (int64_t)Q->goff[qc] + 1; }
-            o[6] = errs; o[7] = score;
-        }
-        ++nout;
+        score += S[last].xs[1]; errs += S[last].xe[1];
+        const int64_t re = S[last].re, qe = S[last].qe;
+        int64_t *o = tmp + 8 * nall++;
+        const uint32_t rc = S[h].rc, qc = S[h].qc;
+        o[0] = rc; o[1] = qc;
+        o[2] = S[h].rs - (int64_t)R->goff[rc] + 1; o[3] = re - 1 - (int64_t)R->goff[rc] + 1;
+        if (!S[h].strand) { o[4] = S[h].qs - (int64_t)Q->goff[qc] + 1; o[5] = qe - 1 - (int64_t)Q->goff[qc] + 1; }
+        else { o[4] = (Q->n_pos - 1 - S[h].qs) - (int64_t)Q->goff[qc] + 1; o[5] = (Q->n_pos - qe) - (int64_t)Q->goff[qc] + 1; }
+        o[6] = errs; o[7] = score;
     }
+    {
+        rowkey_t *ord = (rowkey_t *)malloc(sizeof(rowkey_t) * (size_t)(nall + 1));
+        uint8_t *dup = (uint8_t *)calloc((size_t)nall + 1, 1);
+        for (int64_t i = 0; i < nall; ++i) { memcpy(ord[i].k, tmp + 8 * i, sizeof(int64_t) * 6); ord[i].idx = i; }
+        qsort(ord, (size_t)nall, sizeof(rowkey_t), cmp_row_coords);
+        for (int64_t t = 1; t < nall; ++t)
+            if (memcmp(ord[t].k, ord[t - 1].k, sizeof(int64_t) * 6) == 0) dup[ord[t].idx] = 1; /* ties are ordered by index: the earlier row stays */
+        for (int64_t i = 0; i < nall; ++i) {
+            if (dup[i]) continue;
+            if (nout < cap) memcpy(rows + 8 * nout, tmp + 8 * i, sizeof(int64_t) * 8);
+            ++nout;
+        }
+        free(ord); free(dup);
+    }
+    free(tmp);
     free(A); free(pred); free(succ); free(trim); free(gval); free(head); free(rc_of); free(qc_of);
     free(cw); free(wsum); free(ssum); free(esum); free(tail); free(S);
     return nout;
@@ -940,3 +1091,32 @@ int64_t orc_anib_pair(const orc_genome *Q, const orc_genome *S, int fragsize, in
     free(wsum); free(ssum); free(esum); free(fbase);
     return n_rows;
 }
+
+/* ------------------------------------------------------------------ analysis helper (calibration scripts only)
+ * Optimal GLOBAL affine-gap alignment score of two byte-coded sequences (match sm, mismatch -sx, first gap column -go,
+ * further gap columns -ge); used to test candidate scoring parameters against the alignments nucmer itself reports. */
+int64_t orc_global_score(const uint8_t *R, const uint8_t *Q, int64_t lr, int64_t lq, int sm, int sx, int go, int ge) {
+    const int64_t NEG = -(1ll << 40);
+    int64_t *H = (int64_t *)malloc(sizeof(int64_t) * (size_t)(lq + 1)), *F = (int64_t *)malloc(sizeof(int64_t) * (size_t)(lq + 1));
+    H[0] = 0; F[0] = NEG;
+    for (int64_t j = 1; j <= lq; ++j) { H[j] = -(go + (j - 1) * ge); F[j] = NEG; }
+    for (int64_t i = 1; i <= lr; ++i) {
+        int64_t diag = H[0], hleft = -(go + (i - 1) * ge), eleft = NEG;
+        H[0] = hleft;
+        for (int64_t j = 1; j <= lq; ++j) {
+            int64_t e1 = eleft - ge, e2 = hleft - go, e = e1 > e2 ? e1 : e2;
+            int64_t f1 = F[j] - ge, f2 = H[j] - go, f = f1 > f2 ? f1 : f2;
+            int64_t d = diag + ((R[i - 1] == Q[j - 1] && R[i - 1] < 4) ? sm : -sx);
+            int64_t h = d > e ? d : e;
+            if (f > h) h = f;
+            diag = H[j]; H[j] = h; F[j] = f; hleft = h; eleft = e;
+        }
+    }
+    int64_t v = H[lq];
+    free(H); free(F);
+    return v;
+}
+const uint8_t *orc_genome_fw(const orc_genome *g) { return g->fw; }
+const uint8_t *orc_genome_rc(const orc_genome *g) { return g->rc; }
+int64_t orc_genome_npos(const orc_genome *g) { return g->n_pos; }
+uint64_t orc_genome_goff(const orc_genome *g, uint32_t c) { return g->goff[c]; }

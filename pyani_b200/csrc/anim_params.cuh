@@ -22,6 +22,7 @@
 #define AN_GAPEXT 7
 #define AN_BREAK 104
 #define AN_BRIDGE_DD 100
+#define AN_FUSE_DIAGS 200
 #define AN_CLUSTGAP 90
 #define AN_FILT_OLAP 75
 #define AN_FILT_POW 2

@@ -39,8 +39,28 @@ def partition(costs: np.ndarray, world: int) -> List[Tuple[int, int]]:
     return [(int(bounds[r]), int(bounds[r + 1])) for r in range(world)]
 
 
-def all_gather_results(local: np.ndarray, blocks: List[Tuple[int, int]], device=None, group=None, dtype=ANIM_DTYPE) -> np.ndarray:
-    """One all-gather of the per-rank result arrays (padded to the largest block) -> full array, every rank.
+def deal(pairs: np.ndarray, world: int, chunk: int = 64) -> List[np.ndarray]:
+    """Which rows of ``pairs`` each rank computes: the directed pairs are grouped by unordered genome pair (both directions
+    share one seed pass on the device, so they stay together), the groups sorted by (lower id, higher id) -- the order in
+    which the engine walks them, one reference table hot in L2 after the other -- are cut into chunks of ``chunk`` groups,
+    and the chunks are dealt round-robin.  Costly and cheap comparisons (within- and between-clade pairs differ several-fold
+    in alignment work, and genome ids are normally grouped by clade) are thereby spread evenly without a cost model;
+    every rank can compute every rank's share, so nothing but the results is ever exchanged.
+    -> list of index arrays (ascending walk order), one per rank, together a partition of range(len(pairs))."""
+    p = np.asarray(pairs).reshape(-1, 2)
+    lo, hi = p.min(axis=1).astype(np.int64), p.max(axis=1).astype(np.int64)
+    order = np.lexsort((p[:, 0], hi, lo))
+    if world <= 1:
+        return [order]
+    key = lo[order] * (int(hi.max()) + 1 if len(p) else 1) + hi[order]
+    group = np.concatenate([[0], np.cumsum(key[1:] != key[:-1])]) if len(p) else np.zeros(0, np.int64)
+    owner = (group // max(1, chunk)) % world
+    return [order[owner == r] for r in range(world)]
+
+
+def all_gather_results(local: np.ndarray, blocks, device=None, group=None, dtype=ANIM_DTYPE) -> np.ndarray:
+    """ONE all-gather of the per-rank result arrays (padded to the largest share) -> full array in caller order, on every
+    rank.  ``blocks``: per rank either a contiguous (start, end) range of the pair list or the index array of :func:`deal`.
     ``dtype``: the result struct (ANIM_DTYPE 48 B, ANIB_DTYPE 40 B).
 
     Works with the ``nccl`` backend (tensors on ``device``) and with ``gloo`` (CPU tensors, used by the
@@ -50,7 +70,8 @@ def all_gather_results(local: np.ndarray, blocks: List[Tuple[int, int]], device=
 
     world = dist.get_world_size(group)
     assert len(blocks) == world
-    pad = max(e - s for s, e in blocks)
+    idx = [np.arange(b[0], b[1]) if isinstance(b, tuple) else np.asarray(b) for b in blocks]
+    pad = max(len(i) for i in idx)
     item = dtype.itemsize
     buf = np.zeros(pad * item, dtype=np.uint8)
     raw = np.ascontiguousarray(local).view(np.uint8).reshape(-1)
@@ -61,37 +82,41 @@ def all_gather_results(local: np.ndarray, blocks: List[Tuple[int, int]], device=
     out = torch.empty(world * pad * item, dtype=torch.uint8, device=t.device)
     dist.all_gather_into_tensor(out, t, group=group)
     flat = out.cpu().numpy().reshape(world, pad * item)
-    parts = [flat[r, : (e - s) * item].copy().view(dtype) for r, (s, e) in enumerate(blocks)]
-    return np.concatenate(parts) if parts else np.zeros(0, dtype=dtype)
+    full = np.zeros(sum(len(i) for i in idx), dtype=dtype)
+    for r, i in enumerate(idx):
+        full[i] = flat[r, : len(i) * item].copy().view(dtype)
+    return full
+
+
+def _sharded(run, pairs: np.ndarray, rank: int, world: int, dtype, device, group, chunk: int) -> np.ndarray:
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    shares = deal(pairs, world, chunk)
+    mine = shares[rank]
+    local = run(pairs[mine]) if len(mine) else np.zeros(0, dtype=dtype)
+    if world == 1:
+        full = np.zeros(len(pairs), dtype=dtype)
+        full[mine] = local
+        return full
+    return all_gather_results(local, shares, device=device, group=group, dtype=dtype)
 
 
 def anim_sharded(engine, pairs: np.ndarray, genome_lengths: Sequence[int], rank: int, world: int, *, maxmatch=False,
-                 nofilter=False, device=None, group=None, compute=None) -> np.ndarray:
-    """Run this rank's block of ``pairs`` on ``engine`` and all-gather the full result array.
+                 nofilter=False, device=None, group=None, compute=None, chunk: int = 64) -> np.ndarray:
+    """Run this rank's share of ``pairs`` (see :func:`deal`) on ``engine`` -- every rank holds all genomes -- and
+    all-gather the full result array in the order of ``pairs``.  ``genome_lengths`` is unused by the dealing plan and kept
+    for callers that balance contiguous blocks with :func:`partition` instead.
 
     ``compute`` (tests only) replaces ``engine.anim`` so the sharding logic can be exercised without a GPU."""
-    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
-    blocks = partition(pair_costs(pairs, genome_lengths), world)
-    s, e = blocks[rank]
     fn = compute if compute is not None else (lambda p: engine.anim(p, maxmatch=maxmatch, nofilter=nofilter))
-    local = fn(pairs[s:e]) if e > s else np.zeros(0, dtype=ANIM_DTYPE)
-    if world == 1:
-        return local
-    return all_gather_results(local, blocks, device=device, group=group)
+    return _sharded(fn, pairs, rank, world, ANIM_DTYPE, device, group, chunk)
 
 
 def anib_sharded(engine, pairs: np.ndarray, genome_lengths: Sequence[int], rank: int, world: int, *, fragsize: int = 1020,
-                 device=None, group=None, compute=None) -> np.ndarray:
-    """ANIb counterpart of :func:`anim_sharded`: pairs are (query, subject); the cost model is the same (the query's
-    fragments stream through the subject's table), the gathered structs are the 40-byte ANIb results."""
-    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
-    blocks = partition(pair_costs(pairs, genome_lengths), world)
-    s, e = blocks[rank]
+                 device=None, group=None, compute=None, chunk: int = 64) -> np.ndarray:
+    """ANIb counterpart of :func:`anim_sharded`: pairs are (query, subject), the gathered structs are the 40-byte ANIb
+    results."""
     fn = compute if compute is not None else (lambda p: engine.anib(p, fragsize=fragsize))
-    local = fn(pairs[s:e]) if e > s else np.zeros(0, dtype=ANIB_DTYPE)
-    if world == 1:
-        return local
-    return all_gather_results(local, blocks, device=device, group=group, dtype=ANIB_DTYPE)
+    return _sharded(fn, pairs, rank, world, ANIB_DTYPE, device, group, chunk)
 
 
 def tetra_sharded(engine, genome_ids: Sequence[int], genome_lengths: Sequence[int], rank: int, world: int, *, device=None, group=None,

@@ -147,3 +147,112 @@ def all_directed_pairs(n: int) -> np.ndarray:
     a, b = np.meshgrid(np.arange(n, dtype=np.int32), np.arange(n, dtype=np.int32), indexing="ij")
     m = a != b
     return np.stack([a[m], b[m]], axis=1)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Large sets (BASELINE.json configs[2..4]): every clade is generated from its own SeedSequence child, so clades can be
+# built by independent worker processes (and by different ranks) and still give one reproducible set.
+def _clade_rng(seed: int, *key: int):
+    return np.random.default_rng(np.random.SeedSequence(entropy=seed, spawn_key=tuple(key)))
+
+
+def root_codes(seed: int, length: int) -> np.ndarray:
+    rng = _clade_rng(seed, 0)
+    return random_codes(rng, length, float(rng.uniform(0.35, 0.70)))
+
+
+def make_clade(seed: int, c: int, per_clade: int, root: np.ndarray, *, target_len: int = 0, between=(0.075, 0.125), within=(0.001, 0.05),
+               indel_ratio: float = 0.1, n_rearr: int = 20, specific=(0.02, 0.08), n_rate: float = 1e-4, max_contigs: int = 3) -> List[SynthGenome]:
+    """The `per_clade` strains of clade `c`: the root diverged by 7.5-12.5 % block-wise substitutions (+ indels,
+    rearrangements) gives the clade ancestor -- a star phylogeny, so any two clades are 15-25 % apart (inter-clade
+    ANI ~ 75-85 %) -- and the strains derive from it like in :func:`make_set`.  `target_len` > 0 takes a window of that
+    many bases of the root first (mixed-length sets, configs[4])."""
+    rng = _clade_rng(seed, 1, c)
+    gc = float(rng.uniform(0.35, 0.70))
+    base = root
+    if target_len and target_len < len(root):
+        s = int(rng.integers(0, len(root) - target_len))
+        base = root[s : s + target_len]
+    elif target_len > len(root):  # longer than the root: the root followed by clade-specific sequence
+        base = np.concatenate([root, random_codes(rng, target_len - len(root), gc)])
+    div = float(rng.uniform(*between))
+    anc = indels(rng, substitute_blocks(rng, base, div), div * indel_ratio * 0.5, gc)
+    anc = rearrange(rng, anc, n_rearr)
+    out = []
+    for s in range(per_clade):
+        srng = _clade_rng(seed, 2, c, s)
+        sub = float(srng.uniform(*within))
+        g = substitute(srng, anc, sub)
+        g = indels(srng, g, sub * indel_ratio, gc)
+        g = rearrange(srng, g, n_rearr)
+        g = insert_specific(srng, g, float(srng.uniform(*specific)), gc)
+        out.append(to_genome(srng, f"c{c:03d}s{s:02d}", g, c, int(srng.integers(1, max_contigs + 1)), n_rate))
+    return out
+
+
+def _clade_job(args):
+    seed, c, per_clade, root_len, target_len, outdir = args
+    import os
+
+    root = root_codes(seed, root_len)
+    for s, g in enumerate(make_clade(seed, c, per_clade, root, target_len=target_len)):
+        stem = os.path.join(outdir, f"g{c:04d}_{s:02d}")
+        np.save(stem + ".off.tmp.npy", g.contig_off)
+        os.replace(stem + ".off.tmp.npy", stem + ".off.npy")
+        np.save(stem + ".res.tmp.npy", g.residues)
+        os.replace(stem + ".res.tmp.npy", stem + ".res.npy")  # the residues file appears last: it marks the genome complete
+    return c
+
+
+def clade_lengths(seed: int, n_clades: int, length, mixed: bool) -> List[int]:
+    """Per-clade genome length: constant, or log-uniform in [length[0], length[1]] (configs[4]: 0.5-12 Mb)."""
+    if not mixed:
+        return [0] * n_clades
+    rng = _clade_rng(seed, 3)
+    lo, hi = length
+    return [int(x) for x in np.exp(rng.uniform(np.log(lo), np.log(hi), size=n_clades))]
+
+
+def make_set_cached(n_clades: int, per_clade: int, length, seed: int, *, rank: int = 0, world: int = 1, workers: int = 0,
+                    cache_dir: str = "/dev/shm/b200ani_synth", timeout_s: float = 1800.0, only_clades=None) -> List[SynthGenome]:
+    """n_clades x per_clade genomes, generated once per machine into `cache_dir` (memory-mapped by every caller).
+    Rank r of `world` builds the clades c with c % world == r in a process pool and then waits for the other ranks' files.
+    `length`: int (every clade ~length) or (lo, hi) for a log-uniform mixed-length set.  Call before CUDA is initialised
+    (the pool forks).  `only_clades`: build / load just these clades (the other entries of the returned list are None)."""
+    import os
+    import time
+    from concurrent.futures import ProcessPoolExecutor
+    from multiprocessing import get_context
+
+    mixed = isinstance(length, (tuple, list))
+    root_len = int(length[1] if mixed else length)
+    tag = f"s{seed}_c{n_clades}x{per_clade}_" + (f"L{length[0]}-{length[1]}" if mixed else f"L{length}")
+    outdir = os.path.join(cache_dir, tag)
+    os.makedirs(outdir, exist_ok=True)
+    tl = clade_lengths(seed, n_clades, length, mixed)
+    wanted = set(range(n_clades)) if only_clades is None else set(only_clades)
+    mine = [c for c in sorted(wanted) if c % world == rank and
+            not all(os.path.exists(os.path.join(outdir, f"g{c:04d}_{s:02d}.res.npy")) for s in range(per_clade))]
+    if mine:
+        nw = workers or max(1, min(len(mine), (os.cpu_count() or 1) // max(world, 1), 32))
+        jobs = [(seed, c, per_clade, root_len, tl[c], outdir) for c in mine]
+        if nw == 1:
+            for j in jobs:
+                _clade_job(j)
+        else:
+            with ProcessPoolExecutor(nw, mp_context=get_context("fork")) as ex:
+                list(ex.map(_clade_job, jobs))
+    out: List[SynthGenome] = []
+    t0 = time.time()
+    for c in range(n_clades):
+        for s in range(per_clade):
+            if c not in wanted:
+                out.append(None)
+                continue
+            stem = os.path.join(outdir, f"g{c:04d}_{s:02d}")
+            while not os.path.exists(stem + ".res.npy"):
+                if time.time() - t0 > timeout_s:
+                    raise TimeoutError(f"synthetic genome {stem} was not produced by its rank")
+                time.sleep(0.05)
+            out.append(SynthGenome(f"c{c:03d}s{s:02d}", np.load(stem + ".res.npy", mmap_mode="r"), np.load(stem + ".off.npy"), c))
+    return out

@@ -96,6 +96,17 @@ def main():
         if f.suffix in (".delta", ".filter"):
             shutil.copyfile(f, dd / f.name)
 
+    # nucmer 3.1 output of the legacy driver for the six C. blochmannia genomes (15 pairs x {.delta, .filter}): pins the aligner
+    # on genomes no constant was fitted to
+    import tarfile
+
+    bn = FIX / "C_blochmannia_nucmer"
+    bn.mkdir(exist_ok=True)
+    with tarfile.open(REF / "tests/test_targets/legacy_scripts/ANIm_mpl_Linux_3.1/nucmer_output.tar.gz") as tf:
+        for m in tf.getmembers():
+            if m.isfile() and m.name.endswith((".delta", ".filter")):
+                (bn / Path(m.name).name).write_bytes(tf.extractfile(m).read())
+
     # ---- TETRA
     gold = {"tetramers": oracle.TETRAMERS, "genomes": {}, "edge": {}}
     zs = {}

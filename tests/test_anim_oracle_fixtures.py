@@ -59,8 +59,8 @@ def test_pipeline_within_reference_tolerance(genomes):
             g_ral, g_qal, g_ident, g_errs = gold[f"{r}_vs_{q}.filter"]
             devs.append(100 * (ident - g_ident))
             assert abs(ral / g_ral - 1) < 0.015 and abs(qal / g_qal - 1) < 0.015, (r, q, ral, g_ral)
-            assert abs(devs[-1]) < 0.08, (r, q, ident, g_ident)  # measured 0.057; the reference's own tolerance is 0.1 (test_concordance.py:157-159)
-    assert abs(np.mean(devs)) < 0.06
+            assert abs(devs[-1]) < 0.06, (r, q, ident, g_ident)  # measured 0.041; the reference's own tolerance is 0.1 (test_concordance.py:157-159)
+    assert abs(np.mean(devs)) < 0.03
     # the near-identical pair reproduces nucmer's aligned lengths exactly
     rows, _ = oracle.anim_align(genomes["NC_002696"], genomes["NC_011916"])
     keep = oracle.filter_1to1(rows)
@@ -78,11 +78,11 @@ def test_alignments_reproduce_nucmer_rows(genomes):
             nd = oracle.parse_delta_text(FIXTURES / "anim_deltadir" / f"{r}_vs_{q}.delta")
             ours, nuc = set(map(tuple, rows[:, 2:7].tolist())), set(map(tuple, nd[:, 2:7].tolist()))
             ours_c, nuc_c = set(map(tuple, rows[:, 2:6].tolist())), set(map(tuple, nd[:, 2:6].tolist()))
-            assert len(ours & nuc) >= 0.78 * len(nuc), (r, q, len(ours & nuc), len(nuc))
+            assert len(ours & nuc) >= 0.90 * len(nuc), (r, q, len(ours & nuc), len(nuc))
             same_rows += len(ours & nuc)
             same_coords += len(ours_c & nuc_c)
             total += len(nuc)
-    assert same_rows >= 0.80 * total
+    assert same_rows >= 0.93 * total         # measured: 11,514 of 12,292 = 93.7 %
     assert same_rows >= 0.975 * same_coords  # where the coordinates agree, so does the error count
 
 
@@ -105,6 +105,44 @@ def test_independent_pair_against_nucmer():
         assert abs(100 * (idy - n_idy)) < 0.02, (r, q, idy, n_idy)              # measured: +0.004 / +0.015
         # measured: 1,140,630 vs 1,140,614 on TS32_31; 1,149,872 vs 1,139,819 on TS43_20 (a 10 kb repeat copy aligned twice)
         assert abs(res["ref_aln_len"] / n_ral - 1) < 0.01 and abs(res["qry_aln_len"] / n_qal - 1) < 0.01, (r, q, res, n_ral, n_qal)
-        assert abs(len(kept) - len(nd)) <= 1
+        assert abs(len(kept) - len(nd)) <= 3   # JSpecies ran its own nucmer (not pyani's --mum): 29 vs 32 / 31 alignments
         same = set(map(tuple, kept[:, 2:7].tolist())) & set(map(tuple, nd[:, 2:7].tolist()))
         assert len(same) >= 0.4 * len(nd)                                       # measured: 16 / 32 and 14 / 31 rows identical
+
+
+# ------------------------------------------------------------------------------------------ C. blochmannia (nucmer 3.1, legacy driver)
+BLOCH = sorted((FIXTURES / "C_blochmannia_nucmer").glob("*.delta")) if (FIXTURES / "C_blochmannia_nucmer").exists() else []
+
+
+@pytest.mark.skipif(not BLOCH, reason="C. blochmannia nucmer output not extracted (tests/golden/make_golden.py)")
+def test_blochmannia_filter_and_pipeline():
+    """15 pairs of ~0.75 Mb genomes, 83-98 % identity, coverage 1-100 %: data no constant of the aligner was fitted to.
+    (i) the 1-to-1 filter fed nucmer's .delta rows reproduces nucmer's .filter selection exactly; (ii) whole pipeline:
+    identity of the filtered alignments vs the reference's own parse_delta of nucmer's .filter."""
+    g = {}
+    for f in sorted((FIXTURES / "C_blochmannia").glob("*.fna")):
+        a, off, _ = oracle.read_fasta(f)
+        g[f.stem] = oracle.OGenome(a, off)
+    devs, same, total = [], 0, 0
+    for f in BLOCH:
+        d = oracle.parse_delta_text(f)
+        nf = oracle.parse_delta_text(f.with_suffix(".filter"))
+        assert set(map(tuple, d[oracle.filter_1to1(d)].tolist())) == set(map(tuple, nf.tolist())), f.name
+        r, q = f.stem.split("_vs_")
+        rows, _ = oracle.anim_align(g[r], g[q])
+        keep = oracle.filter_1to1(rows)
+        ral, qal, idy, errs = oracle.parse_delta_reduce(rows[keep][:, :7])
+        n_ral, n_qal, n_idy, n_errs = oracle.parse_delta_reduce(nf[:, :7])
+        devs.append(100 * (idy - n_idy))
+        assert abs(ral / n_ral - 1) < 0.06, (f.name, ral, n_ral)           # measured: within 2 % on 13 pairs, 4-6 % on two 1 %-coverage pairs
+        same += len(set(map(tuple, rows[:, 2:7].tolist())) & set(map(tuple, d[:, 2:7].tolist())))
+        total += len(d)
+    devs = np.abs(devs)
+    assert devs.max() < 0.17 and (devs < 0.1).sum() >= 11, devs  # reference tolerance 0.1 (test_concordance.py:157-159): met on 11 of 15
+    assert same >= 0.93 * total, (same, total)                    # measured: 316 of 335 alignments reproduced row for row
+    # the 98 % pair: nucmer reports ONE 792 kb alignment after filtering, so does the oracle
+    f = FIXTURES / "C_blochmannia_nucmer" / "GCF_000011745.1_ASM1174v1_genomic_vs_GCF_000331065.1_ASM33106v1_genomic.filter"
+    r, q = f.stem.split("_vs_")
+    res, kept, _ = oracle.anim_pair(g[r], g[q])
+    nf = oracle.parse_delta_text(f)
+    assert len(kept) == len(nf) == 1 and (kept[0, 2:6] == nf[0, 2:6]).all() and abs(int(kept[0, 6]) - int(nf[0, 6])) <= 16, (kept, nf)

@@ -82,3 +82,25 @@ def test_two_rank_gloo_all_gather_assembles_full_result():
     zw, ow = _fake_tetra(list(range(7)))
     want = _fake_compute(synth.all_directed_pairs(7)).tobytes() + _fake_compute_b(synth.all_directed_pairs(7)).tobytes() + zw.tobytes() + ow.tobytes()
     assert got[0] == want and got[1] == want  # every rank holds the full, correctly ordered array
+
+
+def test_deal_partitions_and_keeps_directions_together():
+    from pyani_b200 import synth
+
+    pairs = synth.all_directed_pairs(23)
+    for world in (1, 2, 3, 8):
+        shares = pdist.deal(pairs, world, chunk=4)
+        allidx = np.concatenate(shares)
+        assert sorted(allidx.tolist()) == list(range(len(pairs)))
+        owner = np.empty(len(pairs), int)
+        for r, s in enumerate(shares):
+            owner[s] = r
+        lut = {(a, b): owner[i] for i, (a, b) in enumerate(pairs.tolist())}
+        assert all(lut[(a, b)] == lut[(b, a)] for a, b in lut)  # both directions of a genome pair on one rank
+        if world > 1:
+            sizes = [len(s) for s in shares]
+            assert max(sizes) - min(sizes) <= 2 * 4 * 2  # at most one chunk (of 4 unordered pairs) apart, plus the tail
+        # walk order inside a share: (lower id, higher id) ascending, the two directions adjacent
+        s0 = pairs[shares[0]]
+        keys = [(min(a, b), max(a, b)) for a, b in s0.tolist()]
+        assert keys == sorted(keys)
