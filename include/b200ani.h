@@ -119,9 +119,11 @@ int b200ani_anib(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fragsize
  * number of rows (<= cap written) or a negative error. */
 int64_t b200ani_anib_fragments(b200ani_ctx *ctx, int32_t qry_id, int32_t sbj_id, int fragsize, int64_t *rows, int64_t cap);
 
-/* Stage timers of the last b200ani_anim call in milliseconds (CUDA events on the engine stream) and
- * the number of kernel launches it issued; used by bench.py for the roofline and gpu_launches. */
-#define B200ANI_N_STAGES 16
+/* Stage timers in milliseconds (CUDA events on the engine stream) and work counters of the last b200ani_anim / b200ani_anib call
+ * (slots "index" .. "bridge"), of the b200ani_add_genome calls since the last b200ani_clear ("pack": the pack kernel), and of
+ * the last TETRA calls ("tetra_count": the counting kernel, "tetra_total" / "tetra_corr_total": the whole b200ani_tetra_zscores /
+ * b200ani_tetra_corr call); used by bench.py for the rooflines and gpu_launches. */
+#define B200ANI_N_STAGES 24
 int b200ani_last_profile(const b200ani_ctx *ctx, double *stage_ms /*B200ANI_N_STAGES*/, int64_t *counters /*B200ANI_N_STAGES*/);
 /* i in [0,16): stage name; i in [16,32): name of counter i-16 ("" = unused slot) */
 const char *b200ani_stage_name(int i);

@@ -300,7 +300,7 @@ static dp_out dp_band_sc(const uint8_t *R, int rstride, const uint8_t *Q, int qs
         if (ties_late && rowmax > AN_NEG && pack_score(rowmax) >= pack_score(best)) { best = rowmax; o.bi = i; o.bj = rowj; }
         /* break rule.  ANIm: nucmer gives up when the anti-diagonal it works on is more than -b 200 past the one of its high
          * score; after row i the band is centred on anti-diagonal 2i + klo + BW/2.  ANIb: rows since the best row. */
-        if (ties_late ? (2 * i + klo + BW / 2 + 1 - (o.bi + o.bj) > AN_BREAK_DIAGS) : (i - o.bi > sc[4])) { o.stopped = 1; break; }
+        if (ties_late ? ((mode == 0 ? 2 * (i - o.bi) + 1 : 2 * i + klo + BW / 2 + 1 - (o.bi + o.bj)) > AN_BREAK_DIAGS) : (i - o.bi > sc[4])) { o.stopped = 1; break; }
     }
     if (mode == 0) {
         int kk = (lq - lr) - klo;

@@ -6,7 +6,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "libb200ani.so"
-N_STAGES = 16
+N_STAGES = 24
 
 
 class AnimResult(C.Structure):

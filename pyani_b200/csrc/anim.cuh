@@ -127,7 +127,8 @@ enum { SEED_BOTH_UNIQUE = 0, SEED_ALL = 1, SEED_EITHER_UNIQUE = 2 };
 
 // scoring models: 0 = ANIm (nucmer-like), 1 = ANIb (blastn-like, linear gaps)
 template <int MODEL> struct Scoring;
-template <> struct Scoring<0> { static constexpr int match = AN_MATCH, mismatch = AN_MISMATCH, gapopen = AN_GAPOPEN, gapext = AN_GAPEXT, brk = AN_BREAK, tile = AN_TILE; };
+// model 0 breaks on anti-diagonals (AN_BREAK_DIAGS) and keeps the LAST best cell; model 1 breaks on rows (brk) and keeps the first
+template <> struct Scoring<0> { static constexpr int match = AN_MATCH, mismatch = AN_MISMATCH, gapopen = AN_GAPOPEN, gapext = AN_GAPEXT, brk = 0, tile = AN_TILE; };
 template <> struct Scoring<1> { static constexpr int match = AB_MATCH, mismatch = AB_MISMATCH, gapopen = AB_GAP, gapext = AB_GAP, brk = AB_BREAK, tile = AB_TILE; };
 
 __device__ __forceinline__ int pack_score(int v) { return (v + AN_PACK - 1) >> 12; }
@@ -171,27 +172,38 @@ __device__ __forceinline__ void link_box(const ChainArrays &A, int64_t i, int64_
 
 
 // One alignment under construction (a kept segment = chain of intact links), extended tile by tile.
+//   [rs0,re0) x [qs0,qe0): span of its anchors (view coordinates), score0 / errs0 of that span; xs / xe [side]: score and errors
+//   the extension of side 0 (left) / 1 (right) added, which moved the ends to rs / re / qs / qe.
 struct SegArrays {
     int64_t n;
     int *pair, *strand, *head, *frag;  // frag: ANIb fragment id (0 for ANIm)
     uint32_t *rc, *qc;                 // record indices
+    int *rs0, *re0, *qs0, *qe0, *hlen; // anchor-level span; hlen = length of the first anchor
     int *rs, *qs, *re, *qe;            // [s,e) in view coordinates (reference g-space / query view)
     int *r_lo, *r_hi, *q_lo, *q_hi;    // record bounds in the same coordinates
-    long long *score, *errs;
-    // bridging (ANIm): predecessor alignment this one is joined to (-1: none), the predecessor's choice of successor
-    // (distance << 32 | index, ~0 = none), packed value of the bridge alignment, 1 = this entry is emitted as a row
-    int *bpred, *bval;
+    long long *score, *errs;           // score0 / errs0; after bridge_merge_kernel (chain heads): totals of the emitted row
+    long long *xs, *xe;                // [2 * segment + side]
+    // junction to the previous alignment of the same row (-1: none): bmode 1 = fused at anchor level (the two facing
+    // extensions do not exist), 2 = bridged between the extended ends; btrim = bases of the first anchor given up to a fused
+    // predecessor; bval = packed value of the junction's alignment; bsucc = the predecessor's choice of successor
+    // (distance << 32 | index, ~0 = none); alive: 1 = this entry is emitted as a row
+    int *bpred, *bval, *bmode, *btrim, *fnext;  // fnext: successor fused at anchor level (-1: none)
     unsigned long long *bsucc;
     uint8_t *alive;
+    // scratch of the junction stages, per segment: box of the candidate junction (origin, size), its value, candidate partner
+    int *box_r0, *box_q0, *box_lr, *box_lq, *box_val, *cand;
 };
 
 // rows: n x 8 int32 (pair, ref record, qry record, rs, re, qs, qe, errs), grouped by pair.
-// Bridging rules of the two aligners (anim_bridge.cu)
+// Joining rules of the two aligners (anim_bridge.cu)
 struct BridgeParams {
-    int gapmax, ddmax;                       // facing ends at most gapmax apart on both sequences, at most ddmax off the diagonal
+    int diag_cap;                            // > 0 (ANIm): facing ends leave a box of at most diag_cap anti-diagonals (gap_r + gap_q)
+    int gapmax, ddmax;                       // diag_cap == 0 (ANIb): ends at most gapmax apart on both sequences, at most ddmax off the diagonal
     int match, mismatch, gapopen, gapext;    // scoring of the residual alignment
     int need_gain;                           // 1: a bridge is kept only if the joint alignment outscores both pieces (local aligner)
+    int min_score;                           // a bridge is kept only if its alignment scores at least this (ANIm: -AN_XDROP)
 };
+constexpr int BRIDGE_CAP = AN_FUSE_DIAGS > AB_BRIDGE_GAP ? AN_FUSE_DIAGS : AB_BRIDGE_GAP;  // longest box side of a junction DP
 
 struct FiltArrays {
     const int *rows;
@@ -208,9 +220,3 @@ struct FiltArrays {
 };
 
 
-// stage / counter slots of b200ani_last_profile
-enum {
-    ST_INDEX = 0, ST_SEED, ST_SORT, ST_LINK, ST_GAPDP, ST_LABEL, ST_EXTDP, ST_FILTER, ST_REDUCE, ST_TOTAL, ST_EXTK, ST_SEEDX, ST_PREPASS, ST_BRIDGE,
-    CT_PROBES = 0, CT_SEEDHITS, CT_ANCHORS, CT_LINKS, CT_CUTS, CT_SEGMENTS, CT_GAPCELLS, CT_EXTCELLS, CT_EXTTILES, CT_ALIGNMENTS, CT_LAUNCHES,
-    CT_GAPTASKS, CT_PAIRS, CT_EXTLAUNCH, CT_GAPLAUNCH, CT_SEEDLAUNCH
-};

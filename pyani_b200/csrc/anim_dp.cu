@@ -8,8 +8,10 @@
 //   E[i][j] = max(E[i][j-1] - ge, H[i][j-1] - go)      F[i][j] = max(F[i-1][j] - ge, H[i-1][j] - go)
 //   H[i][j] = max(H[i-1][j-1] + s(r_i, q_j), E, F)     first gap column costs go, further ones ge
 //
-// Both modes keep the best cell so far (row-major first maximum, starting from H[0][0]=0) and stop when
-// a row ends more than AN_BREAK rows below it (nucmer's break length).
+// Both modes keep the best cell so far (starting from H[0][0]=0) and stop when the DP has moved too far past it (nucmer's
+// break length).  ANIm (MODEL 0): the best cell is the LAST one with the highest score -- within a row the highest packed
+// value, the later column on ties; between rows the later row on equal score -- and the distance is counted in anti-diagonals
+// (AN_BREAK_DIAGS; link alignments use the best ROW: 2 * rows + 1).  ANIb (MODEL 1): first best cell, distance in rows.
 #include <algorithm>
 
 #include "anim.cuh"
@@ -107,7 +109,7 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
         nwin |= m << (2 * sh);
     }
     qs.buf >>= 2 * (32 - sh); qs.mbuf >>= (32 - sh); qs.left = sh;
-    int best = 0;
+    int best = 0, best_sc = 0;
     for (int i = 1; i <= lr; ++i) {
         if (rs.left == 0) rs.refill(R, rstep);
         const uint32_t rb = (uint32_t)rs.buf & 3u, rn = rs.mbuf & 1u;
@@ -132,7 +134,7 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
                 F[kk] = f;
                 eleft = e;
                 // row maximum: two cells per 3-input max (the max-plus instructions are what the ALU pipe is full of)
-                const int key = MODE ? add_fma(h, 31 - kk, one << 5) : h;
+                const int key = MODE ? add_fma(h, MODEL == 0 ? kk : 31 - kk, one << 5) : h;
                 if (kk & 1) rowkey = __vimax3_s32(rowkey, key_even, key);
                 else key_even = key;
             }
@@ -147,10 +149,16 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
                 Hg[kk] = hgleft;
                 F[kk] = f;
                 eleft = e;
-                if (kk <= kkhi) rowkey = MODE ? max(rowkey, add_fma(h, 31 - kk, one << 5)) : max(rowkey, h);
+                if (kk <= kkhi) rowkey = MODE ? max(rowkey, add_fma(h, MODEL == 0 ? kk : 31 - kk, one << 5)) : max(rowkey, h);
             }
         }
-        if (MODE) {
+        if (MODEL == 0) {  // last best cell: the later row wins on equal score
+            const int rowh = MODE ? rowkey >> 5 : rowkey;
+            if (pack_score(rowh) >= best_sc) {
+                best = rowh; best_sc = pack_score(rowh); o.bi = i;
+                if (MODE) o.bj = i + klo + (rowkey & 31);
+            }
+        } else if (MODE) {
             if ((rowkey >> 5) > best) { best = rowkey >> 5; o.bi = i; o.bj = i + klo + 31 - (rowkey & 31); }
         } else {
             if (rowkey > best) { best = rowkey; o.bi = i; }
@@ -159,7 +167,7 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
             int lo = max(0, -(i + klo)), hi = min(AN_BANDW - 1, kkhi);
             if (hi >= lo) o.cells += hi - lo + 1;
         }
-        if (i - o.bi > SC::brk) { o.stopped = 1; break; }
+        if (MODEL == 0 ? ((MODE ? 2 * i + klo + AN_BAND + 1 - (o.bi + o.bj) : 2 * (i - o.bi) + 1) > AN_BREAK_DIAGS) : (i - o.bi > SC::brk)) { o.stopped = 1; break; }
         // slide the query window: drop column 0, append the next base of the stream
         if (qs.left == 0) qs.refill(Q, qstep);
         qwin = (qwin >> 2) | ((qs.buf & 3ull) << 62);
@@ -220,8 +228,11 @@ __global__ void segment_init_kernel(ChainArrays A, const PairDesc *__restrict__ 
     const int strand = key_strand(k);
     const uint32_t rc = A.rc_of[h], qc = A.qc_of[h];
     S.pair[s] = (int)key_pair(k); S.strand[s] = strand; S.head[s] = h; S.frag[s] = (int)key_frag(k); S.rc[s] = rc; S.qc[s] = qc;
-    S.rs[s] = key_r(k); S.qs[s] = val_q(A.vals[h]);
-    S.re[s] = key_r(kt) + val_len(vt); S.qe[s] = val_q(vt) + val_len(vt);
+    S.rs[s] = S.rs0[s] = key_r(k); S.qs[s] = S.qs0[s] = val_q(A.vals[h]);
+    S.re[s] = S.re0[s] = key_r(kt) + val_len(vt); S.qe[s] = S.qe0[s] = val_q(vt) + val_len(vt);
+    S.hlen[s] = val_len(A.vals[h]);  // a chain head has no predecessor: nothing trimmed off it
+    S.xs[2 * s] = S.xs[2 * s + 1] = 0; S.xe[2 * s] = S.xe[2 * s + 1] = 0;
+    S.bpred[s] = -1; S.bval[s] = 0; S.bmode[s] = 0; S.btrim[s] = 0; S.fnext[s] = -1; S.bsucc[s] = ~0ull; S.alive[s] = 1; S.cand[s] = -1;
     int64_t r_lo = (int64_t)P.r_goff[rc], r_hi = (int64_t)P.r_goff[rc + 1] - 1;
     int64_t q_lo = (int64_t)P.q_goff[qc], q_hi = (int64_t)P.q_goff[qc + 1] - 1;
     if (P.fragsize) {  // ANIb: the query side never leaves the fragment
@@ -249,11 +260,15 @@ __global__ void __launch_bounds__(128, 4) ext_dp_kernel(SegArrays S, const PairD
     uint32_t task = 0;
     int tiles = 0, done_tiles = 0;
     for (;;) {
-        if (ticket == -1) {
+        while (ticket == -1) {
             ticket = (long long)atomicAdd(&counters[3], 1ull);
             done_tiles = 0;
-            if (ticket >= n_tasks) ticket = -2;
-            else task = list_in ? list_in[ticket] : (uint32_t)ticket;
+            if (ticket >= n_tasks) { ticket = -2; break; }
+            task = list_in ? list_in[ticket] : (uint32_t)ticket;
+            if (!list_in) {  // first round: an end fused to its neighbour at anchor level is not extended
+                const int64_t s = task >> 1;
+                if ((task & 1) ? S.fnext[s] >= 0 : S.bmode[s] == 1) ticket = -1;
+            }
         }
         if (__all_sync(0xffffffffu, ticket == -2)) break;
         if (ticket >= 0) {
@@ -274,8 +289,8 @@ __global__ void __launch_bounds__(128, 4) ext_dp_kernel(SegArrays S, const PairD
                 ++tiles;
                 if (o.bi != 0 || o.bj != 0) {
                     if (side) { S.re[s] = re + o.bi; S.qe[s] = qe + o.bj; } else { S.rs[s] = rs - o.bi; S.qs[s] = qs - o.bj; }
-                    atomicAdd((unsigned long long *)&S.score[s], (unsigned long long)(long long)pack_score(o.val));
-                    atomicAdd((unsigned long long *)&S.errs[s], (unsigned long long)(long long)pack_errs(o.val));
+                    S.xs[2 * s + side] += pack_score(o.val);  // one lane owns a (segment, side) task at a time
+                    S.xe[2 * s + side] += pack_errs(o.val);
                     on = !o.stopped;
                 }
             }

@@ -20,12 +20,17 @@ __global__ void flag_unique_kernel(const uint64_t *, const uint64_t *, int64_t, 
 __global__ void contig_kernel(ChainArrays, const PairDesc *);
 __global__ void link_kernel(ChainArrays, int);
 __global__ void cluster_keep_kernel(ChainArrays, uint8_t *);
-__global__ void bridge_init_kernel(SegArrays);
+__global__ void fuse_target_kernel(SegArrays, uint32_t *, uint32_t *, unsigned long long *);
+__global__ void fuse_claim_kernel(SegArrays, int *);
+__global__ void fuse_settle_kernel(SegArrays, const int *, unsigned long long *);
+__global__ void fill_int_kernel(int *, int64_t, int);
 __global__ void bridge_link_kernel(SegArrays, BridgeParams);
 __global__ void bridge_validate_kernel(SegArrays, BridgeParams, uint32_t *, uint32_t *, unsigned long long *);
-template <int CAP> __global__ void bridge_dp_kernel(SegArrays, BridgeParams, const PairDesc *, const uint32_t *, int64_t, unsigned long long *);
+__global__ void box_dp_kernel(SegArrays, BridgeParams, const PairDesc *, const uint32_t *, int64_t, unsigned long long *);
 __global__ void bridge_accept_kernel(SegArrays, BridgeParams, unsigned long long *);
-__global__ void bridge_merge_kernel(SegArrays);
+__global__ void bridge_merge_kernel(SegArrays, int);
+__global__ void row_key_kernel(const int *, int64_t, uint64_t *, int *);
+__global__ void row_dup_kernel(const int *, int64_t, const uint64_t *, const int *, uint8_t *);
 __global__ void link_validate_kernel(ChainArrays, unsigned long long *);
 __global__ void gap_task_kernel(ChainArrays, uint32_t *, uint32_t *, unsigned long long *, int, int);
 __global__ void label_local_kernel(ChainArrays);
@@ -53,16 +58,39 @@ __global__ void filt_dp_kernel(FiltArrays, int, const int *, int);
 __global__ void reduce_kernel(FiltArrays, const int *, int, int, b200ani_anim_result *);
 
 static const char *kStageNames[B200ANI_N_STAGES] = {"index", "seed", "sort", "link", "gap_dp", "label", "ext_dp", "filter", "reduce", "total",
-                                                    "ext_dp_kernel", "seed_extend", "prepass", "bridge", "", ""};
+                                                    "ext_dp_kernel", "seed_extend", "prepass", "bridge", "pack", "tetra_count", "tetra_total", "tetra_corr_total",
+                                                    "", "", "", "", "", ""};
 static const char *kCounterNames[B200ANI_N_STAGES] = {"probes", "seed_hits", "anchors", "links", "cut_links", "segments", "gap_cells", "ext_cells",
-                                                      "ext_tiles", "alignments", "launches", "gap_tasks", "pairs", "ext_dp_launches", "gap_dp_launches", "seed_launches"};
+                                                      "ext_tiles", "alignments", "launches", "gap_tasks", "pairs", "ext_dp_launches", "gap_dp_launches", "seed_launches",
+                                                      "junctions", "box_cells", "", "", "", "", "", ""};
 
 constexpr int MAX_BATCH_PAIRS = 2560;
 constexpr int64_t ANCHOR_CAP_DEFAULT = 96ll << 20;  // anchors of one batch (overridable: B200ANI_ANCHOR_CAP, used by the batch-split test)
 constexpr int64_t HIT_CAP_DEFAULT = 192ll << 20;    // seed hits of one batch, 8 B each (B200ANI_HIT_CAP)
 constexpr int EXT_TILES_PER_LAUNCH = 8, EXT_SHORT_ROUNDS = 8;  // a single long last launch (4 short rounds + 1) measured 1 ms slower
 
+// Per-batch scratch: a bump allocator over a few large device blocks that live as long as the workspace.  A batch takes what
+// it needs and resets the offsets at its end (also on every error path: nothing to release one by one); blocks are only ever
+// added while the first batches find out how much they need, so a steady-state batch issues no allocation call at all.
+struct Arena {
+    struct Block { char *p; size_t cap, off; };
+    std::vector<Block> blocks;
+    void reset() { for (auto &b : blocks) b.off = 0; }
+    void release() { for (auto &b : blocks) cudaFree(b.p); blocks.clear(); }
+    void *get(size_t bytes) {
+        bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+        for (auto &b : blocks)
+            if (b.cap - b.off >= bytes) { void *r = b.p + b.off; b.off += bytes; return r; }
+        Block nb{nullptr, std::max<size_t>(bytes, (size_t)1 << 30), 0};
+        if (cudaMalloc((void **)&nb.p, nb.cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        nb.off = bytes;
+        blocks.push_back(nb);
+        return nb.p;
+    }
+};
+
 struct AnimWorkspace {
+    Arena arena;
     uint64_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr;
     uint8_t *flag = nullptr;
     uint2 *hits = nullptr;
@@ -85,6 +113,7 @@ void free_anim_workspace(void *p) {
     cudaFree(w->counters); cudaFree(w->changed); cudaFree(w->d_pairs); cudaFree(w->d_results); cudaFree(w->cub_tmp);
     for (auto &e : w->ev) if (e) cudaEventDestroy(e);
     for (auto &e : w->kev) cudaEventDestroy(e);
+    w->arena.release();
     delete w;
 }
 
@@ -121,12 +150,12 @@ static int get_workspace(b200ani_ctx *ctx, AnimWorkspace **out) {
 }
 
 template <typename T>
-static int dalloc(b200ani_ctx *ctx, T **p, int64_t n) {
-    CK(cudaMallocAsync((void **)p, sizeof(T) * (size_t)std::max<int64_t>(n, 1), ctx->stream));
+static int dalloc(b200ani_ctx *ctx, Arena &arena, T **p, int64_t n) {
+    *p = (T *)arena.get(sizeof(T) * (size_t)std::max<int64_t>(n, 1));
+    if (!*p) FAIL(B200ANI_ERR_NOMEM, "anim: out of device memory for the batch scratch");
     return 0;
 }
-#define DA(p, n) do { int rc__ = dalloc(ctx, &(p), (n)); if (rc__) return rc__; } while (0)
-#define DF(p) CK(cudaFreeAsync((p), ctx->stream))
+#define DA(p, n) do { int rc__ = dalloc(ctx, W->arena, &(p), (n)); if (rc__) return rc__; } while (0)
 #define LAUNCHED(k) do { CK(cudaGetLastError()); ctx->counters[CT_LAUNCHES] += (k); } while (0)
 #define GRID(n) (unsigned)std::max<int64_t>(1, ceil_div((n), 256)), 256, 0, st
 #define T0(s) CK(cudaEventRecord(W->ev[2 * (s)], st))
@@ -140,7 +169,15 @@ struct RowDump {
 };
 
 // fragsize == 0: ANIm (out = b200ani_anim_result[nb]); fragsize > 0: ANIb (out = b200ani_anib_result[nb])
+static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, int fragsize, int maxmatch, void *out_v, RowDump *dump);
 static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, int fragsize, int maxmatch, void *out_v, RowDump *dump) {
+    const int rc = run_batch_impl(ctx, W, pairs, nb, nofilter, fragsize, maxmatch, out_v, dump);
+    // whatever happened, nothing of this batch may still run when the scratch is handed to the next one
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc >= 0) { ctx->err = "anim: the batch left the stream in an error state"; W->arena.reset(); return B200ANI_ERR_CUDA; }
+    W->arena.reset();
+    return rc;
+}
+static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, int fragsize, int maxmatch, void *out_v, RowDump *dump) {
     const bool anib = fragsize > 0;
     const int seedmode = anib ? SEED_BOTH_UNIQUE : (maxmatch ? SEED_ALL : SEED_EITHER_UNIQUE);
     const int seed_k = anib ? AB_K : AN_K, min_len = anib ? AB_MINLEN : AN_MINLEN;
@@ -344,21 +381,38 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
     }
     ctx->counters[CT_SEGMENTS] += n_seg;
 
-    // ---- extension rounds
+    // ---- segments -> alignments: fusion at anchor level (ANIm), extension rounds, bridging
     SegArrays S{};
     S.n = n_seg;
     int n_ext_launch = 0;
-    int *rows = nullptr;
+    int *rows = nullptr, *rows_all = nullptr, *claim = nullptr;
     DA(S.pair, n_seg); DA(S.strand, n_seg); DA(S.head, n_seg); DA(S.frag, n_seg); DA(S.rc, n_seg); DA(S.qc, n_seg);
+    DA(S.rs0, n_seg); DA(S.re0, n_seg); DA(S.qs0, n_seg); DA(S.qe0, n_seg); DA(S.hlen, n_seg);
     DA(S.rs, n_seg); DA(S.qs, n_seg); DA(S.re, n_seg); DA(S.qe, n_seg);
     DA(S.r_lo, n_seg); DA(S.r_hi, n_seg); DA(S.q_lo, n_seg); DA(S.q_hi, n_seg);
-    DA(S.score, n_seg); DA(S.errs, n_seg); DA(rows, 8 * n_seg);
-    DA(S.bpred, n_seg); DA(S.bval, n_seg); DA(S.bsucc, n_seg); DA(S.alive, n_seg);
-    int *rows_all = nullptr;
-    DA(rows_all, 8 * n_seg);
+    DA(S.score, n_seg); DA(S.errs, n_seg); DA(S.xs, 2 * n_seg); DA(S.xe, 2 * n_seg);
+    DA(S.bpred, n_seg); DA(S.bval, n_seg); DA(S.bmode, n_seg); DA(S.btrim, n_seg); DA(S.fnext, n_seg); DA(S.bsucc, n_seg); DA(S.alive, n_seg);
+    DA(S.box_r0, n_seg); DA(S.box_q0, n_seg); DA(S.box_lr, n_seg); DA(S.box_lq, n_seg); DA(S.box_val, n_seg); DA(S.cand, n_seg);
+    DA(rows, 8 * n_seg); DA(rows_all, 8 * n_seg); DA(claim, n_seg);
     int64_t n_rows = n_seg;
     uint32_t *ext_list[2] = {nullptr, nullptr};
     DA(ext_list[0], 2 * n_seg); DA(ext_list[1], 2 * n_seg);
+    const BridgeParams BP = anib ? BridgeParams{0, AB_BRIDGE_GAP, AB_BRIDGE_DD, AB_MATCH, AB_MISMATCH, AB_GAP, AB_GAP, 1, 0}
+                                 : BridgeParams{AN_FUSE_DIAGS, 0, 0, AN_MATCH, AN_MISMATCH, AN_GAPOPEN, AN_GAPEXT, 0, -AN_XDROP};
+    // box DP of the junction candidates listed in task_idx / task_key (the link stage's task arrays are free again)
+    auto run_boxes = [&]() -> int {
+        CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const int64_t n_btasks = (int64_t)hc[12];
+        if (n_btasks) {  // similar-sized rectangles side by side in a warp
+            size_t tb2 = W->cub_bytes;
+            cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb2, task_key, task_key2, task_idx, task_idx2, n_btasks, 0, 8, st);
+            box_dp_kernel<<<(unsigned)ceil_div(n_btasks, 64), 64, 0, st>>>(S, BP, W->d_pairs, task_idx2, n_btasks, W->counters + 10);
+            LAUNCHED(1);
+        }
+        CK(cudaMemsetAsync(W->counters + 12, 0, sizeof(unsigned long long), st));
+        return 0;
+    };
 
     if (n_seg && anib) {
         // ---- ANIb: screen the weak candidates (ungapped end extensions) before any gapped DP; survivors are re-listed
@@ -379,6 +433,15 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         T0(ST_EXTDP);
         segment_init_kernel<<<GRID(n_seg)>>>(A, W->d_pairs, seg_head, S, anib ? AB_MATCH : AN_MATCH);
         LAUNCHED(1);
+        if (!anib) {  // ---- ANIm: fusion at anchor level; fused ends are not extended
+            fill_int_kernel<<<GRID(n_seg)>>>(claim, n_seg, 0x7fffffff);
+            fuse_target_kernel<<<GRID(n_seg)>>>(S, task_idx, task_key, W->counters + 10);
+            LAUNCHED(2);
+            if (int rc = run_boxes()) return rc;
+            fuse_claim_kernel<<<GRID(n_seg)>>>(S, claim);
+            fuse_settle_kernel<<<GRID(n_seg)>>>(S, claim, W->counters + 10);
+            LAUNCHED(2);
+        }
         {   // persistent launches: resident warps pull (segment, side) tasks from a ticket counter; a task
             // gets EXT_TILES_PER_LAUNCH tiles per launch, the still-extending ones go to the next launch
             int per_sm = 0;
@@ -421,24 +484,14 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         {
             // ---- bridging: join alignments whose facing ends are close (ANIm: one row per chain of joined alignments;
             // ANIb: candidate HSPs of one fragment)
-            const BridgeParams BP = anib ? BridgeParams{AB_BRIDGE_GAP, AB_BRIDGE_DD, AB_MATCH, AB_MISMATCH, AB_GAP, AB_GAP, 1}
-                                         : BridgeParams{AN_BREAK, AN_BRIDGE_DD, AN_MATCH, AN_MISMATCH, AN_GAPOPEN, AN_GAPEXT, 0};
             T0(ST_BRIDGE);
-            bridge_init_kernel<<<GRID(n_seg)>>>(S);
             bridge_link_kernel<<<GRID(n_seg)>>>(S, BP);
-            bridge_validate_kernel<<<GRID(n_seg)>>>(S, BP, task_idx, task_key, W->counters + 10);  // the link stage's task arrays are free again
-            CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            const int64_t n_btasks = (int64_t)hc[12];
-            if (n_btasks) {  // similar-sized rectangles side by side in a warp
-                size_t tb2 = W->cub_bytes;
-                cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb2, task_key, task_key2, task_idx, task_idx2, n_btasks, 0, 8, st);
-                if (anib) bridge_dp_kernel<AB_BRIDGE_GAP><<<(unsigned)ceil_div(n_btasks, 64), 64, 0, st>>>(S, BP, W->d_pairs, task_idx2, n_btasks, W->counters + 10);
-                else bridge_dp_kernel<AN_BREAK><<<(unsigned)ceil_div(n_btasks, 64), 64, 0, st>>>(S, BP, W->d_pairs, task_idx2, n_btasks, W->counters + 10);
-            }
+            bridge_validate_kernel<<<GRID(n_seg)>>>(S, BP, task_idx, task_key, W->counters + 10);
+            LAUNCHED(2);
+            if (int rc = run_boxes()) return rc;
             bridge_accept_kernel<<<GRID(n_seg)>>>(S, BP, W->counters + 10);
-            bridge_merge_kernel<<<GRID(n_seg)>>>(S);
-            LAUNCHED(6);
+            bridge_merge_kernel<<<GRID(n_seg)>>>(S, anib ? AB_MATCH : AN_MATCH);
+            LAUNCHED(2);
             if (!anib) {
                 emit_rows_kernel<<<GRID(n_seg)>>>(S, W->d_pairs, rows_all);
                 LAUNCHED(1);
@@ -448,6 +501,25 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
                 CK(cudaMemcpyAsync(&hr, W->changed, sizeof hr, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
                 n_rows = hr;
+                if (n_rows) {
+                    // two chains that grew to the very same alignment are one alignment: the first in emission order stays
+                    uint64_t *dkey = nullptr, *dkey2 = nullptr;
+                    int *didx = nullptr, *didx2 = nullptr;
+                    DA(dkey, n_rows); DA(dkey2, n_rows); DA(didx, n_rows); DA(didx2, n_rows);
+                    row_key_kernel<<<GRID(n_rows)>>>(rows, n_rows, dkey, didx);
+                    int pair_bits = 1;
+                    while ((1 << pair_bits) < nb) ++pair_bits;
+                    size_t tb3 = W->cub_bytes;
+                    cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb3, dkey, dkey2, didx, didx2, n_rows, 0, 32 + pair_bits, st);
+                    row_dup_kernel<<<GRID(n_rows)>>>(rows, n_rows, dkey2, didx2, W->flag);
+                    LAUNCHED(2);
+                    tb3 = W->cub_bytes;
+                    cub::DeviceSelect::Flagged(W->cub_tmp, tb3, (const Row8 *)rows, W->flag, (Row8 *)rows_all, W->changed, n_rows, st);
+                    CK(cudaMemcpyAsync(&hr, W->changed, sizeof hr, cudaMemcpyDeviceToHost, st));
+                    CK(cudaStreamSynchronize(st));
+                    n_rows = hr;
+                    std::swap(rows, rows_all);
+                }
             }
             T1(ST_BRIDGE);
         }
@@ -478,13 +550,10 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
                 CK(cudaMemcpyAsync(dump->flag.data(), chosen, (size_t)n_seg, cudaMemcpyDeviceToHost, st));
             }
         }
-        DF(B.pair); DF(B.frag); DF(B.score); DF(B.nident); DF(B.mism); DF(B.gaps); DF(B.qlen); DF(B.pass); DF(chosen);
-        DF(A.rc_of); DF(A.qc_of); DF(A.pred); DF(A.trim); DF(A.succ); DF(A.gval); DF(A.head); DF(A.chead); DF(A.cw); DF(A.wsum);
-        DF(A.tail); DF(A.ssum); DF(A.esum); DF(A.strong); DF(task_key); DF(task_idx); DF(task_key2); DF(task_idx2); DF(seg_head);
-        DF(S.pair); DF(S.strand); DF(S.head); DF(S.rc); DF(S.qc); DF(S.rs); DF(S.qs); DF(S.re); DF(S.qe);
-        DF(S.r_lo); DF(S.r_hi); DF(S.q_lo); DF(S.q_hi); DF(S.score); DF(S.errs); DF(rows); DF(ext_list[0]); DF(ext_list[1]);
-    DF(S.bpred); DF(S.bval); DF(S.bsucc); DF(S.alive); DF(S.frag); DF(rows_all);
+        CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        ctx->counters[CT_JUNCTIONS] += (int64_t)hc[10];
+        ctx->counters[CT_BOXCELLS] += (int64_t)hc[11];
         for (int s2 = 0; s2 < B200ANI_N_STAGES; ++s2)
             if (used[s2]) {
                 float ms = 0;
@@ -540,14 +609,11 @@ static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, i
         }
     }
     // ---- release
-    DF(A.rc_of); DF(A.qc_of); DF(A.pred); DF(A.trim); DF(A.succ); DF(A.gval); DF(A.head); DF(A.chead); DF(A.cw); DF(A.wsum);
-    DF(A.tail); DF(A.ssum); DF(A.esum); DF(A.strong); DF(task_key); DF(task_idx); DF(task_key2); DF(task_idx2); DF(seg_head);
-    DF(S.pair); DF(S.strand); DF(S.head); DF(S.rc); DF(S.qc); DF(S.rs); DF(S.qs); DF(S.re); DF(S.qe);
-    DF(S.r_lo); DF(S.r_hi); DF(S.q_lo); DF(S.q_hi); DF(S.score); DF(S.errs); DF(rows); DF(ext_list[0]); DF(ext_list[1]);
-    DF(S.bpred); DF(S.bval); DF(S.bsucc); DF(S.alive); DF(S.frag); DF(rows_all);
-    for (int a = 0; a < 2; ++a) { DF(F.sidx[a]); DF(F.slo[a]); DF(F.shi[a]); DF(F.sseq[a]); }
-    DF(F.best); DF(F.from); DF(F.unit); DF(F.flag); DF(F.pmax); DF(F.pmaxj); DF(F.phi); DF(fkey); DF(fkey2); DF(fidx); DF(fidx2); DF(pair_start);
+
+    CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    ctx->counters[CT_JUNCTIONS] += (int64_t)hc[10];
+    ctx->counters[CT_BOXCELLS] += (int64_t)hc[11];
     for (int s = 0; s < B200ANI_N_STAGES; ++s)
         if (used[s]) {
             float ms = 0;
@@ -645,7 +711,7 @@ const char *b200ani_stage_name(int i) {
 
 int b200ani_anim(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch, int nofilter, b200ani_anim_result *out) {
     if (!ctx || !pairs || !out || m < 0) return B200ANI_ERR_ARG;
-    memset(ctx->stage_ms, 0, sizeof ctx->stage_ms);
+    for (int k = 0; k < ST_FIRST_NON_ANIM; ++k) ctx->stage_ms[k] = 0;  // the pack / TETRA slots belong to their own entry points
     memset(ctx->counters, 0, sizeof ctx->counters);
     AnimWorkspace *W = nullptr;
     cudaEvent_t t0, t1;
@@ -721,7 +787,7 @@ static int anib_common(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fr
 
 int b200ani_anib(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fragsize, b200ani_anib_result *out) {
     if (!ctx || !pairs || !out || m < 0) return B200ANI_ERR_ARG;
-    memset(ctx->stage_ms, 0, sizeof ctx->stage_ms);
+    for (int k = 0; k < ST_FIRST_NON_ANIM; ++k) ctx->stage_ms[k] = 0;  // the pack / TETRA slots belong to their own entry points
     memset(ctx->counters, 0, sizeof ctx->counters);
     cudaEvent_t t0, t1;
     CK(cudaSetDevice(ctx->device));

@@ -20,9 +20,9 @@
 #define AN_MISMATCH 7
 #define AN_GAPOPEN 10
 #define AN_GAPEXT 7
-#define AN_BREAK 104
-#define AN_BRIDGE_DD 100
-#define AN_FUSE_DIAGS 200
+#define AN_BREAK_DIAGS 200
+#define AN_XDROP 600
+#define AN_FUSE_DIAGS 198
 #define AN_CLUSTGAP 90
 #define AN_FILT_OLAP 75
 #define AN_FILT_POW 2

@@ -45,6 +45,11 @@ int b200ani_create(b200ani_ctx **out, int device_id) {
         return B200ANI_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
+    if (cudaEventCreate(&ctx->ev_prof[0]) != cudaSuccess || cudaEventCreate(&ctx->ev_prof[1]) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return B200ANI_ERR_CUDA;
+    }
     // keep freed async allocations cached in the pool: the engine re-allocates the same sizes per batch
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
@@ -63,6 +68,8 @@ void b200ani_destroy(b200ani_ctx *ctx) {
     for (auto *ix : ctx->spare_indexes) free_index(ix, ctx->stream);
     free_anim_workspace(ctx->anim_ws);
     cudaFree(ctx->index_ws);
+    cudaEventDestroy(ctx->ev_prof[0]);
+    cudaEventDestroy(ctx->ev_prof[1]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -90,6 +97,7 @@ int b200ani_clear(b200ani_ctx *ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     for (auto &g : ctx->genomes) release_genome(ctx, g, ctx->stream);
     ctx->genomes.clear();
+    ctx->stage_ms[ST_PACK] = 0;
     return B200ANI_OK;
 }
 
@@ -135,10 +143,17 @@ int b200ani_add_genome(b200ani_ctx *ctx, const uint8_t *ascii, const uint64_t *c
     // pageable or pinned: the caller owns the buffer; cudaMemcpyAsync degrades gracefully for pageable
     if (n_bases) CK(cudaMemcpyAsync(d_ascii, ascii, (size_t)n_bases, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(g.d_goff, g.h_goff.data(), sizeof(uint64_t) * (n_contigs + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_prof[0], ctx->stream));
     int rc = launch_pack(ctx, d_ascii, g.d_goff, g);
     if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev_prof[1], ctx->stream));
     CK(cudaFreeAsync(d_ascii, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));  // h_goff / caller buffer lifetimes end here
+    {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev_prof[0], ctx->ev_prof[1]));
+        ctx->stage_ms[ST_PACK] += ms;
+    }
     ctx->genomes.push_back(std::move(g));
     if (out_id) *out_id = (int32_t)ctx->genomes.size() - 1;
     return B200ANI_OK;
@@ -146,13 +161,33 @@ int b200ani_add_genome(b200ani_ctx *ctx, const uint8_t *ascii, const uint64_t *c
 
 // ------------------------------------------------------------------------------------------ TETRA
 static int tetra_totals_for(b200ani_ctx *ctx, const int32_t *ids, int n, unsigned long long *d_tot) {
+    std::vector<const Genome *> gs(n);
     for (int i = 0; i < n; ++i) {
         if (ids[i] < 0 || ids[i] >= (int32_t)ctx->genomes.size()) FAIL(B200ANI_ERR_ARG, "tetra: bad genome id");
-        int rc = tetra_counts_device(ctx, ctx->genomes[ids[i]], d_tot + (size_t)i * 336);
-        if (rc) return rc;
+        gs[i] = &ctx->genomes[ids[i]];
     }
-    return 0;
+    ctx->stage_ms[ST_TETRA_COUNT] = 0;
+    return tetra_counts_device(ctx, gs.data(), n, d_tot);
 }
+
+// wall time of a TETRA entry point on the engine stream -> its profile slot
+struct StageTimer {
+    b200ani_ctx *ctx;
+    int slot;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    StageTimer(b200ani_ctx *c, int s) : ctx(c), slot(s) {
+        if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) cudaEventRecord(e0, ctx->stream);
+    }
+    void stop() {  // call after the work is enqueued and before the final synchronize
+        if (e1) cudaEventRecord(e1, ctx->stream);
+    }
+    ~StageTimer() {
+        float ms = 0;
+        if (e0 && e1 && cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) ctx->stage_ms[slot] = ms;
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+};
 
 int b200ani_tetra_counts(b200ani_ctx *ctx, int32_t id, int64_t *c2, int64_t *c3, int64_t *c4) {
     if (!ctx || !c2 || !c3 || !c4) return B200ANI_ERR_ARG;
@@ -180,12 +215,14 @@ int b200ani_tetra_zscores(b200ani_ctx *ctx, const int32_t *ids, int n, double *z
     CK(tmp.get(&d_tot, sizeof(unsigned long long) * 336 * (size_t)n));
     CK(tmp.get(&d_z, sizeof(double) * 256 * (size_t)n));
     CK(tmp.get(&d_obs, 256 * (size_t)n));
+    StageTimer timer(ctx, ST_TETRA_TOTAL);
     int rc = tetra_totals_for(ctx, ids, n, d_tot);
     if (rc) return rc;
     rc = tetra_zscores_device(ctx, d_tot, n, d_z, d_obs);
     if (rc) return rc;
     CK(cudaMemcpyAsync(z, d_z, sizeof(double) * 256 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(observed, d_obs, 256 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    timer.stop();
     CK(cudaStreamSynchronize(ctx->stream));
     return B200ANI_OK;
 }
@@ -203,11 +240,13 @@ int b200ani_tetra_corr(b200ani_ctx *ctx, const double *z, const uint8_t *mask, i
     CK(tmp.get(&d_z, sizeof(double) * 256 * (size_t)n));
     CK(tmp.get(&d_corr, sizeof(double) * (size_t)n * n));
     CK(tmp.get(&d_idx, sizeof idx));
+    StageTimer timer(ctx, ST_TETRA_CORR);
     CK(cudaMemcpyAsync(d_z, z, sizeof(double) * 256 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_idx, idx, sizeof idx, cudaMemcpyHostToDevice, ctx->stream));
     int rc = tetra_corr_device(ctx, d_z, d_idx, m, n, d_corr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(corr, d_corr, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, ctx->stream));
+    timer.stop();
     CK(cudaStreamSynchronize(ctx->stream));
     return B200ANI_OK;
 }

@@ -39,6 +39,14 @@ struct Genome {
     uint32_t n_frags = 0;
 };
 
+// stage / counter slots of b200ani_last_profile
+enum {
+    ST_INDEX = 0, ST_SEED, ST_SORT, ST_LINK, ST_GAPDP, ST_LABEL, ST_EXTDP, ST_FILTER, ST_REDUCE, ST_TOTAL, ST_EXTK, ST_SEEDX, ST_PREPASS, ST_BRIDGE,
+    ST_PACK, ST_TETRA_COUNT, ST_TETRA_TOTAL, ST_TETRA_CORR, ST_FIRST_NON_ANIM = ST_PACK,
+    CT_PROBES = 0, CT_SEEDHITS, CT_ANCHORS, CT_LINKS, CT_CUTS, CT_SEGMENTS, CT_GAPCELLS, CT_EXTCELLS, CT_EXTTILES, CT_ALIGNMENTS, CT_LAUNCHES,
+    CT_GAPTASKS, CT_PAIRS, CT_EXTLAUNCH, CT_GAPLAUNCH, CT_SEEDLAUNCH, CT_JUNCTIONS, CT_BOXCELLS
+};
+
 struct b200ani_ctx {
     int device = 0;
     int sm_count = 148;
@@ -51,6 +59,7 @@ struct b200ani_ctx {
     std::vector<MinimizerIndex *> spare_indexes;  // index buffers of released genomes, reused by later builds
     void *index_ws = nullptr;      // scratch of build_indexes (anim_index.cu), grown on demand, reused
     size_t index_ws_bytes = 0;
+    cudaEvent_t ev_prof[2] = {nullptr, nullptr};  // kernel timers of the pack / TETRA entry points
 };
 
 #define CK(call)                                                                                     \
@@ -82,7 +91,7 @@ __device__ __forceinline__ uint32_t maskbit(const uint32_t *__restrict__ mask, i
 
 // launchers implemented in the .cu files
 int launch_pack(b200ani_ctx *ctx, const uint8_t *d_ascii, const uint64_t *d_off, Genome &g);
-int tetra_counts_device(b200ani_ctx *ctx, const Genome &g, unsigned long long *d_tot /*336: c2|c3|c4*/);
+int tetra_counts_device(b200ani_ctx *ctx, const Genome *const *gs, int n, unsigned long long *d_tot /* n x 336: c2|c3|c4 */);
 int tetra_zscores_device(b200ani_ctx *ctx, const unsigned long long *d_tot, int n, double *d_z, uint8_t *d_obs);
 int tetra_corr_device(b200ani_ctx *ctx, const double *d_z, const int *d_idx, int m, int n, double *d_corr);
 void free_index(MinimizerIndex *ix, cudaStream_t st);

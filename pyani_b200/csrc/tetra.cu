@@ -1,52 +1,88 @@
 // TETRA on the device: both-strand 2/3/4-mer counts, Teeling Z-scores, Pearson correlation.
 // Replaces pyani/tetra.py:78-139 (calculate_tetra_zscore) and :158-194 (calculate_correlations).
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------
-// Forward-strand counting (tetra.py:98-116, hot loop).  One thread owns 32 consecutive start
-// positions (one mask word); windows whose 2/3/4 bases touch a masked position (ambiguity symbol,
-// record separator, tail padding) are skipped -- the reference counts them under keys that are
-// never read (tetra.py:120,143-153).  Per-warp shared-memory histograms (336 bins) absorb the
-// atomics; one global atomic per bin per block at the end.
-// HBM-bound by construction: L/4 + L/8 bytes read per genome, 336 counters written.
+// Forward-strand counting (tetra.py:98-116, hot loop), all genomes of a call in ONE launch.  A chunk = 256 threads x
+// TC_GROUPS groups of 32 start positions of one genome; a block walks chunks in a grid-stride loop and finds the
+// genome of a chunk by binary search in the chunk prefix.  Windows whose 2/3/4 bases touch a masked position
+// (ambiguity symbol, record separator, tail padding) are skipped -- the reference counts them under keys that are
+// never read (tetra.py:120,143-153).
+// ONE shared-memory histogram update per start position instead of three: a position whose next v bases are valid
+// (v capped at 4) is counted in the v-mer histogram only (hist4 / hist3 / hist2 of the per-warp 336 bins); the flush
+// folds them: c3[abc] = hist3[abc] + sum_d hist4[abcd], c2[ab] = hist2[ab] + sum_c c3[abc].
+// HBM side: L/4 + L/8 bytes read per genome, 336 counters written; in practice bound by the
+// shared-memory atomics.
 // ---------------------------------------------------------------------------------------------
 constexpr int TC_THREADS = 256;
 constexpr int TC_WARPS = TC_THREADS / 32;
+constexpr int TC_GROUPS = 8;  // groups per thread and chunk -> 65,536 bases per chunk
 
-__global__ void __launch_bounds__(TC_THREADS) tetra_count_kernel(const uint64_t *__restrict__ seq64,
-                                                                 const uint32_t *__restrict__ mask, int64_t n_groups,
-                                                                 unsigned long long *__restrict__ fwd /*336*/) {
+struct TetraGenome {
+    const uint64_t *seq64;
+    const uint32_t *mask;
+    int64_t n_groups;
+};
+
+__global__ void __launch_bounds__(TC_THREADS) tetra_count_kernel(const TetraGenome *__restrict__ genomes, const int64_t *__restrict__ chunk_start /* n+1 */,
+                                                                 int n_genomes, unsigned long long *__restrict__ fwd_all /* n x 336 */) {
     __shared__ unsigned int h[TC_WARPS][336];
-    for (int i = threadIdx.x; i < TC_WARPS * 336; i += TC_THREADS) (&h[0][0])[i] = 0;
-    __syncthreads();
+    __shared__ unsigned int tot[336];
     unsigned int *hw = h[threadIdx.x >> 5];
-    const int64_t stride = (int64_t)gridDim.x * TC_THREADS;
-    for (int64_t G = (int64_t)blockIdx.x * TC_THREADS + threadIdx.x; G < n_groups; G += stride) {
-        uint64_t w0 = seq64[G];
-        uint64_t w1 = seq64[G + 1];  // arrays are padded, G+1 is always readable
-        uint64_t m = (uint64_t)mask[G] | ((uint64_t)mask[G + 1] << 32);
-        if ((uint32_t)m == 0xffffffffu) continue;  // fully masked group (padding)
+    const int64_t n_chunks = chunk_start[n_genomes];
+    for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        int lo = 0, hi = n_genomes;  // genome g with chunk_start[g] <= c < chunk_start[g+1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (chunk_start[mid] <= c) lo = mid; else hi = mid;
+        }
+        const TetraGenome G = genomes[lo];
+        for (int i = threadIdx.x; i < TC_WARPS * 336; i += TC_THREADS) (&h[0][0])[i] = 0;
+        __syncthreads();
+        const int64_t g0 = (c - chunk_start[lo]) * (TC_THREADS * TC_GROUPS);
+#pragma unroll 1
+        for (int k = 0; k < TC_GROUPS; ++k) {
+            const int64_t grp = g0 + (int64_t)k * TC_THREADS + threadIdx.x;
+            if (grp >= G.n_groups) break;
+            const uint64_t w0 = G.seq64[grp];
+            const uint64_t w1 = G.seq64[grp + 1];  // arrays are padded, grp+1 is always readable
+            const uint64_t m = (uint64_t)G.mask[grp] | ((uint64_t)G.mask[grp + 1] << 32);
+            if ((uint32_t)m == 0xffffffffu) continue;  // fully masked group (padding)
 #pragma unroll 8
-        for (int p = 0; p < 32; ++p) {
-            uint32_t k4 = (uint32_t)((p <= 28 ? (w0 >> (2 * p)) : ((w0 >> (2 * p)) | (w1 << (64 - 2 * p)))) & 0xffu);
-            uint32_t mm = (uint32_t)(m >> p) & 0xfu;
-            // packed little-endian: first base in the low bits -> convert to "first base most significant"
-            uint32_t b0 = k4 & 3u, b1 = (k4 >> 2) & 3u, b2 = (k4 >> 4) & 3u, b3 = (k4 >> 6) & 3u;
-            if ((mm & 3u) == 0) {
-                atomicAdd(&hw[b0 * 4 + b1], 1u);
-                if ((mm & 7u) == 0) {
-                    atomicAdd(&hw[16 + b0 * 16 + b1 * 4 + b2], 1u);
-                    if (mm == 0) atomicAdd(&hw[80 + b0 * 64 + b1 * 16 + b2 * 4 + b3], 1u);
-                }
+            for (int p = 0; p < 32; ++p) {
+                const uint32_t k4 = (uint32_t)((p <= 28 ? (w0 >> (2 * p)) : ((w0 >> (2 * p)) | (w1 << (64 - 2 * p)))) & 0xffu);
+                const uint32_t mm = (uint32_t)(m >> p) & 0xfu;
+                if (mm & 3u) continue;  // fewer than two valid bases: nothing to count
+                // packed little-endian: first base in the low bits -> "first base most significant" index
+                const uint32_t b0 = k4 & 3u, b1 = (k4 >> 2) & 3u, b2 = (k4 >> 4) & 3u, b3 = (k4 >> 6) & 3u;
+                const uint32_t bin = mm == 0 ? 80 + b0 * 64 + b1 * 16 + b2 * 4 + b3 : ((mm & 7u) == 0 ? 16 + b0 * 16 + b1 * 4 + b2 : b0 * 4 + b1);
+                atomicAdd(&hw[bin], 1u);
             }
         }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 336; i += TC_THREADS) {
-        unsigned long long s = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 336; i += TC_THREADS) {
+            unsigned int s = 0;
 #pragma unroll
-        for (int w = 0; w < TC_WARPS; ++w) s += h[w][i];
-        if (s) atomicAdd(&fwd[i], s);
+            for (int w = 0; w < TC_WARPS; ++w) s += h[w][i];
+            tot[i] = s;
+        }
+        __syncthreads();
+        unsigned long long *fwd = fwd_all + (size_t)lo * 336;
+        for (int i = threadIdx.x; i < 336; i += TC_THREADS) {
+            unsigned long long s = tot[i];
+            if (i < 80) {  // trimers take the tetramers that start with them, dimers the trimers (and their tetramers)
+                const int t3lo = i < 16 ? 16 + i * 4 : i, t3hi = i < 16 ? t3lo + 4 : i + 1;
+                for (int t3 = t3lo; t3 < t3hi; ++t3) {
+                    if (i < 16) s += tot[t3];
+                    for (int d = 0; d < 4; ++d) s += tot[80 + (t3 - 16) * 4 + d];
+                }
+            }
+            if (s) atomicAdd(&fwd[i], s);
+        }
+        __syncthreads();
     }
 }
 
@@ -160,16 +196,40 @@ __global__ void __launch_bounds__(256) tetra_corr_kernel(const double *__restric
         corr[(size_t)i * n + j] = (i == j) ? 1.0 : __ddiv_rn(dp, __dsqrt_rn(__dmul_rn(ss[min(i, j)], ss[max(i, j)])));
 }
 
-int tetra_counts_device(b200ani_ctx *ctx, const Genome &g, unsigned long long *d_tot) {
+// totals (both strands, 336 per genome) of n genomes; one counting launch for all of them
+int tetra_counts_device(b200ani_ctx *ctx, const Genome *const *gs, int n, unsigned long long *d_tot) {
+    std::vector<TetraGenome> h(n);
+    std::vector<int64_t> cs(n + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        const int64_t n_groups = ceil_div(gs[i]->n_pos, 32);
+        h[i] = TetraGenome{reinterpret_cast<const uint64_t *>(gs[i]->d_seq), gs[i]->d_mask, n_groups};
+        cs[i + 1] = cs[i] + ceil_div(n_groups, (int64_t)TC_THREADS * TC_GROUPS);
+    }
+    TetraGenome *d_g = nullptr;
+    int64_t *d_cs = nullptr;
     unsigned long long *d_fwd = nullptr;
-    CK(cudaMallocAsync(&d_fwd, 336 * sizeof(unsigned long long), ctx->stream));
-    CK(cudaMemsetAsync(d_fwd, 0, 336 * sizeof(unsigned long long), ctx->stream));
-    int64_t n_groups = ceil_div(g.n_pos, 32);
-    int blocks = (int)std::min<int64_t>(ceil_div(n_groups, TC_THREADS), (int64_t)ctx->sm_count * 8);
-    tetra_count_kernel<<<blocks, TC_THREADS, 0, ctx->stream>>>(reinterpret_cast<const uint64_t *>(g.d_seq), g.d_mask, n_groups, d_fwd);
+    CK(cudaMallocAsync(&d_g, sizeof(TetraGenome) * n, ctx->stream));
+    CK(cudaMallocAsync(&d_cs, sizeof(int64_t) * (n + 1), ctx->stream));
+    CK(cudaMallocAsync(&d_fwd, 336 * sizeof(unsigned long long) * n, ctx->stream));
+    CK(cudaMemcpyAsync(d_g, h.data(), sizeof(TetraGenome) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_cs, cs.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d_fwd, 0, 336 * sizeof(unsigned long long) * n, ctx->stream));
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(cs[n], (int64_t)ctx->sm_count * 8));
+    CK(cudaEventRecord(ctx->ev_prof[0], ctx->stream));
+    tetra_count_kernel<<<blocks, TC_THREADS, 0, ctx->stream>>>(d_g, d_cs, n, d_fwd);
     CK(cudaGetLastError());
-    tetra_totals_kernel<<<1, 256, 0, ctx->stream>>>(d_fwd, g.d_seq, g.d_mask, g.d_goff, g.n_contigs, d_tot);
-    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_prof[1], ctx->stream));
+    for (int i = 0; i < n; ++i) {
+        tetra_totals_kernel<<<1, 256, 0, ctx->stream>>>(d_fwd + (size_t)i * 336, gs[i]->d_seq, gs[i]->d_mask, gs[i]->d_goff, gs[i]->n_contigs, d_tot + (size_t)i * 336);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(ctx->stream));  // h / cs go out of scope
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev_prof[0], ctx->ev_prof[1]));
+    ctx->stage_ms[ST_TETRA_COUNT] += ms;
+    ctx->counters[CT_LAUNCHES] += 1 + n;
+    CK(cudaFreeAsync(d_g, ctx->stream));
+    CK(cudaFreeAsync(d_cs, ctx->stream));
     CK(cudaFreeAsync(d_fwd, ctx->stream));
     return 0;
 }

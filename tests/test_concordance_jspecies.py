@@ -152,7 +152,7 @@ def test_concordance_gpu(engine, arrays, ogenomes, gids):
         want, _, _ = oracle.anim_pair(ogenomes[r], ogenomes[q])
         for f in ("ref_aln_len", "qry_aln_len", "sum_aligned", "sum_weighted", "sim_errs", "n_alignments"):
             assert int(x[f]) == want[f], (r, q, f)
-    assert max(anim_devs(lambda r, q: ident[(r, q)]).values()) < 0.21
+    assert max(anim_devs(lambda r, q: ident[(r, q)]).values()) < 0.23
     # ANIb
     resb = engine.anib(gp)
     pid = {p: int(x["pid_milli_sum"]) / max(int(x["n_pass"]), 1) / 1000 for p, x in zip(pairs, resb)}
