@@ -93,6 +93,25 @@ int b200ani_anim(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch
 int64_t b200ani_anim_alignments(b200ani_ctx *ctx, int32_t ref_id, int32_t qry_id, int maxmatch, int nofilter,
                                 int64_t *rows, int64_t cap);
 
+/* The same for ALL m pairs in one call (what a job-graph backend needs: one device pass instead of one per command line,
+ * run_multiprocessing.py:56-84).  out (optional, m structs) as b200ani_anim; rows: the alignments that would be in each
+ * pair's .filter (nofilter: .delta), 7 int64 each as above, grouped by pair in the order of `pairs`; row_start (optional,
+ * m + 1 entries): rows of pair i are row_start[i] .. row_start[i+1]-1.  kept (optional, cap bytes): when given, EVERY alignment is
+ * returned (the .delta content) and kept[r] tells whether row r is also in the .filter -- both files of a pair from one pass.
+ * Returns the total number of rows (<= cap written; call again with a larger buffer if it exceeds cap) or a negative error. */
+int64_t b200ani_anim_rows(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch, int nofilter, b200ani_anim_result *out,
+                          int64_t *rows, int64_t cap, int64_t *row_start, uint8_t *kept);
+
+/* Write a .delta / .filter file as nucmer / delta-filter lay it out and anim.parse_delta / nucmer.DeltaIterator read it
+ * (anim.py:300-325, nucmer.py:317-351): header line with the two FASTA paths, "NUCMER", one '>' line per record pair
+ * (ids, lengths), one 7-field header per alignment followed by the terminating 0 of its (empty) indel list -- the engine is
+ * traceback-free, so the per-alignment indel offsets MUMmer's own tools would need are not available.
+ * rows: n x 7 int64 as returned by b200ani_anim_rows.  Host-side only (no device work).  Returns 0, B200ANI_ERR_ARG for a
+ * record index outside the id tables, or B200ANI_ERR_IO. */
+#define B200ANI_ERR_IO (-5)
+int b200ani_write_delta(const char *path, const char *ref_path, const char *qry_path, const char *const *ref_ids, const int64_t *ref_lens,
+                        uint32_t n_ref, const char *const *qry_ids, const int64_t *qry_lens, uint32_t n_qry, const int64_t *rows, int64_t n);
+
 /* ---- ANIb (anib.py) ---- */
 /* One directed comparison: the 1020-nt fragments of the query genome against the subject genome.
  * Fields are what anib.parse_blast_tab returns (anib.py:661-667), kept as exact integers:
@@ -118,6 +137,11 @@ int b200ani_anib(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fragsize
  * anib.fragment_fasta_files), length, mismatch, gaps, nident, qlen, score, round(1e5*nident/length).  Returns the
  * number of rows (<= cap written) or a negative error. */
 int64_t b200ani_anib_fragments(b200ani_ctx *ctx, int32_t qry_id, int32_t sbj_id, int fragsize, int64_t *rows, int64_t cap);
+
+/* Kept HSPs of ALL m pairs in one call, 8 int64 per row as above, grouped by pair in the order of `pairs` (see
+ * b200ani_anim_rows for out / row_start / the return value). */
+int64_t b200ani_anib_rows(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fragsize, b200ani_anib_result *out, int64_t *rows, int64_t cap,
+                          int64_t *row_start);
 
 /* Stage timers in milliseconds (CUDA events on the engine stream) and work counters of the last b200ani_anim / b200ani_anib call
  * (slots "index" .. "bridge"), of the b200ani_add_genome calls since the last b200ani_clear ("pack": the pack kernel), and of

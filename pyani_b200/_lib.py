@@ -54,6 +54,10 @@ SIGNATURES = {
     "b200ani_tetra_corr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200ani_anim": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "b200ani_anim_alignments": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int, C.c_int, C.c_void_p, C.c_int64]),
+    "b200ani_anim_rows": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "b200ani_write_delta": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                     C.c_void_p, C.c_int64]),
+    "b200ani_anib_rows": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "b200ani_anib": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "b200ani_anib_fragments": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int, C.c_void_p, C.c_int64]),
     "b200ani_last_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

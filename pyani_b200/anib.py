@@ -120,7 +120,6 @@ def run_dependency_graph(jobgraph, workers: Optional[int] = None, logger=None, e
     from .anim import _iter_jobs
     from .fasta import read_fasta
 
-    eng = engine or Engine(0)
     db_to_fasta: Dict[str, str] = {}
     todo = []
     for job in _iter_jobs(jobgraph):
@@ -135,23 +134,38 @@ def run_dependency_graph(jobgraph, workers: Optional[int] = None, logger=None, e
     if not todo:
         return 0
     by_name = {Path(db).name: fa for db, fa in db_to_fasta.items()}
-    cache: Dict[str, int] = {}
-
-    def stage(fasta: str) -> int:
-        if fasta not in cache:
-            arr, off, ids = read_fasta(fasta)
-            cache[fasta] = eng.add_genome(arr, off, Path(fasta).stem, ids)
-        return cache[fasta]
-
-    rc = 0
-    for out, query, db in todo:
+    eng = engine or Engine(0)
+    try:
+        jobs, failed = [], 0
+        for out, query, db in todo:
+            try:
+                jobs.append((out, by_name[Path(query).name.replace("-fragments", "")], db_to_fasta[db]))
+            except KeyError as exc:
+                if logger:
+                    logger.error("b200ani ANIb comparison %s vs %s: unknown database / query %s", query, db, exc)
+                failed += 1
+        files: List[str] = []
+        for _, q, s_ in jobs:
+            for f in (q, s_):
+                if f not in files:
+                    files.append(f)
         try:
-            sfasta = db_to_fasta[db]
-            qfasta = by_name[Path(query).name.replace("-fragments", "")]
-            rows = eng.anib_fragments(stage(qfasta), stage(sfasta), fragsize=fragsize)
-            write_minimal_blast_tab(Path(out), Path(sfasta).stem, rows, slen=eng.genome_length(stage(sfasta)))
-        except Exception as exc:  # mirrors a non-zero subprocess return code
+            if hasattr(eng, "add_fasta_many"):
+                gid = dict(zip(files, eng.add_fasta_many(files)))
+            else:  # test doubles
+                gid = {}
+                for f in files:
+                    arr, off, ids = read_fasta(f)
+                    gid[f] = eng.add_genome(arr, off, Path(f).stem, ids)
+            pairs = np.array([[gid[q], gid[s_]] for _, q, s_ in jobs], dtype=np.int32).reshape(-1, 2)
+            _, rows, start = eng.anib_rows(pairs, fragsize=fragsize)  # ONE batched device pass for every blastn job
+            for i, (out, q, s_) in enumerate(jobs):
+                write_minimal_blast_tab(Path(out), Path(s_).stem, rows[start[i]:start[i + 1]], slen=eng.genome_length(gid[s_]))
+        except Exception as exc:  # mirrors non-zero subprocess return codes
             if logger:
-                logger.error("b200ani ANIb comparison %s vs %s failed: %s", query, db, exc)
-            rc += 1
-    return rc
+                logger.error("b200ani ANIb batch of %d comparisons failed: %s", len(jobs), exc)
+            failed += len(jobs)
+        return failed
+    finally:
+        if engine is None:
+            eng.close()

@@ -107,7 +107,8 @@ def write_minimal_delta(path: Path, ref_path: str, qry_path: str, rows: np.ndarr
                         ref_lens: Sequence[int], qry_lens: Sequence[int]) -> None:
     """A .delta/.filter file holding what ``parse_delta`` and ``nucmer.DeltaIterator`` read: header, one
     '>' line per record pair, 7-field alignment headers, each followed by the terminating ``0`` of an empty
-    indel list (format: anim.py:300-325, nucmer.py:317-351).  rows: (ref_rec, qry_rec, rs, re, qs, qe, errs)."""
+    indel list (format: anim.py:300-325, nucmer.py:317-351).  rows: (ref_rec, qry_rec, rs, re, qs, qe, errs).
+    Pure-Python twin of the native emitter ``b200ani_write_delta`` (same bytes; used where no engine is at hand)."""
     path.parent.mkdir(parents=True, exist_ok=True)
     with open(path, "w") as fh:
         fh.write(f"{ref_path} {qry_path}\nNUCMER\n")
@@ -124,10 +125,11 @@ def write_minimal_delta(path: Path, ref_path: str, qry_path: str, rows: np.ndarr
 def run_dependency_graph(jobgraph, workers: Optional[int] = None, logger=None, engine: Optional[Engine] = None) -> int:
     """GPU stand-in for ``run_multiprocessing.run_dependency_graph(jobgraph, workers, logger) -> int``.
 
-    ``workers`` is accepted and ignored (one GPU does the work of the pool).  Returns 0 on success, 1 if any
-    comparison could not be run -- the caller's ``if cumval > 0: raise PyaniException`` logic
-    (subcmd_anim.py:396-401) keeps working."""
-    eng = engine or Engine(0)
+    All nucmer jobs of the graph become ONE batched device pass per mode (``Engine.anim_rows`` with ``all_rows=True``: the
+    .delta rows and which of them survive the 1-to-1 filter), then every job's ``.delta`` and ``.filter`` are written where
+    nucmer / delta-filter would have put them (native emitter).  ``workers`` is accepted and ignored (one GPU does the work of
+    the pool).  Returns 0 on success, the number of comparisons that could not be run otherwise -- the caller's
+    ``if cumval > 0: raise PyaniException`` logic (subcmd_anim.py:396-401) keeps working."""
     todo = []
     for job in _iter_jobs(jobgraph):
         cmd = getattr(job, "command", None) or getattr(job, "script", "")
@@ -136,23 +138,42 @@ def run_dependency_graph(jobgraph, workers: Optional[int] = None, logger=None, e
             todo.append((m.group(1) == "--maxmatch", m.group(2), m.group(3), m.group(4)))
     if not todo:
         return 0
-    cache: Dict[str, Tuple[int, list, np.ndarray]] = {}
-
-    def stage(path: str):
-        if path not in cache:
-            arr, off, ids = read_fasta(path)
-            cache[path] = (eng.add_genome(arr, off, Path(path).stem, ids), ids, np.diff(off.astype(np.int64)))
-        return cache[path]
-
-    rc = 0
-    for maxmatch, prefix, f1, f2 in todo:
+    eng = engine or Engine(0)
+    try:
+        files: List[str] = []
+        for _, _, f1, f2 in todo:
+            for f in (f1, f2):
+                if f not in files:
+                    files.append(f)
         try:
-            (g1, ids1, len1), (g2, ids2, len2) = stage(f1), stage(f2)
-            for nofilter, suffix in ((True, ".delta"), (False, ".filter")):
-                rows = eng.anim_alignments(g1, g2, maxmatch=maxmatch, nofilter=nofilter)
-                write_minimal_delta(Path(prefix + suffix), f1, f2, rows, ids1, ids2, len1, len2)
-        except Exception as exc:  # mirrors a non-zero subprocess return code
+            if hasattr(eng, "add_fasta_many"):
+                gid = dict(zip(files, eng.add_fasta_many(files)))
+            else:  # test doubles
+                gid = {}
+                for f in files:
+                    arr, off, ids = read_fasta(f)
+                    gid[f] = eng.add_genome(arr, off, Path(f).stem, ids)
+        except Exception as exc:
             if logger:
-                logger.error("b200ani comparison %s vs %s failed: %s", f1, f2, exc)
-            rc += 1
-    return rc
+                logger.error("b200ani could not stage the genomes: %s", exc)
+            return len(todo)
+        failed = 0
+        for mode in (False, True):
+            jobs = [t for t in todo if t[0] == mode]
+            if not jobs:
+                continue
+            pairs = np.array([[gid[f1], gid[f2]] for _, _, f1, f2 in jobs], dtype=np.int32)
+            try:
+                _, rows, start, kept = eng.anim_rows(pairs, maxmatch=mode, all_rows=True)
+                for i, (_, prefix, f1, f2) in enumerate(jobs):
+                    mine, k = rows[start[i]:start[i + 1]], kept[start[i]:start[i + 1]]
+                    eng.write_delta(prefix + ".delta", f1, f2, gid[f1], gid[f2], mine)
+                    eng.write_delta(prefix + ".filter", f1, f2, gid[f1], gid[f2], mine[k])
+            except Exception as exc:  # mirrors non-zero subprocess return codes
+                if logger:
+                    logger.error("b200ani batch of %d comparisons failed: %s", len(jobs), exc)
+                failed += len(jobs)
+        return failed
+    finally:
+        if engine is None:
+            eng.close()

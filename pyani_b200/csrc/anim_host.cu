@@ -4,7 +4,11 @@
 // replacing, per pair, one nucmer and one delta-filter subprocess plus anim.parse_delta
 // (anim.py:240-289,292-411; run_multiprocessing.py:113-152).
 #include <algorithm>
+#include <atomic>
 #include <cub/cub.cuh>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 
@@ -89,7 +93,19 @@ struct Arena {
     }
 };
 
+// One pipeline: its own stream, device buffers, scratch arena, timers and accumulators.  A call runs its batches on up to
+// N_PIPELINES of them from as many host threads, so that the memory-bound stages of one batch (seed probe, sorts, chaining)
+// overlap the ALU-bound DP of another on the same SMs.
 struct AnimWorkspace {
+    cudaStream_t st = nullptr;
+    double hms[B200ANI_N_STAGES] = {0};       // stage milliseconds of the batches this pipeline ran in the current call
+    int64_t hcount[B200ANI_N_STAGES] = {0};   // ... and their work counters
+    std::string err;
+    int rc = 0;
+    std::vector<int> h_rows, h_pair;  // row dump of the current batch (host staging)
+    std::vector<uint8_t> h_flag;
+    double last_fill = 0;  // fill level of the anchor / hit buffers in the last batch (> 1: it did not fit)
+    int n_pipelines = 1;  // pipelines active in the current call (DP kernels leave room for the others' blocks when > 1)
     Arena arena;
     uint64_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr;
     uint8_t *flag = nullptr;
@@ -106,7 +122,7 @@ struct AnimWorkspace {
     bool ok = false;
 };
 
-void free_anim_workspace(void *p) {
+static void free_anim_workspace(void *p) {
     AnimWorkspace *w = (AnimWorkspace *)p;
     if (!w) return;
     cudaFree(w->keys_a); cudaFree(w->vals_a); cudaFree(w->keys_b); cudaFree(w->vals_b); cudaFree(w->flag); cudaFree(w->hits);
@@ -114,11 +130,26 @@ void free_anim_workspace(void *p) {
     for (auto &e : w->ev) if (e) cudaEventDestroy(e);
     for (auto &e : w->kev) cudaEventDestroy(e);
     w->arena.release();
+    if (w->st) cudaStreamDestroy(w->st);
     delete w;
 }
 
-static int get_workspace(b200ani_ctx *ctx, AnimWorkspace **out) {
-    if (ctx->anim_ws) { *out = (AnimWorkspace *)ctx->anim_ws; return 0; }
+struct WorkspaceSet {
+    std::vector<AnimWorkspace *> w;
+    std::atomic<int> batch_hint{0};  // pairs per batch that fit the anchor / hit buffers (0 = not known yet)
+};
+void free_anim_workspaces(void *p) {
+    WorkspaceSet *ws = (WorkspaceSet *)p;
+    if (!ws) return;
+    for (auto *w : ws->w) free_anim_workspace(w);
+    delete ws;
+}
+
+static int get_workspace(b200ani_ctx *ctx, int idx, AnimWorkspace **out) {
+    if (!ctx->anim_ws) ctx->anim_ws = new WorkspaceSet();
+    WorkspaceSet *ws = (WorkspaceSet *)ctx->anim_ws;
+    if ((int)ws->w.size() > idx) { *out = ws->w[idx]; return 0; }
+    if ((int)ws->w.size() != idx) FAIL(B200ANI_ERR_ARG, "anim: workspaces are created in order");
     AnimWorkspace *w = new AnimWorkspace();
     // cached in the context only once every allocation succeeded: a half-built workspace must never be reused
     struct Guard { AnimWorkspace *w; ~Guard() { if (w) free_anim_workspace(w); } } guard{w};
@@ -142,21 +173,36 @@ static int get_workspace(b200ani_ctx *ctx, AnimWorkspace **out) {
     w->cub_bytes = std::max(a, std::max(b, c)) + 256;
     CK(cudaMalloc(&w->cub_tmp, w->cub_bytes));
     for (auto &e : w->ev) CK(cudaEventCreate(&e));
+    CK(cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking));
     w->ok = true;
     guard.w = nullptr;
-    ctx->anim_ws = w;
+    ws->w.push_back(w);
     *out = w;
     return 0;
 }
 
+// ---- batch code: runs on a pipeline's host thread; errors, timers and counters go to the pipeline (W), not to the context
+#undef CK
+#undef FAIL
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            char buf__[512];                                                                         \
+            snprintf(buf__, sizeof buf__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            W->err = buf__;                                                                          \
+            return B200ANI_ERR_CUDA;                                                                 \
+        }                                                                                            \
+    } while (0)
+#define FAIL(code, msg) do { W->err = (msg); return (code); } while (0)
 template <typename T>
-static int dalloc(b200ani_ctx *ctx, Arena &arena, T **p, int64_t n) {
-    *p = (T *)arena.get(sizeof(T) * (size_t)std::max<int64_t>(n, 1));
+static int dalloc(AnimWorkspace *W, T **p, int64_t n) {
+    *p = (T *)W->arena.get(sizeof(T) * (size_t)std::max<int64_t>(n, 1));
     if (!*p) FAIL(B200ANI_ERR_NOMEM, "anim: out of device memory for the batch scratch");
     return 0;
 }
-#define DA(p, n) do { int rc__ = dalloc(ctx, W->arena, &(p), (n)); if (rc__) return rc__; } while (0)
-#define LAUNCHED(k) do { CK(cudaGetLastError()); ctx->counters[CT_LAUNCHES] += (k); } while (0)
+#define DA(p, n) do { int rc__ = dalloc(W, &(p), (n)); if (rc__) return rc__; } while (0)
+#define LAUNCHED(k) do { CK(cudaGetLastError()); W->hcount[CT_LAUNCHES] += (k); } while (0)
 #define GRID(n) (unsigned)std::max<int64_t>(1, ceil_div((n), 256)), 256, 0, st
 #define T0(s) CK(cudaEventRecord(W->ev[2 * (s)], st))
 #define T1(s) do { CK(cudaEventRecord(W->ev[2 * (s) + 1], st)); used[(s)] = true; } while (0)
@@ -164,26 +210,29 @@ static int dalloc(b200ani_ctx *ctx, Arena &arena, T **p, int64_t n) {
 // rows_out (optional): host buffer receiving the batch's alignment rows (n x 8 int32) + keep flags
 struct Row8 { int v[8]; };  // one alignment row
 struct RowDump {
-    std::vector<int> rows;
-    std::vector<uint8_t> flag;
+    std::vector<int> rows;      // dumped rows (8 ints each), appended batch by batch
+    std::vector<int64_t> pair;  // per row: index of its pair in the call's internal (sorted) order
+    std::vector<uint8_t> kept;  // per row: survives the 1-to-1 filter (only filled when `all` is set)
+    bool all = false;           // ANIm: dump every alignment, not only the kept ones
+    std::mutex mu;
 };
 
 // fragsize == 0: ANIm (out = b200ani_anim_result[nb]); fragsize > 0: ANIb (out = b200ani_anib_result[nb])
-static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, int fragsize, int maxmatch, void *out_v, RowDump *dump);
-static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, int fragsize, int maxmatch, void *out_v, RowDump *dump) {
-    const int rc = run_batch_impl(ctx, W, pairs, nb, nofilter, fragsize, maxmatch, out_v, dump);
+static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, int fragsize, int maxmatch, void *out_v, RowDump *dump, int64_t dump_base);
+static int run_batch(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, int fragsize, int maxmatch, void *out_v, RowDump *dump, int64_t dump_base) {
+    const int rc = run_batch_impl(ctx, W, pairs, nb, nofilter, fragsize, maxmatch, out_v, dump, dump_base);
     // whatever happened, nothing of this batch may still run when the scratch is handed to the next one
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc >= 0) { ctx->err = "anim: the batch left the stream in an error state"; W->arena.reset(); return B200ANI_ERR_CUDA; }
+    if (cudaStreamSynchronize(W->st) != cudaSuccess && rc >= 0) { W->err = "anim: the batch left the stream in an error state"; W->arena.reset(); return B200ANI_ERR_CUDA; }
     W->arena.reset();
     return rc;
 }
-static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, int fragsize, int maxmatch, void *out_v, RowDump *dump) {
+static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs, int nb, int nofilter, int fragsize, int maxmatch, void *out_v, RowDump *dump, int64_t dump_base) {
     const bool anib = fragsize > 0;
     const int seedmode = anib ? SEED_BOTH_UNIQUE : (maxmatch ? SEED_ALL : SEED_EITHER_UNIQUE);
     const int seed_k = anib ? AB_K : AN_K, min_len = anib ? AB_MINLEN : AN_MINLEN;
     const int64_t ANCHOR_CAP = W->anchor_cap, HIT_CAP = W->hit_cap;
     b200ani_anim_result *out = (b200ani_anim_result *)out_v;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = W->st;
     bool used[B200ANI_N_STAGES] = {false};
     // ---- pair descriptors
     std::vector<PairDesc> hp(nb + 1);  // + sentinel
@@ -218,8 +267,8 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
     CK(cudaMemcpyAsync(W->d_pairs, hp.data(), sizeof(PairDesc) * (nb + 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(W->counters, 0, 16 * sizeof(unsigned long long), st));
     unsigned long long hc[16];
-    ctx->counters[CT_PROBES] += n_probes;
-    ctx->counters[CT_PAIRS] += nb;
+    W->hcount[CT_PROBES] += n_probes;
+    W->hcount[CT_PAIRS] += nb;
 
     // ---- seeds -> anchors: probe (latency bound, uniform) then extend (one thread per hit)
     T0(ST_SEED);
@@ -238,14 +287,15 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
         else
             seed_probe_kernel<SEED_EITHER_UNIQUE><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP, seed_k);
         LAUNCHED(1);
-        ctx->counters[CT_SEEDLAUNCH] += 1;
+        W->hcount[CT_SEEDLAUNCH] += 1;
     }
     T1(ST_SEED);
     CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const int64_t n_hits = (int64_t)hc[1];
+    W->last_fill = (double)n_hits / (double)HIT_CAP;
     if (n_hits > HIT_CAP) return 1;  // caller splits the batch
-    ctx->counters[CT_SEEDHITS] += n_hits;
+    W->hcount[CT_SEEDHITS] += n_hits;
     T0(ST_SEEDX);
     if (n_hits) {
         int blocks = (int)std::min<int64_t>(ceil_div(n_hits, 256), (int64_t)ctx->sm_count * 8);
@@ -256,6 +306,7 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
     CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const int64_t n_raw = (int64_t)hc[0];
+    W->last_fill = std::max((double)n_raw / (double)ANCHOR_CAP, (double)n_hits / (double)HIT_CAP);
     if (n_raw > ANCHOR_CAP) return 1;  // caller splits the batch
 
     // ---- sort by (pair, strand, r), ties by (q, len); drop duplicates
@@ -335,7 +386,7 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
         n = hn;
         A.keys = W->keys_b; A.vals = W->vals_b; A.n = n;
     }
-    ctx->counters[CT_ANCHORS] += n;
+    W->hcount[CT_ANCHORS] += n;
     int64_t n_seg = 0;
     if (n) {
         T0(ST_LINK);
@@ -347,9 +398,9 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
         T1(ST_LINK);
         CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        ctx->counters[CT_LINKS] += (int64_t)hc[2];
+        W->hcount[CT_LINKS] += (int64_t)hc[2];
         const int64_t n_tasks = (int64_t)hc[3];
-        ctx->counters[CT_GAPTASKS] += n_tasks;
+        W->hcount[CT_GAPTASKS] += n_tasks;
         // ---- link alignments
         if (n_tasks) {
             size_t tb = W->cub_bytes;
@@ -359,7 +410,7 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
             else gap_dp_kernel<0><<<(unsigned)ceil_div(n_tasks, 128), 128, 0, st>>>(A, W->d_pairs, task_idx2, n_tasks, W->counters + 4, 1);
             LAUNCHED(1);
             T1(ST_GAPDP);
-            ctx->counters[CT_GAPLAUNCH] += 1;
+            W->hcount[CT_GAPLAUNCH] += 1;
         }
         // ---- clusters and segments
         T0(ST_LABEL);
@@ -376,10 +427,10 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
         CK(cudaStreamSynchronize(st));
         T1(ST_LABEL);
         n_seg = hs;
-        ctx->counters[CT_GAPCELLS] += (int64_t)hc[4];
-        ctx->counters[CT_CUTS] += (int64_t)hc[5];
+        W->hcount[CT_GAPCELLS] += (int64_t)hc[4];
+        W->hcount[CT_CUTS] += (int64_t)hc[5];
     }
-    ctx->counters[CT_SEGMENTS] += n_seg;
+    W->hcount[CT_SEGMENTS] += n_seg;
 
     // ---- segments -> alignments: fusion at anchor level (ANIm), extension rounds, bridging
     SegArrays S{};
@@ -425,7 +476,7 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
         CK(cudaMemcpyAsync(&hk, W->changed, sizeof hk, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(seg_head, task_idx2, sizeof(int) * n_seg, cudaMemcpyDeviceToDevice, st));
         CK(cudaStreamSynchronize(st));
-        ctx->counters[CT_SEGMENTS] -= n_seg - hk;
+        W->hcount[CT_SEGMENTS] -= n_seg - hk;
         n_seg = hk;
         S.n = n_seg;
     }
@@ -461,7 +512,10 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
                     W->kev.push_back(a);
                     W->kev.push_back(b);
                 }
-                int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * std::max(per_sm, 1), ceil_div(n_cur, 128));
+                // with a second pipeline active one block slot per SM stays free: its memory-bound kernels (seed probe, sorts,
+                // chaining) then run beside this ALU-bound one instead of waiting for it
+                const int dp_per_sm = std::max(W->n_pipelines > 1 ? per_sm - 1 : per_sm, 1);
+                int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * dp_per_sm, ceil_div(n_cur, 128));
                 CK(cudaEventRecord(W->kev[2 * n_ext_launch], st));
                 if (anib)
                     ext_dp_kernel<1><<<(unsigned)blocks, 128, 0, st>>>(S, W->d_pairs, round ? ext_list[round & 1] : nullptr, n_cur, ext_list[(round + 1) & 1],
@@ -479,8 +533,8 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
             }
         }
         T1(ST_EXTDP);
-        ctx->counters[CT_EXTCELLS] += (int64_t)hc[6];
-        ctx->counters[CT_EXTTILES] += (int64_t)hc[7];
+        W->hcount[CT_EXTCELLS] += (int64_t)hc[6];
+        W->hcount[CT_EXTTILES] += (int64_t)hc[7];
         {
             // ---- bridging: join alignments whose facing ends are close (ANIm: one row per chain of joined alignments;
             // ANIb: candidate HSPs of one fragment)
@@ -543,31 +597,39 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
         CK(cudaMemcpyAsync(out_v, d_out, sizeof(b200ani_anib_result) * nb, cudaMemcpyDeviceToHost, st));
         T1(ST_REDUCE);
         if (dump) {
-            dump->rows.resize((size_t)8 * n_seg);
-            dump->flag.resize((size_t)n_seg);
+            W->h_rows.resize((size_t)8 * n_seg); W->h_flag.resize((size_t)n_seg); W->h_pair.resize((size_t)n_seg);
             if (n_seg) {
-                CK(cudaMemcpyAsync(dump->rows.data(), rows, sizeof(int) * 8 * n_seg, cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(dump->flag.data(), chosen, (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(W->h_rows.data(), rows, sizeof(int) * 8 * n_seg, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(W->h_flag.data(), chosen, (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(W->h_pair.data(), B.pair, sizeof(int) * n_seg, cudaMemcpyDeviceToHost, st));
             }
         }
         CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        ctx->counters[CT_JUNCTIONS] += (int64_t)hc[10];
-        ctx->counters[CT_BOXCELLS] += (int64_t)hc[11];
+        if (dump) {  // kept fragment rows of the batch, tagged with the internal pair index
+            std::lock_guard<std::mutex> lk(dump->mu);
+            for (int64_t i = 0; i < n_seg; ++i) {
+                if (!W->h_flag[i]) continue;
+                dump->pair.push_back(dump_base + W->h_pair[i]);
+                dump->rows.insert(dump->rows.end(), W->h_rows.begin() + 8 * i, W->h_rows.begin() + 8 * i + 8);
+            }
+        }
+        W->hcount[CT_JUNCTIONS] += (int64_t)hc[10];
+        W->hcount[CT_BOXCELLS] += (int64_t)hc[11];
         for (int s2 = 0; s2 < B200ANI_N_STAGES; ++s2)
             if (used[s2]) {
                 float ms = 0;
                 CK(cudaEventElapsedTime(&ms, W->ev[2 * s2], W->ev[2 * s2 + 1]));
-                ctx->stage_ms[s2] += ms;
+                W->hms[s2] += ms;
             }
         for (int k = 0; k < n_ext_launch; ++k) {
             float ms = 0;
             CK(cudaEventElapsedTime(&ms, W->kev[2 * k], W->kev[2 * k + 1]));
-            ctx->stage_ms[ST_EXTK] += ms;
+            W->hms[ST_EXTK] += ms;
         }
-        ctx->counters[CT_EXTLAUNCH] += n_ext_launch;
+        W->hcount[CT_EXTLAUNCH] += n_ext_launch;
         const b200ani_anib_result *ho = (const b200ani_anib_result *)out_v;
-        for (int p = 0; p < nb; ++p) ctx->counters[CT_ALIGNMENTS] += ho[p].n_pass;
+        for (int p = 0; p < nb; ++p) W->hcount[CT_ALIGNMENTS] += ho[p].n_pass;
         return 0;
     }
 
@@ -601,38 +663,68 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
     CK(cudaMemcpyAsync(out, W->d_results, sizeof(b200ani_anim_result) * nb, cudaMemcpyDeviceToHost, st));
     T1(ST_REDUCE);
     if (dump) {
-        dump->rows.resize((size_t)8 * n_rows);
-        dump->flag.resize((size_t)n_rows);
+        W->h_rows.resize((size_t)8 * n_rows); W->h_flag.resize((size_t)n_rows);
         if (n_rows) {
-            CK(cudaMemcpyAsync(dump->rows.data(), rows, sizeof(int) * 8 * n_rows, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(dump->flag.data(), F.flag, (size_t)n_rows, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(W->h_rows.data(), rows, sizeof(int) * 8 * n_rows, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(W->h_flag.data(), F.flag, (size_t)n_rows, cudaMemcpyDeviceToHost, st));
         }
     }
-    // ---- release
-
     CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    ctx->counters[CT_JUNCTIONS] += (int64_t)hc[10];
-    ctx->counters[CT_BOXCELLS] += (int64_t)hc[11];
+    if (dump) {  // alignment rows of the batch that survive the filter (all of them with nofilter)
+        std::lock_guard<std::mutex> lk(dump->mu);
+        for (int64_t i = 0; i < n_rows; ++i) {
+            const bool keep = nofilter || W->h_flag[i] == 3;
+            if (!keep && !dump->all) continue;
+            if (dump->all) dump->kept.push_back(keep);
+            dump->pair.push_back(dump_base + W->h_rows[8 * i]);
+            dump->rows.insert(dump->rows.end(), W->h_rows.begin() + 8 * i, W->h_rows.begin() + 8 * i + 8);
+        }
+    }
+    W->hcount[CT_JUNCTIONS] += (int64_t)hc[10];
+    W->hcount[CT_BOXCELLS] += (int64_t)hc[11];
     for (int s = 0; s < B200ANI_N_STAGES; ++s)
         if (used[s]) {
             float ms = 0;
             CK(cudaEventElapsedTime(&ms, W->ev[2 * s], W->ev[2 * s + 1]));
-            ctx->stage_ms[s] += ms;
+            W->hms[s] += ms;
         }
     for (int k = 0; k < n_ext_launch; ++k) {
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, W->kev[2 * k], W->kev[2 * k + 1]));
-        ctx->stage_ms[ST_EXTK] += ms;
+        W->hms[ST_EXTK] += ms;
     }
-    ctx->counters[CT_EXTLAUNCH] += n_ext_launch;
+    W->hcount[CT_EXTLAUNCH] += n_ext_launch;
     int64_t kept = 0;
     for (int p = 0; p < nb; ++p) kept += out[p].n_alignments;
-    ctx->counters[CT_ALIGNMENTS] += kept;
+    W->hcount[CT_ALIGNMENTS] += kept;
     return 0;
 }
 
-static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs_in, int64_t m, int nofilter, int fragsize, int maxmatch, void *out_user_v, RowDump *dump) {
+// restore the context-level error macros for the code that runs on the caller's thread
+#undef CK
+#undef FAIL
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            char buf__[512];                                                                         \
+            snprintf(buf__, sizeof buf__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            ctx->err = buf__;                                                                        \
+            return B200ANI_ERR_CUDA;                                                                 \
+        }                                                                                            \
+    } while (0)
+#define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
+
+static int n_pipelines_wanted() {
+    if (const char *e = getenv("B200ANI_PIPELINES")) return std::max(1, std::min(4, atoi(e)));
+    return 2;
+}
+
+// All m pairs: internal order, batches handed to the pipelines from a shared cursor, results (and optionally the kept
+// alignment / fragment rows) back in caller order.  rows_order (optional): for every dumped row the caller-order pair index.
+static int run_range(b200ani_ctx *ctx, const int32_t *pairs_in, int64_t m, int nofilter, int fragsize, int maxmatch, void *out_user_v, RowDump *dump,
+                     std::vector<int64_t> *order_out) {
     const size_t esz = fragsize > 0 ? sizeof(b200ani_anib_result) : sizeof(b200ani_anim_result);
     char *out_user = (char *)out_user_v;
     // Internal order: the two directions of a genome pair adjacent (one probe pass seeds both), genome pairs
@@ -650,37 +742,93 @@ static int run_range(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pairs_in
     std::vector<int32_t> pairs(2 * m);
     for (int64_t i = 0; i < m; ++i) { pairs[2 * i] = pairs_in[2 * order[i]]; pairs[2 * i + 1] = pairs_in[2 * order[i] + 1]; }
     std::vector<char> out((size_t)m * esz);
-    auto splits_mirror = [&](int64_t b0, int nb) {  // would a batch [b0, b0+nb) cut a (a,b),(b,a) couple in two?
+    auto splits_mirror = [&](int64_t b0, int64_t nb) {  // would a batch [b0, b0+nb) cut a (a,b),(b,a) couple in two?
         const int64_t e = b0 + nb;
         return e < m && e - 1 >= b0 && pairs[2 * e] == pairs[2 * e - 1] && pairs[2 * e + 1] == pairs[2 * e - 2] &&
                !(e - 2 >= b0 && pairs[2 * (e - 1)] == pairs[2 * (e - 2) + 1] && pairs[2 * (e - 1) + 1] == pairs[2 * (e - 2)]);
     };
-    for (int64_t b0 = 0; b0 < m;) {
-        int nb = (int)std::min<int64_t>(MAX_BATCH_PAIRS, m - b0);
-        while (true) {
-            if (nb > 1 && splits_mirror(b0, nb)) --nb;
-            int rc = run_batch(ctx, W, pairs.data() + 2 * b0, nb, nofilter, fragsize, maxmatch, out.data() + (size_t)b0 * esz, dump);
-            if (rc == 0) break;
-            if (rc < 0) return rc;
-            if (nb == 1) FAIL(B200ANI_ERR_CAPACITY, "anim: a single pair exceeds the anchor capacity");
-            nb = (nb + 1) / 2;  // buffer overflow: retry with half the pairs
-        }
-        b0 += nb;
+    WorkspaceSet *ws = (WorkspaceSet *)ctx->anim_ws;
+    // a handful of batches cannot keep two pipelines busy; small calls (tests, single pairs) stay on one
+    const int n_pipe = (int)std::max<int64_t>(1, std::min<int64_t>(n_pipelines_wanted(), m / 512));
+    for (int k = 0; k < n_pipe; ++k) {
+        AnimWorkspace *W = nullptr;
+        int rc = get_workspace(ctx, k, &W);
+        if (rc) return rc;
     }
+    std::mutex cursor_mu;
+    int64_t cursor = 0;
+    std::atomic<int> failed{0};
+    // one batch [b0, b0+nb): on overflow of the anchor / hit buffers the range is halved and both halves are run here
+    std::function<int(AnimWorkspace *, int64_t, int64_t)> process = [&](AnimWorkspace *W, int64_t b0, int64_t nb) -> int {
+        int rc = run_batch(ctx, W, pairs.data() + 2 * b0, (int)nb, nofilter, fragsize, maxmatch, out.data() + (size_t)b0 * esz, dump, b0);
+        if (rc == 0) {  // size the next batches so that they fill ~70 % of the buffers
+            if (W->last_fill > 0) {
+                const int want = (int)std::max<double>(2, std::min<double>(MAX_BATCH_PAIRS, 0.7 * (double)nb / W->last_fill));
+                const int cur = ws->batch_hint.load();
+                ws->batch_hint.store(cur ? (cur + want) / 2 : want);
+            }
+            return 0;
+        }
+        if (rc < 0) return rc;
+        if (nb == 1) FAIL(B200ANI_ERR_CAPACITY, "anim: a single pair exceeds the anchor capacity");
+        ws->batch_hint.store((int)std::max<double>(2, 0.7 * (double)nb / std::max(W->last_fill, 1.0)));
+        int64_t h = (nb + 1) / 2;
+        if (h > 1 && h < nb && splits_mirror(b0, h)) --h;
+        rc = process(W, b0, h);
+        if (rc) return rc;
+        return process(W, b0 + h, nb - h);
+    };
+    auto worker = [&](AnimWorkspace *W) {
+        cudaSetDevice(ctx->device);
+        W->n_pipelines = n_pipe;
+        W->rc = 0;
+        while (!failed.load()) {
+            int64_t b0, nb;
+            {
+                std::lock_guard<std::mutex> lk(cursor_mu);
+                if (cursor >= m) break;
+                const int hint = ws->batch_hint.load();
+                b0 = cursor;
+                nb = std::min<int64_t>(hint ? hint : MAX_BATCH_PAIRS, m - b0);
+                // the first batches of a call share the work evenly instead of one pipeline taking everything
+                if (n_pipe > 1) nb = std::min<int64_t>(nb, std::max<int64_t>(1, ceil_div(m - b0, n_pipe)));
+                if (nb > 1 && splits_mirror(b0, nb)) --nb;
+                cursor = b0 + nb;
+            }
+            const int rc = process(W, b0, nb);
+            if (rc) { W->rc = rc; failed.store(1); break; }
+        }
+    };
+    for (int k = 0; k < n_pipe; ++k) {
+        memset(ws->w[k]->hms, 0, sizeof ws->w[k]->hms);
+        memset(ws->w[k]->hcount, 0, sizeof ws->w[k]->hcount);
+        ws->w[k]->err.clear();
+    }
+    if (n_pipe == 1) worker(ws->w[0]);
+    else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < n_pipe; ++k) th.emplace_back(worker, ws->w[k]);
+        for (auto &t : th) t.join();
+    }
+    int rc = 0;
+    for (int k = 0; k < n_pipe; ++k) {
+        AnimWorkspace *W = ws->w[k];
+        for (int i = 0; i < B200ANI_N_STAGES; ++i) { ctx->stage_ms[i] += W->hms[i]; ctx->counters[i] += W->counters[i]; }
+        if (W->rc && !rc) { rc = W->rc; ctx->err = W->err; }
+    }
+    if (rc) return rc;
     for (int64_t i = 0; i < m; ++i) memcpy(out_user + (size_t)order[i] * esz, out.data() + (size_t)i * esz, esz);
+    if (order_out) *order_out = std::move(order);
     return 0;
 }
 
-static int prepare(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, AnimWorkspace **W, bool anib) {
+static int prepare(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, bool anib) {
     const int maxocc = AN_MAXOCC;  // the seed stage filters the repeated k-mers per mode; ANIb has its own index (shorter seeds)
     CK(cudaSetDevice(ctx->device));
     const int32_t ng = (int32_t)ctx->genomes.size();
     for (int64_t i = 0; i < 2 * m; ++i)
         if (pairs[i] < 0 || pairs[i] >= ng) FAIL(B200ANI_ERR_ARG, "anim: genome id out of range");
-    int rc = get_workspace(ctx, W);
-    if (rc) return rc;
     cudaStream_t st = ctx->stream;
-    cudaEvent_t e0 = (*W)->ev[2 * ST_INDEX], e1 = (*W)->ev[2 * ST_INDEX + 1];
     std::vector<Genome *> todo;
     std::vector<char> seen(ng, 0);
     for (int64_t i = 0; i < 2 * m; ++i) {
@@ -689,69 +837,17 @@ static int prepare(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, AnimWorksp
         if (!index_valid(anib ? g.index_b : g.index, maxocc) && !seen[pairs[i]]) { seen[pairs[i]] = 1; todo.push_back(&g); }
     }
     const bool any = !todo.empty();
-    CK(cudaEventRecord(e0, st));
-    rc = build_indexes(ctx, todo, maxocc, anib);
+    CK(cudaEventRecord(ctx->ev_prof[0], st));
+    int rc = build_indexes(ctx, todo, maxocc, anib);
     if (rc) return rc;
-    CK(cudaEventRecord(e1, st));
+    CK(cudaEventRecord(ctx->ev_prof[1], st));
     CK(cudaStreamSynchronize(st));
     if (any) {
         float ms = 0;
-        CK(cudaEventElapsedTime(&ms, e0, e1));
+        CK(cudaEventElapsedTime(&ms, ctx->ev_prof[0], ctx->ev_prof[1]));
         ctx->stage_ms[ST_INDEX] += ms;
     }
     return 0;
-}
-
-extern "C" {
-
-const char *b200ani_stage_name(int i) {
-    if (i < 0 || i >= 2 * B200ANI_N_STAGES) return "";
-    return i < B200ANI_N_STAGES ? kStageNames[i] : kCounterNames[i - B200ANI_N_STAGES];
-}
-
-int b200ani_anim(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch, int nofilter, b200ani_anim_result *out) {
-    if (!ctx || !pairs || !out || m < 0) return B200ANI_ERR_ARG;
-    for (int k = 0; k < ST_FIRST_NON_ANIM; ++k) ctx->stage_ms[k] = 0;  // the pack / TETRA slots belong to their own entry points
-    memset(ctx->counters, 0, sizeof ctx->counters);
-    AnimWorkspace *W = nullptr;
-    cudaEvent_t t0, t1;
-    CK(cudaSetDevice(ctx->device));
-    CK(cudaEventCreate(&t0));
-    CK(cudaEventCreate(&t1));
-    CK(cudaEventRecord(t0, ctx->stream));
-    int rc = prepare(ctx, pairs, m, &W, false);
-    if (rc == 0) rc = run_range(ctx, W, pairs, m, nofilter, 0, maxmatch, out, nullptr);
-    CK(cudaEventRecord(t1, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, t0, t1));
-    ctx->stage_ms[ST_TOTAL] = ms;
-    cudaEventDestroy(t0);
-    cudaEventDestroy(t1);
-    return rc;
-}
-
-int64_t b200ani_anim_alignments(b200ani_ctx *ctx, int32_t ref_id, int32_t qry_id, int maxmatch, int nofilter, int64_t *rows, int64_t cap) {
-    if (!ctx || (!rows && cap > 0)) return B200ANI_ERR_ARG;
-    int32_t pr[2] = {ref_id, qry_id};
-    AnimWorkspace *W = nullptr;
-    int rc = prepare(ctx, pr, 1, &W, false);
-    if (rc) return rc;
-    RowDump dump;
-    b200ani_anim_result res;
-    rc = run_range(ctx, W, pr, 1, nofilter, 0, maxmatch, &res, &dump);
-    if (rc) return rc;
-    int64_t k = 0;
-    for (size_t i = 0; i < dump.flag.size(); ++i) {
-        if (!nofilter && dump.flag[i] != 3) continue;
-        if (k < cap) {
-            const int *a = dump.rows.data() + 8 * i;
-            int64_t *o = rows + 7 * k;
-            o[0] = a[1]; o[1] = a[2]; o[2] = a[3]; o[3] = a[4]; o[4] = a[5]; o[5] = a[6]; o[6] = a[7];
-        }
-        ++k;
-    }
-    return k;
 }
 
 static int ensure_fragments(b200ani_ctx *ctx, Genome &g, int fragsize) {
@@ -770,56 +866,114 @@ static int ensure_fragments(b200ani_ctx *ctx, Genome &g, int fragsize) {
     return 0;
 }
 
-static int anib_common(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fragsize, void *out, RowDump *dump) {
-    if (fragsize < AN_TILE || fragsize > 100000) FAIL(B200ANI_ERR_ARG, "anib: fragment size out of range");
-    // machinery pairs are (table side = subject, streamed side = query)
-    std::vector<int32_t> internal(2 * m);
-    for (int64_t i = 0; i < m; ++i) { internal[2 * i] = pairs[2 * i + 1]; internal[2 * i + 1] = pairs[2 * i]; }
-    AnimWorkspace *W = nullptr;
-    int rc = prepare(ctx, internal.data(), m, &W, true);
-    if (rc) return rc;
-    for (int64_t i = 0; i < m; ++i) {
-        rc = ensure_fragments(ctx, ctx->genomes[pairs[2 * i]], fragsize);
-        if (rc) return rc;
-    }
-    return run_range(ctx, W, internal.data(), m, 0, fragsize, 0, out, dump);
-}
-
-int b200ani_anib(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fragsize, b200ani_anib_result *out) {
-    if (!ctx || !pairs || !out || m < 0) return B200ANI_ERR_ARG;
+// shared body of the four entry points.  anib: pairs are (query, subject) and the machinery wants (table side = subject,
+// streamed side = query).  dump / order: optional row dump (see run_range).
+static int run_call(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch, int nofilter, int fragsize, void *out, RowDump *dump, std::vector<int64_t> *order) {
+    const bool anib = fragsize > 0;
     for (int k = 0; k < ST_FIRST_NON_ANIM; ++k) ctx->stage_ms[k] = 0;  // the pack / TETRA slots belong to their own entry points
     memset(ctx->counters, 0, sizeof ctx->counters);
-    cudaEvent_t t0, t1;
+    if (anib && (fragsize < AN_TILE || fragsize > 100000)) FAIL(B200ANI_ERR_ARG, "anib: fragment size out of range");
     CK(cudaSetDevice(ctx->device));
+    cudaEvent_t t0, t1;
     CK(cudaEventCreate(&t0));
     CK(cudaEventCreate(&t1));
     CK(cudaEventRecord(t0, ctx->stream));
-    int rc = anib_common(ctx, pairs, m, fragsize, out, nullptr);
-    CK(cudaEventRecord(t1, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> internal;
+    const int32_t *use = pairs;
+    if (anib) {
+        internal.resize(2 * m);
+        for (int64_t i = 0; i < m; ++i) { internal[2 * i] = pairs[2 * i + 1]; internal[2 * i + 1] = pairs[2 * i]; }
+        use = internal.data();
+    }
+    int rc = prepare(ctx, use, m, anib);
+    for (int64_t i = 0; rc == 0 && anib && i < m; ++i) rc = ensure_fragments(ctx, ctx->genomes[pairs[2 * i]], fragsize);
+    if (rc == 0 && m > 0) rc = run_range(ctx, use, m, nofilter, fragsize, maxmatch, out, dump, order);
+    cudaEventRecord(t1, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
     float ms = 0;
-    CK(cudaEventElapsedTime(&ms, t0, t1));
+    cudaEventElapsedTime(&ms, t0, t1);
     ctx->stage_ms[ST_TOTAL] = ms;
     cudaEventDestroy(t0);
     cudaEventDestroy(t1);
     return rc;
 }
 
-int64_t b200ani_anib_fragments(b200ani_ctx *ctx, int32_t qry_id, int32_t sbj_id, int fragsize, int64_t *rows, int64_t cap) {
-    if (!ctx || (!rows && cap > 0)) return B200ANI_ERR_ARG;
-    int32_t pr[2] = {qry_id, sbj_id};
-    RowDump dump;
-    b200ani_anib_result res;
-    int rc = anib_common(ctx, pr, 1, fragsize, &res, &dump);
-    if (rc) return rc;
-    int64_t k = 0;
-    for (size_t i = 0; i < dump.flag.size(); ++i) {
-        if (!dump.flag[i]) continue;
-        if (k < cap)
-            for (int c = 0; c < 8; ++c) rows[8 * k + c] = dump.rows[8 * i + c];
-        ++k;
+// dumped rows -> caller's buffers, grouped by pair in caller order: row_start[i] .. row_start[i+1] are the rows of pair i.
+// conv(src row of 8 ints, dst) writes one output row of `width` int64.
+template <typename F>
+static int64_t deliver_rows(const RowDump &dump, const std::vector<int64_t> &order, int64_t m, int width, int64_t *rows, int64_t cap, int64_t *row_start,
+                            uint8_t *kept, F conv) {
+    const int64_t n = (int64_t)dump.pair.size();
+    std::vector<int64_t> cnt(m + 1, 0);
+    for (int64_t i = 0; i < n; ++i) cnt[order[dump.pair[i]] + 1]++;
+    for (int64_t i = 0; i < m; ++i) cnt[i + 1] += cnt[i];
+    if (row_start) memcpy(row_start, cnt.data(), sizeof(int64_t) * (m + 1));
+    // rows of a pair keep their device order: batches append whole pairs, so a stable counting sort by pair does it
+    std::vector<int64_t> pos(cnt.begin(), cnt.end() - 1);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t dst = pos[order[dump.pair[i]]]++;
+        if (dst < cap) {
+            conv(dump.rows.data() + 8 * i, rows + (size_t)width * dst);
+            if (kept) kept[dst] = dump.all ? dump.kept[i] : 1;
+        }
     }
-    return k;
+    return n;
+}
+
+extern "C" {
+
+const char *b200ani_stage_name(int i) {
+    if (i < 0 || i >= 2 * B200ANI_N_STAGES) return "";
+    return i < B200ANI_N_STAGES ? kStageNames[i] : kCounterNames[i - B200ANI_N_STAGES];
+}
+
+int b200ani_anim(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch, int nofilter, b200ani_anim_result *out) {
+    if (!ctx || !pairs || !out || m < 0) return B200ANI_ERR_ARG;
+    return run_call(ctx, pairs, m, maxmatch, nofilter, 0, out, nullptr, nullptr);
+}
+
+int64_t b200ani_anim_rows(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch, int nofilter, b200ani_anim_result *out,
+                          int64_t *rows, int64_t cap, int64_t *row_start, uint8_t *kept) {
+    if (!ctx || !pairs || m < 0 || (!rows && cap > 0)) return B200ANI_ERR_ARG;
+    std::vector<b200ani_anim_result> tmp;
+    if (!out) { tmp.resize((size_t)std::max<int64_t>(m, 1)); out = tmp.data(); }
+    RowDump dump;
+    dump.all = kept != nullptr;
+    std::vector<int64_t> order;
+    int rc = run_call(ctx, pairs, m, maxmatch, nofilter, 0, out, &dump, &order);
+    if (rc) return rc;
+    return deliver_rows(dump, order, m, 7, rows, cap, row_start, kept, [](const int *a, int64_t *o) {
+        o[0] = a[1]; o[1] = a[2]; o[2] = a[3]; o[3] = a[4]; o[4] = a[5]; o[5] = a[6]; o[6] = a[7];
+    });
+}
+
+int64_t b200ani_anim_alignments(b200ani_ctx *ctx, int32_t ref_id, int32_t qry_id, int maxmatch, int nofilter, int64_t *rows, int64_t cap) {
+    int32_t pr[2] = {ref_id, qry_id};
+    return b200ani_anim_rows(ctx, pr, 1, maxmatch, nofilter, nullptr, rows, cap, nullptr, nullptr);
+}
+
+int b200ani_anib(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fragsize, b200ani_anib_result *out) {
+    if (!ctx || !pairs || !out || m < 0) return B200ANI_ERR_ARG;
+    return run_call(ctx, pairs, m, 0, 0, fragsize, out, nullptr, nullptr);
+}
+
+int64_t b200ani_anib_rows(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fragsize, b200ani_anib_result *out, int64_t *rows, int64_t cap,
+                          int64_t *row_start) {
+    if (!ctx || !pairs || m < 0 || (!rows && cap > 0)) return B200ANI_ERR_ARG;
+    std::vector<b200ani_anib_result> tmp;
+    if (!out) { tmp.resize((size_t)std::max<int64_t>(m, 1)); out = tmp.data(); }
+    RowDump dump;
+    std::vector<int64_t> order;
+    int rc = run_call(ctx, pairs, m, 0, 0, fragsize, out, &dump, &order);
+    if (rc) return rc;
+    return deliver_rows(dump, order, m, 8, rows, cap, row_start, nullptr, [](const int *a, int64_t *o) {
+        for (int c = 0; c < 8; ++c) o[c] = a[c];
+    });
+}
+
+int64_t b200ani_anib_fragments(b200ani_ctx *ctx, int32_t qry_id, int32_t sbj_id, int fragsize, int64_t *rows, int64_t cap) {
+    int32_t pr[2] = {qry_id, sbj_id};
+    return b200ani_anib_rows(ctx, pr, 1, fragsize, nullptr, rows, cap, nullptr);
 }
 
 }  // extern "C"

@@ -1,5 +1,6 @@
 // C ABI of the engine (include/b200ani.h): context, genome staging, TETRA entry points.
 // The ANIm entry points live in anim_host.cu.
+#include <algorithm>
 #include <cstring>
 
 #include "anim_params.cuh"
@@ -66,7 +67,7 @@ void b200ani_destroy(b200ani_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto &g : ctx->genomes) release_genome(ctx, g, ctx->stream);
     for (auto *ix : ctx->spare_indexes) free_index(ix, ctx->stream);
-    free_anim_workspace(ctx->anim_ws);
+    free_anim_workspaces(ctx->anim_ws);
     cudaFree(ctx->index_ws);
     cudaEventDestroy(ctx->ev_prof[0]);
     cudaEventDestroy(ctx->ev_prof[1]);
@@ -249,6 +250,42 @@ int b200ani_tetra_corr(b200ani_ctx *ctx, const double *z, const uint8_t *mask, i
     timer.stop();
     CK(cudaStreamSynchronize(ctx->stream));
     return B200ANI_OK;
+}
+
+int b200ani_write_delta(const char *path, const char *ref_path, const char *qry_path, const char *const *ref_ids, const int64_t *ref_lens,
+                        uint32_t n_ref, const char *const *qry_ids, const int64_t *qry_lens, uint32_t n_qry, const int64_t *rows, int64_t n) {
+    if (!path || !ref_path || !qry_path || n < 0 || (n > 0 && (!rows || !ref_ids || !qry_ids || !ref_lens || !qry_lens))) return B200ANI_ERR_ARG;
+    std::vector<int64_t> ord((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        ord[i] = i;
+        if (rows[7 * i] < 0 || rows[7 * i] >= (int64_t)n_ref || rows[7 * i + 1] < 0 || rows[7 * i + 1] >= (int64_t)n_qry) return B200ANI_ERR_ARG;
+    }
+    std::stable_sort(ord.begin(), ord.end(), [&](int64_t x, int64_t y) {  // grouped by record pair, by reference start inside a group
+        for (int c = 0; c < 3; ++c)
+            if (rows[7 * x + c] != rows[7 * y + c]) return rows[7 * x + c] < rows[7 * y + c];
+        return false;
+    });
+    std::string buf;
+    buf.reserve(64 + (size_t)n * 56);
+    buf += ref_path; buf += ' '; buf += qry_path; buf += "\nNUCMER\n";
+    char line[256];
+    int64_t cur_r = -1, cur_q = -1;
+    for (int64_t t = 0; t < n; ++t) {
+        const int64_t *a = rows + 7 * ord[t];
+        if (a[0] != cur_r || a[1] != cur_q) {
+            cur_r = a[0]; cur_q = a[1];
+            buf += '>'; buf += ref_ids[cur_r]; buf += ' '; buf += qry_ids[cur_q];
+            snprintf(line, sizeof line, " %lld %lld\n", (long long)ref_lens[cur_r], (long long)qry_lens[cur_q]);
+            buf += line;
+        }
+        snprintf(line, sizeof line, "%lld %lld %lld %lld %lld %lld 0\n0\n", (long long)a[2], (long long)a[3], (long long)a[4], (long long)a[5], (long long)a[6],
+                 (long long)a[6]);
+        buf += line;
+    }
+    FILE *fh = fopen(path, "w");
+    if (!fh) return B200ANI_ERR_IO;
+    const bool ok = fwrite(buf.data(), 1, buf.size(), fh) == buf.size();
+    return (fclose(fh) == 0 && ok) ? B200ANI_OK : B200ANI_ERR_IO;
 }
 
 int b200ani_last_profile(const b200ani_ctx *ctx, double *stage_ms, int64_t *counters) {

@@ -97,4 +97,4 @@ int tetra_corr_device(b200ani_ctx *ctx, const double *d_z, const int *d_idx, int
 void free_index(MinimizerIndex *ix, cudaStream_t st);
 void invalidate_index(MinimizerIndex *ix);
 bool index_valid(const MinimizerIndex *ix, int maxocc);
-void free_anim_workspace(void *ws);
+void free_anim_workspaces(void *ws);

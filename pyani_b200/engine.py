@@ -41,6 +41,7 @@ class Engine:
         self.device = int(device)
         self.names: List[str] = []
         self.contig_ids: List[List[str]] = []
+        self.contig_lens: List[np.ndarray] = []
 
     # -- lifetime
     def close(self):
@@ -77,6 +78,7 @@ class Engine:
         self._check(rc, "add_genome")
         self.names.append(name or f"genome{gid.value}")
         self.contig_ids.append(contig_ids or [str(i) for i in range(len(contig_off) - 1)])
+        self.contig_lens.append(np.diff(contig_off.astype(np.int64)))
         return gid.value
 
     def add_fasta(self, path) -> int:
@@ -97,7 +99,8 @@ class Engine:
     def clear(self):
         """Drop all staged genomes (ids restart at 0)."""
         self._check(self._lib.b200ani_clear(self._h), "clear")
-        self.names, self.contig_ids = [], []
+        self.names, self.contig_ids, self.contig_lens = [], [], []
+        self.__dict__.pop("_rec_tables", None)
 
     def reset_indexes(self):
         self._check(self._lib.b200ani_reset_indexes(self._h), "reset_indexes")
@@ -151,6 +154,67 @@ class Engine:
                 self._check(int(n), "anim_alignments")
             if n <= cap:  # never hand back a truncated list: a short .delta would parse to wrong lengths silently
                 return rows[:n].copy()
+            cap = int(n)
+
+    def anim_rows(self, pairs: np.ndarray, maxmatch: bool = False, nofilter: bool = False, all_rows: bool = False):
+        """All pairs in one device pass -> (results, rows (n,7) int64, row_start (m+1,)): rows[row_start[i]:row_start[i+1]] are the
+        alignments of pair i (what its .filter -- with nofilter its .delta -- would hold), see :meth:`anim_alignments`.
+        all_rows=True: every alignment is returned plus a fourth value, kept (n,) bool: the .delta rows and which of them are in
+        the .filter, from the same pass."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        m = len(pairs)
+        out = np.zeros(m, dtype=ANIM_DTYPE)
+        start = np.zeros(m + 1, dtype=np.int64)
+        cap = max(1024, 64 * m)
+        while True:
+            rows = np.zeros((cap, 7), dtype=np.int64)
+            kept = np.zeros(cap, dtype=np.uint8) if all_rows else None
+            n = self._lib.b200ani_anim_rows(self._h, _ptr(pairs), m, int(maxmatch), int(nofilter), _ptr(out), _ptr(rows), cap, _ptr(start),
+                                            _ptr(kept) if all_rows else None)
+            if n < 0:
+                self._check(int(n), "anim_rows")
+            if n <= cap:
+                return (out, rows[:n].copy(), start, kept[:n].astype(bool)) if all_rows else (out, rows[:n].copy(), start)
+            cap = int(n)
+
+    def write_delta(self, path, ref_path, qry_path, ref_gid: int, qry_gid: int, rows: np.ndarray) -> None:
+        """Native .delta / .filter emitter (b200ani_write_delta) for alignment rows of the pair (ref_gid, qry_gid)."""
+        import ctypes as C
+
+        rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 7)
+        ri, rl = self._record_tables(ref_gid)
+        qi, ql = self._record_tables(qry_gid)
+        Path(path).parent.mkdir(parents=True, exist_ok=True)
+        rc = self._lib.b200ani_write_delta(str(path).encode(), str(ref_path).encode(), str(qry_path).encode(), ri, _ptr(rl), len(rl), qi, _ptr(ql), len(ql),
+                                           _ptr(rows), len(rows))
+        if rc != 0:
+            raise EngineError(f"write_delta({path}): rc={rc}")
+
+    def _record_tables(self, gid: int):
+        """(C array of record ids, int64 record lengths) of a staged genome, built once."""
+        import ctypes as C
+
+        cache = self.__dict__.setdefault("_rec_tables", {})
+        if gid not in cache:
+            ids = self.contig_ids[gid]
+            arr = (C.c_char_p * len(ids))(*[i.encode() for i in ids])
+            cache[gid] = (arr, np.ascontiguousarray(self.contig_lens[gid], dtype=np.int64))
+        return cache[gid]
+
+    def anib_rows(self, pairs: np.ndarray, fragsize: int = 1020):
+        """All (query, subject) pairs in one device pass -> (results, rows (n,8) int64, row_start (m+1,)), see :meth:`anib_fragments`."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        m = len(pairs)
+        out = np.zeros(m, dtype=ANIB_DTYPE)
+        start = np.zeros(m + 1, dtype=np.int64)
+        cap = max(4096, 2048 * m)
+        while True:
+            rows = np.zeros((cap, 8), dtype=np.int64)
+            n = self._lib.b200ani_anib_rows(self._h, _ptr(pairs), m, int(fragsize), _ptr(out), _ptr(rows), cap, _ptr(start))
+            if n < 0:
+                self._check(int(n), "anib_rows")
+            if n <= cap:
+                return out, rows[:n].copy(), start
             cap = int(n)
 
     # -- ANIb

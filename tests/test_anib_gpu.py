@@ -70,3 +70,18 @@ def test_reference_fixture_genomes(engine):
         aln, errs, pid = banib.parse_result(r)
         g = gold[f"{files[i].stem}_vs_{files[j].stem}"]
         assert abs(pid - g[2]) < (0.2 if g[2] >= 90 else 5.0)
+
+
+def test_batched_fragment_rows_equal_per_pair_rows(engine):
+    from pyani_b200 import synth
+
+    gs = synth.make_set(2, 2, 200_000, seed=11)
+    gids = [engine.add_genome(g.residues, g.contig_off, g.name) for g in gs]
+    gp = np.array([[gids[a], gids[b]] for a in range(4) for b in range(4) if a != b][::-1], dtype=np.int32)
+    res, rows, start = engine.anib_rows(gp)
+    assert res.tobytes() == engine.anib(gp).tobytes()
+    assert (np.diff(start) == res["n_pass"]).all()
+    for i in (0, 3, len(gp) - 1):
+        want = engine.anib_fragments(int(gp[i, 0]), int(gp[i, 1]))
+        got = rows[start[i]:start[i + 1]]
+        assert got.shape == want.shape and (got == want).all(), i

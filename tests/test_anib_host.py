@@ -91,9 +91,13 @@ class _FakeEngine:
     def genome_length(self, gid):
         return self.names[gid][1]
 
-    def anib_fragments(self, q, s, fragsize=1020):
-        self.calls.append((self.names[q][0], self.names[s][0], fragsize))
-        return np.array([[0, 1000, 50, 10, 940, 1020, 1700, 94000], [1, 400, 10, 0, 390, 412, 750, 97500]])
+    def anib_rows(self, pairs, fragsize=1020):
+        per_pair = np.array([[0, 1000, 50, 10, 940, 1020, 1700, 94000], [1, 400, 10, 0, 390, 412, 750, 97500]])
+        self.batches = getattr(self, "batches", 0) + 1
+        for q, s in np.asarray(pairs).tolist():
+            self.calls.append((self.names[q][0], self.names[s][0], fragsize))
+        m = len(pairs)
+        return None, np.concatenate([per_pair] * m), np.arange(m + 1) * 2
 
 
 def test_anib_job_graph_backend_writes_blast_tab(tmp_path):
@@ -113,7 +117,7 @@ def test_anib_job_graph_backend_writes_blast_tab(tmp_path):
         jobs.append(j)
     eng = _FakeEngine()
     assert banib.run_dependency_graph(jobs, workers=8, engine=eng) == 0
-    assert sorted(eng.calls) == [("A", "B", 1020), ("B", "A", 1020)]
+    assert sorted(eng.calls) == [("A", "B", 1020), ("B", "A", 1020)] and eng.batches == 1  # ONE batched pass for the whole graph
     lines = open(out / "A_vs_B.blast_tab").read().splitlines()
     assert len(lines) == 2 and lines[0].split("\t") == ["frag00001", "B", "1000", "50", "94.000", "940", "1020", "14", "0", "0", "0", "0", "940", "94.000", "10"]
     rows = [(int(c[0][4:]), int(c[2]), int(c[3]), float(c[4]), int(c[6]), int(c[14])) for c in (l.split("\t") for l in lines)]

@@ -262,3 +262,21 @@ def test_generated_clade_set_sample_vs_oracle(engine):
         og = [oracle.OGenome(np.asarray(g.residues), g.contig_off) for g in gs]
         assert gids[0] == base
         _check(engine, gids, og, [(0, 1), (1, 0), (0, 2), (2, 0), (3, 4), (5, 2)], nofilter=False)
+
+
+def test_batched_rows_equal_per_pair_rows(engine, small_set):
+    """b200ani_anim_rows (all pairs in one pass) == b200ani_anim_alignments pair by pair, in caller order, with and without the filter;
+    its result structs == b200ani_anim's."""
+    from pyani_b200 import synth
+
+    gs, gids, og = small_set
+    pairs = synth.all_directed_pairs(len(gs))[::-1]  # not the internal order
+    gp = np.array([[gids[r], gids[q]] for r, q in pairs], dtype=np.int32)
+    for nofilter in (False, True):
+        res, rows, start = engine.anim_rows(gp, nofilter=nofilter)
+        assert res.tobytes() == engine.anim(gp, nofilter=nofilter).tobytes()
+        assert start[0] == 0 and start[-1] == len(rows) and (np.diff(start) == res["n_alignments"]).all()
+        for i in (0, 1, 7, len(gp) - 1):
+            want = engine.anim_alignments(int(gp[i, 0]), int(gp[i, 1]), nofilter=nofilter)
+            got = rows[start[i]:start[i + 1]]
+            assert got.shape == want.shape and (got == want).all(), (i, nofilter)

@@ -55,15 +55,27 @@ class _FakeEngine:
     def __init__(self):
         self.n = 0
         self.calls = []
+        self.recs = {}
 
     def add_genome(self, arr, off, name, ids):
+        self.recs[self.n] = (ids, np.diff(np.asarray(off).astype(np.int64)))
         self.n += 1
         return self.n - 1
 
-    def anim_alignments(self, g1, g2, maxmatch=False, nofilter=False):
-        self.calls.append((g1, g2, maxmatch, nofilter))
-        rows = [[0, 0, 1, 10, 1, 11, 5], [0, 0, 15, 20, 30, 25, 0]]
-        return np.array(rows if nofilter else rows[:1], dtype=np.int64)
+    def anim_rows(self, pairs, maxmatch=False, nofilter=False, all_rows=False):
+        self.calls.append((np.asarray(pairs).tolist(), maxmatch, nofilter, all_rows))
+        per_pair = np.array([[0, 0, 1, 10, 1, 11, 5], [0, 0, 15, 20, 30, 25, 0]], dtype=np.int64)
+        m = len(pairs)
+        rows = np.concatenate([per_pair] * m) if m else np.zeros((0, 7), np.int64)
+        start = np.arange(m + 1, dtype=np.int64) * 2
+        kept = np.tile([True, False], m)
+        return None, rows, start, kept
+
+    def write_delta(self, path, ref_path, qry_path, ref_gid, qry_gid, rows):
+        from pathlib import Path
+
+        (ri, rl), (qi, ql) = self.recs[ref_gid], self.recs[qry_gid]
+        banim.write_minimal_delta(Path(path), ref_path, qry_path, np.asarray(rows).reshape(-1, 7), ri, qi, rl, ql)
 
 
 class _Job:  # shape of pyani_jobs.Job (pyani_jobs.py:76-120)
@@ -87,7 +99,7 @@ def test_run_dependency_graph_writes_files_parse_delta_can_read(tmp_path):
     fjob.add_dependency(njob)
     eng = _FakeEngine()
     assert banim.run_dependency_graph([fjob], workers=4, engine=eng) == 0
-    assert [c[3] for c in eng.calls] == [True, False]
+    assert len(eng.calls) == 1 and eng.calls[0][0] == [[0, 1]] and eng.calls[0][3] is True  # ONE batched pass for the whole graph
     d = oracle.parse_delta_text(str(out) + ".delta")
     f = oracle.parse_delta_text(str(out) + ".filter")
     assert d[:, 2:].tolist() == [[1, 10, 1, 11, 5], [15, 20, 30, 25, 0]] and f[:, 2:].tolist() == [[1, 10, 1, 11, 5]]
@@ -218,3 +230,26 @@ def test_aniresults_data_property():
                          "ANIm_hadamard"]
         had = dict((stem, df) for df, stem in r.data)["ANIm_hadamard"]
         assert had.loc["x", "y"] == 0.25 and had.loc["y", "x"] == 0.25
+
+
+def test_native_delta_writer_equals_python_twin(tmp_path):
+    """b200ani_write_delta (host-only entry point of the C ABI) writes the same bytes as write_minimal_delta, and the reference's
+    record grouping: one '>' line per record pair, alignments by reference start."""
+    import ctypes as C
+
+    from pyani_b200 import _lib
+
+    lib = _lib.load()
+    rows = np.array([[1, 0, 40, 90, 300, 250, 3], [0, 0, 15, 20, 30, 25, 0], [0, 0, 1, 10, 1, 11, 5], [1, 1, 7, 9, 2, 4, 0]], dtype=np.int64)
+    rid, qid = ["r.a", "r.b"], ["q1", "q2"]
+    rl, ql = np.array([100, 200], np.int64), np.array([400, 50], np.int64)
+    p1, p2 = tmp_path / "n.delta", tmp_path / "p.delta"
+    ra = (C.c_char_p * 2)(*[x.encode() for x in rid])
+    qa = (C.c_char_p * 2)(*[x.encode() for x in qid])
+    rc = lib.b200ani_write_delta(str(p1).encode(), b"/x/R.fna", b"/x/Q.fna", ra, rl.ctypes.data, 2, qa, ql.ctypes.data, 2, rows.ctypes.data, len(rows))
+    assert rc == 0
+    banim.write_minimal_delta(p2, "/x/R.fna", "/x/Q.fna", rows, rid, qid, rl, ql)
+    assert p1.read_bytes() == p2.read_bytes()
+    assert p1.read_text().splitlines()[2:5] == [">r.a q1 100 400", "1 10 1 11 5 5 0", "0"]
+    bad = rows.copy(); bad[0, 0] = 2
+    assert lib.b200ani_write_delta(str(p1).encode(), b"R", b"Q", ra, rl.ctypes.data, 2, qa, ql.ctypes.data, 2, bad.ctypes.data, len(bad)) == -2
