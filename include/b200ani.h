@@ -152,6 +152,24 @@ int b200ani_last_profile(const b200ani_ctx *ctx, double *stage_ms /*B200ANI_N_ST
 /* i in [0,16): stage name; i in [16,32): name of counter i-16 ("" = unused slot) */
 const char *b200ani_stage_name(int i);
 
+/* ---- several GPUs of one node behind one handle (run_multiprocessing.py:113-152 / run_sge.py:87-112 for callers that are not
+ * Python; Python callers may also run one process per GPU with pyani_b200.dist).  Genomes are replicated on every device, the
+ * pair list is dealt over the devices (chunks of 64 unordered genome pairs, round-robin; both directions of a pair stay
+ * together), every device runs its share, and ONE ncclAllGather of the result structs -- the communicator belongs to this
+ * context -- assembles the full array on every device; the caller gets it in the order of `pairs`.  NCCL is resolved at run
+ * time (dlopen "libnccl.so.2"); b200ani_create_multi fails if it is absent. */
+typedef struct b200ani_mctx b200ani_mctx;
+int b200ani_create_multi(b200ani_mctx **out, const int *device_ids, int n);
+void b200ani_destroy_multi(b200ani_mctx *mc);
+const char *b200ani_multi_last_error(const b200ani_mctx *mc);
+int b200ani_multi_device_count(const b200ani_mctx *mc);
+/* the single-device context of device slot i (TETRA, profiles, row dumps: everything that needs no sharding) */
+b200ani_ctx *b200ani_multi_device(b200ani_mctx *mc, int i);
+int b200ani_multi_add_genome(b200ani_mctx *mc, const uint8_t *ascii, const uint64_t *contig_off, uint32_t n_contigs, int32_t *out_genome_id);
+int b200ani_multi_clear(b200ani_mctx *mc);
+int b200ani_multi_anim(b200ani_mctx *mc, const int32_t *pairs, int64_t m, int maxmatch, int nofilter, b200ani_anim_result *out);
+int b200ani_multi_anib(b200ani_mctx *mc, const int32_t *pairs, int64_t m, int fragsize, b200ani_anib_result *out);
+
 /* Measured issue rate of the DPX-class max-plus instruction the extend kernel is bound by
  * (__viaddmax_s32), in 10^9 thread-level operations per second on this device; the integer-DP roofline
  * denominator of SURVEY.md 8(d).  ~20 ms micro-benchmark. */

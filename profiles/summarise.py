@@ -49,6 +49,7 @@ def launches(tag):
 
 
 def full(tag):
+    traffic = {}  # workload -> kernel -> mean dram bytes (read + write) per captured launch; bench.py reports it as roofline.traffic
     for rep in sorted(OUT.glob("prof_*.ncu-rep")):
         r = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True)
         rows = list(csv.reader(io.StringIO(r.stdout)))
@@ -56,13 +57,37 @@ def full(tag):
             continue
         hdr, units = rows[0], rows[1]
         out = [f"# {rep.name}: ncu --set full --clock-control none, per launch"]
+        per_kernel = defaultdict(list)
         for row in rows[2:]:
+            try:
+                def val(name):
+                    i = hdr.index(name)
+                    v = float(row[i].replace(",", ""))
+                    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[i], 1)
+                kname = re.sub(r"<.*|\(.*", "", row[hdr.index("Kernel Name")]).split("::")[-1]
+                per_kernel[kname].append(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
+            except (ValueError, IndexError):
+                pass
             out.append(f"## launch id {row[0]} {row[hdr.index('Kernel Name')][:80]}")
             for i, h in enumerate(hdr):
                 if any(h.startswith(k) for k in KEYS):
                     out.append(f"{h:80s} {row[i]:>18s} {units[i]}")
         (ROOT / "profiles" / f"{tag}_{rep.stem}.txt").write_text("\n".join(out) + "\n")
         print("\n".join(out[:70]))
+        # capture files are named prof_<workload>_<kernel pattern>.ncu-rep
+        parts = rep.stem.split("_")
+        if len(parts) >= 3:
+            for k, v in per_kernel.items():
+                traffic.setdefault(parts[1], {})[k] = sum(v) / len(v)
+    if traffic:
+        import json
+
+        f = ROOT / "profiles" / "ncu_traffic.json"
+        old = json.load(open(f)) if f.exists() else {}
+        for w, d in traffic.items():
+            old.setdefault(w, {}).update(d)
+        json.dump(old, open(f, "w"), indent=1, sort_keys=True)
+        print("wrote", f)
 
 
 if __name__ == "__main__":

@@ -11,6 +11,6 @@ plus this thin host-side mirror of the reference's interfaces for the path:
 There is no CPU fallback: importing works anywhere, but creating an :class:`Engine` without the built
 library and a CUDA device raises.
 """
-from .engine import Engine, EngineError, lib_path  # noqa: F401
+from .engine import Engine, EngineError, MultiEngine, lib_path  # noqa: F401
 
 __version__ = "0.1.0"

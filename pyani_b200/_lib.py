@@ -60,6 +60,15 @@ SIGNATURES = {
     "b200ani_anib_rows": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "b200ani_anib": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "b200ani_anib_fragments": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int, C.c_void_p, C.c_int64]),
+    "b200ani_create_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int]),
+    "b200ani_destroy_multi": (None, [C.c_void_p]),
+    "b200ani_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "b200ani_multi_device_count": (C.c_int, [C.c_void_p]),
+    "b200ani_multi_device": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "b200ani_multi_add_genome": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_int32)]),
+    "b200ani_multi_clear": (C.c_int, [C.c_void_p]),
+    "b200ani_multi_anim": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "b200ani_multi_anib": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "b200ani_last_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200ani_stage_name": (C.c_char_p, [C.c_int]),
 }

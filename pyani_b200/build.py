@@ -60,10 +60,12 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     (build_dir / "ptxas.log").write_text("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB)] + [str(o) for o in objs] + ["-lcudart"]
+    tmp = LIB.with_suffix(".so.tmp")  # link next to the target and swap it in atomically: a snapshot never sees a half-written library
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp)] + [str(o) for o in objs] + ["-lcudart", "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
+    os.replace(tmp, LIB)
     return LIB
 
 

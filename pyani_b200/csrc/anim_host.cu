@@ -104,6 +104,7 @@ struct AnimWorkspace {
     int rc = 0;
     std::vector<int> h_rows, h_pair;  // row dump of the current batch (host staging)
     std::vector<uint8_t> h_flag;
+    std::mutex *dp_mu = nullptr;  // shared by the pipelines of a call (null: single pipeline)
     double last_fill = 0;  // fill level of the anchor / hit buffers in the last batch (> 1: it did not fit)
     int n_pipelines = 1;  // pipelines active in the current call (DP kernels leave room for the others' blocks when > 1)
     Arena arena;
@@ -135,6 +136,7 @@ static void free_anim_workspace(void *p) {
 }
 
 struct WorkspaceSet {
+    std::mutex dp_mu;  // one pipeline at a time in the DP stages: keeps the pipelines in anti-phase (see run_batch_impl)
     std::vector<AnimWorkspace *> w;
     std::atomic<int> batch_hint{0};  // pairs per batch that fit the anchor / hit buffers (0 = not known yet)
 };
@@ -234,6 +236,8 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
     b200ani_anim_result *out = (b200ani_anim_result *)out_v;
     cudaStream_t st = W->st;
     bool used[B200ANI_N_STAGES] = {false};
+    std::unique_lock<std::mutex> dp_lock;  // released by its destructor on every exit path
+    if (W->dp_mu) dp_lock = std::unique_lock<std::mutex>(*W->dp_mu, std::defer_lock);
     // ---- pair descriptors
     std::vector<PairDesc> hp(nb + 1);  // + sentinel
     int64_t n_probes = 0;
@@ -401,7 +405,10 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
         W->hcount[CT_LINKS] += (int64_t)hc[2];
         const int64_t n_tasks = (int64_t)hc[3];
         W->hcount[CT_GAPTASKS] += n_tasks;
-        // ---- link alignments
+        // ---- link alignments.  From here to the end of the extension rounds the batch is ALU-bound; with two pipelines only
+        // one of them may be in this stretch at a time, so that the other one's memory-bound stages (seed probe, sorts,
+        // chaining, filter) run beside it instead of both fighting for the same pipe in lockstep.
+        if (W->dp_mu) dp_lock.lock();
         if (n_tasks) {
             size_t tb = W->cub_bytes;
             cub::DeviceRadixSort::SortPairs(W->cub_tmp, tb, task_key, task_key2, task_idx, task_idx2, n_tasks, 0, 11, st);
@@ -533,6 +540,7 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
             }
         }
         T1(ST_EXTDP);
+        if (dp_lock.owns_lock()) dp_lock.unlock();
         W->hcount[CT_EXTCELLS] += (int64_t)hc[6];
         W->hcount[CT_EXTTILES] += (int64_t)hc[7];
         {
@@ -579,6 +587,7 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
         }
     }
 
+    if (dp_lock.owns_lock()) dp_lock.unlock();  // batches without segments skip the extension block
     if (anib) {
         // ---- ANIb: HSP columns, parse_blast_tab filter, best HSP per fragment, per-pair sums
         b200ani_anib_result *d_out = (b200ani_anib_result *)W->d_results;
@@ -716,9 +725,12 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
     } while (0)
 #define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
 
+// Measured (profiles/README.md, round 2): two pipelines in anti-phase gain 1-2 % on the 200-genome ANIm workload -- the seed
+// probe is as issue-bound as the DP, so the "memory-bound" stages of one batch slow the other batch's DP down by as much as
+// they gain.  One pipeline is the default; B200ANI_PIPELINES=2..4 keeps the machinery reachable.
 static int n_pipelines_wanted() {
     if (const char *e = getenv("B200ANI_PIPELINES")) return std::max(1, std::min(4, atoi(e)));
-    return 2;
+    return 1;
 }
 
 // All m pairs: internal order, batches handed to the pipelines from a shared cursor, results (and optionally the kept
@@ -747,7 +759,6 @@ static int run_range(b200ani_ctx *ctx, const int32_t *pairs_in, int64_t m, int n
         return e < m && e - 1 >= b0 && pairs[2 * e] == pairs[2 * e - 1] && pairs[2 * e + 1] == pairs[2 * e - 2] &&
                !(e - 2 >= b0 && pairs[2 * (e - 1)] == pairs[2 * (e - 2) + 1] && pairs[2 * (e - 1) + 1] == pairs[2 * (e - 2)]);
     };
-    WorkspaceSet *ws = (WorkspaceSet *)ctx->anim_ws;
     // a handful of batches cannot keep two pipelines busy; small calls (tests, single pairs) stay on one
     const int n_pipe = (int)std::max<int64_t>(1, std::min<int64_t>(n_pipelines_wanted(), m / 512));
     for (int k = 0; k < n_pipe; ++k) {
@@ -755,6 +766,7 @@ static int run_range(b200ani_ctx *ctx, const int32_t *pairs_in, int64_t m, int n
         int rc = get_workspace(ctx, k, &W);
         if (rc) return rc;
     }
+    WorkspaceSet *ws = (WorkspaceSet *)ctx->anim_ws;  // exists now
     std::mutex cursor_mu;
     int64_t cursor = 0;
     std::atomic<int> failed{0};
@@ -781,6 +793,7 @@ static int run_range(b200ani_ctx *ctx, const int32_t *pairs_in, int64_t m, int n
     auto worker = [&](AnimWorkspace *W) {
         cudaSetDevice(ctx->device);
         W->n_pipelines = n_pipe;
+        W->dp_mu = n_pipe > 1 ? &ws->dp_mu : nullptr;
         W->rc = 0;
         while (!failed.load()) {
             int64_t b0, nb;
@@ -813,7 +826,7 @@ static int run_range(b200ani_ctx *ctx, const int32_t *pairs_in, int64_t m, int n
     int rc = 0;
     for (int k = 0; k < n_pipe; ++k) {
         AnimWorkspace *W = ws->w[k];
-        for (int i = 0; i < B200ANI_N_STAGES; ++i) { ctx->stage_ms[i] += W->hms[i]; ctx->counters[i] += W->counters[i]; }
+        for (int i = 0; i < B200ANI_N_STAGES; ++i) { ctx->stage_ms[i] += W->hms[i]; ctx->counters[i] += W->hcount[i]; }
         if (W->rc && !rc) { rc = W->rc; ctx->err = W->err; }
     }
     if (rc) return rc;

@@ -1,10 +1,25 @@
 // C ABI of the engine (include/b200ani.h): context, genome staging, TETRA entry points.
 // The ANIm entry points live in anim_host.cu.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "anim_params.cuh"
 #include "common.cuh"
+
+// B200ANI_DEBUG_SEGV=1: print a native backtrace (module + offset per frame, resolvable with addr2line) on SIGSEGV / SIGABRT
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void segv_backtrace(int sig) {
+    void *frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "b200ani: fatal signal, native backtrace:\n";
+    (void)!write(2, msg, sizeof msg - 1);
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
 
 static const char *kVersion = "b200ani 0.1.0 (sm_100a)";
 
@@ -32,6 +47,9 @@ const char *b200ani_last_error(const b200ani_ctx *ctx) { return ctx ? ctx->err.c
 int b200ani_create(b200ani_ctx **out, int device_id) {
     if (!out) return B200ANI_ERR_ARG;
     *out = nullptr;
+    if (const char *e = getenv("B200ANI_DEBUG_SEGV")) {
+        if (e[0] == '1') { signal(SIGSEGV, segv_backtrace); signal(SIGABRT, segv_backtrace); }
+    }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0 || device_id < 0 || device_id >= n) {

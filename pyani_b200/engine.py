@@ -256,3 +256,67 @@ ANIB_DTYPE = np.dtype(
      ("n_hsps", "<i4"), ("status", "<i4")]
 )
 assert ANIB_DTYPE.itemsize == 40
+
+
+class MultiEngine:
+    """Several GPUs of one node behind one handle (``b200ani_create_multi``): genomes replicated on every device, the pair list
+    dealt over the devices, ONE NCCL all-gather of the result structs inside the library.  The alternative to one process
+    per GPU (:mod:`pyani_b200.dist`) for callers that want a single process."""
+
+    def __init__(self, devices: Sequence[int]):
+        self._lib = _lib.load()
+        ids = np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        rc = self._lib.b200ani_create_multi(C.byref(h), _ptr(ids), len(ids))
+        if rc != 0 or not h:
+            raise EngineError(f"b200ani_create_multi(devices={list(devices)}) failed with rc={rc} (CUDA devices and NCCL are required)")
+        self._h = h
+        self.devices = [int(d) for d in devices]
+        self.names: List[str] = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200ani_destroy_multi(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise EngineError(f"{what}: rc={rc}: {self._lib.b200ani_multi_last_error(self._h).decode()}")
+
+    def add_genome(self, residues: np.ndarray, contig_off: np.ndarray, name: str = "") -> int:
+        residues = np.ascontiguousarray(residues, dtype=np.uint8)
+        contig_off = np.ascontiguousarray(contig_off, dtype=np.uint64)
+        gid = C.c_int32(-1)
+        self._check(self._lib.b200ani_multi_add_genome(self._h, _ptr(residues), _ptr(contig_off), len(contig_off) - 1, C.byref(gid)), "multi_add_genome")
+        self.names.append(name or f"genome{gid.value}")
+        return gid.value
+
+    def clear(self):
+        self._check(self._lib.b200ani_multi_clear(self._h), "multi_clear")
+        self.names = []
+
+    def anim(self, pairs: np.ndarray, maxmatch: bool = False, nofilter: bool = False) -> np.ndarray:
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        out = np.zeros(len(pairs), dtype=ANIM_DTYPE)
+        if len(pairs):
+            self._check(self._lib.b200ani_multi_anim(self._h, _ptr(pairs), len(pairs), int(maxmatch), int(nofilter), _ptr(out)), "multi_anim")
+        return out
+
+    def anib(self, pairs: np.ndarray, fragsize: int = 1020) -> np.ndarray:
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        out = np.zeros(len(pairs), dtype=ANIB_DTYPE)
+        if len(pairs):
+            self._check(self._lib.b200ani_multi_anib(self._h, _ptr(pairs), len(pairs), int(fragsize), _ptr(out)), "multi_anib")
+        return out

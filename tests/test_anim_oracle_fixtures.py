@@ -59,7 +59,7 @@ def test_pipeline_within_reference_tolerance(genomes):
             g_ral, g_qal, g_ident, g_errs = gold[f"{r}_vs_{q}.filter"]
             devs.append(100 * (ident - g_ident))
             assert abs(ral / g_ral - 1) < 0.015 and abs(qal / g_qal - 1) < 0.015, (r, q, ral, g_ral)
-            assert abs(devs[-1]) < 0.06, (r, q, ident, g_ident)  # measured 0.041; the reference's own tolerance is 0.1 (test_concordance.py:157-159)
+            assert abs(devs[-1]) < 0.06, (r, q, ident, g_ident)  # measured 0.039; the reference's own tolerance is 0.1 (test_concordance.py:157-159)
     assert abs(np.mean(devs)) < 0.03
     # the near-identical pair reproduces nucmer's aligned lengths exactly
     rows, _ = oracle.anim_align(genomes["NC_002696"], genomes["NC_011916"])
@@ -82,7 +82,7 @@ def test_alignments_reproduce_nucmer_rows(genomes):
             same_rows += len(ours & nuc)
             same_coords += len(ours_c & nuc_c)
             total += len(nuc)
-    assert same_rows >= 0.93 * total         # measured: 11,514 of 12,292 = 93.7 %
+    assert same_rows >= 0.93 * total         # measured: 11,501 of 12,229 = 94.0 % (round 1: 81 %)
     assert same_rows >= 0.975 * same_coords  # where the coordinates agree, so does the error count
 
 
