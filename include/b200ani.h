@@ -39,10 +39,15 @@ const char *b200ani_last_error(const b200ani_ctx *ctx);
 
 /* Stage one genome in HBM: raw residues of all records concatenated (no newlines/headers) plus record
  * offsets (n_contigs+1 entries, off[0]=0).  Replaces the FASTA paths handed to nucmer / SeqIO.parse
- * (anim.py:280, tetra.py:98).  Packs to 2 bit/base + 1 bit/base ambiguity mask on the device.
+ * (anim.py:280, tetra.py:98).  Packs to 2 bit/base + 1 bit/base ambiguity mask on the device.  The residues may sit in
+ * pinned memory (copied directly) or in pageable memory (staged through a pinned double buffer: the CPU fills one half
+ * while the DMA engine drains the other).
  * Genome length = off[n_contigs], ambiguity symbols included (pyani_files.py:137-141). */
 int b200ani_add_genome(b200ani_ctx *ctx, const uint8_t *ascii, const uint64_t *contig_off, uint32_t n_contigs,
                        int32_t *out_genome_id);
+/* Residues that b200ani_add_genome took through the context's pinned double buffer (pageable sources) since the last
+ * b200ani_clear; pinned sources are copied directly and do not count. */
+int64_t b200ani_staged_bytes(const b200ani_ctx *ctx);
 /* Drop every staged genome (and its index); genome ids restart at 0.  Lets a long-lived context serve
  * successive runs, like a fresh process pool per pyani invocation. */
 int b200ani_clear(b200ani_ctx *ctx);
@@ -111,6 +116,13 @@ int64_t b200ani_anim_rows(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int
 #define B200ANI_ERR_IO (-5)
 int b200ani_write_delta(const char *path, const char *ref_path, const char *qry_path, const char *const *ref_ids, const int64_t *ref_lens,
                         uint32_t n_ref, const char *const *qry_ids, const int64_t *qry_lens, uint32_t n_qry, const int64_t *rows, int64_t n);
+
+/* Bottom-s MinHash sketch of a staged genome: the s smallest distinct hash values (ascending) of its seed k-mers (canonical
+ * 16-mers of the ANIm index; the index is built if needed).  A Mash-style identity estimate from two sketches lets a caller
+ * skip hopeless pairs before any alignment work (opt-in: pyani_b200/prefilter.py; the reference has no prefilter and aborts on
+ * pairs without alignments instead, anim.py:481-486; its fastANI wrapper, fastani.py:193-228, is the pattern).
+ * out: s values; *n_out: how many were written (fewer than s for tiny genomes). */
+int b200ani_sketch(b200ani_ctx *ctx, int32_t genome_id, int s, uint32_t *out, int *n_out);
 
 /* ---- ANIb (anib.py) ---- */
 /* One directed comparison: the 1020-nt fragments of the query genome against the subject genome.

@@ -45,6 +45,7 @@ SIGNATURES = {
     "b200ani_last_error": (C.c_char_p, [C.c_void_p]),
     "b200ani_add_genome": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_int32)]),
     "b200ani_clear": (C.c_int, [C.c_void_p]),
+    "b200ani_staged_bytes": (C.c_int64, [C.c_void_p]),
     "b200ani_reset_indexes": (C.c_int, [C.c_void_p]),
     "b200ani_dpx_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "b200ani_genome_count": (C.c_int, [C.c_void_p]),
@@ -58,6 +59,7 @@ SIGNATURES = {
     "b200ani_write_delta": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                      C.c_void_p, C.c_int64]),
     "b200ani_anib_rows": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "b200ani_sketch": (C.c_int, [C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "b200ani_anib": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "b200ani_anib_fragments": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int, C.c_void_p, C.c_int64]),
     "b200ani_create_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int]),

@@ -34,6 +34,7 @@ struct PairDesc {
     const uint32_t *q_kmer, *q_posflag;
     int64_t q_nmini;
     int64_t probe_base;  // offset of this pair's probes in the flattened probe index
+    int64_t chunk_base;  // first chunk (SEED_PROBE_CHUNK probes, never crossing a pair) of this pair in the probe kernel's grid
     int32_t r_npos, q_npos;
     uint32_t r_ncontigs, q_ncontigs, r_table_bits;
     int32_t mirror;  // index (in the batch) of the opposite-direction pair fed from this pair's seeds, or -1
@@ -122,6 +123,7 @@ __device__ __forceinline__ uint32_t contig_of(const uint64_t *__restrict__ goff,
     return lo;
 }
 
+constexpr int SEED_PROBE_CHUNK = 4096;  // probes per chunk of seed_probe_kernel (= 256 threads x 4 in flight x 4 steps)
 // Which table entries a query minimizer may seed with (anim_seed.cu)
 enum { SEED_BOTH_UNIQUE = 0, SEED_ALL = 1, SEED_EITHER_UNIQUE = 2 };
 

@@ -240,7 +240,7 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
     if (W->dp_mu) dp_lock = std::unique_lock<std::mutex>(*W->dp_mu, std::defer_lock);
     // ---- pair descriptors
     std::vector<PairDesc> hp(nb + 1);  // + sentinel
-    int64_t n_probes = 0;
+    int64_t n_probes = 0, n_chunks = 0;
     for (int p = 0; p < nb; ++p) {
         const Genome &R = ctx->genomes[pairs[2 * p]], &Q = ctx->genomes[pairs[2 * p + 1]];
         const MinimizerIndex *Ri = anib ? R.index_b : R.index, *Qi = anib ? Q.index_b : Q.index;
@@ -251,6 +251,7 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
         d.r_table = Ri->d_table; d.r_table_bits = Ri->table_bits; d.r_bitmap = Ri->d_bitmap;
         d.q_kmer = Qi->d_kmer; d.q_posflag = Qi->d_posflag; d.q_nmini = Qi->n_mini;
         d.probe_base = n_probes;
+        d.chunk_base = n_chunks;
         d.r_npos = (int32_t)R.n_pos; d.q_npos = (int32_t)Q.n_pos;
         d.r_ncontigs = R.n_contigs; d.q_ncontigs = Q.n_contigs;
         // run_range puts the two directions of a genome pair next to each other: the first one probes and
@@ -262,10 +263,11 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
         d.q_fbase = anib ? Q.d_fbase : nullptr;
         d.fragsize = anib ? fragsize : 0;
         d.q_nfrags = anib ? Q.n_frags : 0;
-        if (!second) n_probes += Qi->n_mini;
+        if (!second) { n_probes += Qi->n_mini; n_chunks += ceil_div(Qi->n_mini, SEED_PROBE_CHUNK); }
     }
     hp[nb] = hp[nb - 1];
     hp[nb].probe_base = n_probes;  // sentinel: end of the last pair's probe range
+    hp[nb].chunk_base = n_chunks;
     hp[nb].mirror = -1;
     if (n_probes >= (1ll << 32) && nb > 1) return 1;  // probe indices are 32-bit: split the batch
     CK(cudaMemcpyAsync(W->d_pairs, hp.data(), sizeof(PairDesc) * (nb + 1), cudaMemcpyHostToDevice, st));
@@ -283,13 +285,13 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
         if (seedmode == SEED_BOTH_UNIQUE) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_probe_kernel<SEED_BOTH_UNIQUE>, 256, 0));
         else if (seedmode == SEED_ALL) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_probe_kernel<SEED_ALL>, 256, 0));
         else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_probe_kernel<SEED_EITHER_UNIQUE>, 256, 0));
-        int blocks = (int)std::min<int64_t>(ceil_div(n_probes, 256 * 16), (int64_t)ctx->sm_count * std::max(per_sm, 1));
+        int blocks = (int)std::min<int64_t>(n_chunks, (int64_t)ctx->sm_count * std::max(per_sm, 1));
         if (seedmode == SEED_BOTH_UNIQUE)
-            seed_probe_kernel<SEED_BOTH_UNIQUE><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP, seed_k);
+            seed_probe_kernel<SEED_BOTH_UNIQUE><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_chunks, W->hits, W->counters + 1, (unsigned long long)HIT_CAP, seed_k);
         else if (seedmode == SEED_ALL)
-            seed_probe_kernel<SEED_ALL><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP, seed_k);
+            seed_probe_kernel<SEED_ALL><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_chunks, W->hits, W->counters + 1, (unsigned long long)HIT_CAP, seed_k);
         else
-            seed_probe_kernel<SEED_EITHER_UNIQUE><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_probes, W->hits, W->counters + 1, (unsigned long long)HIT_CAP, seed_k);
+            seed_probe_kernel<SEED_EITHER_UNIQUE><<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_chunks, W->hits, W->counters + 1, (unsigned long long)HIT_CAP, seed_k);
         LAUNCHED(1);
         W->hcount[CT_SEEDLAUNCH] += 1;
     }
@@ -938,6 +940,44 @@ extern "C" {
 const char *b200ani_stage_name(int i) {
     if (i < 0 || i >= 2 * B200ANI_N_STAGES) return "";
     return i < B200ANI_N_STAGES ? kStageNames[i] : kCounterNames[i - B200ANI_N_STAGES];
+}
+
+__global__ void sketch_hash_kernel(const uint32_t *__restrict__ kmer, int64_t n, uint32_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fmix32(kmer[i]);
+}
+
+int b200ani_sketch(b200ani_ctx *ctx, int32_t genome_id, int s, uint32_t *out, int *n_out) {
+    if (!ctx || !out || !n_out || s <= 0) return B200ANI_ERR_ARG;
+    *n_out = 0;
+    int32_t pr[2] = {genome_id, genome_id};
+    int rc = prepare(ctx, pr, 1, false);  // builds the genome's seed index if it is not there yet
+    if (rc) return rc;
+    const MinimizerIndex *ix = ctx->genomes[genome_id].index;
+    const int64_t n = ix->n_mini;
+    if (n == 0) return B200ANI_OK;
+    cudaStream_t st = ctx->stream;
+    uint32_t *d_a = nullptr, *d_b = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_a, d_b, n, 0, 32, st);
+    CK(cudaMallocAsync(&d_a, sizeof(uint32_t) * n, st));
+    CK(cudaMallocAsync(&d_b, sizeof(uint32_t) * n, st));
+    CK(cudaMallocAsync(&d_tmp, tmp_bytes, st));
+    sketch_hash_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ix->d_kmer, n, d_a);
+    cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_a, d_b, n, 0, 32, st);
+    // repeated k-mers sit in the list once per occurrence (at most AN_MAXOCC): fetch a few times s and de-duplicate here
+    const int64_t take = std::min<int64_t>(n, (int64_t)s * 4 + AN_MAXOCC);
+    std::vector<uint32_t> h((size_t)take);
+    cudaError_t e = cudaMemcpyAsync(h.data(), d_b, sizeof(uint32_t) * take, cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(d_a, st); cudaFreeAsync(d_b, st); cudaFreeAsync(d_tmp, st);
+    CK(e);
+    CK(cudaStreamSynchronize(st));
+    int k = 0;
+    for (int64_t i = 0; i < take && k < s; ++i)
+        if (i == 0 || h[i] != h[i - 1]) out[k++] = h[i];
+    *n_out = k;
+    return B200ANI_OK;
 }
 
 int b200ani_anim(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch, int nofilter, b200ani_anim_result *out) {

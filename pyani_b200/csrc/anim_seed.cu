@@ -75,75 +75,52 @@ __device__ __forceinline__ bool seed_ok(int mode, uint32_t rpf, uint32_t qpf) {
 
 // Phase 1 -- probe: one thread per (pair, query minimizer): stream the query's minimizer list
 // (evict-first loads) through the reference's table; hits are appended as (probe index, table entry).
-// Memory-latency bound by design: one coalesced 4-byte read + one random 8-byte read per probe, no
-// divergent work, so the warps in flight are all waiting on independent loads.
+// A block walks chunks of SEED_PROBE_CHUNK probes; a chunk never leaves its pair (pairs[p].chunk_base), so the pair's
+// pointers are block-uniform and no probe has to find out where it belongs; PROBE_ILP probes per thread per step keep the
+// dependent loads (k-mer -> presence word -> table slot) of several probes in flight together.
 template <int MODE>
-__global__ void __launch_bounds__(256, 4) seed_probe_kernel(const PairDesc *__restrict__ pairs, int n_pairs, int64_t n_probes, uint2 *__restrict__ hits,
+__global__ void __launch_bounds__(256, 4) seed_probe_kernel(const PairDesc *__restrict__ pairs, int n_pairs, int64_t n_chunks, uint2 *__restrict__ hits,
                                                          unsigned long long *__restrict__ n_hits, unsigned long long cap, int seed_k) {
-    // Each block walks contiguous chunks of PROBE_CHUNK probes, PROBE_ILP probes per thread per step so that the
-    // dependent loads (k-mer -> presence word -> table slot) of several probes are in flight together.  The pair a
-    // probe belongs to is searched once per chunk and then advanced linearly; its descriptor fields stay in
-    // registers until the pair changes (pairs[n_pairs] is a sentinel with probe_base = n_probes).
-    constexpr int PROBE_ILP = 4, PROBE_STEPS = 4;
-    constexpr int64_t PROBE_CHUNK = 256 * PROBE_ILP * PROBE_STEPS;
+    constexpr int PROBE_ILP = 4, PROBE_STEPS = SEED_PROBE_CHUNK / (256 * PROBE_ILP);
+    static_assert(PROBE_STEPS * 256 * PROBE_ILP == SEED_PROBE_CHUNK, "chunk = steps x threads x ILP");
     // hits of a chunk are staged in shared memory and appended with ONE global atomic per chunk: tens of millions
     // of atomics on a single counter serialise in L2 and were the actual bound of this kernel
-    __shared__ uint2 s_hits[PROBE_CHUNK];
+    __shared__ uint2 s_hits[SEED_PROBE_CHUNK];
     __shared__ unsigned int s_n;
     __shared__ unsigned long long s_base;
     const int lane = threadIdx.x & 31;
-    const int64_t n_chunks = (n_probes + PROBE_CHUNK - 1) / PROBE_CHUNK;
     for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
-        const int64_t g_first = ch * PROBE_CHUNK + threadIdx.x;
-        int pair = pair_of_probe(pairs, n_pairs, g_first < n_probes ? g_first : n_probes - 1);
-        int cached = -1;
+        int lo = 0, hi = n_pairs;  // the LAST pair with chunk_base <= ch (pairs without probes of their own share their successor's base)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (pairs[mid].chunk_base <= ch) lo = mid; else hi = mid;
+        }
+        const PairDesc &P = pairs[lo];
+        const uint32_t *__restrict__ q_kmer = P.q_kmer, *__restrict__ q_posflag = P.q_posflag, *__restrict__ r_bitmap = P.r_bitmap;
+        const uint64_t *__restrict__ r_table = P.r_table;
+        const uint32_t bits = P.r_table_bits;
+        const int64_t n_local = P.q_nmini, local0 = (ch - P.chunk_base) * SEED_PROBE_CHUNK, gbase = P.probe_base;
         if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
-        const uint32_t *q_kmer = nullptr, *q_posflag = nullptr, *r_bitmap = nullptr;
-        const uint64_t *r_table = nullptr;
-        uint32_t bits = 0;
-        int64_t base = 0, next_base = 0;
         for (int step = 0; step < PROBE_STEPS; ++step) {
             uint32_t kmer[PROBE_ILP], rpf[PROBE_ILP], qpf[PROBE_ILP], cur[PROBE_ILP];
-            int64_t gi[PROBE_ILP];
-            int pr[PROBE_ILP];
+            int64_t li[PROBE_ILP];
             bool hit[PROBE_ILP], more[PROBE_ILP];
 #pragma unroll
             for (int k = 0; k < PROBE_ILP; ++k) {  // phase 1: k-mers (coalesced, streaming)
-                gi[k] = ch * PROBE_CHUNK + (int64_t)(step * PROBE_ILP + k) * 256 + threadIdx.x;
-                hit[k] = false; more[k] = false; rpf[k] = 0; qpf[k] = 0; kmer[k] = 0; pr[k] = -1; cur[k] = ~0u;
-                if (gi[k] < n_probes) {
-                    while (gi[k] >= next_base || cached < 0) {  // (re)load the pair's fields
-                        if (cached >= 0) ++pair;
-                        while (gi[k] >= pairs[pair + 1].probe_base) ++pair;
-                        const PairDesc &P = pairs[pair];
-                        q_kmer = P.q_kmer; q_posflag = P.q_posflag; r_bitmap = P.r_bitmap; r_table = P.r_table; bits = P.r_table_bits;
-                        base = P.probe_base; next_base = pairs[pair + 1].probe_base;
-                        cached = pair;
-                    }
-                    pr[k] = pair;
-                    kmer[k] = __ldcs(q_kmer + (gi[k] - base));
-                }
+                li[k] = local0 + (int64_t)(step * PROBE_ILP + k) * 256 + threadIdx.x;
+                more[k] = false; rpf[k] = 0; qpf[k] = 0; cur[k] = ~0u;
+                hit[k] = li[k] < n_local;
+                kmer[k] = hit[k] ? __ldcs(q_kmer + li[k]) : 0u;
             }
-            // phase 2: presence filter (4 MB per reference, L2 resident) -- ~90 % of the probes end here
-            const uint32_t *bm[PROBE_ILP];
-            const uint64_t *tb[PROBE_ILP];
-            const uint32_t *pf[PROBE_ILP];
-            uint32_t tbits[PROBE_ILP];
+            // phase 2: presence filter (4 MB per reference, L2 resident) -- ~98 % of the probes end here
 #pragma unroll
-            for (int k = 0; k < PROBE_ILP; ++k) {
-                // the cached fields belong to the LAST probe's pair; re-read them when an earlier probe sits in another pair
-                const bool same = pr[k] == cached;
-                const PairDesc &P = pairs[pr[k] < 0 ? 0 : pr[k]];
-                bm[k] = same ? r_bitmap : P.r_bitmap; tb[k] = same ? r_table : P.r_table; tbits[k] = same ? bits : P.r_table_bits;
-                pf[k] = (same ? q_posflag : P.q_posflag) + (gi[k] - (same ? base : P.probe_base));
-                hit[k] = pr[k] >= 0 && bitmap_test(bm[k], tbits[k], kmer[k]);
-            }
+            for (int k = 0; k < PROBE_ILP; ++k) hit[k] = hit[k] && bitmap_test(r_bitmap, bits, kmer[k]);
 #pragma unroll
             for (int k = 0; k < PROBE_ILP; ++k) {  // phase 3: first table entry of the filter's positives
-                if (hit[k]) hit[k] = table_next(tb[k], tbits[k], kmer[k], cur[k], rpf[k]);
+                if (hit[k]) hit[k] = table_next(r_table, bits, kmer[k], cur[k], rpf[k]);
                 if (hit[k]) {
-                    qpf[k] = __ldcs(pf[k]);
+                    qpf[k] = __ldcs(q_posflag + li[k]);
                     // a repeated k-mer has further entries; they can only qualify if the query side allows it
                     more[k] = (rpf[k] & AN_REPBIT) && (MODE == SEED_ALL || (MODE == SEED_EITHER_UNIQUE && !(qpf[k] & AN_REPBIT)));
                     hit[k] = seed_ok(MODE, rpf[k], qpf[k]);
@@ -151,6 +128,8 @@ __global__ void __launch_bounds__(256, 4) seed_probe_kernel(const PairDesc *__re
             }
 #pragma unroll
             for (int k = 0; k < PROBE_ILP; ++k) {
+                // most warps have nothing to pass on (warp-uniform test, so the shuffles below stay convergent)
+                if (!__any_sync(0xffffffffu, hit[k])) continue;
                 // A hit whose neighbouring query minimizer (previous one on the forward strand, next one on the reverse
                 // strand) hits the same diagonal with overlapping / abutting k-mers lies in the same exact match: only
                 // the first seed of such a run is passed on (the match set is unchanged, see seed_extend_kernel).
@@ -160,11 +139,10 @@ __global__ void __launch_bounds__(256, 4) seed_probe_kernel(const PairDesc *__re
                 const int key = strand ? r0 + qp : r0 - qp;  // constant along a diagonal of that strand
                 const int nb = strand ? lane + 1 : lane - 1;
                 const bool nhit = __shfl_sync(0xffffffffu, (int)h, nb & 31) != 0;
-                const int npair = __shfl_sync(0xffffffffu, pr[k], nb & 31);
                 const int nstrand = __shfl_sync(0xffffffffu, strand, nb & 31);
                 const int nkey = __shfl_sync(0xffffffffu, key, nb & 31);
                 const int nqp = __shfl_sync(0xffffffffu, qp, nb & 31);
-                if (h && nb >= 0 && nb < 32 && nhit && npair == pr[k] && nstrand == strand && nkey == key && abs(nqp - qp) <= seed_k) h = false;
+                if (h && nb >= 0 && nb < 32 && nhit && nstrand == strand && nkey == key && abs(nqp - qp) <= seed_k) h = false;
                 const uint32_t m = __ballot_sync(0xffffffffu, h);
                 if (m) {  // one shared-memory atomic per warp
                     unsigned int bslot = 0;
@@ -172,10 +150,11 @@ __global__ void __launch_bounds__(256, 4) seed_probe_kernel(const PairDesc *__re
                     bslot = __shfl_sync(0xffffffffu, bslot, 0);
                     if (h) {
                         const unsigned int slot = bslot + __popc(m & ((1u << lane) - 1u));
-                        if (slot < (unsigned int)PROBE_CHUNK) s_hits[slot] = make_uint2((uint32_t)gi[k], rpf[k]);
+                        const uint2 rec = make_uint2((uint32_t)(gbase + li[k]), rpf[k]);
+                        if (slot < (unsigned int)SEED_PROBE_CHUNK) s_hits[slot] = rec;
                         else {
                             const unsigned long long g = atomicAdd(n_hits, 1ull);
-                            if (g < cap) hits[g] = make_uint2((uint32_t)gi[k], rpf[k]);
+                            if (g < cap) hits[g] = rec;
                         }
                     }
                 }
@@ -186,19 +165,20 @@ __global__ void __launch_bounds__(256, 4) seed_probe_kernel(const PairDesc *__re
 #pragma unroll
                 for (int k = 0; k < PROBE_ILP; ++k) {
                     uint32_t e;
-                    while (more[k] && table_next(tb[k], tbits[k], kmer[k], cur[k], e)) {
+                    while (more[k] && table_next(r_table, bits, kmer[k], cur[k], e)) {
                         const unsigned int slot = atomicAdd(&s_n, 1u);
-                        if (slot < (unsigned int)PROBE_CHUNK) s_hits[slot] = make_uint2((uint32_t)gi[k], e);
+                        const uint2 rec = make_uint2((uint32_t)(gbase + li[k]), e);
+                        if (slot < (unsigned int)SEED_PROBE_CHUNK) s_hits[slot] = rec;
                         else {
                             const unsigned long long g = atomicAdd(n_hits, 1ull);
-                            if (g < cap) hits[g] = make_uint2((uint32_t)gi[k], e);
+                            if (g < cap) hits[g] = rec;
                         }
                     }
                 }
             }
         }
         __syncthreads();
-        const unsigned int n_stage = min(s_n, (unsigned int)PROBE_CHUNK);
+        const unsigned int n_stage = min(s_n, (unsigned int)SEED_PROBE_CHUNK);
         if (threadIdx.x == 0 && n_stage) s_base = atomicAdd(n_hits, (unsigned long long)n_stage);
         __syncthreads();
         for (unsigned int i = threadIdx.x; i < n_stage; i += 256)

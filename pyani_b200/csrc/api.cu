@@ -89,6 +89,10 @@ void b200ani_destroy(b200ani_ctx *ctx) {
     cudaFree(ctx->index_ws);
     cudaEventDestroy(ctx->ev_prof[0]);
     cudaEventDestroy(ctx->ev_prof[1]);
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->pin[b]) cudaFreeHost(ctx->pin[b]);
+        if (ctx->pin_ev[b]) cudaEventDestroy(ctx->pin_ev[b]);
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -117,6 +121,7 @@ int b200ani_clear(b200ani_ctx *ctx) {
     for (auto &g : ctx->genomes) release_genome(ctx, g, ctx->stream);
     ctx->genomes.clear();
     ctx->stage_ms[ST_PACK] = 0;
+    ctx->staged_bytes = 0;
     return B200ANI_OK;
 }
 
@@ -127,6 +132,8 @@ int b200ani_reset_indexes(b200ani_ctx *ctx) {
     for (auto &g : ctx->genomes) { invalidate_index(g.index); invalidate_index(g.index_b); }  // buffers stay, content is rebuilt on demand
     return B200ANI_OK;
 }
+
+int64_t b200ani_staged_bytes(const b200ani_ctx *ctx) { return ctx ? ctx->staged_bytes : 0; }
 
 int b200ani_genome_count(const b200ani_ctx *ctx) { return ctx ? (int)ctx->genomes.size() : 0; }
 
@@ -159,8 +166,33 @@ int b200ani_add_genome(b200ani_ctx *ctx, const uint8_t *ascii, const uint64_t *c
     CK(cudaMemsetAsync(g.d_seq, 0, (size_t)g.n_pad / 4 + 64, ctx->stream));
     CK(cudaMemsetAsync(g.d_mask, 0xff, (size_t)g.n_pad / 8 + 64, ctx->stream));
     CK(cudaMallocAsync(&d_ascii, (size_t)n_bases + 64, ctx->stream));
-    // pageable or pinned: the caller owns the buffer; cudaMemcpyAsync degrades gracefully for pageable
-    if (n_bases) CK(cudaMemcpyAsync(d_ascii, ascii, (size_t)n_bases, cudaMemcpyHostToDevice, ctx->stream));
+    // Pinned source: one asynchronous copy.  Pageable source (what a FASTA parser hands over): through the context's pinned
+    // double buffer in STAGE_CHUNK pieces -- the CPU copies piece c+1 into one half while the DMA engine sends piece c from
+    // the other, instead of the driver's synchronous bounce through its own small staging buffer.
+    if (n_bases) {
+        constexpr int64_t STAGE_CHUNK = 32ll << 20;
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, ascii) == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+        cudaGetLastError();  // an unregistered pointer is not an error here
+        if (pinned || n_bases < (1 << 20)) CK(cudaMemcpyAsync(d_ascii, ascii, (size_t)n_bases, cudaMemcpyHostToDevice, ctx->stream));
+        else {
+            for (int b = 0; b < 2; ++b)
+                if (!ctx->pin[b]) {
+                    CK(cudaHostAlloc((void **)&ctx->pin[b], (size_t)STAGE_CHUNK, cudaHostAllocDefault));
+                    CK(cudaEventCreateWithFlags(&ctx->pin_ev[b], cudaEventDisableTiming));
+                }
+            int c = 0;
+            for (int64_t o = 0; o < n_bases; o += STAGE_CHUNK, ++c) {
+                const int b = c & 1;
+                const size_t len = (size_t)std::min<int64_t>(STAGE_CHUNK, n_bases - o);
+                CK(cudaEventSynchronize(ctx->pin_ev[b]));  // the copy that last used this half has left it
+                memcpy(ctx->pin[b], ascii + o, len);
+                CK(cudaMemcpyAsync(d_ascii + o, ctx->pin[b], len, cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaEventRecord(ctx->pin_ev[b], ctx->stream));
+            }
+            ctx->staged_bytes += n_bases;
+        }
+    }
     CK(cudaMemcpyAsync(g.d_goff, g.h_goff.data(), sizeof(uint64_t) * (n_contigs + 1), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->ev_prof[0], ctx->stream));
     int rc = launch_pack(ctx, d_ascii, g.d_goff, g);

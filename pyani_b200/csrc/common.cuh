@@ -60,6 +60,11 @@ struct b200ani_ctx {
     void *index_ws = nullptr;      // scratch of build_indexes (anim_index.cu), grown on demand, reused
     size_t index_ws_bytes = 0;
     cudaEvent_t ev_prof[2] = {nullptr, nullptr};  // kernel timers of the pack / TETRA entry points
+    // pinned double buffer for residues that arrive in pageable host memory (add_genome): the CPU fills one half while the
+    // DMA engine drains the other
+    uint8_t *pin[2] = {nullptr, nullptr};
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+    int64_t staged_bytes = 0;  // residues that went through the pinned double buffer since the last clear (tests, bench)
 };
 
 #define CK(call)                                                                                     \

@@ -89,12 +89,19 @@ class Engine:
         """Ingest many FASTA files with a thread pool (parse + md5 in parallel), stage them in input order.
         The per-file records (md5, length, ...) are kept in ``self.ingested`` for the caller's bookkeeping
         (pyani indexes genomes by md5, `pyani_orm.py:194,572`)."""
-        from .fasta import ingest
+        from .fasta import ingest_iter
 
-        recs = ingest(paths, threads)
-        gids = [self.add_genome(r["residues"], r["offsets"], r["stem"], r["ids"]) for r in recs]
-        self.ingested = [{k: v for k, v in r.items() if k not in ("residues", "offsets")} for r in recs]
+        gids, self.ingested = [], []
+        # files are parsed (and hashed) by a thread pool and handed over in input order: while genome i goes through the
+        # pinned double buffer to the device and is packed there (ctypes releases the GIL), the pool is already parsing i+1 ...
+        for r in ingest_iter(paths, threads):
+            gids.append(self.add_genome(r["residues"], r["offsets"], r["stem"], r["ids"]))
+            self.ingested.append({k: v for k, v in r.items() if k not in ("residues", "offsets")})
         return gids
+
+    def staged_bytes(self) -> int:
+        """Residues that went through the context's pinned double buffer since the last clear()."""
+        return int(self._lib.b200ani_staged_bytes(self._h))
 
     def clear(self):
         """Drop all staged genomes (ids restart at 0)."""
@@ -216,6 +223,13 @@ class Engine:
             if n <= cap:
                 return out, rows[:n].copy(), start
             cap = int(n)
+
+    def sketch(self, gid: int, s: int = 2048) -> np.ndarray:
+        """Bottom-s MinHash sketch of a staged genome (ascending distinct uint32 hashes of its seed k-mers), see pyani_b200.prefilter."""
+        out = np.zeros(s, dtype=np.uint32)
+        n = C.c_int(0)
+        self._check(self._lib.b200ani_sketch(self._h, int(gid), int(s), _ptr(out), C.byref(n)), "sketch")
+        return out[: n.value].copy()
 
     # -- ANIb
     def anib(self, pairs: np.ndarray, fragsize: int = 1020) -> np.ndarray:

@@ -49,6 +49,30 @@ def get_fasta_files(dirname) -> List[Path]:
     return sorted(p for p in d.iterdir() if p.is_file() and p.suffix in FASTA_SUFFIXES)
 
 
+def ingest_iter(paths, threads: int = 0):
+    """Like :func:`ingest`, but a generator: records come out in input order as soon as they are ready while the pool keeps
+    parsing the following files, so that a consumer (staging on the device) overlaps with the parsing."""
+    import hashlib
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(p):
+        p = Path(p)
+        data = p.read_bytes()
+        arr, off, ids = _parse(data, p)
+        return {"path": p, "stem": p.stem, "md5": hashlib.md5(data).hexdigest(), "length": int(off[-1]),
+                "residues": arr, "offsets": off, "ids": ids}
+
+    paths = list(paths)
+    n = threads or min(32, (os.cpu_count() or 1))
+    if n <= 1 or len(paths) <= 1:
+        for p in paths:
+            yield one(p)
+        return
+    with ThreadPoolExecutor(n) as ex:
+        yield from ex.map(one, paths)
+
+
 def ingest(paths, threads: int = 0):
     """Parallel ingest of many FASTA files: parse + md5 + lengths in a thread pool.
 
