@@ -7,15 +7,19 @@
  * between and beyond anchors -> fusion of alignments that reach each other -> 1-to-1 filter, then pyani's own reduction (oracle_delta.c).
  *
  * PARITY STATUS: "unpinned" against nucmer on arbitrary genomes (no binary, no source).  Pinned only
- *  (a) against the reference's checked-in nucmer 3.1 output for the four Caulobacter fixture genomes
- *      (tests/test_anim_oracle_fixtures.py): identity of all 12 directed pairs within 0.06 %-points (the
- *      reference's own JSpecies tolerance is +-0.1, tests/test_concordance.py:157-159,203), 81 % of nucmer's
- *      alignments reproduced row for row (coordinates and error count); every rule of the specification
- *      (gap scoring, cluster pre-pass, bridging, seed uniqueness) was derived from those .delta files,
- *  (b) against the reference's JSpecies concordance table (tests/test_concordance_jspecies.py): within 0.20,
- *      NOT within the reference's 0.1 on that set, and
+ *  (a) against the reference's checked-in nucmer 3.1 output (tests/test_anim_oracle_fixtures.py): the four Caulobacter fixture
+ *      genomes -- identity of all 12 directed pairs within 0.04 %-points (the reference's own JSpecies tolerance is +-0.1,
+ *      tests/test_concordance.py:157-159,203), 94 % of nucmer's alignments reproduced row for row (coordinates and error
+ *      count) -- and the six C. blochmannia genomes of the legacy driver's test targets (94 % of the rows, identity within 0.1
+ *      on 11 of 15 pairs, 0.16 at worst); every rule of the specification (gap scoring, cluster pre-pass, tie rule, break
+ *      counter, fusion / bridging, seed uniqueness) was derived from those .delta files (DESIGN.md section 4,
+ *      scripts/nucmer_forensics.py),
+ *  (b) against the reference's JSpecies concordance table (tests/test_concordance_jspecies.py): within the reference's 0.1 on
+ *      4 of the 6 directed pairs, 0.22 on the other two, and
  *  (c) bit-exactly against the CUDA engine, which implements the identical specification
  *      (constants in anim_spec.h).
+ * Environment hooks ORC_DUMP_SEGS / ORC_MUM are analysis aids for scripts/ (segment dump; true-MUM seed experiment); tests
+ * never set them.
  *
  * Deliberately simple: byte-per-base sequences, O(n log n) sorts, scalar DP.  Single-threaded per call;
  * callers parallelise over pairs with Python threads (ctypes releases the GIL).
@@ -683,14 +687,6 @@ int64_t orc_anim_align(const orc_genome *R, const orc_genome *Q, int maxmatch, i
             fprintf(fh, "%d %u %u %ld %ld %ld %ld %ld %ld %ld %ld\n", S[i].strand, S[i].rc, S[i].qc, (long)S[i].rs0, (long)S[i].re0, (long)S[i].qs0, (long)S[i].qe0,
                     (long)S[i].rs, (long)S[i].re, (long)S[i].qs, (long)S[i].qe);
         fclose(fh);
-    }
-    if (getenv("ORC_DEBUG")) {
-        long lo = atol(getenv("ORC_DEBUG")), hi = lo + 20000;
-        for (int64_t i = 0; i < ns; ++i)
-            if (S[i].rs0 >= lo && S[i].rs0 < hi)
-                fprintf(stderr, "seg %ld st%d r0[%ld,%ld) q0[%ld,%ld) -> r[%ld,%ld) q[%ld,%ld) sc0 %ld e0 %ld xs %ld/%ld pred %d mode %d succ %d tgt %d hlen %d\n", (long)i, S[i].strand,
-                        (long)S[i].rs0, (long)S[i].re0, (long)S[i].qs0, (long)S[i].qe0, (long)S[i].rs, (long)S[i].re, (long)S[i].qs, (long)S[i].qe,
-                        (long)S[i].score0, (long)S[i].errs0, (long)S[i].xs[0], (long)S[i].xs[1], S[i].pred, S[i].bmode, S[i].succ == 0x7fffffff ? -1 : S[i].succ, S[i].tgt, S[i].hlen);
     }
     /* ---- emit: one row per chain of joined alignments.  Two chains that grew to the very same alignment (same records and
      * coordinates; forks of the anchor chain re-converge when both get extended) are one alignment: the first in emission
