@@ -234,6 +234,33 @@ def anim_pair(R: OGenome, Q: OGenome, nofilter: bool = False, maxmatch: bool = F
     return res, kept, stats
 
 
+def anim_pairs_mt(genomes, pairs, threads: int = 0, maxmatch: bool = False):
+    """Whole oracle pipeline for many directed pairs on `threads` OpenMP threads (0 = all), no Python in the loop.
+    genomes: list of OGenome; pairs: (m, 2) indices into it.  -> (array (m, 6): ref_aln_len, qry_aln_len, sum_aligned,
+    sum_weighted, sim_errs, n_alignments; threads used)."""
+    L = lib()
+    L.orc_anim_pairs_mt.restype = ctypes.c_int
+    L.orc_anim_pairs_mt.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    handles = (ctypes.c_void_p * len(genomes))(*[g._h for g in genomes])
+    p = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    out = np.zeros((len(p), 6), dtype=np.int64)
+    used = L.orc_anim_pairs_mt(handles, p.ctypes.data, len(p), int(bool(maxmatch)), int(threads), out.ctypes.data)
+    return out, int(used)
+
+
+def anib_pairs_mt(genomes, pairs, threads: int = 0, fragsize: int = 1020):
+    """ANIb counterpart of :func:`anim_pairs_mt`; pairs: (m, 2) (query, subject) indices.  -> (array (m, 6): aln_length, sim_errs,
+    pid_milli_sum, n_frags, n_pass, n_hsps; threads used)."""
+    L = lib()
+    L.orc_anib_pairs_mt.restype = ctypes.c_int
+    L.orc_anib_pairs_mt.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    handles = (ctypes.c_void_p * len(genomes))(*[g.anib_handle for g in genomes])
+    p = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    out = np.zeros((len(p), 6), dtype=np.int64)
+    used = L.orc_anib_pairs_mt(handles, p.ctypes.data, len(p), int(fragsize), int(threads), out.ctypes.data)
+    return out, int(used)
+
+
 # ----------------------------------------------------------------------------- ANIb reduction (anib.py:569-667)
 def parse_blast_tab_reduce(rows: np.ndarray):
     """(aln_length, sim_errors, mean_pid) exactly as anib.parse_blast_tab(mode="ANIb").

@@ -1116,3 +1116,88 @@ const uint8_t *orc_genome_fw(const orc_genome *g) { return g->fw; }
 const uint8_t *orc_genome_rc(const orc_genome *g) { return g->rc; }
 int64_t orc_genome_npos(const orc_genome *g) { return g->n_pos; }
 uint64_t orc_genome_goff(const orc_genome *g, uint32_t c) { return g->goff[c]; }
+
+/* ------------------------------------------------------------------ many pairs on all host threads (bench.py's CPU arm)
+ * The whole pipeline of one directed pair per work item: alignments -> 1-to-1 filter -> parse_delta reduction; `nthreads`
+ * POSIX threads pull items from a shared counter.  out: m x 6 int64 (ref_aln_len, qry_aln_len, sum_aligned, sum_weighted,
+ * sim_errs, n_alignments).  No Python in the loop: the timing is the C code's, not the interpreter's. */
+#include <pthread.h>
+void orc_parse_delta_reduce(const int64_t *aln, int64_t n, int64_t *out);
+typedef struct {
+    const orc_genome *const *G;
+    const int32_t *pairs;
+    int64_t m, *out, next;
+    int maxmatch;
+    pthread_mutex_t mu;
+} mt_job;
+static void *mt_worker(void *arg) {
+    enum { CAP = 1 << 16 };
+    mt_job *J = (mt_job *)arg;
+    int64_t *rows = (int64_t *)malloc(sizeof(int64_t) * 8 * CAP), *kept = (int64_t *)malloc(sizeof(int64_t) * 7 * CAP);
+    uint8_t *keep = (uint8_t *)malloc(CAP);
+    int64_t stats[ORC_NSTATS];
+    for (;;) {
+        pthread_mutex_lock(&J->mu);
+        const int64_t i = J->next++;
+        pthread_mutex_unlock(&J->mu);
+        if (i >= J->m) break;
+        int64_t n = orc_anim_align(J->G[J->pairs[2 * i]], J->G[J->pairs[2 * i + 1]], J->maxmatch, rows, CAP, stats);
+        if (n > CAP) n = CAP;
+        if (n < 0) n = 0;
+        orc_filter_1to1(rows, n, keep);
+        int64_t k = 0;
+        for (int64_t a = 0; a < n; ++a)
+            if (keep[a]) { memcpy(kept + 7 * k, rows + 8 * a, sizeof(int64_t) * 7); ++k; }
+        orc_parse_delta_reduce(kept, k, J->out + 6 * i);
+        J->out[6 * i + 5] = k;
+    }
+    free(rows); free(kept); free(keep);
+    return NULL;
+}
+int orc_anim_pairs_mt(const orc_genome *const *G, const int32_t *pairs, int64_t m, int maxmatch, int nthreads, int64_t *out) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 1024) nthreads = 1024;
+    mt_job J = {G, pairs, m, out, 0, maxmatch, PTHREAD_MUTEX_INITIALIZER};
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    int started = 0;
+    for (int t = 0; t < nthreads; ++t)
+        if (pthread_create(&th[t], NULL, mt_worker, &J) == 0) ++started; else break;
+    if (started == 0) mt_worker(&J);
+    for (int t = 0; t < started; ++t) pthread_join(th[t], NULL);
+    free(th);
+    return started ? started : 1;
+}
+
+/* the same for ANIb: pairs are (query, subject) indices into G (genomes carrying the ANIb index); out: m x 6 as orc_anib_pair */
+typedef struct {
+    const orc_genome *const *G;
+    const int32_t *pairs;
+    int64_t m, *out, next;
+    int fragsize;
+    pthread_mutex_t mu;
+} mtb_job;
+static void *mtb_worker(void *arg) {
+    mtb_job *J = (mtb_job *)arg;
+    int64_t stats[ORC_NSTATS];
+    for (;;) {
+        pthread_mutex_lock(&J->mu);
+        const int64_t i = J->next++;
+        pthread_mutex_unlock(&J->mu);
+        if (i >= J->m) break;
+        orc_anib_pair(J->G[J->pairs[2 * i]], J->G[J->pairs[2 * i + 1]], J->fragsize, J->out + 6 * i, NULL, 0, stats);
+    }
+    return NULL;
+}
+int orc_anib_pairs_mt(const orc_genome *const *G, const int32_t *pairs, int64_t m, int fragsize, int nthreads, int64_t *out) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 1024) nthreads = 1024;
+    mtb_job J = {G, pairs, m, out, 0, fragsize, PTHREAD_MUTEX_INITIALIZER};
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    int started = 0;
+    for (int t = 0; t < nthreads; ++t)
+        if (pthread_create(&th[t], NULL, mtb_worker, &J) == 0) ++started; else break;
+    if (started == 0) mtb_worker(&J);
+    for (int t = 0; t < started; ++t) pthread_join(th[t], NULL);
+    free(th);
+    return started ? started : 1;
+}
