@@ -117,6 +117,21 @@ int64_t b200ani_anim_rows(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int
 int b200ani_write_delta(const char *path, const char *ref_path, const char *qry_path, const char *const *ref_ids, const int64_t *ref_lens,
                         uint32_t n_ref, const char *const *qry_ids, const int64_t *qry_lens, uint32_t n_qry, const int64_t *rows, int64_t n);
 
+/* ---- seed indexes shared between GPUs.  With every genome replicated on every GPU, rebuilding all seed indexes on
+ * every GPU is the one part of a sharded run that does not shrink with the number of GPUs.  Instead a GPU builds the indexes of
+ * its share of the genomes (b200ani_index_build), copies them into a device buffer of the caller (b200ani_index_export: kmer and
+ * posflag lists of n_mini uint32 each, table of 2^table_bits uint64, presence filter of 2^(table_bits-2) uint32; sizes from
+ * b200ani_index_info), the caller moves the buffers between the GPUs (NCCL over NVLink) and every GPU adopts the arrays of the
+ * genomes it did not build (b200ani_index_adopt).  Adopted arrays stay the caller's: they must live until the genome is
+ * released or b200ani_reset_indexes / b200ani_clear is called, and are never written or freed by the engine.
+ * export is asynchronous on the engine's stream: b200ani_sync before the buffers are read by anyone else. */
+int b200ani_index_build(b200ani_ctx *ctx, const int32_t *genome_ids, int n);
+int b200ani_index_info(const b200ani_ctx *ctx, int32_t genome_id, int64_t *n_mini, uint32_t *table_bits);
+int b200ani_index_export(b200ani_ctx *ctx, int32_t genome_id, void *d_kmer, void *d_posflag, void *d_table, void *d_bitmap);
+int b200ani_index_adopt(b200ani_ctx *ctx, int32_t genome_id, const void *d_kmer, const void *d_posflag, const void *d_table, const void *d_bitmap,
+                        int64_t n_mini, uint32_t table_bits);
+int b200ani_sync(b200ani_ctx *ctx);
+
 /* Bottom-s MinHash sketch of a staged genome: the s smallest distinct hash values (ascending) of its seed k-mers (canonical
  * 16-mers of the ANIm index; the index is built if needed).  A Mash-style identity estimate from two sketches lets a caller
  * skip hopeless pairs before any alignment work (opt-in: pyani_b200/prefilter.py; the reference has no prefilter and aborts on

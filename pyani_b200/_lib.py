@@ -59,6 +59,11 @@ SIGNATURES = {
     "b200ani_write_delta": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                      C.c_void_p, C.c_int64]),
     "b200ani_anib_rows": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "b200ani_index_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "b200ani_index_info": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_uint32)]),
+    "b200ani_index_export": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200ani_index_adopt": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32]),
+    "b200ani_sync": (C.c_int, [C.c_void_p]),
     "b200ani_sketch": (C.c_int, [C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "b200ani_anib": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "b200ani_anib_fragments": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int, C.c_void_p, C.c_int64]),

@@ -12,6 +12,7 @@ constexpr uint32_t AN_POSMASK = (1u << AN_POSBITS) - 1u, AN_REPBIT = 1u << AN_PO
 
 struct MinimizerIndex {
     bool valid = false;             // false after b200ani_reset_indexes: buffers are kept, content is rebuilt
+    bool external = false;          // arrays live in caller-owned device memory (b200ani_index_adopt): never freed, never rebuilt in place
     int maxocc = AN_MAXOCC;         // k-mers with more occurrences in the genome are not indexed
     int k = AN_K, w = AN_W;         // seed length / minimizer window (ANIm: AN_K / AN_W; ANIb: AB_K / AB_W)
     int64_t cap_mini = 0;           // capacity of d_kmer / d_posflag

@@ -942,6 +942,67 @@ const char *b200ani_stage_name(int i) {
     return i < B200ANI_N_STAGES ? kStageNames[i] : kCounterNames[i - B200ANI_N_STAGES];
 }
 
+// ---- seed indexes shared between GPUs ("build each genome's seed index once on its home GPU and replicate via
+// NVLink"): a rank builds the indexes of ITS genomes, exports them into a caller-owned device slab, the caller moves the slabs
+// (one NCCL all-gather, pyani_b200/dist.py:share_indexes) and every rank adopts the arrays of the genomes it did not build.
+int b200ani_index_build(b200ani_ctx *ctx, const int32_t *genome_ids, int n) {
+    if (!ctx || !genome_ids || n <= 0) return B200ANI_ERR_ARG;
+    for (int k = 0; k < ST_FIRST_NON_ANIM; ++k) ctx->stage_ms[k] = 0;
+    std::vector<int32_t> pr(2 * (size_t)n);
+    for (int i = 0; i < n; ++i) pr[2 * i] = pr[2 * i + 1] = genome_ids[i];
+    return prepare(ctx, pr.data(), n, false);
+}
+
+int b200ani_index_info(const b200ani_ctx *ctx, int32_t genome_id, int64_t *n_mini, uint32_t *table_bits) {
+    if (!ctx || genome_id < 0 || genome_id >= (int32_t)ctx->genomes.size()) return B200ANI_ERR_ARG;
+    const MinimizerIndex *ix = ctx->genomes[genome_id].index;
+    if (!index_valid(ix, AN_MAXOCC)) return B200ANI_ERR_ARG;
+    if (n_mini) *n_mini = ix->n_mini;
+    if (table_bits) *table_bits = ix->table_bits;
+    return B200ANI_OK;
+}
+
+int b200ani_index_export(b200ani_ctx *ctx, int32_t genome_id, void *d_kmer, void *d_posflag, void *d_table, void *d_bitmap) {
+    if (!ctx || genome_id < 0 || genome_id >= (int32_t)ctx->genomes.size() || !d_kmer || !d_posflag || !d_table || !d_bitmap) return B200ANI_ERR_ARG;
+    const MinimizerIndex *ix = ctx->genomes[genome_id].index;
+    if (!index_valid(ix, AN_MAXOCC)) FAIL(B200ANI_ERR_ARG, "index_export: the genome has no valid seed index");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d_kmer, ix->d_kmer, sizeof(uint32_t) * (size_t)ix->n_mini, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(d_posflag, ix->d_posflag, sizeof(uint32_t) * (size_t)ix->n_mini, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(d_table, ix->d_table, sizeof(uint64_t) << ix->table_bits, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(d_bitmap, ix->d_bitmap, sizeof(uint32_t) << (ix->table_bits + 3 - 5), cudaMemcpyDeviceToDevice, st));
+    return B200ANI_OK;
+}
+
+int b200ani_index_adopt(b200ani_ctx *ctx, int32_t genome_id, const void *d_kmer, const void *d_posflag, const void *d_table, const void *d_bitmap,
+                        int64_t n_mini, uint32_t table_bits) {
+    if (!ctx || genome_id < 0 || genome_id >= (int32_t)ctx->genomes.size() || !d_kmer || !d_posflag || !d_table || !d_bitmap) return B200ANI_ERR_ARG;
+    if (n_mini < 0 || table_bits < 4 || table_bits > 31 || (1ll << table_bits) < 2 * n_mini) FAIL(B200ANI_ERR_ARG, "index_adopt: inconsistent sizes");
+    Genome &g = ctx->genomes[genome_id];
+    CK(cudaSetDevice(ctx->device));
+    if (g.index && !index_is_external(g.index)) {  // its own buffers go back to the pool of reusable ones
+        invalidate_index(g.index);
+        ctx->spare_indexes.push_back(g.index);
+        g.index = nullptr;
+    }
+    if (!g.index) g.index = new MinimizerIndex();
+    MinimizerIndex *ix = g.index;
+    ix->external = true;
+    ix->d_kmer = (uint32_t *)d_kmer; ix->d_posflag = (uint32_t *)d_posflag; ix->d_table = (uint64_t *)d_table; ix->d_bitmap = (uint32_t *)d_bitmap;
+    ix->n_mini = n_mini; ix->table_bits = table_bits; ix->cap_mini = n_mini; ix->cap_bits = table_bits;
+    ix->maxocc = AN_MAXOCC; ix->k = AN_K; ix->w = AN_W;
+    ix->valid = true;
+    return B200ANI_OK;
+}
+
+int b200ani_sync(b200ani_ctx *ctx) {
+    if (!ctx) return B200ANI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200ANI_OK;
+}
+
 __global__ void sketch_hash_kernel(const uint32_t *__restrict__ kmer, int64_t n, uint32_t *__restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = fmix32(kmer[i]);

@@ -167,13 +167,25 @@ __global__ void split_bypos_kernel(const uint64_t *__restrict__ key2s, const uin
 
 void free_index(MinimizerIndex *ix, cudaStream_t st) {
     if (!ix) return;
-    cudaFreeAsync(ix->d_kmer, st);
-    cudaFreeAsync(ix->d_posflag, st);
-    cudaFreeAsync(ix->d_table, st);
-    cudaFreeAsync(ix->d_bitmap, st);
+    if (!ix->external) {
+        cudaFreeAsync(ix->d_kmer, st);
+        cudaFreeAsync(ix->d_posflag, st);
+        cudaFreeAsync(ix->d_table, st);
+        cudaFreeAsync(ix->d_bitmap, st);
+    }
     delete ix;
 }
-void invalidate_index(MinimizerIndex *ix) { if (ix) ix->valid = false; }
+// content is rebuilt on demand; adopted arrays belong to the caller and may be gone by then: forget them
+void invalidate_index(MinimizerIndex *ix) {
+    if (!ix) return;
+    ix->valid = false;
+    if (ix->external) {
+        ix->external = false;
+        ix->d_kmer = ix->d_posflag = nullptr; ix->d_table = nullptr; ix->d_bitmap = nullptr;
+        ix->cap_bits = 0; ix->cap_mini = 0;
+    }
+}
+bool index_is_external(const MinimizerIndex *ix) { return ix && ix->external; }
 bool index_valid(const MinimizerIndex *ix, int maxocc) { return ix && ix->valid && ix->maxocc == maxocc; }
 static_assert(AB_K <= 16 && AN_K <= 16 && AB_W <= AN_W, "k-mers are packed into 32 bits; the selection tile's halo is AN_W - 1");
 

@@ -105,9 +105,10 @@ static void release_genome(b200ani_ctx *ctx, Genome &g, cudaStream_t st) {
     if (g.d_fbase) cudaFreeAsync(g.d_fbase, st);
     g.d_fbase = nullptr;
     for (MinimizerIndex **slot : {&g.index, &g.index_b}) {
-        if (*slot) {  // keep the buffers for the next genome of similar size
+        if (*slot) {  // keep the buffers for the next genome of similar size (adopted arrays are the caller's: nothing to keep)
+            const bool ext = index_is_external(*slot);
             invalidate_index(*slot);
-            ctx->spare_indexes.push_back(*slot);
+            if (ext) free_index(*slot, st); else ctx->spare_indexes.push_back(*slot);
         }
         *slot = nullptr;
     }

@@ -102,4 +102,5 @@ int tetra_corr_device(b200ani_ctx *ctx, const double *d_z, const int *d_idx, int
 void free_index(MinimizerIndex *ix, cudaStream_t st);
 void invalidate_index(MinimizerIndex *ix);
 bool index_valid(const MinimizerIndex *ix, int maxocc);
+bool index_is_external(const MinimizerIndex *ix);
 void free_anim_workspaces(void *ws);

@@ -119,6 +119,70 @@ def anib_sharded(engine, pairs: np.ndarray, genome_lengths: Sequence[int], rank:
     return _sharded(fn, pairs, rank, world, ANIB_DTYPE, device, group, chunk)
 
 
+def index_layout(n_mini: np.ndarray, world: int):
+    """Where every genome's four index arrays sit in the shared slab: genome g belongs to rank ``block_of[g]`` (contiguous,
+    equal-count blocks), every rank's block has the same size (the largest one, what a single all-gather needs).
+    -> (block_of, offsets (n, 4) relative to the slab start: kmer, posflag, table, bitmap; table_bits (n,); block_bytes)."""
+    n = len(n_mini)
+    nm = np.asarray(n_mini, dtype=np.int64)
+    bits = np.maximum(4, np.ceil(np.log2(np.maximum(2 * nm, 1))).astype(np.int64))
+    bits = np.where((1 << bits) < 2 * nm, bits + 1, bits)  # the engine's rule: smallest power of two >= 2 * n_mini (at least 2^4)
+    per = (n + world - 1) // world
+    block_of = np.minimum(np.arange(n) // max(per, 1), world - 1)
+
+    def al(x):
+        return (x + 255) & ~255
+
+    sizes = np.stack([al(4 * nm), al(4 * nm), al(8 << bits), al(4 << (bits - 2))], axis=1)
+    rel = np.zeros((n, 4), dtype=np.int64)
+    block_bytes = 0
+    for r in range(world):
+        o = 0
+        for g in np.flatnonzero(block_of == r):
+            for a in range(4):
+                rel[g, a] = o
+                o += int(sizes[g, a])
+        block_bytes = max(block_bytes, o)
+    offsets = rel + (block_of * block_bytes)[:, None]
+    return block_of, offsets, bits, int(block_bytes)
+
+
+def share_indexes(engine, gids: Sequence[int], rank: int, world: int, device, group=None):
+    """Seed indexes of ``gids`` (the same staged genomes on every rank) built ONCE across the ranks: rank r builds its block of
+    the genomes, the blocks travel in one all-gather over NVLink, every rank adopts the arrays of the genomes it did not build
+    (SURVEY.md 8e).  Replaces rebuilding all indexes on every rank -- the one cost of a sharded run that does not shrink with
+    the number of GPUs.  Returns the slab tensor; the caller keeps it alive while the engine uses the adopted indexes (until
+    ``reset_indexes`` / ``clear``)."""
+    import torch
+    import torch.distributed as dist
+
+    gids = [int(g) for g in gids]
+    n = len(gids)
+    per = (n + world - 1) // world
+    mine = [k for k in range(n) if min(k // max(per, 1), world - 1) == rank]
+    engine.index_build([gids[k] for k in mine])
+    nm_local = torch.zeros(n, dtype=torch.int64, device=device)
+    for k in mine:
+        nm_local[k] = engine.index_info(gids[k])[0]
+    if world > 1:
+        dist.all_reduce(nm_local, op=dist.ReduceOp.SUM, group=group)  # disjoint supports: the sum is the union
+    n_mini = nm_local.cpu().numpy()
+    block_of, off, bits, block_bytes = index_layout(n_mini, world)
+    slab = torch.empty(world * block_bytes, dtype=torch.uint8, device=device)
+    base = slab.data_ptr()
+    for k in mine:
+        engine.index_export(gids[k], *(base + int(o) for o in off[k]))
+    engine.sync()
+    if world > 1:
+        torch.cuda.current_stream(device).synchronize()
+        dist.all_gather_into_tensor(slab, slab[rank * block_bytes:(rank + 1) * block_bytes].clone(), group=group)
+        torch.cuda.current_stream(device).synchronize()
+    for k in range(n):
+        if block_of[k] != rank:
+            engine.index_adopt(gids[k], *(base + int(o) for o in off[k]), int(n_mini[k]), int(bits[k]))
+    return slab
+
+
 def tetra_sharded(engine, genome_ids: Sequence[int], genome_lengths: Sequence[int], rank: int, world: int, *, device=None, group=None,
                   compute=None) -> Tuple[np.ndarray, np.ndarray]:
     """TETRA across ranks: every rank counts and scores a contiguous, length-balanced block of the genomes,

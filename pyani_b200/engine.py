@@ -224,6 +224,31 @@ class Engine:
                 return out, rows[:n].copy(), start
             cap = int(n)
 
+    # -- seed indexes shared between GPUs (pyani_b200.dist.share_indexes)
+    def index_build(self, gids: Sequence[int]) -> None:
+        ids = np.ascontiguousarray(gids, dtype=np.int32)
+        if len(ids):
+            self._check(self._lib.b200ani_index_build(self._h, _ptr(ids), len(ids)), "index_build")
+
+    def index_info(self, gid: int) -> Tuple[int, int]:
+        """(n_mini, table_bits) of a genome's valid seed index."""
+        n, b = C.c_int64(0), C.c_uint32(0)
+        self._check(self._lib.b200ani_index_info(self._h, int(gid), C.byref(n), C.byref(b)), "index_info")
+        return n.value, b.value
+
+    def index_export(self, gid: int, d_kmer: int, d_posflag: int, d_table: int, d_bitmap: int) -> None:
+        """Copy the index arrays to device addresses of the caller (asynchronous: :meth:`sync` before anyone else reads them)."""
+        self._check(self._lib.b200ani_index_export(self._h, int(gid), C.c_void_p(d_kmer), C.c_void_p(d_posflag), C.c_void_p(d_table), C.c_void_p(d_bitmap)),
+                    "index_export")
+
+    def index_adopt(self, gid: int, d_kmer: int, d_posflag: int, d_table: int, d_bitmap: int, n_mini: int, table_bits: int) -> None:
+        """Use index arrays in caller-owned device memory (built on another GPU) for this genome; they must outlive their use."""
+        self._check(self._lib.b200ani_index_adopt(self._h, int(gid), C.c_void_p(d_kmer), C.c_void_p(d_posflag), C.c_void_p(d_table), C.c_void_p(d_bitmap),
+                                                  int(n_mini), int(table_bits)), "index_adopt")
+
+    def sync(self) -> None:
+        self._check(self._lib.b200ani_sync(self._h), "sync")
+
     def sketch(self, gid: int, s: int = 2048) -> np.ndarray:
         """Bottom-s MinHash sketch of a staged genome (ascending distinct uint32 hashes of its seed k-mers), see pyani_b200.prefilter."""
         out = np.zeros(s, dtype=np.uint32)

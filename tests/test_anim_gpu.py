@@ -280,3 +280,31 @@ def test_batched_rows_equal_per_pair_rows(engine, small_set):
             want = engine.anim_alignments(int(gp[i, 0]), int(gp[i, 1]), nofilter=nofilter)
             got = rows[start[i]:start[i + 1]]
             assert got.shape == want.shape and (got == want).all(), (i, nofilter)
+
+
+def test_exported_and_adopted_index_gives_identical_results(engine, small_set):
+    """Seed indexes shared between GPUs (dist.share_indexes), here on one device: genome 0 is staged a second time, the index
+    built for the first copy is exported into a torch buffer laid out by dist.index_layout and adopted by the second copy; every
+    comparison that uses the second copy as reference or query returns what the first copy returns."""
+    import torch
+
+    from pyani_b200 import dist as pdist
+
+    gs, gids, og = small_set
+    twin = engine.add_genome(gs[0].residues, gs[0].contig_off, "twin")
+    engine.index_build([gids[0]])
+    n_mini, bits = engine.index_info(gids[0])
+    block_of, off, lbits, block_bytes = pdist.index_layout(np.array([n_mini]), 1)
+    assert int(lbits[0]) == bits and block_bytes >= 8 * n_mini + (8 << bits)
+    slab = torch.zeros(block_bytes, dtype=torch.uint8, device="cuda:0")
+    base = slab.data_ptr()
+    engine.index_export(gids[0], *(base + int(o) for o in off[0]))
+    engine.sync()
+    engine.index_adopt(twin, *(base + int(o) for o in off[0]), n_mini, bits)
+    a = engine.anim(np.array([[gids[0], gids[1]], [gids[1], gids[0]], [gids[0], gids[4]]], np.int32))
+    b = engine.anim(np.array([[twin, gids[1]], [gids[1], twin], [twin, gids[4]]], np.int32))
+    assert a.tobytes() == b.tobytes()
+    engine.reset_indexes()   # adopted arrays are forgotten; the next call rebuilds the twin's own index
+    del slab
+    c = engine.anim(np.array([[twin, gids[1]], [gids[1], twin], [twin, gids[4]]], np.int32))
+    assert c.tobytes() == a.tobytes()
