@@ -110,7 +110,10 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
     }
     qs.buf >>= 2 * (32 - sh); qs.mbuf >>= (32 - sh); qs.left = sh;
     int best = 0, best_sc = 0;
-    for (int i = 1; i <= lr; ++i) {
+    // extension tiles: rows beyond lq - klo hold no cell with j <= lq (ANIb fragments end long before a 256-row tile does);
+    // they are not computed, their only effect -- the break rule counting them -- is applied after the loop
+    const int lr_run = MODE ? min(lr, lq - klo) : lr;
+    for (int i = 1; i <= lr_run; ++i) {
         if (rs.left == 0) rs.refill(R, rstep);
         const uint32_t rb = (uint32_t)rs.buf & 3u, rn = rs.mbuf & 1u;
         rs.buf >>= 2; rs.mbuf >>= 1; --rs.left;
@@ -173,6 +176,9 @@ __device__ __forceinline__ DpResult dp_band(const SeqView &R, int64_t r0, int rs
         qwin = (qwin >> 2) | ((qs.buf & 3ull) << 62);
         nwin = (nwin >> 2) | ((uint64_t)(qs.mbuf & 1u) << 62);
         qs.buf >>= 2; qs.mbuf >>= 1; --qs.left;
+    }
+    if (MODE == 1 && !o.stopped && lr_run < lr) {  // the skipped rows: the break condition is monotone in the row, test the last one
+        if (MODEL == 0 ? (2 * lr + klo + AN_BAND + 1 - (o.bi + o.bj) > AN_BREAK_DIAGS) : (lr - o.bi > SC::brk)) o.stopped = 1;
     }
     if (MODE == 0) {
         const int kend = (lq - lr) - klo;
