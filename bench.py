@@ -299,7 +299,7 @@ def workload_config(args, n_gpus: int):
                         f"divergence 15-25 %, within-clade 0.1-5 %), BASELINE.json configs[{cfg}]" + (" [--small harness check]" if args.small else ""),
             "genomes": n, "seed": seed,
             "parallelism": (f"strong scaling: genomes replicated on {n_gpus} GPUs, seed indexes built once across the GPUs and shared by one all-gather, "
-                            f"pair list dealt in chunks of 64 genome pairs, one all-gather of result structs"
+                            f"unordered genome pairs dealt round-robin in walk order, one all-gather of result structs"
                             if n_gpus > 1 else "single GPU"),
             "l2": "inputs larger than L2 (packed genomes + seed indexes: ~50 MB per genome)"}
 
@@ -538,9 +538,22 @@ def main():
             "gap_dp_kernel": {"ms": stage_tot["gap_dp"] / K, "launches": counters_last["gap_dp_launches"]},
             "ext_dp_kernel": {"ms": stage_tot["ext_dp_kernel"] / K, "launches": counters_last["ext_dp_launches"]},
         }
+        if kind == "anib":  # the 11-mer word stage: one launch per batch like the seed probe
+            kern["word_probe_kernel"] = {"ms": stage_tot.get("words", 0.0) / K, "launches": counters_last["seed_launches"]}
+        word_hits = counters_last.get("word_hits", 0)
 
         def roofline_of(name):
             ms_k, launches = kern[name]["ms"], max(1, kern[name]["launches"])
+            if name == "word_probe_kernel":
+                # algorithmic bytes: both strands of every probing query once (2 bit + 1 bit per base), 8 B of group
+                # starts per position, 16 B per occurrence looked at; the bound is L2 random access, reported against HBM peak
+                mean_len = float(np.mean(lengths))
+                qbytes = (len(my_pairs) / 2) * 2 * (mean_len / 4 + mean_len / 8 + 8 * mean_len)  # one pass per unordered pair
+                alg = qbytes + word_hits * 16
+                ach = alg / (ms_k * 1e-3) / 1e9 if ms_k else 0.0
+                return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                        "traffic": traffic.get(name), "peak_source": peak_src, "per_launch_ms": ms_k / launches,
+                        "algorithmic_bytes_per_launch": alg / launches, "occurrences_per_s": word_hits / (ms_k * 1e-3) if ms_k else 0.0}
             if name.startswith("seed"):
                 # algorithmic bytes: probe = 4 B k-mer streamed + 4 B presence-filter word + 8 B written per hit (+ 8 B
                 # table slot per hit); extend = 8 B hit + 4 B posflag + 2 x 16 B packed sequence per hit, 16 B per anchor written

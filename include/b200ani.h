@@ -181,7 +181,7 @@ const char *b200ani_stage_name(int i);
 
 /* ---- several GPUs of one node behind one handle (run_multiprocessing.py:113-152 / run_sge.py:87-112 for callers that are not
  * Python; Python callers may also run one process per GPU with pyani_b200.dist).  Genomes are replicated on every device, the
- * pair list is dealt over the devices (chunks of 64 unordered genome pairs, round-robin; both directions of a pair stay
+ * pair list is dealt over the devices (unordered genome pairs round-robin in walk order; both directions of a pair stay
  * together), every device runs its share, and ONE ncclAllGather of the result structs -- the communicator belongs to this
  * context -- assembles the full array on every device; the caller gets it in the order of `pairs`.  NCCL is resolved at run
  * time (dlopen "libnccl.so.2"); b200ani_create_multi fails if it is absent. */

@@ -142,7 +142,7 @@ def read_fasta(path):
 # ----------------------------------------------------------------------------- ANIm aligner (oracle_anim.c)
 ANIM_NSTATS = 16
 ANIM_STAT_NAMES = ["anchors", "links", "cut_links", "segments", "gap_cells", "ext_cells", "ext_tiles", "seed_hits", "raw_anchors", "bridges",
-                   "bridge_cells", "", "", "", "", ""]
+                   "bridge_cells", "word_hits", "word_anchors", "", "", ""]
 
 
 class OGenome:
@@ -259,6 +259,14 @@ def anib_pairs_mt(genomes, pairs, threads: int = 0, fragsize: int = 1020):
     out = np.zeros((len(p), 6), dtype=np.int64)
     used = L.orc_anib_pairs_mt(handles, p.ctypes.data, len(p), int(fragsize), int(threads), out.ctypes.data)
     return out, int(used)
+
+
+def anib_results_mt(genomes, pairs, threads: int = 0, fragsize: int = 1020):
+    """:func:`anib_pair` result dicts for many (query, subject) index pairs into ``genomes``, computed on host threads
+    (the word stage makes a 4 Mb pair take ~10 s on one core)."""
+    out, _ = anib_pairs_mt(genomes, pairs, threads, fragsize)
+    return [dict(aln_length=int(o[0]), sim_errs=int(o[1]), pid_milli_sum=int(o[2]), n_frags=int(o[3]), n_pass=int(o[4]), n_hsps=int(o[5]),
+                 status=0 if o[4] else 1) for o in out]
 
 
 # ----------------------------------------------------------------------------- ANIb reduction (anib.py:569-667)

@@ -45,12 +45,16 @@
 #define AB_W 2           /* ... and minimizer window: every exact match >= AB_K + AB_W - 1 = 14 is seeded */
 #define AB_MINLEN 14     /* ANIb minimum exact-match length (blastn words are 11; shorter seeds stop paying: k-mers must stay unique) */
 #define AB_SCREEN_W 28   /* ANIb screen: chains with fewer matched bases than this must pass the ungapped test ... */
-#define AB_SCREEN_MIN 12 /* ... minimum summed score of the two ungapped end extensions (+2 / -3) ... */
+#define AB_SCREEN_MIN 20 /* ... minimum summed score of the two ungapped end extensions (+2 / -3) ... */
 #define AB_SCREEN_LEN 64 /* ... over at most this many bases per end ... */
 #define AB_SCREEN_DROP 20 /* ... each stopping once it falls this far below its best (X-drop) */
 #define AB_BRIDGE_GAP 250 /* ANIb bridging: max distance between two candidate HSPs of a fragment that are joined ... */
 #define AB_BRIDGE_DD 120  /* ... and max diagonal offset between them (blastn's gapped extension is not banded) */
 #define AB_MINPIECE 11   /* shortest anchor piece kept after clipping to a fragment (blastn word size) */
+#define AB_WORD 11       /* ANIb word anchors: every maximal exact match of at least this length (blastn -task blastn word size) ... */
+#define AB_WORD_FLANK 16 /* ... whose diagonal, over its leftmost word and this many bases to either side of that word, ... */
+#define AB_WORD_MIN 14   /* ... scores at least this much (+2 / -3; = at most 14 mismatches among the 32 flank bases): stands in for blastn's ungapped extension test */
+#define AB_WORD_MAXOCC 16 /* words with more occurrences than this in either genome are not looked up */
 #define AB_FRAGSIZE 1020 /* pyani_config.FRAGSIZE (pyani_config.py:95) */
 #define AN_PACK 4096     /* DP value = score*PACK - errs */
 #define AN_NEG (-(1 << 29))

@@ -28,6 +28,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 
 #include "anim_spec.h"
 
@@ -49,6 +50,9 @@ typedef struct {
     uint64_t *table;        /* open addressing: kmer<<32 | posflag ; empty = ~0 */
     uint32_t table_bits;
     int k, w;               /* seed length and minimizer window of this index (ANIm: AN_K / AN_W, ANIb: AB_K / AB_W) */
+    /* ANIb word index (built on first use): every forward position whose AB_WORD-mer is free of non-ACGT codes, grouped by
+     * word value (first base most significant), ascending position inside a group: positions w_pos[w_off[v] .. w_off[v+1]) */
+    uint32_t *w_off, *w_pos;
 } orc_genome;
 
 static inline int base_code(uint8_t c) {
@@ -78,6 +82,7 @@ static int cmp_u64(const void *a, const void *b) {
 void orc_genome_free(orc_genome *g) {
     if (!g) return;
     free(g->goff); free(g->fw); free(g->rc); free(g->mini_kmer); free(g->mini_posflag); free(g->table);
+    free(g->w_off); free(g->w_pos);
     free(g);
 }
 
@@ -829,6 +834,41 @@ static int cmp_fanchor(const void *a, const void *b) {
     return x->len - y->len;
 }
 
+#define AB_NWORDS (1u << (2 * AB_WORD))
+static void build_words(orc_genome *g) {
+    const int64_t n = g->n_pos;
+    uint32_t *off = (uint32_t *)calloc((size_t)AB_NWORDS + 2, sizeof(uint32_t));
+    uint32_t *wv = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n + 1));
+    uint32_t w = 0;
+    int valid = 0;
+    for (int64_t p = 0; p < n; ++p) { /* word ENDING at p */
+        uint8_t b = g->fw[p];
+        if (b > 3) { valid = 0; w = 0; } else { w = ((w << 2) | b) & (AB_NWORDS - 1); ++valid; }
+        int64_t st = p - AB_WORD + 1;
+        if (st >= 0) { wv[st] = valid >= AB_WORD ? w : 0xffffffffu; if (valid >= AB_WORD) off[w + 1]++; }
+    }
+    for (uint32_t i = 0; i < AB_NWORDS; ++i) off[i + 1] += off[i];
+    uint32_t *pos = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(off[AB_NWORDS] + 1));
+    uint32_t *cur = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)AB_NWORDS);
+    memcpy(cur, off, sizeof(uint32_t) * (size_t)AB_NWORDS);
+    for (int64_t st = 0; st + AB_WORD <= n; ++st) if (wv[st] != 0xffffffffu) pos[cur[wv[st]]++] = (uint32_t)st;
+    free(cur); free(wv);
+    g->w_pos = pos;
+    __atomic_store_n(&g->w_off, off, __ATOMIC_RELEASE);
+}
+static pthread_mutex_t g_words_mu = PTHREAD_MUTEX_INITIALIZER;
+static void need_words(const orc_genome *g) { /* the threaded driver shares genomes between its workers */
+    if (__atomic_load_n(&g->w_off, __ATOMIC_ACQUIRE)) return;
+    pthread_mutex_lock(&g_words_mu);
+    if (!g->w_off) build_words((orc_genome *)g);
+    pthread_mutex_unlock(&g_words_mu);
+}
+static inline uint32_t word_revcomp(uint32_t w) {
+    uint32_t r = 0;
+    for (int i = 0; i < AB_WORD; ++i) { r = (r << 2) | (3u - (w & 3u)); w >>= 2; }
+    return r;
+}
+
 int64_t orc_anib_pair(const orc_genome *Q, const orc_genome *S, int fragsize, int64_t *out, int64_t *frag_rows, int64_t cap_rows, int64_t *stats) {
     memset(stats, 0, sizeof(int64_t) * ORC_NSTATS);
     memset(out, 0, sizeof(int64_t) * 6);
@@ -880,6 +920,64 @@ int64_t orc_anib_pair(const orc_genome *Q, const orc_genome *S, int fragsize, in
             A[na].frag = (int32_t)(fbase[c] + k); A[na].strand = strand;
             A[na].r = (int32_t)(rs + t0); A[na].q = (int32_t)(qs + t0); A[na].len = (int32_t)(b - a);
             ++na;
+        }
+    }
+    /* ---- word anchors (blastn's 11-mer words + ungapped extension test): every maximal exact match of at least AB_WORD
+     * bases -- unique or not, as long as its leftmost word occurs at most AB_WORD_MAXOCC times in either genome -- whose
+     * diagonal scores at least AB_WORD_MIN over that leftmost word and AB_WORD_FLANK bases to either side of it (+2 / -3; a
+     * flank ends at the first non-ACGT code or sequence end; the right flank holds the rest of a longer match).  The window
+     * is fixed relative to the word, so the engine can keep it next to every indexed position and reject a chance hit
+     * without touching the sequence.  Every rule is symmetric in the two genomes, so the opposite direction of the pair
+     * sees the same matches.  A match found by a seed above as well is the same (fragment, strand, r, q, len) record and is
+     * removed by the sort + unique below. */
+    need_words(R);
+    need_words(Q);
+    for (int strand = 0; strand < 2; ++strand) {
+        const uint8_t *Qs = strand ? Q->rc : Q->fw;
+        uint32_t w = 0;
+        int valid = 0;
+        for (int64_t p = 0; p < Q->n_pos; ++p) {
+            uint8_t b = Qs[p];
+            if (b > 3) { valid = 0; w = 0; continue; }
+            w = ((w << 2) | b) & (AB_NWORDS - 1); ++valid;
+            if (valid < AB_WORD) continue;
+            const int64_t q0 = p - AB_WORD + 1;
+            const uint32_t lo = R->w_off[w], hi = R->w_off[w + 1];
+            if (hi == lo || hi - lo > AB_WORD_MAXOCC) continue;
+            const uint32_t wq = strand ? word_revcomp(w) : w; /* the word as the query's own (forward) index holds it */
+            if (Q->w_off[wq + 1] - Q->w_off[wq] > AB_WORD_MAXOCC) continue;
+            for (uint32_t t = lo; t < hi; ++t) {
+                const int64_t r0 = R->w_pos[t];
+                stats[11]++;
+                if (r0 > 0 && q0 > 0 && R->fw[r0 - 1] < 4 && R->fw[r0 - 1] == Qs[q0 - 1]) continue; /* not the leftmost word of its match */
+                int sc = AB_MATCH * AB_WORD;
+                for (int side = 0; side < 2; ++side)
+                    for (int x = 0; x < AB_WORD_FLANK; ++x) {
+                        const int64_t rp = side ? r0 + AB_WORD + x : r0 - 1 - x, qp = side ? q0 + AB_WORD + x : q0 - 1 - x;
+                        if (rp < 0 || rp >= R->n_pos || qp < 0 || qp >= Q->n_pos) break;
+                        const uint8_t a = R->fw[rp], c = Qs[qp];
+                        if (a > 3 || c > 3) break;
+                        sc += a == c ? AB_MATCH : -AB_MISMATCH;
+                    }
+                if (sc < AB_WORD_MIN) continue;
+                stats[12]++;
+                int64_t len = AB_WORD;
+                while (r0 + len < R->n_pos && q0 + len < Q->n_pos && R->fw[r0 + len] < 4 && R->fw[r0 + len] == Qs[q0 + len]) ++len;
+                const int64_t fa = strand ? Q->n_pos - q0 - len : q0, fb = fa + len;
+                const uint32_t c = contig_of(Q->goff, Q->n_contigs, fa);
+                const int64_t rec0 = (int64_t)Q->goff[c];
+                for (int64_t k = (fa - rec0) / fragsize; rec0 + k * fragsize < fb; ++k) {
+                    int64_t a = rec0 + k * fragsize, bnd = a + fragsize;
+                    if (a < fa) a = fa;
+                    if (bnd > fb) bnd = fb;
+                    if (bnd - a < AB_MINPIECE) continue;
+                    const int64_t t0 = strand ? (Q->n_pos - bnd) - q0 : a - q0;
+                    if (na == acap) { acap *= 2; A = (fanchor *)realloc(A, sizeof(fanchor) * (size_t)acap); }
+                    A[na].frag = (int32_t)(fbase[c] + k); A[na].strand = strand;
+                    A[na].r = (int32_t)(r0 + t0); A[na].q = (int32_t)(q0 + t0); A[na].len = (int32_t)(bnd - a);
+                    ++na;
+                }
+            }
         }
     }
     qsort(A, (size_t)na, sizeof(fanchor), cmp_fanchor);

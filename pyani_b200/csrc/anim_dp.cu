@@ -317,6 +317,23 @@ __global__ void __launch_bounds__(128, 4) ext_dp_kernel(SegArrays S, const PairD
     }
 }
 
+// First-launch order of the ANIb extension tasks: rows the first tile of task (2 * segment + side) will run.  Fragments end
+// anywhere inside a 256-row tile, so unsorted neighbours in a warp run 0..272 rows and wait for the longest; handing the
+// tickets out by descending row count keeps the lanes of a warp on equally long tiles (the link alignments do the same).
+template <int MODEL>
+__global__ void ext_task_rows_kernel(SegArrays S, uint32_t *__restrict__ rows, uint32_t *__restrict__ task) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * S.n) return;
+    const int64_t s = t >> 1;
+    const int side = (int)(t & 1);
+    const int64_t ar = side ? S.r_hi[s] - S.re[s] : S.rs[s] - S.r_lo[s];
+    const int64_t aq = side ? S.q_hi[s] - S.qe[s] : S.qs[s] - S.q_lo[s];
+    const int lr = (int)min(ar, (int64_t)Scoring<MODEL>::tile), lq = (int)min(aq, (int64_t)(Scoring<MODEL>::tile + AN_BAND));
+    rows[t] = (lr > 0 && lq > 0) ? (uint32_t)min(lr, lq + AN_BAND) : 0u;
+    task[t] = (uint32_t)t;
+}
+template __global__ void ext_task_rows_kernel<1>(SegArrays, uint32_t *, uint32_t *);
+
 // Finished segments -> alignment rows (pair, ref record, qry record, rs, re, qs, qe, errs) in .delta
 // conventions (1-based closed, reverse strand qs > qe; anim.py:300-310).
 __global__ void emit_rows_kernel(SegArrays S, const PairDesc *__restrict__ pairs, int *__restrict__ rows /* n x 8 */) {

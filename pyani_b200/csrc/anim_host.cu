@@ -15,10 +15,12 @@
 #include "anim.cuh"
 
 int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc, bool anib);
+int build_word_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo);  // anib_words.cu
 
 // kernels defined in the other translation units
 template <int MODE> __global__ void seed_probe_kernel(const PairDesc *, int, int64_t, uint2 *, unsigned long long *, unsigned long long, int);
 __global__ void seed_extend_kernel(const PairDesc *, int, const uint2 *, int64_t, uint64_t *, uint64_t *, unsigned long long *, unsigned long long, int, int, int);
+__global__ void word_probe_kernel(const PairDesc *, int, int64_t, uint64_t *, uint64_t *, unsigned long long *, unsigned long long, unsigned long long *);
 __global__ void tie_fix_kernel(uint64_t *, uint64_t *, int64_t);
 __global__ void flag_unique_kernel(const uint64_t *, const uint64_t *, int64_t, uint8_t *);
 __global__ void contig_kernel(ChainArrays, const PairDesc *);
@@ -44,6 +46,7 @@ __global__ void segment_accum_kernel(ChainArrays, int);
 __global__ void segment_flag_kernel(ChainArrays, uint8_t *);
 template <int MODEL> __global__ void gap_dp_kernel(ChainArrays, const PairDesc *, const uint32_t *, int64_t, unsigned long long *, int);
 __global__ void segment_init_kernel(ChainArrays, const PairDesc *, const int *, SegArrays, int);
+template <int MODEL> __global__ void ext_task_rows_kernel(SegArrays, uint32_t *, uint32_t *);
 template <int MODEL> __global__ void ext_dp_kernel(SegArrays, const PairDesc *, const uint32_t *, long long, uint32_t *, int, unsigned long long *, int);
 struct AnibSeg {
     int *pair, *frag, *score, *nident, *mism, *gaps, *qlen;
@@ -63,10 +66,10 @@ __global__ void reduce_kernel(FiltArrays, const int *, int, int, b200ani_anim_re
 
 static const char *kStageNames[B200ANI_N_STAGES] = {"index", "seed", "sort", "link", "gap_dp", "label", "ext_dp", "filter", "reduce", "total",
                                                     "ext_dp_kernel", "seed_extend", "prepass", "bridge", "pack", "tetra_count", "tetra_total", "tetra_corr_total",
-                                                    "", "", "", "", "", ""};
+                                                    "words", "", "", "", "", ""};
 static const char *kCounterNames[B200ANI_N_STAGES] = {"probes", "seed_hits", "anchors", "links", "cut_links", "segments", "gap_cells", "ext_cells",
                                                       "ext_tiles", "alignments", "launches", "gap_tasks", "pairs", "ext_dp_launches", "gap_dp_launches", "seed_launches",
-                                                      "junctions", "box_cells", "", "", "", "", "", ""};
+                                                      "junctions", "box_cells", "word_hits", "word_anchors", "", "", "", ""};
 
 constexpr int MAX_BATCH_PAIRS = 2560;
 constexpr int64_t ANCHOR_CAP_DEFAULT = 96ll << 20;  // anchors of one batch (overridable: B200ANI_ANCHOR_CAP, used by the batch-split test)
@@ -240,7 +243,7 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
     if (W->dp_mu) dp_lock = std::unique_lock<std::mutex>(*W->dp_mu, std::defer_lock);
     // ---- pair descriptors
     std::vector<PairDesc> hp(nb + 1);  // + sentinel
-    int64_t n_probes = 0, n_chunks = 0;
+    int64_t n_probes = 0, n_chunks = 0, n_wtiles = 0;
     for (int p = 0; p < nb; ++p) {
         const Genome &R = ctx->genomes[pairs[2 * p]], &Q = ctx->genomes[pairs[2 * p + 1]];
         const MinimizerIndex *Ri = anib ? R.index_b : R.index, *Qi = anib ? Q.index_b : Q.index;
@@ -263,11 +266,15 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
         d.q_fbase = anib ? Q.d_fbase : nullptr;
         d.fragsize = anib ? fragsize : 0;
         d.q_nfrags = anib ? Q.n_frags : 0;
+        d.r_woff = anib ? Ri->d_woff : nullptr; d.r_went = anib ? Ri->d_went : nullptr; d.q_wover = anib ? Qi->d_wover : nullptr;
+        d.wtile_base = n_wtiles;
         if (!second) { n_probes += Qi->n_mini; n_chunks += ceil_div(Qi->n_mini, SEED_PROBE_CHUNK); }
+        if (!second && anib) n_wtiles += 2 * ceil_div(Q.n_pos, WORD_TILE);  // both strands of the query
     }
     hp[nb] = hp[nb - 1];
     hp[nb].probe_base = n_probes;  // sentinel: end of the last pair's probe range
     hp[nb].chunk_base = n_chunks;
+    hp[nb].wtile_base = n_wtiles;
     hp[nb].mirror = -1;
     if (n_probes >= (1ll << 32) && nb > 1) return 1;  // probe indices are 32-bit: split the batch
     CK(cudaMemcpyAsync(W->d_pairs, hp.data(), sizeof(PairDesc) * (nb + 1), cudaMemcpyHostToDevice, st));
@@ -309,8 +316,19 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
         LAUNCHED(1);
     }
     T1(ST_SEEDX);
+    if (n_wtiles) {  // ---- ANIb word anchors: appended to the same anchor list (a match both stages find is one record after the sort)
+        T0(ST_WORDS);
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, word_probe_kernel, 256, 0));
+        const int blocks = (int)std::min<int64_t>(n_wtiles, (int64_t)ctx->sm_count * std::max(per_sm, 1));
+        word_probe_kernel<<<blocks, 256, 0, st>>>(W->d_pairs, nb, n_wtiles, W->keys_a, W->vals_a, W->counters, (unsigned long long)ANCHOR_CAP, W->counters + 14);
+        LAUNCHED(1);
+        T1(ST_WORDS);
+    }
     CK(cudaMemcpyAsync(hc, W->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    W->hcount[CT_WORDHITS] += (int64_t)hc[14];
+    W->hcount[CT_WORDANCHORS] += (int64_t)hc[15];
     const int64_t n_raw = (int64_t)hc[0];
     W->last_fill = std::max((double)n_raw / (double)ANCHOR_CAP, (double)n_hits / (double)HIT_CAP);
     if (n_raw > ANCHOR_CAP) return 1;  // caller splits the batch
@@ -508,6 +526,14 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
             if (anib) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ext_dp_kernel<1>, 128, 0));
             else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ext_dp_kernel<0>, 128, 0));
             long long n_cur = 2 * n_seg;
+            if (anib) {  // tickets in descending order of first-tile rows (see ext_task_rows_kernel)
+                uint32_t *rows_key = nullptr, *rows_key2 = nullptr, *ids = nullptr;
+                DA(rows_key, 2 * n_seg); DA(rows_key2, 2 * n_seg); DA(ids, 2 * n_seg);
+                ext_task_rows_kernel<1><<<GRID(2 * n_seg)>>>(S, rows_key, ids);
+                LAUNCHED(1);
+                size_t tb = W->cub_bytes;
+                cub::DeviceRadixSort::SortPairsDescending(W->cub_tmp, tb, rows_key, rows_key2, ids, ext_list[0], 2 * n_seg, 0, 10, st);
+            }
             // the first EXT_SHORT_ROUNDS launches hand out EXT_TILES_PER_LAUNCH tiles per task; by then only a few long crawls
             // are left whose launches are pure latency (8 tiles in sequence), so one last launch lets them run to the tile cap
             int tiles_done = 0;
@@ -527,7 +553,7 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
                 int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * dp_per_sm, ceil_div(n_cur, 128));
                 CK(cudaEventRecord(W->kev[2 * n_ext_launch], st));
                 if (anib)
-                    ext_dp_kernel<1><<<(unsigned)blocks, 128, 0, st>>>(S, W->d_pairs, round ? ext_list[round & 1] : nullptr, n_cur, ext_list[(round + 1) & 1],
+                    ext_dp_kernel<1><<<(unsigned)blocks, 128, 0, st>>>(S, W->d_pairs, ext_list[round & 1], n_cur, ext_list[(round + 1) & 1],
                                                                       tiles_now, W->counters + 6, 1);
                 else
                     ext_dp_kernel<0><<<(unsigned)blocks, 128, 0, st>>>(S, W->d_pairs, round ? ext_list[round & 1] : nullptr, n_cur, ext_list[(round + 1) & 1],
@@ -851,10 +877,20 @@ static int prepare(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, bool anib)
         if (g.n_contigs >= 65535) FAIL(B200ANI_ERR_CAPACITY, "anim: genomes with >= 65535 records are not supported");
         if (!index_valid(anib ? g.index_b : g.index, maxocc) && !seen[pairs[i]]) { seen[pairs[i]] = 1; todo.push_back(&g); }
     }
-    const bool any = !todo.empty();
     CK(cudaEventRecord(ctx->ev_prof[0], st));
     int rc = build_indexes(ctx, todo, maxocc, anib);
     if (rc) return rc;
+    bool any = !todo.empty();
+    if (anib) {  // the word index rides on the ANIb seed index
+        std::vector<Genome *> wtodo;
+        std::fill(seen.begin(), seen.end(), 0);
+        for (int64_t i = 0; i < 2 * m; ++i) {
+            Genome &g = ctx->genomes[pairs[i]];
+            if (!g.index_b->words_valid && !seen[pairs[i]]) { seen[pairs[i]] = 1; wtodo.push_back(&g); }
+        }
+        any = any || !wtodo.empty();
+        if ((rc = build_word_indexes(ctx, wtodo))) return rc;
+    }
     CK(cudaEventRecord(ctx->ev_prof[1], st));
     CK(cudaStreamSynchronize(st));
     if (any) {
@@ -886,6 +922,7 @@ static int ensure_fragments(b200ani_ctx *ctx, Genome &g, int fragsize) {
 static int run_call(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int maxmatch, int nofilter, int fragsize, void *out, RowDump *dump, std::vector<int64_t> *order) {
     const bool anib = fragsize > 0;
     for (int k = 0; k < ST_FIRST_NON_ANIM; ++k) ctx->stage_ms[k] = 0;  // the pack / TETRA slots belong to their own entry points
+    ctx->stage_ms[ST_WORDS] = 0;
     memset(ctx->counters, 0, sizeof ctx->counters);
     if (anib && (fragsize < AN_TILE || fragsize > 100000)) FAIL(B200ANI_ERR_ARG, "anib: fragment size out of range");
     CK(cudaSetDevice(ctx->device));
@@ -948,6 +985,7 @@ const char *b200ani_stage_name(int i) {
 int b200ani_index_build(b200ani_ctx *ctx, const int32_t *genome_ids, int n) {
     if (!ctx || !genome_ids || n <= 0) return B200ANI_ERR_ARG;
     for (int k = 0; k < ST_FIRST_NON_ANIM; ++k) ctx->stage_ms[k] = 0;
+    ctx->stage_ms[ST_WORDS] = 0;
     std::vector<int32_t> pr(2 * (size_t)n);
     for (int i = 0; i < n; ++i) pr[2 * i] = pr[2 * i + 1] = genome_ids[i];
     return prepare(ctx, pr.data(), n, false);

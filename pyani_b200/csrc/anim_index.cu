@@ -165,8 +165,10 @@ __global__ void split_bypos_kernel(const uint64_t *__restrict__ key2s, const uin
     g.posflag_out[o] = vals[src];
 }
 
+void free_word_index(MinimizerIndex *ix, cudaStream_t st);  // anib_words.cu
 void free_index(MinimizerIndex *ix, cudaStream_t st) {
     if (!ix) return;
+    free_word_index(ix, st);
     if (!ix->external) {
         cudaFreeAsync(ix->d_kmer, st);
         cudaFreeAsync(ix->d_posflag, st);
@@ -179,6 +181,7 @@ void free_index(MinimizerIndex *ix, cudaStream_t st) {
 void invalidate_index(MinimizerIndex *ix) {
     if (!ix) return;
     ix->valid = false;
+    ix->words_valid = false;
     if (ix->external) {
         ix->external = false;
         ix->d_kmer = ix->d_posflag = nullptr; ix->d_table = nullptr; ix->d_bitmap = nullptr;
@@ -315,6 +318,7 @@ int build_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo, int maxocc, boo
             hd[k].bits = bits; hd[k].out0 = n_kept;
             n_kept += h_nu;
             ix->valid = true;
+            ix->words_valid = false;  // the buffers may come from another genome
             ix->maxocc = maxocc;
             ix->k = k; ix->w = w;
         }

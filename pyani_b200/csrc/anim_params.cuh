@@ -35,12 +35,16 @@
 #define AB_W 2
 #define AB_MINLEN 14
 #define AB_SCREEN_W 28
-#define AB_SCREEN_MIN 12
+#define AB_SCREEN_MIN 20
 #define AB_SCREEN_LEN 64
 #define AB_SCREEN_DROP 20
 #define AB_BRIDGE_GAP 250
 #define AB_BRIDGE_DD 120
 #define AB_MINPIECE 11
+#define AB_WORD 11
+#define AB_WORD_FLANK 16
+#define AB_WORD_MIN 14
+#define AB_WORD_MAXOCC 16
 #define AB_FRAGSIZE 1020
 #define AN_PACK 4096
 #define AN_NEG (-(1 << 29))

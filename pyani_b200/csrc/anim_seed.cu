@@ -308,6 +308,139 @@ __global__ void __launch_bounds__(256) seed_extend_kernel(const PairDesc *__rest
     }
 }
 
+// ---- ANIb word anchors (blastn's 11-mer words + ungapped extension test; specification: oracle/oracle_anim.c "word anchors")
+// 32 bases of a view starting at any x: positions outside [0, n) come back masked
+__device__ __forceinline__ uint64_t chunk_any(const SeqView &v, int64_t x, uint32_t &mk) {
+    if (x >= 0 && x + 32 <= v.n) return view_chunk(v, x, mk);
+    uint64_t c = 0;
+    uint32_t m = 0;
+#pragma unroll 1
+    for (int k = 0; k < 32; ++k) {
+        const int code = view_code(v, x + k);
+        if (code > 3) m |= 1u << k; else c |= (uint64_t)code << (2 * k);
+    }
+    mk = m;
+    return c;
+}
+__device__ __forceinline__ uint32_t word_revcomp(uint32_t w) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < AB_WORD; ++i) { r = (r << 2) | (3u - (w & 3u)); w >>= 2; }
+    return r;
+}
+__device__ __forceinline__ uint64_t rev2_words(uint64_t x) {  // reverse the order of 32 packed bases (no complement)
+    uint64_t y = __brevll(x);
+    return ((y & 0x5555555555555555ull) << 1) | ((y >> 1) & 0x5555555555555555ull);
+}
+// The word test from the sequences themselves (windows with a masked base or at a sequence end): is the word at (r0, q0) the
+// leftmost / rightmost of its exact match, and what does its diagonal score over the word and AB_WORD_FLANK bases to either
+// side, each flank ending at the first masked base or sequence end
+__device__ __noinline__ int word_eval_slow(const SeqView &R, const SeqView &Q, int64_t r0, int64_t q0, bool &leftmost, bool &rightmost) {
+    const int pa = view_code(R, r0 - 1), pb = view_code(Q, q0 - 1), na = view_code(R, r0 + AB_WORD), nb = view_code(Q, q0 + AB_WORD);
+    leftmost = !(pa < 4 && pa == pb);
+    rightmost = !(na < 4 && na == nb);
+    int sc = AB_MATCH * AB_WORD;
+    for (int side = 0; side < 2; ++side)
+        for (int x = 0; x < AB_WORD_FLANK; ++x) {
+            const int a = view_code(R, side ? r0 + AB_WORD + x : r0 - 1 - x), b = view_code(Q, side ? q0 + AB_WORD + x : q0 - 1 - x);
+            if (a > 3 || b > 3) break;
+            sc += a == b ? AB_MATCH : -AB_MISMATCH;
+        }
+    return sc;
+}
+
+// One block step = one tile of WORD_TILE query positions of one strand of one pair (tiles never leave their pair:
+// pairs[p].wtile_base); a thread walks 16 consecutive positions of the strand's view with the 43-base windows around them in
+// registers: word -> the subject's entry list -> per entry ONE 16-byte load brings the occurrence's position and its own
+// window, so the test (at most 14 mismatches among the 32 flank bases) and the leftmost / rightmost question are a few logic
+// ops and a chance hit never touches the subject's sequence.  Accepted words extend to their maximal match and become
+// anchors (clipped to the query's fragments).  The opposite direction of the pair is fed from the same pass: on the forward
+// strand it sees the same leftmost word; on the reverse strand ITS leftmost word is this direction's rightmost one.
+// Bound: L2 random access (8 B of group starts per position, 16 B per occurrence); the query side streams.
+__global__ void __launch_bounds__(256) word_probe_kernel(const PairDesc *__restrict__ pairs, int n_pairs, int64_t n_tiles, uint64_t *__restrict__ keys,
+                                                         uint64_t *__restrict__ vals, unsigned long long *__restrict__ n_anchors, unsigned long long cap,
+                                                         unsigned long long *__restrict__ wcount /*0: occurrences looked at, 1: words accepted*/) {
+    constexpr uint64_t EVEN = 0x5555555555555555ull;
+    constexpr int WIN = 2 * AB_WORD_FLANK + AB_WORD;                                   // 43 bases
+    constexpr int MAXMM = (AB_MATCH * (AB_WORD + 2 * AB_WORD_FLANK) - AB_WORD_MIN) / (AB_MATCH + AB_MISMATCH);  // mismatches the flanks may hold
+    __shared__ AnchorStage stage;
+    if (threadIdx.x == 0) stage.n = 0;
+    __syncthreads();
+    unsigned long long hits = 0, accepted = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int lo = 0, hi = n_pairs;  // the LAST pair with wtile_base <= tile (pairs without tiles of their own share their successor's base)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (pairs[mid].wtile_base <= tile) lo = mid; else hi = mid;
+        }
+        const PairDesc &P = pairs[lo];
+        const int64_t per_strand = ((int64_t)P.q_npos + WORD_TILE - 1) / WORD_TILE, lt = tile - P.wtile_base;
+        const int strand = lt >= per_strand;
+        const int64_t p0 = (lt - (int64_t)strand * per_strand) * WORD_TILE + (int64_t)threadIdx.x * 16;
+        if (p0 < P.q_npos) {
+            SeqView R{P.r_seq, P.r_mask, P.r_npos, 0}, Q{P.q_seq, P.q_mask, P.q_npos, strand};
+            uint32_t ma, mb;
+            const uint64_t ca = chunk_any(Q, p0 - AB_WORD_FLANK, ma), cb = chunk_any(Q, p0 - AB_WORD_FLANK + 32, mb);  // view bases p0-16 .. p0+47
+            const uint64_t cm = (uint64_t)ma | ((uint64_t)mb << 32);
+            for (int i = 0; i < 16; ++i) {
+                // window of position p0 + i: view bases [p0 + i - 16, p0 + i + 27) = bases i .. i+42 of the two chunks
+                const uint64_t wm = (cm >> i) & ((1ull << WIN) - 1ull);
+                if ((wm >> AB_WORD_FLANK) & ((1ull << AB_WORD) - 1ull)) continue;  // the word itself holds a masked base / leaves the view
+                const uint64_t wlo = i ? (ca >> (2 * i)) | (cb << (64 - 2 * i)) : ca;
+                const uint32_t whi = (uint32_t)(cb >> (2 * i)) & ((1u << (2 * AB_WORD)) - 1u);
+                const uint32_t w = (uint32_t)(rev2_words(wlo) >> (2 * (32 - AB_WORD_FLANK - AB_WORD))) & (AB_NWORDS - 1u);
+                const uint32_t o0 = __ldg(P.r_woff + w), o1 = __ldg(P.r_woff + w + 1);
+                if (o1 == o0 || o1 - o0 > AB_WORD_MAXOCC) continue;
+                const uint32_t wq = strand ? word_revcomp(w) : w;  // the word as the query's own (forward) index holds it
+                if ((__ldg(P.q_wover + (wq >> 5)) >> (wq & 31u)) & 1u) continue;
+                const int64_t q0 = p0 + i;
+                for (uint32_t t = o0; t < o1; ++t) {
+                    const uint4 e = __ldg(P.r_went + t);
+                    const int64_t r0 = e.x & 0x7fffffffu;
+                    ++hits;
+                    bool leftmost, rightmost;
+                    int sc;
+                    if ((e.x >> 31) | (wm != 0)) {
+                        sc = word_eval_slow(R, Q, r0, q0, leftmost, rightmost);
+                    } else {
+                        const uint64_t dlo = wlo ^ ((uint64_t)e.z | ((uint64_t)e.w << 32));
+                        const uint32_t dhi = whi ^ e.y;
+                        const uint64_t mlo = (dlo | (dlo >> 1)) & EVEN;
+                        const uint32_t mhi = (dhi | (dhi >> 1)) & 0x155555u;
+                        // window bases 0..15 = left flank, 16..26 = the word, 27..31 (mlo) and 32..42 (mhi) = right flank
+                        const int mm = __popc((uint32_t)mlo) + __popcll(mlo >> (2 * (AB_WORD_FLANK + AB_WORD))) + __popc(mhi);
+                        leftmost = (mlo >> (2 * (AB_WORD_FLANK - 1))) & 1ull;
+                        rightmost = (mlo >> (2 * (AB_WORD_FLANK + AB_WORD))) & 1ull;
+                        sc = mm <= MAXMM ? AB_WORD_MIN : AB_WORD_MIN - 1;
+                    }
+                    if (sc < AB_WORD_MIN) continue;
+                    const bool to_mirror = P.mirror >= 0 && (strand ? rightmost : leftmost);
+                    if (!leftmost && !to_mirror) continue;
+                    ++accepted;
+                    if (leftmost) {
+                        const int64_t len = AB_WORD + match_right(R, Q, r0 + AB_WORD, q0 + AB_WORD);
+                        emit_anchor(stage, P, lo, strand, r0, q0, len, keys, vals, n_anchors, cap);
+                        if (to_mirror && !strand) emit_anchor(stage, pairs[P.mirror], P.mirror, 0, q0, r0, len, keys, vals, n_anchors, cap);
+                    }
+                    if (to_mirror && strand) {  // the opposite direction's leftmost word: its match ends here and starts l bases to the left
+                        const int64_t l = match_left(R, Q, r0, q0), len = AB_WORD + l, rs = r0 - l, qs = q0 - l;
+                        emit_anchor(stage, pairs[P.mirror], P.mirror, 1, (int64_t)P.q_npos - qs - len, (int64_t)P.r_npos - rs - len, len, keys, vals, n_anchors, cap);
+                    }
+                }
+            }
+        }
+        flush_stage(stage, keys, vals, n_anchors, cap);
+    }
+    for (int off = 16; off; off >>= 1) {
+        hits += __shfl_down_sync(0xffffffffu, hits, off);
+        accepted += __shfl_down_sync(0xffffffffu, accepted, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (hits) atomicAdd(&wcount[0], hits);
+        if (accepted) atomicAdd(&wcount[1], accepted);
+    }
+}
+
 // After the radix sort by key: order runs of equal keys by value (rare: two matches starting at the same
 // reference position), then flag the first of each group of identical (key, value).
 __global__ void tie_fix_kernel(uint64_t *__restrict__ keys, uint64_t *__restrict__ vals, int64_t n) {

@@ -42,9 +42,9 @@ struct Genome {
 // stage / counter slots of b200ani_last_profile
 enum {
     ST_INDEX = 0, ST_SEED, ST_SORT, ST_LINK, ST_GAPDP, ST_LABEL, ST_EXTDP, ST_FILTER, ST_REDUCE, ST_TOTAL, ST_EXTK, ST_SEEDX, ST_PREPASS, ST_BRIDGE,
-    ST_PACK, ST_TETRA_COUNT, ST_TETRA_TOTAL, ST_TETRA_CORR, ST_FIRST_NON_ANIM = ST_PACK,
+    ST_PACK, ST_TETRA_COUNT, ST_TETRA_TOTAL, ST_TETRA_CORR, ST_WORDS, ST_FIRST_NON_ANIM = ST_PACK,
     CT_PROBES = 0, CT_SEEDHITS, CT_ANCHORS, CT_LINKS, CT_CUTS, CT_SEGMENTS, CT_GAPCELLS, CT_EXTCELLS, CT_EXTTILES, CT_ALIGNMENTS, CT_LAUNCHES,
-    CT_GAPTASKS, CT_PAIRS, CT_EXTLAUNCH, CT_GAPLAUNCH, CT_SEEDLAUNCH, CT_JUNCTIONS, CT_BOXCELLS
+    CT_GAPTASKS, CT_PAIRS, CT_EXTLAUNCH, CT_GAPLAUNCH, CT_SEEDLAUNCH, CT_JUNCTIONS, CT_BOXCELLS, CT_WORDHITS, CT_WORDANCHORS
 };
 
 struct b200ani_ctx {

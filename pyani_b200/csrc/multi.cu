@@ -42,7 +42,7 @@ struct NcclApi {
     }
 };
 constexpr int NCCL_UINT8 = 1;  // ncclUint8 (nccl.h)
-constexpr int DEAL_CHUNK = 64;  // unordered genome pairs per dealt chunk (pyani_b200/dist.py:deal)
+constexpr int DEAL_CHUNK = 1;   // unordered genome pairs per dealt chunk (pyani_b200/dist.py:deal)
 }  // namespace
 
 struct b200ani_mctx {

@@ -3,9 +3,11 @@ all-gather of the fixed-size per-pair result structs at the end.
 
 The reference distributes the same independent units as one OS process per pair
 (run_multiprocessing.py:130-144) or SGE array tasks (run_sge.py:87-112) and exchanges results through
-files; here every rank holds all packed genomes (tiny next to 180 GB of HBM), takes a contiguous,
-cost-balanced block of the pair list and contributes its 48-byte result structs to a single
-``all_gather`` so that every rank ends up with the full matrices.
+files; here every rank holds all packed genomes (tiny next to 180 GB of HBM), is dealt its share of the
+pair list (:func:`deal`: unordered genome pairs round-robin in walk order) and contributes its 48-byte
+result structs to a single ``all_gather`` so that every rank ends up with the full matrices.  Optionally
+(:func:`share_indexes`) the seed indexes are built once across the ranks -- each rank builds those of 1/N
+of the genomes and one all-gather of the index slab hands every rank all of them.
 """
 from __future__ import annotations
 
@@ -39,13 +41,17 @@ def partition(costs: np.ndarray, world: int) -> List[Tuple[int, int]]:
     return [(int(bounds[r]), int(bounds[r + 1])) for r in range(world)]
 
 
-def deal(pairs: np.ndarray, world: int, chunk: int = 64) -> List[np.ndarray]:
+def deal(pairs: np.ndarray, world: int, chunk: int = 1) -> List[np.ndarray]:
     """Which rows of ``pairs`` each rank computes: the directed pairs are grouped by unordered genome pair (both directions
     share one seed pass on the device, so they stay together), the groups sorted by (lower id, higher id) -- the order in
     which the engine walks them, one reference table hot in L2 after the other -- are cut into chunks of ``chunk`` groups,
     and the chunks are dealt round-robin.  Costly and cheap comparisons (within- and between-clade pairs differ several-fold
-    in alignment work, and genome ids are normally grouped by clade) are thereby spread evenly without a cost model;
-    every rank can compute every rank's share, so nothing but the results is ever exchanged.
+    in alignment work, and genome ids are normally grouped by clade) are thereby spread evenly without a cost model.  The
+    default deals single genome pairs: the costly pairs of one genome are its <= ~10 clade mates, which sit next to each
+    other in walk order, so any chunk longer than that hands them to one rank as a lump (8 ranks, 500 genomes in clades of
+    10: 3.5 % slowest-rank excess measured with chunks of 64, 0.2 % expected with 1); a rank still meets every reference's
+    partners consecutively (runs of ~n/2 partners per genome, every world-th one is its own), so the table stays hot.
+    Every rank can compute every rank's share, so nothing but the results is ever exchanged.
     -> list of index arrays (ascending walk order), one per rank, together a partition of range(len(pairs))."""
     p = np.asarray(pairs).reshape(-1, 2)
     lo, hi = p.min(axis=1).astype(np.int64), p.max(axis=1).astype(np.int64)
@@ -101,7 +107,7 @@ def _sharded(run, pairs: np.ndarray, rank: int, world: int, dtype, device, group
 
 
 def anim_sharded(engine, pairs: np.ndarray, genome_lengths: Sequence[int], rank: int, world: int, *, maxmatch=False,
-                 nofilter=False, device=None, group=None, compute=None, chunk: int = 64) -> np.ndarray:
+                 nofilter=False, device=None, group=None, compute=None, chunk: int = 1) -> np.ndarray:
     """Run this rank's share of ``pairs`` (see :func:`deal`) on ``engine`` -- every rank holds all genomes -- and
     all-gather the full result array in the order of ``pairs``.  ``genome_lengths`` is unused by the dealing plan and kept
     for callers that balance contiguous blocks with :func:`partition` instead.
@@ -112,7 +118,7 @@ def anim_sharded(engine, pairs: np.ndarray, genome_lengths: Sequence[int], rank:
 
 
 def anib_sharded(engine, pairs: np.ndarray, genome_lengths: Sequence[int], rank: int, world: int, *, fragsize: int = 1020,
-                 device=None, group=None, compute=None, chunk: int = 64) -> np.ndarray:
+                 device=None, group=None, compute=None, chunk: int = 1) -> np.ndarray:
     """ANIb counterpart of :func:`anim_sharded`: pairs are (query, subject), the gathered structs are the 40-byte ANIb
     results."""
     fn = compute if compute is not None else (lambda p: engine.anib(p, fragsize=fragsize))

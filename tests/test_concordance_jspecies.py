@@ -8,9 +8,11 @@ oracle/_ref/fixtures/concordance by tests/golden/make_golden.py (git-ignored, sh
 Where this engine stands against those targets (CPU oracle == CUDA engine, bit for bit):
   TETRA  within 1e-3 of JSpecies                                   (reference tolerance 0.1: met)
   ANIm   98.31 vs 98.19, 84.23 vs 84.11/84.09, 84.35 vs 84.53/84.55  (reference tolerance 0.1: NOT met, worst 0.20)
-  ANIb   98.28..98.33 vs 98.17/98.19                                (tolerance 0.2: met)
-         73.3..73.5 vs 68.7..68.8 on the two distant pairs          (tolerance 5: met, +4.5..+4.7 -- exact-match
-         seeds >= 14 find only the better-conserved fragments at < 70 % identity; blastn's 11-mer words find more)
+  ANIb   98.25..98.30 vs 98.17/98.19                                (tolerance 0.2: met)
+         73.5 vs 68.7..68.8 on the two distant pairs                (tolerance 5: met, +4.7..+4.85.  The reference keeps that
+         tolerance wide because JSpecies ran legacy BLAST and "the results can be quite different" from BLAST+ below 90 %,
+         test_concordance.py:119-127; with the 11-mer word anchors 25 % more fragments pass here than with unique exact
+         seeds >= 14 alone, at the same mean identity)
 The assertions below pin the current deviations (so they can only shrink) and state the reference tolerance next
 to each; the unmet one (ANIm) is also written as an xfail test so the gap shows up in every test report.
 """
@@ -156,8 +158,8 @@ def test_concordance_gpu(engine, arrays, ogenomes, gids):
     # ANIb
     resb = engine.anib(gp)
     pid = {p: int(x["pid_milli_sum"]) / max(int(x["n_pass"]), 1) / 1000 for p, x in zip(pairs, resb)}
-    for (q, s), x in zip(pairs, resb):
-        want, _, _ = oracle.anib_pair(ogenomes[q], ogenomes[s])
+    wants = oracle.anib_results_mt([ogenomes[n] for n in names], [(names.index(q), names.index(s)) for q, s in pairs])
+    for (q, s), x, want in zip(pairs, resb, wants):
         for f in ("aln_length", "sim_errs", "pid_milli_sum", "n_frags", "n_pass"):
             assert int(x[f]) == want[f], (q, s, f)
     hi, lo = anib_devs(lambda q, s: pid[(q, s)])
@@ -185,6 +187,8 @@ def test_caulobacter_table_oracle():
     z = np.array([oracle.tetra_zscores(*oracle.tetra_counts(*arrays[n]))[0] for n in names])
     corr = oracle.tetra_corr(z)
     worst = {"anim": 0.0, "anib_hi": 0.0, "anib_lo": 0.0, "tetra": 0.0}
+    bpairs = [(i, j) for i in range(len(names)) for j in range(len(names)) if i != j]
+    anib = dict(zip(bpairs, oracle.anib_results_mt([og[n] for n in names], bpairs)))
     for i, a in enumerate(names):
         for j, b in enumerate(names):
             if a == b:
@@ -192,7 +196,7 @@ def test_caulobacter_table_oracle():
             res, _, _ = oracle.anim_pair(og[a], og[b])
             idy = 100 * res["sum_weighted"] / res["sum_aligned"]
             worst["anim"] = max(worst["anim"], max(abs(idy - x) for x in target4("ANIm", a, b)))
-            rb, _, _ = oracle.anib_pair(og[a], og[b])
+            rb = anib[(i, j)]
             pid = rb["pid_milli_sum"] / rb["n_pass"] / 1000
             tb = target4("ANIb", a, b)
             k = "anib_hi" if min(tb) > 90 else "anib_lo"
