@@ -157,6 +157,8 @@ typedef struct {
 
 /* All m directed pairs (pairs[2*i] = QUERY genome id whose fragments are aligned, pairs[2*i+1] = SUBJECT id).
  * Replaces, per pair, makeblastdb + blastn (anib.py:378-391,451-471) and anib.parse_blast_tab (anib.py:569-667).
+ * Device memory: besides the packed genome, every genome that takes part gets a 13-mer seed index (~14 bytes per base) and an
+ * 11-mer word index (16 bytes per base + 17 MB), built on first use and kept until the genome is released: ~160 MB per 5 Mb genome.
  * fragsize: pyani_config.FRAGSIZE = 1020. */
 int b200ani_anib(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int fragsize, b200ani_anib_result *out);
 

@@ -23,16 +23,22 @@ struct MinimizerIndex {
     uint64_t *d_table = nullptr;    // open addressing, slot = kmer << 32 | posflag, empty = ~0
     uint32_t *d_bitmap = nullptr;   // presence filter, 2^(table_bits+3) bits: answers most misses from L2
     uint32_t table_bits = 0;
-    // ANIb word index (anib_words.cu; always owned by this context, also next to adopted seed arrays): every forward position
-    // whose AB_WORD-mer is free of masked bases, grouped by word value (first base most significant), ascending inside a group.
-    // An entry carries the position AND the 43 bases around it, so a chance hit is rejected without touching the sequence:
-    //   x = position | slow << 31 (slow: the window holds a masked base or leaves the genome -> evaluate from the sequence)
-    //   z | w << 32 = window bases 0..31, y = window bases 32..42 (2 bits each, base i of the window = genome base position - 16 + i)
+    // ANIb word index (anib_words.cu; always owned by this context, also next to adopted seed arrays): one entry per forward
+    // position whose AB_WORD-mer is free of masked bases, sorted by the CANONICAL word (the smaller of the word and its reverse
+    // complement, first base most significant; odd length: never equal), ascending position inside a group.  The same list
+    // serves a genome as subject and as query: walking the query's entries in list order makes the subject's groups come up in
+    // order too, so both sides stream.  Entries of one group whose words have the same orientation match on the forward strand,
+    // the others on the reverse strand.  An entry carries the 43 bases around its position, so a chance hit is rejected without
+    // touching either sequence:
+    //   x = position (30 bits) | slow << 31 (the window holds a masked base or leaves the genome -> evaluate from the sequences);
+    //       0xffffffff = unused tail entry
+    //   y = window bases 32..42 (22 bits) | over << 30 (the word occurs more than AB_WORD_MAXOCC times in this genome)
+    //       | orientation << 31 (1: the reverse complement is the canonical form)
+    //   z | w << 32 = window bases 0..31 (2 bits each; base i of the window = genome base position - 16 + i)
     bool words_valid = false;
     int64_t cap_went = 0;
     uint32_t *d_woff = nullptr;     // 4^AB_WORD + 1 group starts into d_went
     uint4 *d_went = nullptr;
-    uint32_t *d_wover = nullptr;    // 1 bit per word value: more than AB_WORD_MAXOCC occurrences
 };
 static_assert(AB_WORD == 11 && AB_WORD_FLANK == 16, "the word window is 16 + 11 + 16 = 43 bases: 64 + 22 bits");
 constexpr uint32_t AB_NWORDS = 1u << (2 * AB_WORD);
@@ -55,12 +61,12 @@ struct PairDesc {
     const uint32_t *q_fbase;
     int32_t fragsize;  // 0 = ANIm (no fragments)
     uint32_t q_nfrags;
-    // ANIb only: word index of the subject, over-represented words of the query, first tile of this pair in word_probe_kernel's grid
-    const uint32_t *r_woff, *q_wover;
-    const uint4 *r_went;
+    // ANIb only: word index of the subject, word entries of the query, first tile of this pair in word_probe_kernel's grid
+    const uint32_t *r_woff;
+    const uint4 *r_went, *q_went;
     int64_t wtile_base;
 };
-constexpr int WORD_TILE = 4096;  // query positions per block step of word_probe_kernel (256 threads x 16)
+constexpr int WORD_TILE = 2048;  // query entries per block step of word_probe_kernel (256 threads x 8)
 
 __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;

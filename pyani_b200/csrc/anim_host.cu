@@ -266,10 +266,10 @@ static int run_batch_impl(b200ani_ctx *ctx, AnimWorkspace *W, const int32_t *pai
         d.q_fbase = anib ? Q.d_fbase : nullptr;
         d.fragsize = anib ? fragsize : 0;
         d.q_nfrags = anib ? Q.n_frags : 0;
-        d.r_woff = anib ? Ri->d_woff : nullptr; d.r_went = anib ? Ri->d_went : nullptr; d.q_wover = anib ? Qi->d_wover : nullptr;
+        d.r_woff = anib ? Ri->d_woff : nullptr; d.r_went = anib ? Ri->d_went : nullptr; d.q_went = anib ? Qi->d_went : nullptr;
         d.wtile_base = n_wtiles;
         if (!second) { n_probes += Qi->n_mini; n_chunks += ceil_div(Qi->n_mini, SEED_PROBE_CHUNK); }
-        if (!second && anib) n_wtiles += 2 * ceil_div(Q.n_pos, WORD_TILE);  // both strands of the query
+        if (!second && anib) n_wtiles += ceil_div(Q.n_pos, WORD_TILE);  // one entry per query position; both strands in one pass
     }
     hp[nb] = hp[nb - 1];
     hp[nb].probe_base = n_probes;  // sentinel: end of the last pair's probe range

@@ -349,19 +349,21 @@ __device__ __noinline__ int word_eval_slow(const SeqView &R, const SeqView &Q, i
     return sc;
 }
 
-// One block step = one tile of WORD_TILE query positions of one strand of one pair (tiles never leave their pair:
-// pairs[p].wtile_base); a thread walks 16 consecutive positions of the strand's view with the 43-base windows around them in
-// registers: word -> the subject's entry list -> per entry ONE 16-byte load brings the occurrence's position and its own
-// window, so the test (at most 14 mismatches among the 32 flank bases) and the leftmost / rightmost question are a few logic
-// ops and a chance hit never touches the subject's sequence.  Accepted words extend to their maximal match and become
-// anchors (clipped to the query's fragments).  The opposite direction of the pair is fed from the same pass: on the forward
-// strand it sees the same leftmost word; on the reverse strand ITS leftmost word is this direction's rightmost one.
-// Bound: L2 random access (8 B of group starts per position, 16 B per occurrence); the query side streams.
+// One block step = one tile of WORD_TILE entries of the query's word list (tiles never leave their pair: pairs[p].wtile_base);
+// a thread takes one query entry at a time -- position, 43-base window, canonical word -- and the subject's group of the same
+// canonical word: because both lists are sorted by it, neighbouring threads read neighbouring group starts and neighbouring
+// subject entries, so the subject's list streams through once per pair instead of being probed at random (the first version
+// walked the query by position: 34 s per 39,800-pair step, bound by random DRAM sectors).  Per subject entry ONE 16-byte load
+// brings the occurrence's position and its own window: equal orientation = forward-strand hit, windows compared as they are;
+// different orientation = reverse-strand hit, the query window reverse-complemented.  The test (at most 14 mismatches among the
+// 32 flank bases) and the leftmost / rightmost question are a few logic ops; a chance hit never touches either sequence.
+// Accepted words extend to their maximal match and become anchors (clipped to the query's fragments).  The opposite direction
+// of the pair is fed from the same pass: on the forward strand it sees the same leftmost word; on the reverse strand ITS
+// leftmost word is this direction's rightmost one.
 __global__ void __launch_bounds__(256) word_probe_kernel(const PairDesc *__restrict__ pairs, int n_pairs, int64_t n_tiles, uint64_t *__restrict__ keys,
                                                          uint64_t *__restrict__ vals, unsigned long long *__restrict__ n_anchors, unsigned long long cap,
                                                          unsigned long long *__restrict__ wcount /*0: occurrences looked at, 1: words accepted*/) {
     constexpr uint64_t EVEN = 0x5555555555555555ull;
-    constexpr int WIN = 2 * AB_WORD_FLANK + AB_WORD;                                   // 43 bases
     constexpr int MAXMM = (AB_MATCH * (AB_WORD + 2 * AB_WORD_FLANK) - AB_WORD_MIN) / (AB_MATCH + AB_MISMATCH);  // mismatches the flanks may hold
     __shared__ AnchorStage stage;
     if (threadIdx.x == 0) stage.n = 0;
@@ -374,58 +376,60 @@ __global__ void __launch_bounds__(256) word_probe_kernel(const PairDesc *__restr
             if (pairs[mid].wtile_base <= tile) lo = mid; else hi = mid;
         }
         const PairDesc &P = pairs[lo];
-        const int64_t per_strand = ((int64_t)P.q_npos + WORD_TILE - 1) / WORD_TILE, lt = tile - P.wtile_base;
-        const int strand = lt >= per_strand;
-        const int64_t p0 = (lt - (int64_t)strand * per_strand) * WORD_TILE + (int64_t)threadIdx.x * 16;
-        if (p0 < P.q_npos) {
-            SeqView R{P.r_seq, P.r_mask, P.r_npos, 0}, Q{P.q_seq, P.q_mask, P.q_npos, strand};
-            uint32_t ma, mb;
-            const uint64_t ca = chunk_any(Q, p0 - AB_WORD_FLANK, ma), cb = chunk_any(Q, p0 - AB_WORD_FLANK + 32, mb);  // view bases p0-16 .. p0+47
-            const uint64_t cm = (uint64_t)ma | ((uint64_t)mb << 32);
-            for (int i = 0; i < 16; ++i) {
-                // window of position p0 + i: view bases [p0 + i - 16, p0 + i + 27) = bases i .. i+42 of the two chunks
-                const uint64_t wm = (cm >> i) & ((1ull << WIN) - 1ull);
-                if ((wm >> AB_WORD_FLANK) & ((1ull << AB_WORD) - 1ull)) continue;  // the word itself holds a masked base / leaves the view
-                const uint64_t wlo = i ? (ca >> (2 * i)) | (cb << (64 - 2 * i)) : ca;
-                const uint32_t whi = (uint32_t)(cb >> (2 * i)) & ((1u << (2 * AB_WORD)) - 1u);
-                const uint32_t w = (uint32_t)(rev2_words(wlo) >> (2 * (32 - AB_WORD_FLANK - AB_WORD))) & (AB_NWORDS - 1u);
-                const uint32_t o0 = __ldg(P.r_woff + w), o1 = __ldg(P.r_woff + w + 1);
-                if (o1 == o0 || o1 - o0 > AB_WORD_MAXOCC) continue;
-                const uint32_t wq = strand ? word_revcomp(w) : w;  // the word as the query's own (forward) index holds it
-                if ((__ldg(P.q_wover + (wq >> 5)) >> (wq & 31u)) & 1u) continue;
-                const int64_t q0 = p0 + i;
-                for (uint32_t t = o0; t < o1; ++t) {
-                    const uint4 e = __ldg(P.r_went + t);
-                    const int64_t r0 = e.x & 0x7fffffffu;
-                    ++hits;
-                    bool leftmost, rightmost;
-                    int sc;
-                    if ((e.x >> 31) | (wm != 0)) {
-                        sc = word_eval_slow(R, Q, r0, q0, leftmost, rightmost);
-                    } else {
-                        const uint64_t dlo = wlo ^ ((uint64_t)e.z | ((uint64_t)e.w << 32));
-                        const uint32_t dhi = whi ^ e.y;
-                        const uint64_t mlo = (dlo | (dlo >> 1)) & EVEN;
-                        const uint32_t mhi = (dhi | (dhi >> 1)) & 0x155555u;
-                        // window bases 0..15 = left flank, 16..26 = the word, 27..31 (mlo) and 32..42 (mhi) = right flank
-                        const int mm = __popc((uint32_t)mlo) + __popcll(mlo >> (2 * (AB_WORD_FLANK + AB_WORD))) + __popc(mhi);
-                        leftmost = (mlo >> (2 * (AB_WORD_FLANK - 1))) & 1ull;
-                        rightmost = (mlo >> (2 * (AB_WORD_FLANK + AB_WORD))) & 1ull;
-                        sc = mm <= MAXMM ? AB_WORD_MIN : AB_WORD_MIN - 1;
-                    }
-                    if (sc < AB_WORD_MIN) continue;
-                    const bool to_mirror = P.mirror >= 0 && (strand ? rightmost : leftmost);
-                    if (!leftmost && !to_mirror) continue;
-                    ++accepted;
-                    if (leftmost) {
-                        const int64_t len = AB_WORD + match_right(R, Q, r0 + AB_WORD, q0 + AB_WORD);
-                        emit_anchor(stage, P, lo, strand, r0, q0, len, keys, vals, n_anchors, cap);
-                        if (to_mirror && !strand) emit_anchor(stage, pairs[P.mirror], P.mirror, 0, q0, r0, len, keys, vals, n_anchors, cap);
-                    }
-                    if (to_mirror && strand) {  // the opposite direction's leftmost word: its match ends here and starts l bases to the left
-                        const int64_t l = match_left(R, Q, r0, q0), len = AB_WORD + l, rs = r0 - l, qs = q0 - l;
-                        emit_anchor(stage, pairs[P.mirror], P.mirror, 1, (int64_t)P.q_npos - qs - len, (int64_t)P.r_npos - rs - len, len, keys, vals, n_anchors, cap);
-                    }
+        const int64_t t0 = (tile - P.wtile_base) * WORD_TILE;
+        const SeqView R{P.r_seq, P.r_mask, P.r_npos, 0};
+        for (int k = 0; k < WORD_TILE / 256; ++k) {
+            const int64_t t = t0 + k * 256 + threadIdx.x;
+            if (t >= P.q_npos) break;
+            const uint4 eq = __ldcs(P.q_went + t);
+            if (eq.x == 0xffffffffu || ((eq.y >> 30) & 1u)) continue;  // unused tail / over-represented in the query
+            const int64_t pq = eq.x & 0x3fffffffu;
+            const uint32_t oq = eq.y >> 31;
+            const uint64_t wlo = (uint64_t)eq.z | ((uint64_t)eq.w << 32);
+            const uint32_t whi = eq.y & (AB_NWORDS - 1u);
+            const uint32_t w = (uint32_t)(rev2_words(wlo) >> (2 * (32 - AB_WORD_FLANK - AB_WORD))) & (AB_NWORDS - 1u);
+            const uint32_t c = oq ? word_revcomp(w) : w;
+            const uint32_t o0 = __ldg(P.r_woff + c), o1 = __ldg(P.r_woff + c + 1);
+            if (o1 == o0) continue;
+            // the query window on the reverse strand: bases in reverse order, complemented
+            const uint64_t ra = rev2_words(~wlo);                                                      // base j = comp(window base 31 - j)
+            const uint64_t rh = rev2_words(~(uint64_t)whi) >> (2 * (32 - AB_WORD));                    // base j = comp(window base 42 - j), j < 11
+            const uint64_t rlo = rh | (ra << (2 * AB_WORD));
+            const uint32_t rhi = (uint32_t)(ra >> (64 - 2 * AB_WORD));
+            for (uint32_t u = o0; u < o1; ++u) {
+                const uint4 e = __ldg(P.r_went + u);
+                if ((e.y >> 30) & 1u) continue;  // over-represented in the subject
+                const int strand = (int)((e.y >> 31) ^ oq);
+                const int64_t r0 = e.x & 0x3fffffffu, q0 = strand ? (int64_t)P.q_npos - AB_WORD - pq : pq;
+                ++hits;
+                const SeqView Q{P.q_seq, P.q_mask, P.q_npos, strand};
+                bool leftmost, rightmost;
+                int sc;
+                if ((e.x | eq.x) >> 31) {
+                    sc = word_eval_slow(R, Q, r0, q0, leftmost, rightmost);
+                } else {
+                    const uint64_t dlo = (strand ? rlo : wlo) ^ ((uint64_t)e.z | ((uint64_t)e.w << 32));
+                    const uint32_t dhi = (strand ? rhi : whi) ^ (e.y & (AB_NWORDS - 1u));
+                    const uint64_t mlo = (dlo | (dlo >> 1)) & EVEN;
+                    const uint32_t mhi = (dhi | (dhi >> 1)) & 0x155555u;
+                    // window bases 0..15 = left flank, 16..26 = the word, 27..31 (mlo) and 32..42 (mhi) = right flank
+                    const int mm = __popc((uint32_t)mlo) + __popcll(mlo >> (2 * (AB_WORD_FLANK + AB_WORD))) + __popc(mhi);
+                    leftmost = (mlo >> (2 * (AB_WORD_FLANK - 1))) & 1ull;
+                    rightmost = (mlo >> (2 * (AB_WORD_FLANK + AB_WORD))) & 1ull;
+                    sc = mm <= MAXMM ? AB_WORD_MIN : AB_WORD_MIN - 1;
+                }
+                if (sc < AB_WORD_MIN) continue;
+                const bool to_mirror = P.mirror >= 0 && (strand ? rightmost : leftmost);
+                if (!leftmost && !to_mirror) continue;
+                ++accepted;
+                if (leftmost) {
+                    const int64_t len = AB_WORD + match_right(R, Q, r0 + AB_WORD, q0 + AB_WORD);
+                    emit_anchor(stage, P, lo, strand, r0, q0, len, keys, vals, n_anchors, cap);
+                    if (to_mirror && !strand) emit_anchor(stage, pairs[P.mirror], P.mirror, 0, q0, r0, len, keys, vals, n_anchors, cap);
+                }
+                if (to_mirror && strand) {  // the opposite direction's leftmost word: its match ends here and starts l bases to the left
+                    const int64_t l = match_left(R, Q, r0, q0), len = AB_WORD + l, rs = r0 - l, qs = q0 - l;
+                    emit_anchor(stage, pairs[P.mirror], P.mirror, 1, (int64_t)P.q_npos - qs - len, (int64_t)P.r_npos - rs - len, len, keys, vals, n_anchors, cap);
                 }
             }
         }
