@@ -76,10 +76,15 @@ __global__ void word_entry_kernel(const uint64_t *__restrict__ seq, const uint32
     SeqView V{seq, mask, (int32_t)n_pos, 0};
     uint32_t ma, mb;
     const uint64_t a = fw_chunk_any(V, p - AB_WORD_FLANK, ma), b = fw_chunk_any(V, p - AB_WORD_FLANK + 32, mb);
-    const uint64_t wm = ((uint64_t)ma | ((uint64_t)mb << 32)) & ((1ull << (2 * AB_WORD_FLANK + AB_WORD)) - 1ull);
+    const uint64_t wm = (uint64_t)ma | ((uint64_t)mb << 32);
+    // how many flank bases next to the word are free of masked bases / inside the genome (0 .. AB_WORD_FLANK)
+    const uint32_t lm = (uint32_t)wm & ((1u << AB_WORD_FLANK) - 1u), rm = (uint32_t)(wm >> (AB_WORD_FLANK + AB_WORD)) & ((1u << AB_WORD_FLANK) - 1u);
+    const uint32_t llen = lm ? (uint32_t)(AB_WORD_FLANK - 1 - (31 - __clz((int)lm))) : AB_WORD_FLANK;
+    const uint32_t rlen = rm ? (uint32_t)(__ffs((int)rm) - 1) : AB_WORD_FLANK;
     const uint32_t w = (uint32_t)(words_rev2(a) >> (2 * (32 - AB_WORD_FLANK - AB_WORD))) & (AB_NWORDS - 1u);  // window bases 16..26
     const uint32_t orient = words_revcomp(w) < w, over = cnt[w] > AB_WORD_MAXOCC;
-    ent[t] = make_uint4((uint32_t)p | (wm ? 0x80000000u : 0u), ((uint32_t)b & (AB_NWORDS - 1u)) | (over << 30) | (orient << 31), (uint32_t)a, (uint32_t)(a >> 32));
+    ent[t] = make_uint4((uint32_t)p | ((rlen >> 3) << 30), ((uint32_t)b & (AB_NWORDS - 1u)) | (llen << 22) | ((rlen & 7u) << 27) | (over << 30) | (orient << 31),
+                        (uint32_t)a, (uint32_t)(a >> 32));
 }
 
 void free_word_index(MinimizerIndex *ix, cudaStream_t st) {
@@ -95,7 +100,7 @@ void free_word_index(MinimizerIndex *ix, cudaStream_t st) {
 // Word indexes of the genomes in `todo` (their ANIb seed index exists).  Scratch: the index workspace of the context.
 int build_word_indexes(b200ani_ctx *ctx, std::vector<Genome *> &todo) {
     if (todo.empty()) return 0;
-    static_assert(AN_POSBITS <= 30, "entry.x keeps bit 31 for the slow flag");
+    static_assert(AN_POSBITS <= 30, "entry.x keeps bits 30..31 for the flank length");
     cudaStream_t st = ctx->stream;
     int64_t max_pos = 0;
     for (Genome *g : todo) max_pos = std::max(max_pos, g->n_pos);

@@ -30,11 +30,12 @@ struct MinimizerIndex {
     // order too, so both sides stream.  Entries of one group whose words have the same orientation match on the forward strand,
     // the others on the reverse strand.  An entry carries the 43 bases around its position, so a chance hit is rejected without
     // touching either sequence:
-    //   x = position (30 bits) | slow << 31 (the window holds a masked base or leaves the genome -> evaluate from the sequences);
-    //       0xffffffff = unused tail entry
-    //   y = window bases 32..42 (22 bits) | over << 30 (the word occurs more than AB_WORD_MAXOCC times in this genome)
+    //   x = position (30 bits) | bits 3..4 of rlen << 30;   0xffffffff = unused tail entry
+    //   y = window bases 32..42 (22 bits) | llen << 22 (5 bits) | bits 0..2 of rlen << 27
+    //       | over << 30 (the word occurs more than AB_WORD_MAXOCC times in this genome)
     //       | orientation << 31 (1: the reverse complement is the canonical form)
     //   z | w << 32 = window bases 0..31 (2 bits each; base i of the window = genome base position - 16 + i)
+    //   llen / rlen = flank bases next to the word, walking away from it, before the first masked base or genome end (0 .. 16)
     bool words_valid = false;
     int64_t cap_went = 0;
     uint32_t *d_woff = nullptr;     // 4^AB_WORD + 1 group starts into d_went

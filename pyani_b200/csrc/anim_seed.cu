@@ -332,31 +332,15 @@ __device__ __forceinline__ uint64_t rev2_words(uint64_t x) {  // reverse the ord
     uint64_t y = __brevll(x);
     return ((y & 0x5555555555555555ull) << 1) | ((y >> 1) & 0x5555555555555555ull);
 }
-// The word test from the sequences themselves (windows with a masked base or at a sequence end): is the word at (r0, q0) the
-// leftmost / rightmost of its exact match, and what does its diagonal score over the word and AB_WORD_FLANK bases to either
-// side, each flank ending at the first masked base or sequence end
-__device__ __noinline__ int word_eval_slow(const SeqView &R, const SeqView &Q, int64_t r0, int64_t q0, bool &leftmost, bool &rightmost) {
-    const int pa = view_code(R, r0 - 1), pb = view_code(Q, q0 - 1), na = view_code(R, r0 + AB_WORD), nb = view_code(Q, q0 + AB_WORD);
-    leftmost = !(pa < 4 && pa == pb);
-    rightmost = !(na < 4 && na == nb);
-    int sc = AB_MATCH * AB_WORD;
-    for (int side = 0; side < 2; ++side)
-        for (int x = 0; x < AB_WORD_FLANK; ++x) {
-            const int a = view_code(R, side ? r0 + AB_WORD + x : r0 - 1 - x), b = view_code(Q, side ? q0 + AB_WORD + x : q0 - 1 - x);
-            if (a > 3 || b > 3) break;
-            sc += a == b ? AB_MATCH : -AB_MISMATCH;
-        }
-    return sc;
-}
-
 // One block step = one tile of WORD_TILE entries of the query's word list (tiles never leave their pair: pairs[p].wtile_base);
 // a thread takes one query entry at a time -- position, 43-base window, canonical word -- and the subject's group of the same
 // canonical word: because both lists are sorted by it, neighbouring threads read neighbouring group starts and neighbouring
 // subject entries, so the subject's list streams through once per pair instead of being probed at random (the first version
 // walked the query by position: 34 s per 39,800-pair step, bound by random DRAM sectors).  Per subject entry ONE 16-byte load
-// brings the occurrence's position and its own window: equal orientation = forward-strand hit, windows compared as they are;
-// different orientation = reverse-strand hit, the query window reverse-complemented.  The test (at most 14 mismatches among the
-// 32 flank bases) and the leftmost / rightmost question are a few logic ops; a chance hit never touches either sequence.
+// brings the occurrence's position, its own window and how far that window is free of masked bases on either side: equal
+// orientation = forward-strand hit, windows compared as they are; different orientation = reverse-strand hit, the query window
+// reverse-complemented.  The test (at most 14 mismatches among 32 flank bases) and the leftmost / rightmost question are a few
+// logic ops; a chance hit never touches either sequence, masked bases included.
 // Accepted words extend to their maximal match and become anchors (clipped to the query's fragments).  The opposite direction
 // of the pair is fed from the same pass: on the forward strand it sees the same leftmost word; on the reverse strand ITS
 // leftmost word is this direction's rightmost one.
@@ -364,7 +348,6 @@ __global__ void __launch_bounds__(256) word_probe_kernel(const PairDesc *__restr
                                                          uint64_t *__restrict__ vals, unsigned long long *__restrict__ n_anchors, unsigned long long cap,
                                                          unsigned long long *__restrict__ wcount /*0: occurrences looked at, 1: words accepted*/) {
     constexpr uint64_t EVEN = 0x5555555555555555ull;
-    constexpr int MAXMM = (AB_MATCH * (AB_WORD + 2 * AB_WORD_FLANK) - AB_WORD_MIN) / (AB_MATCH + AB_MISMATCH);  // mismatches the flanks may hold
     __shared__ AnchorStage stage;
     if (threadIdx.x == 0) stage.n = 0;
     __syncthreads();
@@ -385,6 +368,7 @@ __global__ void __launch_bounds__(256) word_probe_kernel(const PairDesc *__restr
             if (eq.x == 0xffffffffu || ((eq.y >> 30) & 1u)) continue;  // unused tail / over-represented in the query
             const int64_t pq = eq.x & 0x3fffffffu;
             const uint32_t oq = eq.y >> 31;
+            const int lq = (int)((eq.y >> 22) & 31u), rq = (int)(((eq.y >> 27) & 7u) | ((eq.x >> 30) << 3));  // valid flank bases of the query window
             const uint64_t wlo = (uint64_t)eq.z | ((uint64_t)eq.w << 32);
             const uint32_t whi = eq.y & (AB_NWORDS - 1u);
             const uint32_t w = (uint32_t)(rev2_words(wlo) >> (2 * (32 - AB_WORD_FLANK - AB_WORD))) & (AB_NWORDS - 1u);
@@ -403,21 +387,19 @@ __global__ void __launch_bounds__(256) word_probe_kernel(const PairDesc *__restr
                 const int64_t r0 = e.x & 0x3fffffffu, q0 = strand ? (int64_t)P.q_npos - AB_WORD - pq : pq;
                 ++hits;
                 const SeqView Q{P.q_seq, P.q_mask, P.q_npos, strand};
-                bool leftmost, rightmost;
-                int sc;
-                if ((e.x | eq.x) >> 31) {
-                    sc = word_eval_slow(R, Q, r0, q0, leftmost, rightmost);
-                } else {
-                    const uint64_t dlo = (strand ? rlo : wlo) ^ ((uint64_t)e.z | ((uint64_t)e.w << 32));
-                    const uint32_t dhi = (strand ? rhi : whi) ^ (e.y & (AB_NWORDS - 1u));
-                    const uint64_t mlo = (dlo | (dlo >> 1)) & EVEN;
-                    const uint32_t mhi = (dhi | (dhi >> 1)) & 0x155555u;
-                    // window bases 0..15 = left flank, 16..26 = the word, 27..31 (mlo) and 32..42 (mhi) = right flank
-                    const int mm = __popc((uint32_t)mlo) + __popcll(mlo >> (2 * (AB_WORD_FLANK + AB_WORD))) + __popc(mhi);
-                    leftmost = (mlo >> (2 * (AB_WORD_FLANK - 1))) & 1ull;
-                    rightmost = (mlo >> (2 * (AB_WORD_FLANK + AB_WORD))) & 1ull;
-                    sc = mm <= MAXMM ? AB_WORD_MIN : AB_WORD_MIN - 1;
-                }
+                // a flank reaches as far as both windows are free of masked bases (on the reverse strand the query's flanks swap)
+                const int L = min((int)((e.y >> 22) & 31u), strand ? rq : lq);
+                const int Rr = min((int)(((e.y >> 27) & 7u) | ((e.x >> 30) << 3)), strand ? lq : rq);
+                const uint64_t dlo = (strand ? rlo : wlo) ^ ((uint64_t)e.z | ((uint64_t)e.w << 32));
+                const uint32_t dhi = (strand ? rhi : whi) ^ (e.y & (AB_NWORDS - 1u));
+                const uint64_t mlo = (dlo | (dlo >> 1)) & EVEN;
+                const uint32_t mhi = (dhi | (dhi >> 1)) & 0x155555u;
+                // window bases 0..15 = left flank (15 next to the word), 16..26 = the word, 27..42 = right flank (mlo bits 54.., then mhi)
+                const uint32_t ml = (uint32_t)mlo, mr = (uint32_t)(mlo >> (2 * (AB_WORD_FLANK + AB_WORD))) | (mhi << (2 * (32 - AB_WORD_FLANK - AB_WORD)));
+                const uint32_t maskl = L ? 0x55555555u & ~((1u << (2 * (AB_WORD_FLANK - L))) - 1u) : 0u;
+                const uint32_t maskr = Rr >= AB_WORD_FLANK ? 0x55555555u : 0x55555555u & ((1u << (2 * Rr)) - 1u);
+                const int sc = AB_MATCH * (AB_WORD + L + Rr) - (AB_MATCH + AB_MISMATCH) * (__popc(ml & maskl) + __popc(mr & maskr));
+                const bool leftmost = L == 0 || ((ml >> (2 * (AB_WORD_FLANK - 1))) & 1u), rightmost = Rr == 0 || (mr & 1u);
                 if (sc < AB_WORD_MIN) continue;
                 const bool to_mirror = P.mirror >= 0 && (strand ? rightmost : leftmost);
                 if (!leftmost && !to_mirror) continue;
