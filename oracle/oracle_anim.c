@@ -93,8 +93,11 @@ orc_genome *orc_genome_create_kw(const uint8_t *ascii, const uint64_t *off, uint
 orc_genome *orc_genome_create(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs) {
     return orc_genome_create_kw(ascii, off, n_contigs, AN_MAXOCC, AN_K, AN_W);
 }
+static void build_words(orc_genome *g);
 orc_genome *orc_genome_create_anib(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs) {
-    return orc_genome_create_kw(ascii, off, n_contigs, AN_MAXOCC, AB_K, AB_W);
+    orc_genome *g = orc_genome_create_kw(ascii, off, n_contigs, AN_MAXOCC, AB_K, AB_W);
+    build_words(g); /* the ANIb word index belongs to the ANIb index (built here, not inside the first comparison) */
+    return g;
 }
 orc_genome *orc_genome_create_occ(const uint8_t *ascii, const uint64_t *off, uint32_t n_contigs, int maxocc) {
     return orc_genome_create_kw(ascii, off, n_contigs, maxocc, AN_K, AN_W);

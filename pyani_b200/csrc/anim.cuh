@@ -67,7 +67,7 @@ struct PairDesc {
     const uint4 *r_went, *q_went;
     int64_t wtile_base;
 };
-constexpr int WORD_TILE = 2048;  // query entries per block step of word_probe_kernel (256 threads x 8)
+constexpr int WORD_TILE = 4096;  // query entries per block step of word_probe_kernel (256 threads x 16)
 
 __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;

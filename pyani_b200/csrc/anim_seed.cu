@@ -415,8 +415,10 @@ __global__ void __launch_bounds__(256) word_probe_kernel(const PairDesc *__restr
                 }
             }
         }
-        flush_stage(stage, keys, vals, n_anchors, cap);
+        // anchors are rare here (tens per tile): the stage is flushed when half full, not after every tile
+        if (__syncthreads_or(stage.n > STAGE_CAP / 2)) flush_stage(stage, keys, vals, n_anchors, cap);
     }
+    flush_stage(stage, keys, vals, n_anchors, cap);
     for (int off = 16; off; off >>= 1) {
         hits += __shfl_down_sync(0xffffffffu, hits, off);
         accepted += __shfl_down_sync(0xffffffffu, accepted, off);
