@@ -64,7 +64,7 @@ def full(tag):
                     i = hdr.index(name)
                     v = float(row[i].replace(",", ""))
                     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[i], 1)
-                kname = re.sub(r"<.*|\(.*", "", row[hdr.index("Kernel Name")]).split("::")[-1]
+                kname = re.sub(r"<.*|\(.*", "", row[hdr.index("Kernel Name")]).split("::")[-1].replace("void ", "").strip()
                 per_kernel[kname].append(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
             except (ValueError, IndexError):
                 pass
@@ -78,7 +78,9 @@ def full(tag):
         parts = rep.stem.split("_")
         if len(parts) >= 3:
             for k, v in per_kernel.items():
-                traffic.setdefault(parts[1], {})[k] = sum(v) / len(v)
+                v = [x for x in v if x == x]  # a launch whose counters ncu could not read comes back as nan
+                if v:
+                    traffic.setdefault(parts[1], {})[k] = sum(v) / len(v)
     if traffic:
         import json
 
