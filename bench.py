@@ -134,24 +134,27 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_sample(n_clades: int, per_clade: int, cores: int):
+def cpu_sample(n_clades: int, per_clade: int, cores: int, min_pairs: int = 0, max_pairs: int = 0):
     """Genomes and directed pairs of the bounded CPU sample: `g` genomes spread as evenly as possible over the first `nc`
-    clades, ALL directed pairs among them -- at least 2 x cores pairs (every host thread stays busy) with the within-clade
-    share closest to the full list's (per_clade-1)/(n_clades*per_clade-1)."""
+    clades, ALL directed pairs among them -- at least `min_pairs` (default 2 x cores: every host thread stays busy) and, if it can
+    be had, at most `max_pairs` (default 6 x cores) pairs with the within-clade share closest to the full list's
+    (per_clade-1)/(n_clades*per_clade-1)."""
+    min_pairs = min_pairs or 2 * cores
+    max_pairs = max_pairs or 6 * cores
     full_within = (per_clade - 1) / max(1, n_clades * per_clade - 1)
     n_all = n_clades * per_clade
     best = None
     for nc in range(2, n_clades + 1):
         for g in range(nc, nc * per_clade + 1):
             pairs = g * (g - 1)
-            if pairs < 2 * cores and g < n_all:
+            if pairs < min_pairs and g < n_all:
                 continue
             q, r = divmod(g, nc)  # r clades hold q+1 strains, nc-r hold q
             within = r * (q + 1) * q + (nc - r) * q * (q - 1)
-            cand = (pairs > 6 * cores and g < n_all, abs(within / pairs - full_within), pairs, nc, g)
+            cand = (pairs > max_pairs and g < n_all, abs(within / pairs - full_within), pairs, nc, g)
             if best is None or cand < best:
                 best = cand
-            if pairs > 6 * cores:
+            if pairs > max_pairs:
                 break
     _, _, _, nc, g = best
     q, r = divmod(g, nc)
@@ -167,7 +170,9 @@ def run_cpu_sample(args, kind: str, cores: int):
     from concurrent.futures import ThreadPoolExecutor
 
     _, n_clades, per_clade, _, _, _ = workload_params(args)
-    idx, pairs, within, full_within = cpu_sample(n_clades, per_clade, cores)
+    # ANIb: one comparison of two 5 Mb genomes keeps a core busy for ~40 s (the word stage is scalar here), so the sample is one
+    # pair per thread (a single round) instead of >= 2 per thread
+    idx, pairs, within, full_within = cpu_sample(n_clades, per_clade, cores, *((int(0.8 * cores), int(1.2 * cores)) if kind == "anib" else ()))
     genomes = make_genomes(args, 0, 1, only_clades=sorted({i // per_clade for i in idx}))
     by_id = {i: genomes[i] for i in idx}
     def make(res, off):
