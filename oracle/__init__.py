@@ -264,7 +264,7 @@ def anib_pairs_mt(genomes, pairs, threads: int = 0, fragsize: int = 1020):
 def anib_results_mt(genomes, pairs, threads: int = 0, fragsize: int = 1020):
     """:func:`anib_pair` result dicts for many (query, subject) index pairs into ``genomes``, computed on host threads
     (the word stage makes a 4 Mb pair take ~10 s on one core)."""
-    out, _ = anib_pairs_mt(genomes, pairs, threads, fragsize)
+    out, _ = anib_pairs_mt(genomes, pairs, threads or min(len(pairs), os.cpu_count() or 1), fragsize)
     return [dict(aln_length=int(o[0]), sim_errs=int(o[1]), pid_milli_sum=int(o[2]), n_frags=int(o[3]), n_pass=int(o[4]), n_hsps=int(o[5]),
                  status=0 if o[4] else 1) for o in out]
 
