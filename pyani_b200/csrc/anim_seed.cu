@@ -309,19 +309,6 @@ __global__ void __launch_bounds__(256) seed_extend_kernel(const PairDesc *__rest
 }
 
 // ---- ANIb word anchors (blastn's 11-mer words + ungapped extension test; specification: oracle/oracle_anim.c "word anchors")
-// 32 bases of a view starting at any x: positions outside [0, n) come back masked
-__device__ __forceinline__ uint64_t chunk_any(const SeqView &v, int64_t x, uint32_t &mk) {
-    if (x >= 0 && x + 32 <= v.n) return view_chunk(v, x, mk);
-    uint64_t c = 0;
-    uint32_t m = 0;
-#pragma unroll 1
-    for (int k = 0; k < 32; ++k) {
-        const int code = view_code(v, x + k);
-        if (code > 3) m |= 1u << k; else c |= (uint64_t)code << (2 * k);
-    }
-    mk = m;
-    return c;
-}
 __device__ __forceinline__ uint32_t word_revcomp(uint32_t w) {
     uint32_t r = 0;
 #pragma unroll
