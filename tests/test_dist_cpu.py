@@ -104,3 +104,35 @@ def test_deal_partitions_and_keeps_directions_together():
         s0 = pairs[shares[0]]
         keys = [(min(a, b), max(a, b)) for a, b in s0.tolist()]
         assert keys == sorted(keys)
+
+
+def test_default_dealing_balances_clade_structured_costs():
+    """Genome ids grouped by clade (10 strains each), a within-clade comparison 20 x as costly as a between-clade one: the
+    default deal (single unordered pairs, round-robin in walk order) keeps every rank within 1 % of the mean cost -- chunks
+    of 64 hand the clade mates of a genome to one rank as a lump (several per cent apart, what the 8-GPU run measured)."""
+    from pyani_b200 import synth
+
+    n, world = 200, 8
+    pairs = synth.all_directed_pairs(n)
+    cost = np.where(pairs[:, 0] // 10 == pairs[:, 1] // 10, 20.0, 1.0)
+
+    def spread(chunk):
+        tot = np.array([cost[s].sum() for s in pdist.deal(pairs, world, chunk=chunk)])
+        return tot.max() / tot.mean()
+
+    assert spread(1) == pytest.approx(spread(pdist.deal.__defaults__[0]))  # the default IS single dealing
+    assert spread(1) < 1.01 < spread(64)
+
+
+def test_bench_cpu_sample_keeps_every_core_busy_with_the_full_lists_clade_mix():
+    import importlib.util
+    from pathlib import Path
+
+    spec = importlib.util.spec_from_file_location("bench_mod", Path(__file__).resolve().parents[1] / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    idx, pairs, within, full_within = bench.cpu_sample(50, 10, 128)  # ANIm, configs[3] on a 128-thread host
+    assert 2 * 128 <= len(pairs) <= 6 * 128 and len(pairs) == len(idx) * (len(idx) - 1)
+    assert abs(within / len(pairs) - full_within) < 0.005
+    idx, pairs, within, full_within = bench.cpu_sample(20, 10, 128, 102, 153)  # ANIb: one pair per thread
+    assert 102 <= len(pairs) <= 153 and abs(within / len(pairs) - full_within) < 0.01
