@@ -136,3 +136,20 @@ def test_bench_cpu_sample_keeps_every_core_busy_with_the_full_lists_clade_mix():
     assert abs(within / len(pairs) - full_within) < 0.005
     idx, pairs, within, full_within = bench.cpu_sample(20, 10, 128, 102, 153)  # ANIb: one pair per thread
     assert 102 <= len(pairs) <= 153 and abs(within / len(pairs) - full_within) < 0.01
+
+
+def test_index_layout_blocks_are_disjoint_aligned_and_equal_sized():
+    """dist.index_layout (the slab the ranks all-gather their seed indexes through): every genome's four arrays lie inside its
+    owner's block, 256-byte aligned, without overlap; table sizes follow the engine's rule (smallest power of two >= 2 x minimizers)."""
+    rng = np.random.default_rng(3)
+    n_mini = rng.integers(1_000, 2_000_000, size=37)
+    for world in (1, 2, 8):
+        block_of, off, bits, block_bytes = pdist.index_layout(n_mini, world)
+        assert (np.diff(block_of) >= 0).all() and block_of.max() <= world - 1
+        assert ((1 << bits) >= 2 * n_mini).all() and ((1 << (bits - 1)) < 2 * n_mini).all()
+        sizes = np.stack([4 * n_mini, 4 * n_mini, 8 << bits, 4 << (bits - 2)], axis=1)
+        spans = sorted((int(off[g, a]), int(off[g, a] + sizes[g, a]), g) for g in range(len(n_mini)) for a in range(4))
+        assert all(s % 256 == 0 for s, _, _ in spans)
+        assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+        for s, e, g in spans:
+            assert block_of[g] * block_bytes <= s and e <= (block_of[g] + 1) * block_bytes
