@@ -21,8 +21,8 @@
  * Environment hooks ORC_DUMP_SEGS / ORC_MUM are analysis aids for scripts/ (segment dump; true-MUM seed experiment); tests
  * never set them.
  *
- * Deliberately simple: byte-per-base sequences, O(n log n) sorts, scalar DP.  Single-threaded per call;
- * callers parallelise over pairs with Python threads (ctypes releases the GIL).
+ * Deliberately simple: byte-per-base sequences, O(n log n) sorts, scalar DP.  Single-threaded per call; the
+ * orc_*_pairs_mt drivers at the end run independent pairs on POSIX threads (bench.py's CPU arm, the slow fixture tests).
  */
 #include <stdint.h>
 #include <stdio.h>
@@ -821,6 +821,9 @@ void orc_filter_1to1(const int64_t *rows /* n x 8 */, int64_t n, uint8_t *keep) 
  * tolerance (tests/test_concordance.py:118-153).
  *
  * Same machinery as the ANIm aligner with the subject as "reference" (table side):
+ *   seeds = 13-mer minimizers unique in both genomes PLUS word anchors (every exact match >= 11 whose leftmost word passes
+ *   the diagonal test below: blastn's word lookup + ungapped extension; pinned on the BLAST+ fixtures: aligned length 0.96-0.985
+ *   of BLAST's on the 80-84 % pairs, tests/test_anib_oracle_fixtures.py);
  *   anchors are clipped to the query's fragments (pieces >= AB_MINPIECE kept), linking / link alignment /
  *   extension never leave the fragment, every chain is a candidate HSP; scoring +2 / -3 / 5 per gap column
  *   (linear, so the gap columns follow from score, errors and consumed bases: G = L - 5E - score);
