@@ -173,7 +173,7 @@ int64_t b200ani_anib_rows(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int
                           int64_t *row_start);
 
 /* Stage timers in milliseconds (CUDA events on the engine stream) and work counters of the last b200ani_anim / b200ani_anib call
- * (slots "index" .. "bridge"), of the b200ani_add_genome calls since the last b200ani_clear ("pack": the pack kernel), and of
+ * (slots "index" .. "bridge" and "words": the ANIb word stage), of the b200ani_add_genome calls since the last b200ani_clear ("pack": the pack kernel), and of
  * the last TETRA calls ("tetra_count": the counting kernel, "tetra_total" / "tetra_corr_total": the whole b200ani_tetra_zscores /
  * b200ani_tetra_corr call); used by bench.py for the rooflines and gpu_launches. */
 #define B200ANI_N_STAGES 24
