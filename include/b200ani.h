@@ -178,7 +178,7 @@ int64_t b200ani_anib_rows(b200ani_ctx *ctx, const int32_t *pairs, int64_t m, int
  * b200ani_tetra_corr call); used by bench.py for the rooflines and gpu_launches. */
 #define B200ANI_N_STAGES 24
 int b200ani_last_profile(const b200ani_ctx *ctx, double *stage_ms /*B200ANI_N_STAGES*/, int64_t *counters /*B200ANI_N_STAGES*/);
-/* i in [0,16): stage name; i in [16,32): name of counter i-16 ("" = unused slot) */
+/* i in [0, B200ANI_N_STAGES): stage name; i in [B200ANI_N_STAGES, 2 * B200ANI_N_STAGES): name of counter i - B200ANI_N_STAGES ("" = unused slot) */
 const char *b200ani_stage_name(int i);
 
 /* ---- several GPUs of one node behind one handle (run_multiprocessing.py:113-152 / run_sge.py:87-112 for callers that are not
